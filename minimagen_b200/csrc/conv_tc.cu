@@ -1,0 +1,394 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05 + TMEM), im2col-free.
+//
+// Replaces every dense `nn.Conv2d` / `nn.Linear` on the U-Net hot path whose channel counts are multiples of 64
+// (reference call sites: minimagen/layers.py:129 (Block.project 3x3), :415 (res_conv 1x1), :319 (Downsample 4x4 s2),
+// :514 (Upsample conv), :157/:160 (ChanFeedForward 1x1), :41-42/:48/:213-214/:217 (attention projections);
+// minimagen/Unet.py:234).
+//
+// GEMM view:  D[M = B*H*W pixels, N = C_out] = sum over taps t, channels c of  A_t[pixel shifted by tap t, c] * Wp[n, t*C_in + c]
+//   * activations live in HBM as NHWC fp16 (optionally with a leading "phase" axis, see below);
+//   * one A tile (128 pixels x 64 channels) for tap (dh, dw) is ONE TMA box load from the 5-D tensor
+//     (C, W, H, P, B) at coordinates (c0, w0 + dw, h0 + dh, p, b0): TMA zero-fills out-of-bounds coordinates, which
+//     IS the convolution's zero padding -- no im2col buffer, no halo handling in the kernel;
+//   * stride-2 convs read a phase-split copy of the input (P = 4 phases) so that every tap is again a unit-stride box;
+//   * weights are pre-packed [C_out][taps*C_in] fp16 (K-major), one 2-D TMA box (64 x BLOCK_N) per k-block;
+//   * both operands land in shared memory in the 128-byte-swizzled K-major layout that tcgen05.mma consumes directly;
+//   * accumulators: fp32 in TMEM, double-buffered (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+//     main loop of tile i+1; persistent CTAs (one per SM) walk the tile list round-robin.
+//
+// Warp roles (256 threads): warp0 = TMA producer (1 lane), warp1 = MMA issuer (1 lane), warp2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM -> registers -> +bias +residual -> global fp32 and/or fp16).
+#include "conv_tc.cuh"
+
+#include <cuda_runtime.h>
+#include <mutex>
+#include <stdio.h>
+
+#include "ptx.cuh"
+
+namespace mi {
+
+namespace {
+
+constexpr int kNumThreads = 256;
+constexpr uint32_t kABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB per stage
+
+template <int BLOCK_N>
+struct Cfg {
+    static constexpr uint32_t kBBytes = BLOCK_N * kConvBlockK * 2;
+    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    // fill ~192 KiB with stages
+    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr uint32_t kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);   // powers of two for our BLOCK_Ns
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ ConvTcArgs args) {
+    using C = Cfg<BLOCK_N>;
+    constexpr int STAGES = C::kStages;
+
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte aligned stage bases
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStageBytes);
+    uint64_t* full_bar = bars;                    // [STAGES]  TMA -> MMA
+    uint64_t* empty_bar = bars + STAGES;          // [STAGES]  MMA -> TMA
+    uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int* err = args.err_flag;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 128);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_kb = args.num_taps * args.chunks_per_tap;
+    const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
+    const int total_tiles = tiles_m * args.tiles_n;
+    const int BW = 1 << args.bw_log2, BH = 1 << args.bh_log2;
+    const int BB = kConvBlockM >> (args.bw_log2 + args.bh_log2);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % args.tiles_n;
+                const int mt = tile / args.tiles_n;
+                const int w0 = (mt % args.tiles_w) * BW;
+                const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
+                const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
+                const int n0 = nt * BLOCK_N;
+                int kb = 0;
+                for (int t = 0; t < args.num_taps; ++t) {
+                    const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
+                    for (int j = 0; j < args.chunks_per_tap; ++j, ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
+                        uint8_t* sa = smem + stage * C::kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                        ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
+                                         h0 + dh, ph, b0);
+                        ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0 /*fp16*/);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase, err, 300 + stage);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kConvBlockK / 16; ++k) {
+                        // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
+                        ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    ptx::umma_commit(&empty_bar[stage]);             // frees the smem slot when these MMAs retire
+                    if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[as]);   // accumulator complete
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int ew = warp & 3;                 // TMEM lane quarter this warp may access
+        const int m = ew * 32 + lane;            // row of the tile == TMEM lane
+        const int bw = m & (BW - 1);
+        const int bh = (m >> args.bw_log2) & (BH - 1);
+        const int bb = m >> (args.bw_log2 + args.bh_log2);
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int nt = tile % args.tiles_n;
+            const int mt = tile / args.tiles_n;
+            const int w = (mt % args.tiles_w) * BW + bw;
+            const int h = ((mt / args.tiles_w) % args.tiles_h) * BH + bh;
+            const int b = (mt / (args.tiles_w * args.tiles_h)) * BB + bb;
+            const int n0 = nt * BLOCK_N;
+            const bool valid = (b < args.B) && (h < args.H) && (w < args.W);
+            const long long pix = (long long)b * args.out_sb + (long long)h * args.out_sh + (long long)w * args.out_sw;
+
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 16) {
+                uint32_t v[16];
+                ptx::tmem_ld_x16(taddr + c, v);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    const int n = n0 + c;
+                    if (args.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(args.bias + n + i));
+                            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                        }
+                    }
+                    if (args.residual) {
+                        const float* r = args.residual + pix + n;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 rv = *reinterpret_cast<const float4*>(r + i);
+                            f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
+                        }
+                    }
+                    if (args.out_f32) {
+                        float* o = args.out_f32 + pix + n;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4)
+                            *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                    }
+                    if (args.out_f16) {
+                        __half* o = args.out_f16 + pix + n;
+                        uint32_t p[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                            p[i] = *reinterpret_cast<uint32_t*>(&h2);
+                        }
+                        *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+                        *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int ilog2_exact(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return ((1 << l) == v) ? l : -1;
+}
+
+template <int BLOCK_N>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& args, int total_tiles, int num_sms,
+           cudaStream_t stream) {
+    using C = Cfg<BLOCK_N>;
+    static bool attr_set = false;   // per-template-instance; benign race (idempotent call)
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::kSmemBytes);
+        if (e != cudaSuccess) return -10;
+        attr_set = true;
+    }
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    return cudaGetLastError() == cudaSuccess ? 0 : -11;
+}
+
+}  // namespace
+
+const char* conv_tc_strerror(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case -1: return "conv_tc: C_in (per tap) must be a positive multiple of 64";
+        case -2: return "conv_tc: C_out must be a multiple of 16";
+        case -3: return "conv_tc: W must be a power of two >= 8 or a multiple of 128; H*W tiling unsupported";
+        case -4: return "conv_tc: too many taps (max 16)";
+        case -5: return "conv_tc: cuTensorMapEncodeTiled unavailable";
+        case -6: return "conv_tc: tensor map encode failed (activations)";
+        case -7: return "conv_tc: tensor map encode failed (weights)";
+        case -8: return "conv_tc: pointer/stride alignment (16 B) violated";
+        case -10: return "conv_tc: cudaFuncSetAttribute(max dynamic smem) failed";
+        case -11: return "conv_tc: kernel launch failed";
+        default: return "conv_tc: unknown error";
+    }
+}
+
+bool conv_tc_supported(int H, int W, int Cin, int Cout) {
+    if (Cin <= 0 || Cin % kConvBlockK != 0 || Cout <= 0 || Cout % 16 != 0) return false;
+    if (W >= 128) return W % 128 == 0;                    // BW = 128, BH = 1, BB = 1
+    if (ilog2_exact(W) < 3) return false;                 // W in {8,16,32,64}
+    const int bh = 128 / W;
+    if (H >= bh) return H % bh == 0;                      // BH = 128 / W rows of one image
+    return ilog2_exact(H) >= 0;                           // BH = H, the tile spans 128 / (W*H) images
+}
+
+int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
+    if (p.Cin <= 0 || p.Cin % kConvBlockK != 0) return -1;
+    if (p.Cout % 16 != 0) return -2;
+    if (p.num_taps < 1 || p.num_taps > kConvMaxTaps) return -4;
+    if (!conv_tc_supported(p.H, p.W, p.Cin, p.Cout)) return -3;
+    if ((reinterpret_cast<uintptr_t>(p.act) & 15) || (reinterpret_cast<uintptr_t>(p.wpacked) & 15) ||
+        (p.lda % 8) != 0)
+        return -8;
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return -5;
+
+    ConvTcArgs a{};
+    a.num_taps = p.num_taps;
+    a.chunks_per_tap = p.Cin / kConvBlockK;
+    int BW = p.W >= 128 ? 128 : p.W;
+    int BH = 128 / BW;
+    if (BH > p.H) BH = p.H;
+    int BB = 128 / (BW * BH);
+    a.bw_log2 = ilog2_exact(BW);
+    a.bh_log2 = ilog2_exact(BH);
+    a.tiles_w = p.W / BW;
+    a.tiles_h = p.H / BH;
+    a.tiles_b = (p.B + BB - 1) / BB;
+    a.B = p.B; a.H = p.H; a.W = p.W;
+    a.a_chan_off = p.a_chan_off;
+    a.out_sb = p.out_sb; a.out_sh = p.out_sh; a.out_sw = p.out_sw;
+    a.out_f32 = p.out_f32; a.out_f16 = p.out_f16; a.bias = p.bias; a.residual = p.residual;
+    a.err_flag = p.err_flag;
+    for (int t = 0; t < p.num_taps; ++t) { a.dh[t] = p.dh[t]; a.dw[t] = p.dw[t]; a.ph[t] = p.ph[t]; }
+
+    // BLOCK_N: largest of {256,128,64,32,16} dividing C_out that still yields >= 1 wave of tiles if possible
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static int num_sms_cache[64] = {0};
+    if (dev < 64 && num_sms_cache[dev] == 0)
+        cudaDeviceGetAttribute(&num_sms_cache[dev], cudaDevAttrMultiProcessorCount, dev);
+    const int num_sms = dev < 64 ? num_sms_cache[dev] : 148;
+    const int tiles_m = a.tiles_w * a.tiles_h * a.tiles_b;
+    int block_n = 0;
+    const int cands[5] = {256, 128, 64, 32, 16};
+    if (p.block_n_hint > 0 && p.Cout % p.block_n_hint == 0) {
+        for (int i = 0; i < 5; ++i)
+            if (cands[i] == p.block_n_hint) block_n = cands[i];
+    }
+    if (block_n == 0) {
+        // largest BLOCK_N dividing C_out that still gives every SM a tile; never shrink below 64 for that reason
+        for (int i = 0; i < 5; ++i) {
+            if (p.Cout % cands[i] != 0) continue;
+            block_n = cands[i];
+            if (tiles_m * (p.Cout / cands[i]) >= num_sms || cands[i] <= 64) break;
+        }
+    }
+    a.tiles_n = p.Cout / block_n;
+    const int total_tiles = tiles_m * a.tiles_n;
+
+    // activation map: (C, W, H, P, B), fp16, box (64, BW, BH, 1, BB), 128B swizzle, OOB -> zeros
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.phases,
+                              (cuuint64_t)p.B};
+        cuuint64_t gstr[4] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.W * p.lda * 2, (cuuint64_t)p.H * p.W * p.lda * 2,
+                              (cuuint64_t)p.phases * p.H * p.W * p.lda * 2};
+        cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)BW, (cuuint32_t)BH, 1, (cuuint32_t)BB};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(p.act), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -6;
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)p.num_taps * p.Cin;
+        cuuint64_t gdim[2] = {K, (cuuint64_t)p.Cout};
+        cuuint64_t gstr[1] = {K * 2};
+        cuuint32_t box[2] = {kConvBlockK, (cuuint32_t)block_n};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.wpacked), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -7;
+    }
+
+    switch (block_n) {
+        case 256: return launch<256>(tmA, tmB, a, total_tiles, num_sms, stream);
+        case 128: return launch<128>(tmA, tmB, a, total_tiles, num_sms, stream);
+        case 64: return launch<64>(tmA, tmB, a, total_tiles, num_sms, stream);
+        case 32: return launch<32>(tmA, tmB, a, total_tiles, num_sms, stream);
+        default: return launch<16>(tmA, tmB, a, total_tiles, num_sms, stream);
+    }
+}
+
+}  // namespace mi

@@ -1,0 +1,52 @@
+// Host/device interface of the tcgen05 implicit-GEMM convolution (see conv_tc.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mi {
+
+constexpr int kConvBlockM = 128;   // pixels per tile (UMMA M)
+constexpr int kConvBlockK = 64;    // fp16 channels per k-block (= one 128-byte swizzle row)
+constexpr int kConvMaxTaps = 16;   // 4x4 kernel
+
+// Kernel-side arguments (passed as one __grid_constant__ struct).
+struct ConvTcArgs {
+    int num_taps, chunks_per_tap;
+    int bw_log2, bh_log2;                 // tile box: BW x BH pixels x BB images, BW*BH*BB == 128
+    int tiles_w, tiles_h, tiles_b, tiles_n;
+    int B, H, W;                          // output pixel grid (== TMA pixel grid of every phase)
+    int a_chan_off;                       // first input channel inside the activation buffer
+    long long out_sb, out_sh, out_sw;     // output (and residual) strides in elements
+    float* out_f32;                       // optional
+    __half* out_f16;                      // optional
+    const float* bias;                    // optional, [C_out]
+    const float* residual;                // optional, fp32, same strides as the output
+    int* err_flag;                        // optional: pipeline-timeout code is written here before trapping
+    int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
+};
+
+// Host-side problem description.
+struct ConvTcProblem {
+    const void* act;        // fp16 activations, layout [B][phases][H][W][lda]
+    int B, H, W;            // pixel grid of each phase == output pixel grid
+    int phases;             // 1, or 4 for the phase-split input of a stride-2 conv
+    int lda;                // elements per pixel in the activation buffer (>= a_chan_off + Cin)
+    int a_channels;         // channel extent visible to TMA (usually lda)
+    int a_chan_off;         // first channel used
+    int Cin;                // channels per tap
+    const void* wpacked;    // fp16 [Cout][num_taps*Cin]
+    int Cout;
+    int num_taps;
+    int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
+    float* out_f32; __half* out_f16; const float* bias; const float* residual;
+    long long out_sb, out_sh, out_sw;
+    int block_n_hint;       // 0 = auto
+    int* err_flag;
+};
+
+bool conv_tc_supported(int H, int W, int Cin, int Cout);
+int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream);
+const char* conv_tc_strerror(int code);
+
+}  // namespace mi

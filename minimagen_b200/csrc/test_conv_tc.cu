@@ -1,0 +1,239 @@
+// Standalone GPU self-test + micro-benchmark of the tcgen05 implicit-GEMM conv (no Python, no torch).
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo conv_tc.cu test_conv_tc.cu -o test_conv_tc
+// Run:    ./test_conv_tc [check|perf|all]
+// Correctness reference: direct convolution in double over the same fp16-rounded operands (exact up to fp32
+// accumulation order), so the tolerance can be tight.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "conv_tc.cuh"
+
+using namespace mi;
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            printf("CUDA error %s at %s:%d (%s)\n", cudaGetErrorString(e_), __FILE__, __LINE__, #x); \
+            fflush(stdout);                                                                     \
+            exit(2);                                                                            \
+        }                                                                                       \
+    } while (0)
+
+static uint32_t rng_state = 12345u;
+static float frand() {   // uniform in [-1, 1)
+    rng_state = rng_state * 1664525u + 1013904223u;
+    return ((rng_state >> 8) & 0xFFFFFF) / 8388608.0f - 1.0f;
+}
+
+struct Case {
+    const char* name;
+    int B, H, W, Cin, Cout, k, stride;   // stride 1 (k=1|3) or 2 (k=4, pad 1)
+    bool bias, residual, f16out;
+    int hint;
+};
+
+static int* g_err = nullptr;   // host-mapped
+
+// returns max abs error (or -1 on failure)
+static double run_case(const Case& c, bool check, int reps, double* ms_out) {
+    const int Ho = c.H / c.stride, Wo = c.W / c.stride;
+    const int pad = (c.k == 3) ? 1 : (c.k == 4 ? 1 : 0);
+    const int taps = c.k * c.k;
+    const size_t n_in = (size_t)c.B * c.H * c.W * c.Cin;
+    const size_t n_w = (size_t)c.Cout * taps * c.Cin;
+    const size_t n_out = (size_t)c.B * Ho * Wo * c.Cout;
+    std::vector<__half> h_in(n_in), h_w(n_w);
+    std::vector<float> f_in, f_w;
+    std::vector<float> h_bias(c.Cout), h_res;
+    if (check) { f_in.resize(n_in); f_w.resize(n_w); }
+    for (size_t i = 0; i < n_in; ++i) { __half v = __float2half_rn(frand()); h_in[i] = v; if (check) f_in[i] = __half2float(v); }
+    const float wscale = 1.0f / sqrtf((float)(taps * c.Cin));
+    for (size_t i = 0; i < n_w; ++i) { __half v = __float2half_rn(frand() * wscale * 4.f); h_w[i] = v; if (check) f_w[i] = __half2float(v); }
+    for (int i = 0; i < c.Cout; ++i) h_bias[i] = frand();
+    if (c.residual) { h_res.resize(n_out); for (size_t i = 0; i < n_out; ++i) h_res[i] = frand(); }
+
+    // device input layout: stride 1 -> [B][1][H][W][C]; stride 2 -> phase split [B][4][Ho][Wo][C], phase = (h&1)*2 + (w&1)
+    std::vector<__half> h_dev_in(n_in);
+    if (c.stride == 1) {
+        h_dev_in = h_in;
+    } else {
+        for (int b = 0; b < c.B; ++b)
+            for (int h = 0; h < c.H; ++h)
+                for (int w = 0; w < c.W; ++w) {
+                    const int p = (h & 1) * 2 + (w & 1);
+                    const size_t dst = ((((size_t)b * 4 + p) * Ho + (h >> 1)) * Wo + (w >> 1)) * c.Cin;
+                    const size_t src = (((size_t)b * c.H + h) * c.W + w) * c.Cin;
+                    memcpy(&h_dev_in[dst], &h_in[src], c.Cin * sizeof(__half));
+                }
+    }
+    // weights are generated directly in packed order [Cout][tap][Cin], tap = r*k + s
+
+    __half *d_in, *d_w, *d_o16 = nullptr;
+    float *d_o32, *d_bias = nullptr, *d_res = nullptr;
+    CK(cudaMalloc(&d_in, n_in * 2));
+    CK(cudaMalloc(&d_w, n_w * 2));
+    CK(cudaMalloc(&d_o32, n_out * 4));
+    CK(cudaMemset(d_o32, 0xFF, n_out * 4));
+    CK(cudaMemcpy(d_in, h_dev_in.data(), n_in * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_w, h_w.data(), n_w * 2, cudaMemcpyHostToDevice));
+    if (c.bias) { CK(cudaMalloc(&d_bias, c.Cout * 4)); CK(cudaMemcpy(d_bias, h_bias.data(), c.Cout * 4, cudaMemcpyHostToDevice)); }
+    if (c.residual) { CK(cudaMalloc(&d_res, n_out * 4)); CK(cudaMemcpy(d_res, h_res.data(), n_out * 4, cudaMemcpyHostToDevice)); }
+    if (c.f16out) { CK(cudaMalloc(&d_o16, n_out * 2)); CK(cudaMemset(d_o16, 0xFF, n_out * 2)); }
+
+    ConvTcProblem p{};
+    p.act = d_in; p.B = c.B; p.H = Ho; p.W = Wo; p.phases = c.stride == 2 ? 4 : 1;
+    p.lda = c.Cin; p.a_channels = c.Cin; p.a_chan_off = 0; p.Cin = c.Cin;
+    p.wpacked = d_w; p.Cout = c.Cout; p.num_taps = taps;
+    for (int r = 0; r < c.k; ++r)
+        for (int s = 0; s < c.k; ++s) {
+            const int t = r * c.k + s;
+            if (c.stride == 1) { p.dh[t] = r - pad; p.dw[t] = s - pad; p.ph[t] = 0; }
+            else {
+                // input row = 2*ho + r - 1  ->  phase row (r-1)&1, block shift floor((r-1)/2)
+                const int rr = r - 1, ss = s - 1;
+                p.dh[t] = (rr < 0) ? -1 : (rr >> 1); p.dw[t] = (ss < 0) ? -1 : (ss >> 1);
+                p.ph[t] = (rr & 1) * 2 + (ss & 1);
+            }
+        }
+    p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
+    p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
+    p.block_n_hint = c.hint; p.err_flag = g_err;
+
+    *g_err = 0;
+    int rc = conv_tc_launch(p, 0);
+    if (rc != 0) { printf("[%s] launch rc=%d (%s)\n", c.name, rc, conv_tc_strerror(rc)); return -1; }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("[%s] KERNEL FAILED: %s, err_flag=%d\n", c.name, cudaGetErrorString(e), *g_err);
+        fflush(stdout);
+        exit(3);
+    }
+    if (reps > 0) {
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; ++i) conv_tc_launch(p, 0);
+        CK(cudaEventRecord(e0));
+        for (int i = 0; i < reps; ++i) conv_tc_launch(p, 0);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_out = ms / reps;
+    }
+
+    double maxerr = 0, maxref = 0;
+    if (check) {
+        std::vector<float> h_out(n_out);
+        std::vector<__half> h_out16;
+        CK(cudaMemcpy(h_out.data(), d_o32, n_out * 4, cudaMemcpyDeviceToHost));
+        if (c.f16out) { h_out16.resize(n_out); CK(cudaMemcpy(h_out16.data(), d_o16, n_out * 2, cudaMemcpyDeviceToHost)); }
+        double max16 = 0;
+        size_t bad_i = 0;
+        for (int b = 0; b < c.B; ++b)
+            for (int ho = 0; ho < Ho; ++ho)
+                for (int wo = 0; wo < Wo; ++wo)
+                    for (int n = 0; n < c.Cout; ++n) {
+                        double acc = 0;
+                        for (int r = 0; r < c.k; ++r) {
+                            const int hi = ho * c.stride + r - pad;
+                            if (hi < 0 || hi >= c.H) continue;
+                            for (int s = 0; s < c.k; ++s) {
+                                const int wi = wo * c.stride + s - pad;
+                                if (wi < 0 || wi >= c.W) continue;
+                                const float* a = &f_in[(((size_t)b * c.H + hi) * c.W + wi) * c.Cin];
+                                const float* wv = &f_w[((size_t)n * taps + r * c.k + s) * c.Cin];
+                                double d = 0;
+                                for (int ci = 0; ci < c.Cin; ++ci) d += (double)a[ci] * wv[ci];
+                                acc += d;
+                            }
+                        }
+                        const size_t oi = (((size_t)b * Ho + ho) * Wo + wo) * c.Cout + n;
+                        if (c.bias) acc += h_bias[n];
+                        if (c.residual) acc += h_res[oi];
+                        const double err = fabs(acc - (double)h_out[oi]);
+                        if (!(err <= maxerr)) { maxerr = err; bad_i = oi; }   // also catches NaN
+                        if (fabs(acc) > maxref) maxref = fabs(acc);
+                        if (c.f16out) {
+                            const double e16 = fabs(acc - (double)__half2float(h_out16[oi]));
+                            if (!(e16 <= max16)) max16 = e16;
+                        }
+                    }
+        printf("[%s] B=%d %dx%d Cin=%d Cout=%d k=%d s=%d hint=%d : max_abs_err=%.3e (max |ref|=%.3f, worst idx %zu)%s",
+               c.name, c.B, c.H, c.W, c.Cin, c.Cout, c.k, c.stride, c.hint, maxerr, maxref, bad_i,
+               (maxerr <= 2e-3 * (1 + maxref)) ? "  OK" : "  **MISMATCH**");
+        if (c.f16out) printf("  f16out_err=%.3e%s", max16, (max16 <= 4e-3 * (1 + maxref)) ? " OK" : " **MISMATCH**");
+        printf("\n");
+        if (!(maxerr <= 2e-3 * (1 + maxref))) {
+            // dump a few values to help diagnose layout bugs
+            for (int i = 0; i < 8; ++i) printf("   out[%d]=%f\n", i, h_out[i]);
+        }
+    }
+    cudaFree(d_in); cudaFree(d_w); cudaFree(d_o32);
+    if (d_bias) cudaFree(d_bias);
+    if (d_res) cudaFree(d_res);
+    if (d_o16) cudaFree(d_o16);
+    fflush(stdout);
+    return maxerr;
+}
+
+int main(int argc, char** argv) {
+    const char* mode = argc > 1 ? argv[1] : "all";
+    CK(cudaSetDeviceFlags(cudaDeviceMapHost));
+    CK(cudaHostAlloc(&g_err, sizeof(int), cudaHostAllocMapped));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
+
+    int failures = 0;
+    if (!strcmp(mode, "check") || !strcmp(mode, "all")) {
+        const Case cases[] = {
+            {"gemm1x1_n64", 1, 16, 16, 64, 64, 1, 1, false, false, false, 0},
+            {"gemm1x1_k128", 1, 16, 16, 128, 64, 1, 1, false, false, false, 0},
+            {"c3_16x16", 2, 16, 16, 64, 128, 3, 1, false, false, false, 0},
+            {"c3_32x32", 1, 32, 32, 128, 128, 3, 1, true, false, false, 0},
+            {"c3_8x8_bb2", 3, 8, 8, 64, 64, 3, 1, true, true, true, 0},
+            {"c3_w256", 1, 4, 256, 64, 64, 3, 1, false, false, false, 0},
+            {"c3_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256},
+            {"c3_n512", 2, 16, 16, 64, 512, 3, 1, true, false, false, 256},
+            {"c3_n16", 1, 16, 16, 64, 16, 3, 1, true, false, false, 0},
+            {"c3_n32", 1, 16, 16, 64, 32, 3, 1, true, false, false, 0},
+            {"c4_s2", 2, 32, 32, 64, 128, 4, 2, true, false, true, 0},
+            {"c3_persist", 8, 64, 64, 64, 64, 3, 1, true, true, false, 0},
+            {"c3_deepk", 1, 16, 16, 1024, 128, 3, 1, false, false, false, 0},
+        };
+        for (const Case& c : cases) {
+            double ms = 0;
+            double err = run_case(c, true, 0, &ms);
+            if (err < 0) ++failures;
+        }
+    }
+    if (!strcmp(mode, "perf") || !strcmp(mode, "all")) {
+        const Case cases[] = {
+            {"sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256},
+            {"sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 128},
+            {"sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256},
+            {"sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256},
+            {"sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 128},
+            {"sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256},
+            {"sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 128},
+            {"sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128},
+            {"sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128},
+            {"sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128},
+            {"pw_16_2048", 32, 16, 16, 2048, 1024, 1, 1, true, false, false, 256},
+        };
+        for (const Case& c : cases) {
+            double ms = 0;
+            run_case(c, false, 10, &ms);
+            const double flops = 2.0 * c.B * (c.H / c.stride) * (c.W / c.stride) * (double)c.Cout * c.k * c.k * c.Cin;
+            printf("[perf %s hint=%d] B=%d %dx%d %d->%d k=%d : %.3f ms  %.1f TFLOP/s\n", c.name, c.hint, c.B, c.H, c.W,
+                   c.Cin, c.Cout, c.k, ms, flops / ms * 1e-9);
+            fflush(stdout);
+        }
+    }
+    printf("done, launch failures=%d\n", failures);
+    return failures ? 1 : 0;
+}
