@@ -1,0 +1,150 @@
+/*
+ * minimagen_b200 -- C ABI of the B200-native (sm_100a) kernels behind MinImagen's U-Net denoising hot path.
+ *
+ * This header is the drop-in boundary: plain `extern "C"` entry points, raw device pointers + sizes + a CUDA stream
+ * (passed as void*), no torch types.  The reference is pure Python/PyTorch, so the "FFI" a maintainer would bind is
+ * ctypes; every entry point below names the reference call site(s) (file:line under
+ * /root/reference) whose stock torch op it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - activations inside the U-Net are NHWC; "f32" buffers are float, "f16" buffers are IEEE half;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or retained by the library;
+ *   - kernels are enqueued on `stream` (a cudaStream_t) and return immediately -> CUDA-graph capturable;
+ *   - return value: 0 on success, negative on error; mi_last_error() returns a static description of the last
+ *     failing call of the calling thread.  No entry point ever falls back to a CPU implementation.
+ */
+#ifndef MINIMAGEN_B200_H_
+#define MINIMAGEN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MI_ABI_VERSION 1
+
+int mi_abi_version(void);
+const char* mi_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only target), else 0 */
+int mi_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------- weights
+ * One-time repack of a conv / linear weight from the reference's checkpoint layout (C_out, C_in, KH, KW) fp32
+ * (nn.Conv2d.weight, nn.Linear.weight with KH=KW=1) into the tensor-core layout [C_out][(r*KW+s)*C_in + c] fp16,
+ * multiplied by `scale` (used to fold q * dim_head**-0.5, layers.py:59/:237, into to_q).
+ * Replaces nothing at run time in the reference; it is the load_state_dict-side half of mi_conv2d_igemm_f16. */
+int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, int kw, float scale, void* out_f16,
+                            void* stream);
+
+/* ------------------------------------------------------------------------------------------------- convolution
+ * Tensor-core (tcgen05 + TMA + TMEM) implicit-GEMM convolution / linear layer.
+ * Replaces nn.Conv2d / nn.Linear forward at: layers.py:129,145 (Block.project 3x3), layers.py:415,439 (res_conv 1x1),
+ * layers.py:319 (Downsample 4x4 stride 2), layers.py:514 (Upsample conv 3x3), layers.py:157,160 (ChanFeedForward 1x1),
+ * layers.py:41-42,48 and :213-214,217 (attention to_q / to_kv / to_out), Unet.py:234 (Parallel 3x3 + 1x1).
+ *
+ *   act_f16   [B][phases][H][W][lda] fp16; channels [c_off, c_off+c_in) are consumed
+ *   (H, W)    OUTPUT pixel grid.  mode 0: stride 1, "same" zero padding, kh x kw odd taps, phases = 1.
+ *             mode 1: the reference's Downsample (4x4, stride 2, pad 1); act is the 4-phase split of the
+ *             (2H x 2W) input produced by mi_cast_act(mode=2).
+ *   w_f16     packed by mi_pack_conv_weight_f16, [c_out][kh*kw*c_in]
+ *   bias      [c_out] fp32 or NULL;  residual: fp32 or NULL, added in the epilogue, addressed like the output
+ *   out_f32 / out_f16   either or both; element (b,h,w,n) is written at  b*out_sb + h*out_sh + w*out_sw + n
+ *   block_n   0 = auto, or one of 16/32/64/128/256 (tile width; must divide c_out)
+ * Requirements: c_in % 64 == 0, c_out % 16 == 0, W a power of two >= 8 (or W >= 128), see mi_conv2d_igemm_supported.
+ * A plain GEMM  out[M][N] = act[M][K] * w[N][K]^T  is the case B=1, H=1, W=M, kh=kw=1. */
+int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out);
+int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c_off, int c_in, const void* w_f16,
+                        int c_out, int kh, int kw, int mode, const float* bias, const float* residual, float* out_f32,
+                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, int block_n,
+                        int* err_flag, void* stream);
+
+/* Direct fp32 convolution for shapes outside the tensor-core path: the CrossEmbedLayer stem (layers.py:300, 3/6 input
+ * channels, k = 3/7/15), final_conv (Unet.py:327, 3 output channels) and every conv of the tiny test config.
+ *   in        [B][Hin][Win][ldi] fp32 (channel-contiguous, ldi % 4 == 0, channels >= c_in up to the next multiple of 4
+ *             must be readable and finite)
+ *   w_oihw    the reference's own (c_out, c_in, kh, kw) fp32 parameter, unpacked
+ *   out       element (b,ho,wo,n) at b*out_sb + ho*out_sh + wo*out_sw + n*out_sc (so NHWC slices and NCHW both work)
+ */
+int mi_conv2d_direct_f32(const float* in, int B, int Hin, int Win, int c_in, int ldi, const float* w_oihw, int c_out,
+                         int kh, int kw, int stride, int pad, const float* bias, const float* residual, float* out,
+                         int Hout, int Wout, long long out_sb, long long out_sh, long long out_sw, long long out_sc,
+                         void* stream);
+
+/* ------------------------------------------------------------------------------------------------- normalisation
+ * nn.GroupNorm statistics (layers.py:127,136): per (sample, group) sum / sum-of-squares of the virtual concatenation
+ * cat(src0[.., C0], src1[.., C1] * scale1) (skip connection, Unet.py:445; pass src1 = NULL, C1 = 0 otherwise).
+ * sums: [B][groups][2] double, MUST be zero on entry (accumulated with atomics). */
+int mi_gn_stats(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
+                double* sums, void* stream);
+/* Block.forward (layers.py:136-144): SiLU( GroupNorm(x) * (scale + 1) + shift ) -> conv operand (fp16 or fp32).
+ * scale_shift: [B][2*C] fp32 (time_mlp output, layers.py:427-429: first half scale, second half shift) or NULL. */
+int mi_gn_apply_silu(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
+                     const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
+                     void* out, int out_is_f16, void* stream);
+/* Raw conv operands with the skip concat folded in; mode 0 plain copy/cast, 1 nearest x2 upsample (layers.py:513),
+ * 2 four-phase split for the stride-2 Downsample conv (layers.py:319). out: fp16 or fp32. */
+int mi_cast_act(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W, int mode,
+                void* out, int out_is_f16, void* stream);
+/* Row LayerNorm over the last dim: layers.py:342 (LayerNorm, gamma + zero beta), layers.py:174-177 (ChanLayerNorm ==
+ * per-pixel LN in NHWC), Unet.py:142,632 (nn.LayerNorm).  pre_gelu applies the exact-erf GELU of ChanFeedForward
+ * (layers.py:158) to the input first; residual (fp32 [R][C]) is added after (layers.py:435,497-498). */
+int mi_ln_rows(const float* in, long long rows, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
+               const float* residual, float* out_f32, void* out_f16, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- conditioning
+ * out = act_out( act_in(in)[M][K] @ W[N][K]^T + bias + addend ) * out_scale, fp32 CUDA-core path for the conditioning
+ * MLPs (Unet.py:101-161, :523-533, :613; layers.py:396-399,427) and non-tensor-core-shaped projections.
+ * in_act/out_act: 0 none, 1 SiLU.  W is the reference's nn.Linear.weight as is. */
+int mi_linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
+                  const float* addend, float* out_f32, void* out_f16, float out_scale, void* stream);
+/* SinusoidalPosEmb.forward (layers.py:455-465); t: int64 [B]; out [B][dim] */
+int mi_sinusoidal_posemb(const long long* t, int B, int dim, float* out, void* stream);
+/* Unet._text_condition (Unet.py:578-610): truncate/zero-pad projected tokens to max_len rows, replace rows where
+ * (text_mask & keep) is false by null_text_embed, write them at rows [row_off, row_off+max_len) of c_out [B][m][D],
+ * mean-pool them into pooled [B][D].  mask: uint8 [B][L] or NULL; keep: uint8 [B]. */
+int mi_text_tokens(const float* proj, int B, int L, int D, const uint8_t* mask, const uint8_t* keep,
+                   const float* null_embed, int max_len, float* c_out, int m, int row_off, float* pooled,
+                   void* stream);
+/* copy [B][r][D] rows into c_out [B][m][D] at row_off (time tokens, Unet.py:534,629) */
+int mi_place_rows(const float* src, int B, int r, int D, float* dst, int m, int row_off, void* stream);
+/* where(keep[b], a[b], null) + addend   (Unet.py:619-626) */
+int mi_select_rows(const float* a, const float* null_row, const uint8_t* keep, const float* addend, int B, int N,
+                   float* out, void* stream);
+/* torch.cat((x, lowres_cond_img), dim=1) (Unet.py:397) + NCHW -> NHWC with channels zero-padded to c_pad */
+int mi_nchw_to_nhwc(const float* a, int ca, const float* b, int cb, int B, int hw, int c_pad, float* out,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------- attention
+ * Fused softmax attention, dim_head 64: CrossAttention.forward (layers.py:220-251) with kv_head_stride = 64, and the
+ * multi-query Attention.forward (layers.py:52-104) with kv_head_stride = 0.  q must already carry the dim_head**-0.5
+ * scale.  Key 0 is the learned null_kv [2][64] fp32 (layers.py:65-67,232-235); key_mask: uint8 [B][m] or NULL
+ * (masked_fill(~mask, -FLT_MAX), layers.py:92-95,242-245).  q/out: [B][n][ld] with head h at column h*64. */
+int mi_attention_fwd(const void* q_f16, long long q_bs, int ldq, const void* k_f16, const void* v_f16, long long kv_bs,
+                     int ldkv, int kv_head_stride, const float* null_kv, const uint8_t* key_mask, int B, int heads,
+                     int n, int m, void* out_f16, long long o_bs, int ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------- DDPM step
+ * Imagen._p_mean_variance / _p_sample after the U-Net (Imagen.py:307-326, :361-370).  Images are NCHW fp32 [B][n].
+ * Schedule tables are GaussianDiffusion's fp32 buffers (diffusion_model.py:42-66); t is int64 [B]. */
+int mi_step_x0(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+               const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod, int B, int n,
+               float* x0, void* stream);
+/* s[b] = max( lerp(sorted|x0[b]|[rank_lo], sorted|x0[b]|[rank_hi], weight), min_s ) -- exact (radix select) */
+int mi_step_quantile(const float* x0, int B, int n, int rank_lo, int rank_hi, float weight, float min_s, float* s,
+                     void* stream);
+int mi_step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
+                      const float* posterior_mean_coef1, const float* posterior_mean_coef2, const float* sigma, int B,
+                      int n, float* out, void* stream);
+/* clamp_(-1,1) and (x+1)*0.5 (Imagen.py:418-419) */
+int mi_step_finalize(const float* x, long long n, int unnormalize, float* out, void* stream);
+/* GaussianDiffusion.q_sample (diffusion_model.py:127-147) followed by v*post_scale + post_shift */
+int mi_q_sample(const float* x0, const float* noise, const long long* t, const float* sqrt_alphas_cumprod,
+                const float* sqrt_one_minus_alphas_cumprod, int B, int n, float post_scale, float post_shift,
+                float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINIMAGEN_B200_H_ */

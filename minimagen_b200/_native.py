@@ -1,0 +1,93 @@
+"""ctypes binding of the C ABI declared in include/minimagen_b200.h (built by minimagen_b200/build_ext.py).
+
+This is the ONLY compute backend of the package: if the shared library is missing, or a tensor is not on a CUDA
+device, the ops raise -- there is no CPU / PyTorch fallback on the product path.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libminimagen_b200.so")
+
+_P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/minimagen_b200.h one to one
+SIGNATURES = {
+    "mi_abi_version": [],
+    "mi_last_error": [],
+    "mi_device_ok": [],
+    "mi_pack_conv_weight_f16": [_P, _I, _I, _I, _I, _F, _P, _P],
+    "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
+    "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _L, _L, _I, _P, _P],
+    "mi_conv2d_direct_f32": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _P],
+    "mi_gn_stats": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P],
+    "mi_gn_apply_silu": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _F, _P, _I, _P],
+    "mi_cast_act": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _I, _P],
+    "mi_ln_rows": [_P, _L, _I, _P, _P, _F, _I, _P, _P, _P, _P],
+    "mi_linear_f32": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P],
+    "mi_sinusoidal_posemb": [_P, _I, _I, _P, _P],
+    "mi_text_tokens": [_P, _I, _I, _I, _P, _P, _P, _I, _P, _I, _I, _P, _P],
+    "mi_place_rows": [_P, _I, _I, _I, _P, _I, _I, _P],
+    "mi_select_rows": [_P, _P, _P, _P, _I, _I, _P, _P],
+    "mi_nchw_to_nhwc": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "mi_attention_fwd": [_P, _L, _I, _P, _P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _L, _I, _P],
+    "mi_step_x0": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _P, _P],
+    "mi_step_quantile": [_P, _I, _I, _I, _I, _F, _F, _P, _P],
+    "mi_step_posterior": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
+    "mi_step_finalize": [_P, _L, _I, _P, _P],
+    "mi_q_sample": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
+}
+_RESTYPES = {"mi_last_error": c_char_p}
+
+_lib = None
+launch_count = 0   # number of kernel launches issued through this binding (bench.py reports it)
+
+
+def load():
+    """Load the shared library (once).  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"minimagen_b200: native library not found at {LIB_PATH}. Build it with "
+            f"`python -m minimagen_b200.build_ext` (or __graft_entry__.build()). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+    if lib.mi_abi_version() != 1:
+        raise RuntimeError("minimagen_b200: ABI version mismatch between _native.py and the shared library")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().mi_last_error().decode()
+
+
+def call(name, *args):
+    """Invoke an entry point; raise RuntimeError (the reference's convention is a Python exception) on failure."""
+    global launch_count
+    rc = getattr(load(), name)(*args)
+    if rc != 0:
+        raise RuntimeError(f"minimagen_b200.{name} failed: {last_error()}")
+    launch_count += 1
+    return rc
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Refuses non-CUDA tensors: no CPU path exists."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("minimagen_b200: tensor is not on a CUDA device; the kernels have no CPU fallback")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,167 @@
+// C ABI (include/minimagen_b200.h) over the kernel launchers.  No torch, no allocation, no CPU fallback.
+#include "../../include/minimagen_b200.h"
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+
+#include "conv_tc.cuh"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local char g_err[256] = "ok";
+
+int fail(int code, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s (code %d)", what, code);
+    return code;
+}
+int check(int rc, const char* fn) {
+    if (rc == 0) return 0;
+    if (rc == -1) return fail(rc, (std::string(fn) + ": unsupported shape / alignment").c_str());
+    if (rc == -2) {
+        cudaError_t e = cudaGetLastError();
+        return fail(rc, (std::string(fn) + ": kernel launch failed: " + cudaGetErrorString(e)).c_str());
+    }
+    return fail(rc, (std::string(fn) + ": error").c_str());
+}
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace
+
+extern "C" {
+
+int mi_abi_version(void) { return MI_ABI_VERSION; }
+const char* mi_last_error(void) { return g_err; }
+
+int mi_device_ok(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+
+int mi_pack_conv_weight_f16(const float* w, int c_out, int c_in, int kh, int kw, float scale, void* out, void* stream) {
+    return check(mi::pack_conv_weight(w, c_out, c_in, kh, kw, scale, (__half*)out, S(stream)), "mi_pack_conv_weight_f16");
+}
+
+int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out) { return mi::conv_tc_supported(H, W, c_in, c_out) ? 1 : 0; }
+
+int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* w, int c_out,
+                        int kh, int kw, int mode, const float* bias, const float* residual, float* out_f32,
+                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, int block_n,
+                        int* err_flag, void* stream) {
+    mi::ConvTcProblem p{};
+    p.act = act; p.B = B; p.H = H; p.W = W; p.lda = lda; p.a_channels = lda; p.a_chan_off = c_off; p.Cin = c_in;
+    p.wpacked = w; p.Cout = c_out;
+    p.out_f32 = out_f32; p.out_f16 = (__half*)out_f16; p.bias = bias; p.residual = residual;
+    p.out_sb = out_sb; p.out_sh = out_sh; p.out_sw = out_sw; p.block_n_hint = block_n; p.err_flag = err_flag;
+    if (mode == 0) {
+        if (!(kh & 1) || !(kw & 1) || kh * kw > mi::kConvMaxTaps) return fail(-4, "mi_conv2d_igemm_f16: mode 0 needs odd kh,kw with kh*kw <= 16");
+        p.phases = 1; p.num_taps = kh * kw;
+        for (int r = 0; r < kh; ++r)
+            for (int s = 0; s < kw; ++s) {
+                const int t = r * kw + s;
+                p.dh[t] = (int8_t)(r - kh / 2); p.dw[t] = (int8_t)(s - kw / 2); p.ph[t] = 0;
+            }
+    } else if (mode == 1) {
+        if (kh != 4 || kw != 4) return fail(-4, "mi_conv2d_igemm_f16: mode 1 is the 4x4 stride-2 pad-1 conv");
+        p.phases = 4; p.num_taps = 16;
+        for (int r = 0; r < 4; ++r)
+            for (int s = 0; s < 4; ++s) {
+                // input row 2*ho + r - 1 lives in phase row (r-1)&1 at phase-grid row ho + floor((r-1)/2)
+                const int t = r * 4 + s, rr = r - 1, ss = s - 1;
+                p.dh[t] = (int8_t)(rr < 0 ? -1 : (rr >> 1)); p.dw[t] = (int8_t)(ss < 0 ? -1 : (ss >> 1));
+                p.ph[t] = (int8_t)((rr & 1) * 2 + (ss & 1));
+            }
+    } else {
+        return fail(-4, "mi_conv2d_igemm_f16: unknown mode");
+    }
+    if ((out_sw % 4) || (out_sh % 4) || (out_sb % 4)) return fail(-8, "mi_conv2d_igemm_f16: output strides must be multiples of 4 elements");
+    const int rc = mi::conv_tc_launch(p, S(stream));
+    if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
+    return 0;
+}
+
+int mi_conv2d_direct_f32(const float* in, int B, int Hin, int Win, int c_in, int ldi, const float* w, int c_out, int kh,
+                         int kw, int stride, int pad, const float* bias, const float* residual, float* out, int Hout,
+                         int Wout, long long out_sb, long long out_sh, long long out_sw, long long out_sc,
+                         void* stream) {
+    return check(mi::conv_direct_f32(in, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out,
+                                     Hout, Wout, out_sb, out_sh, out_sw, out_sc, S(stream)),
+                 "mi_conv2d_direct_f32");
+}
+
+int mi_gn_stats(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
+                double* sums, void* stream) {
+    return check(mi::gn_stats(src0, c0, src1, c1, scale1, B, hw, groups, sums, S(stream)), "mi_gn_stats");
+}
+int mi_gn_apply_silu(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
+                     const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
+                     void* out, int out_is_f16, void* stream) {
+    return check(mi::gn_apply_silu(src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, eps, out,
+                                   out_is_f16, S(stream)),
+                 "mi_gn_apply_silu");
+}
+int mi_cast_act(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W, int mode,
+                void* out, int out_is_f16, void* stream) {
+    return check(mi::cast_act(src0, c0, src1, c1, scale1, B, H, W, mode, out, out_is_f16, S(stream)), "mi_cast_act");
+}
+int mi_ln_rows(const float* in, long long rows, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
+               const float* residual, float* out_f32, void* out_f16, void* stream) {
+    return check(mi::ln_rows(in, rows, C, gamma, beta, eps, pre_gelu, residual, out_f32, (__half*)out_f16, S(stream)),
+                 "mi_ln_rows");
+}
+int mi_linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
+                  const float* addend, float* out_f32, void* out_f16, float out_scale, void* stream) {
+    return check(mi::linear_f32(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, (__half*)out_f16, out_scale,
+                                S(stream)),
+                 "mi_linear_f32");
+}
+int mi_sinusoidal_posemb(const long long* t, int B, int dim, float* out, void* stream) {
+    return check(mi::posemb(t, B, dim, out, S(stream)), "mi_sinusoidal_posemb");
+}
+int mi_text_tokens(const float* proj, int B, int L, int D, const uint8_t* mask, const uint8_t* keep,
+                   const float* null_embed, int max_len, float* c_out, int m, int row_off, float* pooled, void* stream) {
+    return check(mi::text_tokens(proj, B, L, D, mask, keep, null_embed, max_len, c_out, m, row_off, pooled, S(stream)),
+                 "mi_text_tokens");
+}
+int mi_place_rows(const float* src, int B, int r, int D, float* dst, int m, int row_off, void* stream) {
+    return check(mi::place_rows(src, B, r, D, dst, m, row_off, S(stream)), "mi_place_rows");
+}
+int mi_select_rows(const float* a, const float* null_row, const uint8_t* keep, const float* addend, int B, int N,
+                   float* out, void* stream) {
+    return check(mi::select_rows(a, null_row, keep, addend, B, N, out, S(stream)), "mi_select_rows");
+}
+int mi_nchw_to_nhwc(const float* a, int ca, const float* b, int cb, int B, int hw, int c_pad, float* out, void* stream) {
+    return check(mi::nchw_to_nhwc(a, ca, b, cb, B, hw, c_pad, out, S(stream)), "mi_nchw_to_nhwc");
+}
+int mi_attention_fwd(const void* q, long long q_bs, int ldq, const void* k, const void* v, long long kv_bs, int ldkv,
+                     int kv_head_stride, const float* null_kv, const uint8_t* key_mask, int B, int heads, int n, int m,
+                     void* out, long long o_bs, int ldo, void* stream) {
+    return check(mi::attention_fwd((const __half*)q, q_bs, ldq, (const __half*)k, (const __half*)v, kv_bs, ldkv,
+                                   kv_head_stride, null_kv, key_mask, B, heads, n, m, (__half*)out, o_bs, ldo, S(stream)),
+                 "mi_attention_fwd");
+}
+int mi_step_x0(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+               const float* tab_a, const float* tab_b, int B, int n, float* x0, void* stream) {
+    return check(mi::step_x0(x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, B, n, x0, S(stream)), "mi_step_x0");
+}
+int mi_step_quantile(const float* x0, int B, int n, int rank_lo, int rank_hi, float weight, float min_s, float* s,
+                     void* stream) {
+    return check(mi::step_quantile(x0, B, n, rank_lo, rank_hi, weight, min_s, s, S(stream)), "mi_step_quantile");
+}
+int mi_step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
+                      const float* c1, const float* c2, const float* sigma, int B, int n, float* out, void* stream) {
+    return check(mi::step_posterior(x0, x_t, noise, s, t, c1, c2, sigma, B, n, out, S(stream)), "mi_step_posterior");
+}
+int mi_step_finalize(const float* x, long long n, int unnormalize, float* out, void* stream) {
+    return check(mi::step_finalize(x, n, unnormalize, out, S(stream)), "mi_step_finalize");
+}
+int mi_q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_b, int B,
+                int n, float post_scale, float post_shift, float* out, void* stream) {
+    return check(mi::q_sample(x0, noise, t, tab_a, tab_b, B, n, post_scale, post_shift, out, S(stream)), "mi_q_sample");
+}
+
+}  // extern "C"

@@ -294,7 +294,7 @@ const char* conv_tc_strerror(int code) {
 
 bool conv_tc_supported(int H, int W, int Cin, int Cout) {
     if (Cin <= 0 || Cin % kConvBlockK != 0 || Cout <= 0 || Cout % 16 != 0) return false;
-    if (W >= 128) return W % 128 == 0;                    // BW = 128, BH = 1, BB = 1
+    if (W >= 128) return true;                            // BW = 128, BH = 1, BB = 1; ragged tail rows are masked
     if (ilog2_exact(W) < 3) return false;                 // W in {8,16,32,64}
     const int bh = 128 / W;
     if (H >= bh) return H % bh == 0;                      // BH = 128 / W rows of one image
@@ -321,7 +321,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     int BB = 128 / (BW * BH);
     a.bw_log2 = ilog2_exact(BW);
     a.bh_log2 = ilog2_exact(BH);
-    a.tiles_w = p.W / BW;
+    a.tiles_w = (p.W + BW - 1) / BW;
     a.tiles_h = p.H / BH;
     a.tiles_b = (p.B + BB - 1) / BB;
     a.B = p.B; a.H = p.H; a.W = p.W;

@@ -1,0 +1,477 @@
+// HBM-bound elementwise / reduction kernels of the U-Net hot path (NHWC activations, fp32 residual stream).
+// Each kernel cites the reference op it replaces.  All are plain CUDA-core kernels: coalesced 16-byte accesses,
+// fp32 math, double accumulation where a global reduction is involved.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace mi {
+
+namespace {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Load 4 consecutive channels [c, c+4) of pixel `pix` from the virtual concatenation
+//   cat(src0[.., C0], src1[.., C1] * scale1)     (reference: torch.cat((x, skip * 2**-0.5), dim=1), Unet.py:445)
+__device__ __forceinline__ float4 load_cat4(const float* __restrict__ src0, int C0, const float* __restrict__ src1,
+                                             int C1, float scale1, long long pix, int c) {
+    if (c < C0) return *reinterpret_cast<const float4*>(src0 + pix * C0 + c);
+    float4 v = *reinterpret_cast<const float4*>(src1 + pix * C1 + (c - C0));
+    v.x *= scale1; v.y *= scale1; v.z *= scale1; v.w *= scale1;
+    return v;
+}
+
+__device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
+    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&lo);
+    r.y = *reinterpret_cast<uint32_t*>(&hi);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm stats
+// nn.GroupNorm(groups, C) statistics (layers.py:127): per (sample, group) sum and sum of squares over (C/groups)*H*W.
+// grid = (ceil(HW / kGnChunk), B); sums[b][g][0..1] accumulated with double atomics (buffer pre-zeroed by the caller).
+constexpr int kGnChunk = 64;
+
+__global__ void __launch_bounds__(256)
+gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1, int HW,
+                int groups, double* __restrict__ sums) {
+    extern __shared__ double s_acc[];   // [groups][2]
+    const int C = C0 + C1;
+    const int V = C >> 2;
+    const int Cg = C / groups;
+    const int b = blockIdx.y;
+    const int p0 = blockIdx.x * kGnChunk;
+    const int npix = min(kGnChunk, HW - p0);
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.0;
+    __syncthreads();
+
+    int cv0, plane, nplanes, cv_step;
+    if (V <= (int)blockDim.x) {
+        nplanes = blockDim.x / V; cv0 = threadIdx.x % V; plane = threadIdx.x / V; cv_step = V;
+        if (plane >= nplanes) cv0 = V;   // inactive
+    } else {
+        nplanes = 1; cv0 = threadIdx.x; plane = 0; cv_step = blockDim.x;
+    }
+    const long long pix_base = (long long)b * HW + p0;
+    for (int cv = cv0; cv < V; cv += cv_step) {
+        const int c = cv << 2;
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = plane; p < npix; p += nplanes) {
+            const float4 v = load_cat4(src0, C0, src1, C1, scale1, pix_base + p, c);
+            s[0] += v.x; q[0] += v.x * v.x;
+            s[1] += v.y; q[1] += v.y * v.y;
+            s[2] += v.z; q[2] += v.z * v.z;
+            s[3] += v.w; q[3] += v.w * v.w;
+        }
+        const int g0 = c / Cg, g3 = (c + 3) / Cg;
+        if (g0 == g3) {
+            atomicAdd(&s_acc[2 * g0], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
+            atomicAdd(&s_acc[2 * g0 + 1], (double)q[0] + (double)q[1] + (double)q[2] + (double)q[3]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int g = (c + e) / Cg;
+                atomicAdd(&s_acc[2 * g], (double)s[e]);
+                atomicAdd(&s_acc[2 * g + 1], (double)q[e]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) atomicAdd(&sums[(long long)b * groups * 2 + i], s_acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ GroupNorm apply
+// Block.forward (layers.py:138-144): y = SiLU( GN(x) * (scale + 1) + shift ), written as the conv's fp16 operand
+// (tensor-core path) or fp32 (small-channel path).  grid = (ceil(HW*C/8 / 256), B)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+gn_apply_silu_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1,
+                     int HW, int groups, const double* __restrict__ sums, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ scale_shift, float eps,
+                     OutT* __restrict__ out) {
+    __shared__ float s_mean[32], s_rstd[32];
+    const int C = C0 + C1;
+    const int Cg = C / groups;
+    const int b = blockIdx.y;
+    if (threadIdx.x < groups) {
+        const double n = (double)Cg * HW;
+        const double su = sums[((long long)b * groups + threadIdx.x) * 2];
+        const double sq = sums[((long long)b * groups + threadIdx.x) * 2 + 1];
+        const double mean = su / n;
+        double var = sq / n - mean * mean;
+        if (var < 0) var = 0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const int V8 = C >> 3;
+    const long long total = (long long)HW * V8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % V8) << 3;
+    const long long pix = (long long)b * HW + idx / V8;
+    float v[8];
+    {
+        const float4 a = load_cat4(src0, C0, src1, C1, scale1, pix, c);
+        const float4 d = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int ch = c + e;
+        const int g = ch / Cg;
+        float y = (v[e] - s_mean[g]) * s_rstd[g] * __ldg(gamma + ch) + __ldg(beta + ch);
+        if (scale_shift) {
+            const float sc = __ldg(scale_shift + (long long)b * 2 * C + ch);
+            const float sh = __ldg(scale_shift + (long long)b * 2 * C + C + ch);
+            y = y * (sc + 1.0f) + sh;
+        }
+        v[e] = silu_f(y);
+    }
+    if constexpr (sizeof(OutT) == 2) {
+        const uint2 lo = pack_half4(v[0], v[1], v[2], v[3]), hi = pack_half4(v[4], v[5], v[6], v[7]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + pix * C + c) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+        float* o = reinterpret_cast<float*>(out) + pix * C + c;
+        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ cast / resample
+// Raw (un-normalised) conv operands: res_conv input (layers.py:439), Downsample input (layers.py:319, stride 2 ->
+// phase split), Upsample input (layers.py:513 nn.Upsample(nearest, x2)), with the skip concat folded in.
+//   mode 0: out[b][h][w][c]                     = in[b][h][w][c]
+//   mode 1: out[b][2h+i][2w+j][c]               = in[b][h][w][c]                  (nearest x2)
+//   mode 2: out[b][(h&1)*2+(w&1)][h/2][w/2][c]  = in[b][h][w][c]                  (phase split for 4x4 s2 convs)
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+cast_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1, int B, int H,
+            int W, int mode, OutT* __restrict__ out) {
+    const int C = C0 + C1;
+    const int V8 = C >> 3;
+    const long long total = (long long)B * H * W * V8;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = (int)(idx % V8) << 3;
+    const long long pix = idx / V8;
+    const float4 a = load_cat4(src0, C0, src1, C1, scale1, pix, c);
+    const float4 d = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    long long opix[4];
+    int nout = 1;
+    if (mode == 0) {
+        opix[0] = pix;
+    } else if (mode == 1) {
+        nout = 4;
+        const long long base = (b * 2 * H + 2 * h) * (2LL * W) + 2 * w;
+        opix[0] = base; opix[1] = base + 1; opix[2] = base + 2LL * W; opix[3] = base + 2LL * W + 1;
+    } else {
+        const int p = (h & 1) * 2 + (w & 1);
+        opix[0] = ((b * 4 + p) * (H >> 1) + (h >> 1)) * (long long)(W >> 1) + (w >> 1);
+    }
+    for (int i = 0; i < nout; ++i) {
+        if constexpr (sizeof(OutT) == 2) {
+            const uint2 lo = pack_half4(a.x, a.y, a.z, a.w), hi = pack_half4(d.x, d.y, d.z, d.w);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + opix[i] * C + c) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+            float* o = reinterpret_cast<float*>(out) + opix[i] * C + c;
+            *reinterpret_cast<float4*>(o) = a;
+            *reinterpret_cast<float4*>(o + 4) = d;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ row LayerNorm
+// F.layer_norm over the last dim (layers.py:342 LayerNorm; layers.py:174-177 ChanLayerNorm == per-pixel LN in NHWC;
+// Unet.py:142 nn.LayerNorm).  Optional exact-erf GELU applied to the input first (ChanFeedForward, layers.py:158-159),
+// optional residual added after (x = attn(x) + x, layers.py:435/:497).  One warp per row, two-pass variance.
+__global__ void __launch_bounds__(256)
+ln_rows_kernel(const float* __restrict__ in, long long R, int C, const float* __restrict__ gamma,
+               const float* __restrict__ beta, float eps, int pre_gelu, const float* __restrict__ residual,
+               float* __restrict__ out_f32, __half* __restrict__ out_f16) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const int lane = threadIdx.x & 31;
+    const float* x = in + row * C;
+    float s = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(x + c);
+        if (pre_gelu) { v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w); }
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(x + c);
+        if (pre_gelu) { v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w); }
+        const float a = v.x - mean, b2 = v.y - mean, c2 = v.z - mean, d = v.w - mean;
+        q += (a * a + b2 * b2) + (c2 * c2 + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    for (int c = lane * 4; c < C; c += 128) {
+        float4 v = *reinterpret_cast<const float4*>(x + c);
+        if (pre_gelu) { v.x = gelu_erf_f(v.x); v.y = gelu_erf_f(v.y); v.z = gelu_erf_f(v.z); v.w = gelu_erf_f(v.w); }
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+        float4 y;
+        y.x = (v.x - mean) * rstd * g.x; y.y = (v.y - mean) * rstd * g.y;
+        y.z = (v.z - mean) * rstd * g.z; y.w = (v.w - mean) * rstd * g.w;
+        if (beta) {
+            const float4 bt = *reinterpret_cast<const float4*>(beta + c);
+            y.x += bt.x; y.y += bt.y; y.z += bt.z; y.w += bt.w;
+        }
+        if (residual) {
+            const float4 r = *reinterpret_cast<const float4*>(residual + row * C + c);
+            y.x += r.x; y.y += r.y; y.z += r.z; y.w += r.w;
+        }
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + row * C + c) = y;
+        if (out_f16) *reinterpret_cast<uint2*>(out_f16 + row * C + c) = pack_half4(y.x, y.y, y.z, y.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ small fp32 linear
+// out[M][N] = act_out( act_in(in)[M][K] @ W[N][K]^T + bias + addend ).  For the conditioning MLPs (M = batch rows;
+// Unet.py:101-161, layers.py:396-399) and for projections whose K/N are not tensor-core shaped (tiny config).
+// One warp per (8-row tile, output column); lanes split K.
+constexpr int kLinRows = 8;
+
+__global__ void __launch_bounds__(256)
+linear_f32_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias,
+                  int N, int in_act, int out_act, const float* __restrict__ addend, float* __restrict__ out_f32,
+                  __half* __restrict__ out_f16, float out_scale) {
+    const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int m0 = blockIdx.y * kLinRows;
+    if (n >= N) return;
+    const int lane = threadIdx.x & 31;
+    const int rows = min(kLinRows, M - m0);
+    float acc[kLinRows];
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
+    const float* w = W + (long long)n * K;
+    for (int k = lane * 4; k < K; k += 128) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + k);
+#pragma unroll
+        for (int r = 0; r < kLinRows; ++r) {
+            if (r < rows) {
+                float4 xv = *reinterpret_cast<const float4*>(in + (long long)(m0 + r) * K + k);
+                if (in_act == 1) { xv.x = silu_f(xv.x); xv.y = silu_f(xv.y); xv.z = silu_f(xv.z); xv.w = silu_f(xv.w); }
+                acc[r] += xv.x * wv.x + xv.y * wv.y + xv.z * wv.z + xv.w * wv.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+    }
+    if (lane == 0) {
+        const float bv = bias ? bias[n] : 0.f;
+        for (int r = 0; r < rows; ++r) {
+            float y = acc[r] + bv;
+            const long long oi = (long long)(m0 + r) * N + n;
+            if (addend) y += addend[oi];
+            if (out_act == 1) y = silu_f(y);
+            y *= out_scale;
+            if (out_f32) out_f32[oi] = y;
+            if (out_f16) out_f16[oi] = __float2half_rn(y);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ conditioning bits
+// SinusoidalPosEmb.forward (layers.py:461-465): emb_j = exp(j * -(ln(1e4)/(half-1))) in fp32, arg = float(t) * emb_j,
+// out = cat(sin(arg), cos(arg)).
+__global__ void posemb_kernel(const long long* __restrict__ t, int B, int dim, float neg_log_step,
+                              float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int half = dim >> 1;
+    if (i >= B * half) return;
+    const int b = i / half, j = i % half;
+    const float f = expf((float)j * neg_log_step);
+    const float arg = (float)t[b] * f;
+    out[(long long)b * dim + j] = sinf(arg);
+    out[(long long)b * dim + half + j] = cosf(arg);
+}
+
+// Unet._text_condition (Unet.py:578-610): pad/truncate projected text tokens to 256 rows, substitute the learned null
+// embedding where (text_mask & keep) is false, write them below the time tokens of the conditioning sequence, and
+// mean-pool the 256 rows.   grid = B, block = min(D, 256)
+__global__ void text_tokens_kernel(const float* __restrict__ proj /*[B][L][D]*/, int L, int D,
+                                   const uint8_t* __restrict__ mask /*[B][L] or null*/,
+                                   const uint8_t* __restrict__ keep /*[B]*/, const float* __restrict__ null_embed,
+                                   int max_len, float* __restrict__ c_out /*[B][m][D]*/, int m, int row_off,
+                                   float* __restrict__ pooled /*[B][D]*/) {
+    const int b = blockIdx.x;
+    const bool kp = keep[b] != 0;
+    const int Lc = min(L, max_len);
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < max_len; ++l) {
+            const float v = (l < Lc) ? proj[((long long)b * L + l) * D + d] : 0.f;
+            bool cond = kp;
+            if (mask) cond = cond && (l < Lc) && (mask[(long long)b * L + l] != 0);
+            const float o = cond ? v : null_embed[(long long)l * D + d];
+            c_out[((long long)b * m + row_off + l) * D + d] = o;
+            s += o;
+        }
+        pooled[(long long)b * D + d] = s / (float)max_len;
+    }
+}
+
+// copy rows [B][r][D] into the conditioning sequence [B][m][D] at row offset (time tokens, Unet.py:534/:629)
+__global__ void place_rows_kernel(const float* __restrict__ src, int B, int r, int D, float* __restrict__ dst, int m,
+                                  int row_off) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * r * D) return;
+    const int d = (int)(i % D);
+    const int rr = (int)((i / D) % r);
+    const long long b = i / ((long long)D * r);
+    dst[(b * m + row_off + rr) * D + d] = src[i];
+}
+
+// where(keep[b], a[b][:], null[:]) (+ addend) -- Unet.py:619-626
+__global__ void select_rows_kernel(const float* __restrict__ a, const float* __restrict__ nullv,
+                                   const uint8_t* __restrict__ keep, const float* __restrict__ addend, int B, int N,
+                                   float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * N) return;
+    const int n = (int)(i % N);
+    const long long b = i / N;
+    float v = keep[b] ? a[i] : nullv[n];
+    if (addend) v += addend[i];
+    out[i] = v;
+}
+
+// NCHW fp32 (two sources, e.g. x and lowres_cond_img: torch.cat(dim=1), Unet.py:397) -> NHWC fp32 with C padded to Cp
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b2, int Cb, int B,
+                                    int HW, int Cp, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * HW * Cp) return;
+    const int c = (int)(i % Cp);
+    const long long pix = i / Cp;
+    const long long b = pix / HW, p = pix % HW;
+    float v = 0.f;
+    if (c < Ca) v = a[(b * Ca + c) * HW + p];
+    else if (c < Ca + Cb) v = b2[(b * Cb + (c - Ca)) * HW + p];
+    out[i] = v;
+}
+
+// weight packing: OIHW fp32 -> [O][(r*KW+s)*I + c] fp16 (* scale)  (one-time, on load_state_dict)
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int KH, int KW, float scale,
+                                        __half* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)O * I * KH * KW;
+    if (i >= total) return;
+    const int c = (int)(i % I);
+    const int t = (int)((i / I) % (KH * KW));
+    const long long o = i / ((long long)I * KH * KW);
+    out[i] = __float2half_rn(w[((o * I + c) * KH + t / KW) * KW + t % KW] * scale);
+}
+
+inline unsigned grid1d(long long total, int block) { return (unsigned)((total + block - 1) / block); }
+
+}  // namespace
+
+// ================================================================================================ launchers
+int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
+             double* sums, cudaStream_t st) {
+    const int C = C0 + C1;
+    if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
+    dim3 grid((HW + kGnChunk - 1) / kGnChunk, B);
+    gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(double), st>>>(src0, C0, src1, C1, scale1, HW, groups, sums);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
+                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
+                  void* out, int out_is_f16, cudaStream_t st) {
+    const int C = C0 + C1;
+    if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
+    dim3 grid(grid1d((long long)HW * (C / 8), 256), B);
+    if (out_is_f16)
+        gn_apply_silu_kernel<__half><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma, beta,
+                                                           scale_shift, eps, (__half*)out);
+    else
+        gn_apply_silu_kernel<float><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma, beta,
+                                                          scale_shift, eps, (float*)out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int cast_act(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int H, int W, int mode,
+             void* out, int out_is_f16, cudaStream_t st) {
+    const int C = C0 + C1;
+    if (C % 8 || C0 % 4 || mode < 0 || mode > 2) return -1;
+    if (mode == 2 && ((H | W) & 1)) return -1;
+    const unsigned grid = grid1d((long long)B * H * W * (C / 8), 256);
+    if (out_is_f16)
+        cast_kernel<__half><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, B, H, W, mode, (__half*)out);
+    else
+        cast_kernel<float><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, B, H, W, mode, (float*)out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int ln_rows(const float* in, long long R, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
+            const float* residual, float* out_f32, __half* out_f16, cudaStream_t st) {
+    if (C % 4) return -1;
+    ln_rows_kernel<<<grid1d(R, 8), 256, 0, st>>>(in, R, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
+               const float* addend, float* out_f32, __half* out_f16, float out_scale, cudaStream_t st) {
+    if (K % 4) return -1;
+    dim3 grid((N + 7) / 8, (M + kLinRows - 1) / kLinRows);
+    linear_f32_kernel<<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16, out_scale);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int posemb(const long long* t, int B, int dim, float* out, cudaStream_t st) {
+    const int half = dim / 2;
+    // reference: emb = math.log(10000) / (half_dim - 1) in double, multiplied into an fp32 tensor
+    const float neg_log_step = (float)(-(log(10000.0) / (double)(half - 1)));
+    posemb_kernel<<<grid1d((long long)B * half, 128), 128, 0, st>>>(t, B, dim, neg_log_step, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int text_tokens(const float* proj, int B, int L, int D, const uint8_t* mask, const uint8_t* keep,
+                const float* null_embed, int max_len, float* c_out, int m, int row_off, float* pooled,
+                cudaStream_t st) {
+    text_tokens_kernel<<<B, D < 256 ? D : 256, 0, st>>>(proj, L, D, mask, keep, null_embed, max_len, c_out, m, row_off,
+                                                        pooled);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int place_rows(const float* src, int B, int r, int D, float* dst, int m, int row_off, cudaStream_t st) {
+    place_rows_kernel<<<grid1d((long long)B * r * D, 256), 256, 0, st>>>(src, B, r, D, dst, m, row_off);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int select_rows(const float* a, const float* nullv, const uint8_t* keep, const float* addend, int B, int N, float* out,
+                cudaStream_t st) {
+    select_rows_kernel<<<grid1d((long long)B * N, 256), 256, 0, st>>>(a, nullv, keep, addend, B, N, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int nchw_to_nhwc(const float* a, int Ca, const float* b, int Cb, int B, int HW, int Cp, float* out, cudaStream_t st) {
+    nchw_to_nhwc_kernel<<<grid1d((long long)B * HW * Cp, 256), 256, 0, st>>>(a, Ca, b, Cb, B, HW, Cp, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int pack_conv_weight(const float* w, int O, int I, int KH, int KW, float scale, __half* out, cudaStream_t st) {
+    pack_conv_weight_kernel<<<grid1d((long long)O * I * KH * KW, 256), 256, 0, st>>>(w, O, I, KH, KW, scale, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace mi

@@ -1,0 +1,54 @@
+// Internal C++ declarations of the kernel launchers (one translation unit per kernel family).
+// The public boundary is the C ABI in include/minimagen_b200.h (capi.cu).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mi {
+
+// elementwise.cu
+int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
+             double* sums, cudaStream_t st);
+int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
+                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
+                  void* out, int out_is_f16, cudaStream_t st);
+int cast_act(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int H, int W, int mode,
+             void* out, int out_is_f16, cudaStream_t st);
+int ln_rows(const float* in, long long R, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
+            const float* residual, float* out_f32, __half* out_f16, cudaStream_t st);
+int linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
+               const float* addend, float* out_f32, __half* out_f16, float out_scale, cudaStream_t st);
+int posemb(const long long* t, int B, int dim, float* out, cudaStream_t st);
+int text_tokens(const float* proj, int B, int L, int D, const uint8_t* mask, const uint8_t* keep,
+                const float* null_embed, int max_len, float* c_out, int m, int row_off, float* pooled,
+                cudaStream_t st);
+int place_rows(const float* src, int B, int r, int D, float* dst, int m, int row_off, cudaStream_t st);
+int select_rows(const float* a, const float* nullv, const uint8_t* keep, const float* addend, int B, int N, float* out,
+                cudaStream_t st);
+int nchw_to_nhwc(const float* a, int Ca, const float* b, int Cb, int B, int HW, int Cp, float* out, cudaStream_t st);
+int pack_conv_weight(const float* w, int O, int I, int KH, int KW, float scale, __half* out, cudaStream_t st);
+
+// conv_direct.cu
+int conv_direct_f32(const float* in, int B, int Hin, int Win, int Cin, int ldi, const float* w, int Cout, int KH,
+                    int KW, int stride, int pad, const float* bias, const float* residual, float* out, int Hout,
+                    int Wout, long long osb, long long osh, long long osw, long long osc, cudaStream_t st);
+
+// attention.cu
+int attention_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
+                  int kv_hs, const float* null_kv, const uint8_t* mask, int B, int heads, int n, int m, __half* out,
+                  long long o_bs, int ldo, cudaStream_t st);
+
+// step.cu
+int step_x0(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+            const float* tab_recip, const float* tab_recipm1, int B, int n_per_img, float* x0, cudaStream_t st);
+int step_quantile(const float* x0, int B, int n_per_img, int rank_lo, int rank_hi, float weight, float min_s,
+                  float* s_out, cudaStream_t st);
+int step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
+                   const float* tab_c1, const float* tab_c2, const float* tab_sigma, int B, int n_per_img, float* out,
+                   cudaStream_t st);
+int step_finalize(const float* x, long long n, int unnormalize, float* out, cudaStream_t st);
+int q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_b, int B,
+             int n_per_img, float post_scale, float post_shift, float* out, cudaStream_t st);
+
+}  // namespace mi

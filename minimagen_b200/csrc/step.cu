@@ -1,0 +1,200 @@
+// DDPM reverse-step epilogue (everything in Imagen._p_sample after the U-Net call), NCHW fp32 like the reference:
+//   1. classifier-free-guidance combine            null + (cond - null) * w                 (Unet.py:506)
+//      + predict_start_from_noise                  x0 = a[t] * x_t - b[t] * eps             (diffusion_model.py:159-162)
+//   2. dynamic threshold                           s = max(quantile(|x0|, p), 1) per image  (Imagen.py:313-320)
+//      exact: radix select on the uint32 bit patterns of |x0| (order statistics lo / hi chosen on the host with
+//      torch's own fp32 rank arithmetic), linear interpolation like at::lerp
+//   3. clamp(x0, -s, s) / s, posterior mean c1[t] * x0 + c2[t] * x_t, + sigma[t] * noise (zero at t == 0)
+//                                                                  (Imagen.py:323, diffusion_model.py:118-125, Imagen.py:361-370)
+// The per-image schedule gathers (helpers.extract) happen inside the kernels from the fp32 tables.
+// Products and sums are kept un-fused (__fmul_rn/__fadd_rn) so that the arithmetic matches torch's op-by-op rounding.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace mi {
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+x0_kernel(const float* __restrict__ x_t, const float* __restrict__ eps_cond, const float* __restrict__ eps_null,
+          float cond_scale, const long long* __restrict__ t, const float* __restrict__ tab_recip,
+          const float* __restrict__ tab_recipm1, int n_per_img, float* __restrict__ x0) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_per_img) return;
+    const long long idx = (long long)b * n_per_img + i;
+    const long long tb = t[b];
+    const float a = tab_recip[tb], bb = tab_recipm1[tb];
+    float e = eps_cond[idx];
+    if (eps_null) {
+        const float nl = eps_null[idx];
+        e = __fadd_rn(nl, __fmul_rn(__fsub_rn(e, nl), cond_scale));
+    }
+    x0[idx] = __fsub_rn(__fmul_rn(a, x_t[idx]), __fmul_rn(bb, e));
+}
+
+// One CTA per image.  Exact k-th order statistics of |x| by 4 x 8-bit radix passes over the float bit patterns.
+constexpr int kSelThreads = 1024;
+
+__device__ __forceinline__ uint32_t absbits(float v) { return __float_as_uint(v) & 0x7FFFFFFFu; }
+
+__global__ void __launch_bounds__(kSelThreads)
+quantile_kernel(const float* __restrict__ x0, int n, int rank_lo, int rank_hi, float weight, float min_s,
+                float* __restrict__ s_out) {
+    __shared__ unsigned hist[257];
+    __shared__ uint32_t sh_prefix, sh_k, sh_eq;
+    __shared__ uint32_t sh_min[32];
+    const float* x = x0 + (long long)blockIdx.x * n;
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t prefix = 0, maskbits = 0, k = (uint32_t)rank_lo;
+    const int n_round = (n + 31) & ~31;
+
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = tid; i < 257; i += kSelThreads) hist[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < n_round; i += kSelThreads) {
+            unsigned bin = 256;
+            if (i < n) {
+                const uint32_t key = absbits(x[i]);
+                if ((key & maskbits) == prefix) bin = (key >> shift) & 0xFF;
+            }
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t cum = 0;
+            int d = 0;
+            for (; d < 256; ++d) {
+                if (k < cum + hist[d]) break;
+                cum += hist[d];
+            }
+            sh_prefix = prefix | ((uint32_t)d << shift);
+            sh_k = k - cum;
+            sh_eq = hist[d];
+        }
+        __syncthreads();
+        prefix = sh_prefix;
+        k = sh_k;
+        maskbits |= 0xFFu << shift;
+        __syncthreads();
+    }
+    // prefix == bit pattern of sorted[rank_lo]; k == index inside its run of equal values; sh_eq == run length
+    const uint32_t v_lo = prefix;
+    uint32_t v_hi = v_lo;
+    if (rank_hi > rank_lo && k + 1 >= sh_eq) {
+        // next order statistic = smallest key strictly greater than v_lo
+        uint32_t mn = 0xFFFFFFFFu;
+        for (int i = tid; i < n; i += kSelThreads) {
+            const uint32_t key = absbits(x[i]);
+            if (key > v_lo && key < mn) mn = key;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) sh_min[tid >> 5] = mn;
+        __syncthreads();
+        if (tid < 32) {
+            mn = sh_min[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (tid == 0) sh_min[0] = mn;
+        }
+        __syncthreads();
+        v_hi = sh_min[0];
+        if (v_hi == 0xFFFFFFFFu) v_hi = v_lo;   // cannot happen for rank_hi < n
+    }
+    if (tid == 0) {
+        const float lo = __uint_as_float(v_lo), hi = __uint_as_float(v_hi);
+        // at::lerp (vectorised CPU form): base + coeff * (end - start), weight < 0.5 ? (start, w) : (end, w - 1)
+        const float diff = __fsub_rn(hi, lo);
+        const float s = (weight < 0.5f) ? fmaf(weight, diff, lo) : fmaf(__fsub_rn(weight, 1.0f), diff, hi);
+        s_out[blockIdx.x] = fmaxf(s, min_s);   // s.clamp_(min=1.)
+    }
+}
+
+__global__ void __launch_bounds__(256)
+posterior_kernel(const float* __restrict__ x0, const float* __restrict__ x_t, const float* __restrict__ noise,
+                 const float* __restrict__ s, const long long* __restrict__ t, const float* __restrict__ tab_c1,
+                 const float* __restrict__ tab_c2, const float* __restrict__ tab_sigma, int n_per_img,
+                 float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_per_img) return;
+    const long long idx = (long long)b * n_per_img + i;
+    const long long tb = t[b];
+    const float sb = s[b];
+    const float c1 = tab_c1[tb], c2 = tab_c2[tb];
+    const float sig = (tb == 0) ? 0.f : tab_sigma[tb];   // nonzero_mask * exp(0.5 * log_var)
+    float xs = x0[idx];
+    xs = fminf(fmaxf(xs, -sb), sb);
+    xs = __fdiv_rn(xs, sb);
+    const float mean = __fadd_rn(__fmul_rn(c1, xs), __fmul_rn(c2, x_t[idx]));
+    out[idx] = __fadd_rn(mean, __fmul_rn(sig, noise[idx]));
+}
+
+// img.clamp_(-1, 1); (img + 1) * 0.5      (Imagen.py:418-419, helpers.py:183)
+__global__ void finalize_kernel(const float* __restrict__ x, long long n, int unnormalize, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = fminf(fmaxf(x[i], -1.f), 1.f);
+    if (unnormalize) v = __fmul_rn(__fadd_rn(v, 1.f), 0.5f);
+    out[i] = v;
+}
+
+// q_sample: a[t] * x0 + b[t] * noise   (diffusion_model.py:142-145); optional pre-normalisation x*2-1 is NOT applied
+// here (the reference noises the [0,1] image first, Imagen.py:483, and normalises afterwards, Imagen.py:393).
+__global__ void q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                                const long long* __restrict__ t, const float* __restrict__ tab_a,
+                                const float* __restrict__ tab_b, int n_per_img, float post_scale, float post_shift,
+                                float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_per_img) return;
+    const long long idx = (long long)b * n_per_img + i;
+    const long long tb = t[b];
+    float v = __fadd_rn(__fmul_rn(tab_a[tb], x0[idx]), __fmul_rn(tab_b[tb], noise[idx]));
+    v = __fadd_rn(__fmul_rn(v, post_scale), post_shift);   // post_scale=2, post_shift=-1: normalize_neg_one_to_one
+    out[idx] = v;
+}
+
+}  // namespace
+
+int step_x0(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+            const float* tab_recip, const float* tab_recipm1, int B, int n_per_img, float* x0, cudaStream_t st) {
+    dim3 grid((n_per_img + 255) / 256, B);
+    x0_kernel<<<grid, 256, 0, st>>>(x_t, eps_cond, eps_null, cond_scale, t, tab_recip, tab_recipm1, n_per_img, x0);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int step_quantile(const float* x0, int B, int n_per_img, int rank_lo, int rank_hi, float weight, float min_s,
+                  float* s_out, cudaStream_t st) {
+    if (rank_lo < 0 || rank_hi < rank_lo || rank_hi >= n_per_img) return -1;
+    quantile_kernel<<<B, kSelThreads, 0, st>>>(x0, n_per_img, rank_lo, rank_hi, weight, min_s, s_out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
+                   const float* tab_c1, const float* tab_c2, const float* tab_sigma, int B, int n_per_img, float* out,
+                   cudaStream_t st) {
+    dim3 grid((n_per_img + 255) / 256, B);
+    posterior_kernel<<<grid, 256, 0, st>>>(x0, x_t, noise, s, t, tab_c1, tab_c2, tab_sigma, n_per_img, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int step_finalize(const float* x, long long n, int unnormalize, float* out, cudaStream_t st) {
+    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, unnormalize, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_b, int B,
+             int n_per_img, float post_scale, float post_shift, float* out, cudaStream_t st) {
+    dim3 grid((n_per_img + 255) / 256, B);
+    q_sample_kernel<<<grid, 256, 0, st>>>(x0, noise, t, tab_a, tab_b, n_per_img, post_scale, post_shift, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace mi

@@ -1,0 +1,610 @@
+"""Building blocks of the U-Net, B200-native.
+
+Every class keeps the NAME, constructor signature, sub-module attribute names and parameter shapes of its counterpart
+in the reference's `minimagen/layers.py` (so `state_dict()` keys are identical -- the checkpoint ABI), but none of the
+reference's torch forward code: each module lowers itself onto the sm_100a kernels through `run(...)`, which works on
+NHWC fp32 activations `[B, H, W, C]` and makes C-ABI calls via `minimagen_b200.ops`.
+
+`forward(...)` keeps the reference's NCHW (or `[b, n, c]` for attention) calling convention for stand-alone use and
+simply wraps `run`.  Inference only: there is no autograd through the kernels (training is SURVEY.md 8f-2, "next").
+"""
+import math
+
+import torch
+from torch import nn
+
+from .helpers import default, exists
+from .ops import get_ops
+
+F16, F32, F64 = torch.float16, torch.float32, torch.float64
+
+
+# ------------------------------------------------------------------------------------------------ plumbing
+class Cat:
+    """Virtual channel concatenation cat(a, b * scale) of two NHWC tensors (the up-path skip connection,
+    reference Unet.py:445).  Never materialised in fp32: the GroupNorm / cast kernels read both sources."""
+
+    def __init__(self, a, b, scale):
+        assert a.shape[:3] == b.shape[:3]
+        self.a, self.b, self.scale = a, b, float(scale)
+
+    @property
+    def shape(self):
+        return (*self.a.shape[:3], self.a.shape[3] + self.b.shape[3])
+
+    @property
+    def device(self):
+        return self.a.device
+
+
+def _srcs(x):
+    """-> (src0, C0, src1, C1, scale1)"""
+    if isinstance(x, Cat):
+        return x.a, x.a.shape[3], x.b, x.b.shape[3], x.scale
+    return x, x.shape[3], None, 0, 1.0
+
+
+def _no_grad_check(*tensors):
+    if torch.is_grad_enabled() and any(exists(t) and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            "minimagen_b200 implements the inference (sampling) hot path only; autograd through the sm_100a kernels "
+            "(training, SURVEY.md 8f-2) is not built yet. Call under torch.no_grad().")
+
+
+def to_nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def to_nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+class _PackCache:
+    """fp16 tensor-core copy of a weight, rebuilt when the parameter changes (load_state_dict bumps `_version`)."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, param, scale=1.0):
+        key = (param.data_ptr(), param._version, str(param.device), float(scale))
+        if key != self._key:
+            self._val = get_ops().pack_conv_weight(param, scale)
+            self._key = key
+        return self._val
+
+
+def _linear_rows(x_f32, x_f16, M, K, weight, pack, Nout, bias=None, residual=None, want_f16=False, scale=1.0):
+    """Row-major linear layer out[M][Nout] = x[M][K] @ weight[Nout][K]^T (+bias)(+residual), `scale` folded into the
+    weight.  Tensor-core implicit GEMM when (K, Nout) are tensor-core shaped, fp32 CUDA-core kernel otherwise.
+    Exactly one of x_f32 / x_f16 is needed (the one matching the chosen path).  Returns fp16 if want_f16 else fp32."""
+    ops = get_ops()
+    dev = (x_f32 if x_f32 is not None else x_f16).device
+    out = torch.empty((M, Nout), dtype=F16 if want_f16 else F32, device=dev)
+    if x_f16 is not None:
+        ops.conv_igemm(x_f16, 1, 1, M, K, 0, K, pack.get(weight, scale), Nout, 1, 1, 0, bias, residual,
+                       None if want_f16 else out, out if want_f16 else None, (0, 0, Nout))
+    else:
+        w2 = weight.detach().reshape(Nout, K)
+        ops.linear_f32(x_f32, M, K, w2, bias, Nout, 0, 0, residual, None if want_f16 else out,
+                       out if want_f16 else None, scale)
+    return out
+
+
+def _tc_linear_ok(M, K, Nout):
+    return get_ops().igemm_supported(1, M, K, Nout) and M >= 128
+
+
+# ------------------------------------------------------------------------------------------------ simple modules
+class Identity(nn.Module):
+    """reference: layers.py:322-330"""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__()
+
+    def forward(self, x, *args, **kwargs):
+        return x
+
+    def run(self, x, *args, **kwargs):
+        return x
+
+
+class LayerNorm(nn.Module):
+    """reference: layers.py:333-343 -- learnable gamma, beta is a zero *buffer* (part of the checkpoint)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.gamma = nn.Parameter(torch.ones(dim))
+        self.register_buffer('beta', torch.zeros(dim))
+
+    def run_rows(self, rows_f32, R, C, residual=None, out_dtype=F32, pre_gelu=False):
+        out = torch.empty((R, C), dtype=out_dtype, device=rows_f32.device)
+        get_ops().ln_rows(rows_f32, R, C, self.gamma, self.beta, 1e-5, pre_gelu, residual,
+                          out if out_dtype == F32 else None, out if out_dtype == F16 else None)
+        return out
+
+    def forward(self, x):
+        _no_grad_check(x, self.gamma)
+        C = x.shape[-1]
+        return self.run_rows(x.reshape(-1, C).contiguous(), x.numel() // C, C).reshape(x.shape)
+
+
+class ChanLayerNorm(nn.Module):
+    """reference: layers.py:164-177 -- LayerNorm over the channel dim of an image == row LN in NHWC."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.g = nn.Parameter(torch.ones(1, dim, 1, 1))
+
+    def run_rows(self, rows_f32, R, C, out_dtype=F32, pre_gelu=False):
+        out = torch.empty((R, C), dtype=out_dtype, device=rows_f32.device)
+        get_ops().ln_rows(rows_f32, R, C, self.g.detach().reshape(C), None, self.eps, pre_gelu, None,
+                          out if out_dtype == F32 else None, out if out_dtype == F16 else None)
+        return out
+
+    def forward(self, x):
+        _no_grad_check(x, self.g)
+        B, C, H, W = x.shape
+        return to_nchw(self.run_rows(to_nhwc(x).reshape(-1, C), B * H * W, C).reshape(B, H, W, C))
+
+
+class SinusoidalPosEmb(nn.Module):
+    """reference: layers.py:442-465"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, x):
+        B = x.shape[0]
+        out = torch.empty((B, self.dim), dtype=F32, device=x.device)
+        get_ops().posemb(x.to(torch.int64).contiguous(), B, self.dim, out)
+        return out
+
+
+class Residual(nn.Module):
+    """reference: layers.py:359-368"""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def forward(self, x, **kwargs):
+        return self.fn(x, **kwargs) + x
+
+
+class Parallel(nn.Module):
+    """reference: layers.py:346-356 -- sum of parallel branches (last non-memory-efficient down layer,
+    Unet.py:233-234: conv3x3(x) + conv1x1(x)).  Lowered as: second conv accumulates onto the first via the
+    residual input of the conv epilogue."""
+
+    def __init__(self, *fns):
+        super().__init__()
+        self.fns = nn.ModuleList(fns)
+
+    def run(self, x):
+        out = None
+        for fn in self.fns:
+            out = fn.run(x, residual=out)
+        return out
+
+    def forward(self, x):
+        _no_grad_check(x)
+        return to_nchw(self.run(to_nhwc(x)))
+
+
+class TokenView(nn.Module):
+    """Stand-in for einops_exts.torch.EinopsToAndFrom('b c h w', 'b (h w) c', fn) (reference layers.py:403, :492,
+    Unet.py:272).  In NHWC the rearrangement is a free view, so this only keeps the `fn` attribute name that the
+    checkpoint keys (`...cross_attn.fn.*`, `...attn.fn.*`, `mid_attn.fn.fn.*`) depend on."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+    def run(self, x, **kwargs):
+        return self.fn.run(x, **kwargs)
+
+    def forward(self, x, **kwargs):
+        _no_grad_check(x)
+        return to_nchw(self.run(to_nhwc(x), **kwargs))
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+class Conv2d(nn.Conv2d):
+    """nn.Conv2d parameter container (same keys / shapes) lowered onto the tcgen05 implicit GEMM
+    (mi_conv2d_igemm_f16) or, for non-tensor-core shapes, the direct fp32 kernel (mi_conv2d_direct_f32).
+
+    Supported geometries = the ones the reference U-Net uses: k x k stride 1 'same' padding (k odd), and the
+    Downsample conv 4x4 / stride 2 / pad 1 (layers.py:319)."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self._pack = _PackCache()
+
+    @property
+    def _geom(self):
+        kh, kw = self.kernel_size
+        s, p = self.stride[0], self.padding[0]
+        if s == 1 and kh == kw and kh % 2 == 1 and p == kh // 2:
+            return 'same'
+        if s == 2 and kh == 4 and kw == 4 and p == 1:
+            return 'down'
+        raise NotImplementedError(f"conv geometry k={self.kernel_size} s={self.stride} p={self.padding}")
+
+    def tc_ok(self, H, W):
+        """(H, W) = OUTPUT grid."""
+        kh, kw = self.kernel_size
+        return kh * kw <= 16 and get_ops().igemm_supported(H, W, self.in_channels, self.out_channels)
+
+    def run_prepared(self, a, B, H, W, residual=None):
+        """Conv over an already prepared operand `a`:
+           tensor-core path: fp16 [B, P, H, W, C_in] (P = 4 phases for the stride-2 geometry), (H, W) = output grid;
+           direct path:      fp32 [B, H_in, W_in, C_in].
+        Returns fp32 NHWC [B, H, W, C_out] (bias added, `residual` fp32 NHWC added if given)."""
+        ops = get_ops()
+        Cin, Cout = self.in_channels, self.out_channels
+        kh, kw = self.kernel_size
+        out = torch.empty((B, H, W, Cout), dtype=F32, device=a.device)
+        strides = (H * W * Cout, W * Cout, Cout)
+        if a.dtype == F16:
+            mode = 1 if self._geom == 'down' else 0
+            ops.conv_igemm(a, B, H, W, Cin, 0, Cin, self._pack.get(self.weight), Cout, kh, kw, mode, self.bias,
+                           residual, out, None, strides)
+        else:
+            Hin, Win = a.shape[1], a.shape[2]
+            ops.conv_direct(a, B, Hin, Win, Cin, a.shape[3], self.weight.detach(), Cout, kh, kw, self.stride[0],
+                            self.padding[0], self.bias, residual, out, H, W, (*strides, 1))
+        return out
+
+    def run(self, x, residual=None, upsample=False):
+        """x: NHWC fp32 tensor or Cat.  `upsample` applies nn.Upsample(scale_factor=2, 'nearest') first (layers.py:513)."""
+        ops = get_ops()
+        s0, C0, s1, C1, sc = _srcs(x)
+        B, H, W, C = x.shape
+        assert C == self.in_channels, (C, self.in_channels)
+        geom = self._geom
+        if upsample:
+            assert geom == 'same'
+            Ho, Wo = 2 * H, 2 * W
+        elif geom == 'down':
+            Ho, Wo = H // 2, W // 2
+        else:
+            Ho, Wo = H, W
+        if self.tc_ok(Ho, Wo):
+            if upsample:
+                a = torch.empty((B, 1, Ho, Wo, C), dtype=F16, device=x.device)
+                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 1, a)
+            elif geom == 'down':
+                a = torch.empty((B, 4, Ho, Wo, C), dtype=F16, device=x.device)
+                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 2, a)
+            else:
+                a = torch.empty((B, 1, H, W, C), dtype=F16, device=x.device)
+                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 0, a)
+        else:
+            if upsample:
+                a = torch.empty((B, Ho, Wo, C), dtype=F32, device=x.device)
+                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 1, a)
+            elif isinstance(x, Cat):
+                a = torch.empty((B, H, W, C), dtype=F32, device=x.device)
+                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 0, a)
+            else:
+                a = x
+        return self.run_prepared(a, B, Ho, Wo, residual)
+
+    def forward(self, x):
+        _no_grad_check(x, self.weight)
+        return to_nchw(self.run(to_nhwc(x)))
+
+
+def Downsample(dim, dim_out=None):
+    """reference: layers.py:308-319 -- 4x4 stride-2 pad-1 conv."""
+    return Conv2d(dim, default(dim_out, dim), kernel_size=4, stride=2, padding=1)
+
+
+class _UpsampleSeq(nn.Sequential):
+    """nn.Sequential(nn.Upsample(x2, nearest), Conv2d 3x3) with the reference's key layout ('1.weight', '1.bias');
+    lowered as ONE cast kernel (nearest x2 fused into the operand preparation) + one conv."""
+
+    def run(self, x):
+        return self[1].run(x, upsample=True)
+
+    def forward(self, x):
+        _no_grad_check(x)
+        return to_nchw(self.run(to_nhwc(x)))
+
+
+def Upsample(dim, dim_out=None):
+    """reference: layers.py:502-515"""
+    return _UpsampleSeq(nn.Upsample(scale_factor=2, mode='nearest'), Conv2d(dim, default(dim_out, dim), 3, padding=1))
+
+
+class CrossEmbedLayer(nn.Module):
+    """reference: layers.py:254-305 -- parallel convs (k = 3/7/15 for the U-Net stem) whose outputs are channel
+    concatenated.  Each conv writes straight into its channel slice of one NHWC buffer (no torch.cat)."""
+
+    def __init__(self, dim_in, kernel_sizes, dim_out=None, stride=2):
+        super().__init__()
+        assert all((k % 2) == (stride % 2) for k in kernel_sizes)
+        dim_out = default(dim_out, dim_in)
+        kernel_sizes = sorted(kernel_sizes)
+        num_scales = len(kernel_sizes)
+        dim_scales = [int(dim_out / (2 ** i)) for i in range(1, num_scales)]
+        dim_scales = [*dim_scales, dim_out - sum(dim_scales)]
+        self.dim_in, self.dim_out, self.stride = dim_in, dim_out, stride
+        self.convs = nn.ModuleList([
+            Conv2d(dim_in, ds, k, stride=stride, padding=(k - stride) // 2) for k, ds in zip(kernel_sizes, dim_scales)])
+
+    def run_padded(self, x_pad, B, H, W):
+        """x_pad: fp32 NHWC [B, H, W, ld] holding dim_in channels (zero padded to ld). stride must be 1."""
+        assert self.stride == 1
+        ops = get_ops()
+        out = torch.empty((B, H, W, self.dim_out), dtype=F32, device=x_pad.device)
+        C = self.dim_out
+        off = 0
+        for conv in self.convs:
+            k = conv.kernel_size[0]
+            ops.conv_direct(x_pad, B, H, W, self.dim_in, x_pad.shape[3], conv.weight.detach(), conv.out_channels, k, k,
+                            1, conv.padding[0], conv.bias, None, out[..., off:], H, W, (H * W * C, W * C, C, 1))
+            off += conv.out_channels
+        return out
+
+    def forward(self, x):
+        _no_grad_check(x)
+        B, Cin, H, W = x.shape
+        cp = (Cin + 3) // 4 * 4
+        x_pad = torch.empty((B, H, W, cp), dtype=F32, device=x.device)
+        get_ops().nchw_to_nhwc(x.contiguous(), Cin, None, 0, B, H * W, cp, x_pad)
+        return to_nchw(self.run_padded(x_pad, B, H, W))
+
+
+# ------------------------------------------------------------------------------------------------ ResNet
+class Block(nn.Module):
+    """reference: layers.py:107-145 -- GroupNorm -> (scale+1, shift) -> SiLU -> Conv2d 3x3.
+    Lowered as: mi_gn_stats, mi_gn_apply_silu (writes the conv operand), conv with bias/residual epilogue."""
+
+    def __init__(self, dim, dim_out, groups=8, norm=True):
+        super().__init__()
+        self.groupnorm = nn.GroupNorm(groups, dim) if norm else Identity()
+        self.activation = nn.SiLU()
+        self.project = Conv2d(dim, dim_out, 3, padding=1)
+
+    def run(self, x, scale_shift=None, residual=None):
+        ops = get_ops()
+        s0, C0, s1, C1, sc = _srcs(x)
+        B, H, W, C = x.shape
+        gn = self.groupnorm
+        assert isinstance(gn, nn.GroupNorm), "Block(norm=False) is never instantiated by the U-Net"
+        G = gn.num_groups
+        sums = torch.zeros((B, G, 2), dtype=F64, device=x.device)
+        ops.gn_stats(s0, C0, s1, C1, sc, B, H * W, G, sums)
+        tc = self.project.tc_ok(H, W)
+        a = torch.empty((B, 1, H, W, C) if tc else (B, H, W, C), dtype=F16 if tc else F32, device=x.device)
+        ops.gn_apply_silu(s0, C0, s1, C1, sc, B, H * W, G, sums, gn.weight, gn.bias, scale_shift, gn.eps, a)
+        return self.project.run_prepared(a, B, H, W, residual)
+
+    def forward(self, x, scale_shift=None):
+        _no_grad_check(x)
+        ss = None
+        if exists(scale_shift):
+            scale, shift = scale_shift
+            ss = torch.cat((scale.reshape(x.shape[0], -1), shift.reshape(x.shape[0], -1)), dim=1).contiguous()
+        return to_nchw(self.run(to_nhwc(x), ss))
+
+
+class ResnetBlock(nn.Module):
+    """reference: layers.py:371-439"""
+
+    def __init__(self, dim, dim_out, *, cond_dim=None, time_cond_dim=None, groups=8):
+        super().__init__()
+        self.time_mlp = None
+        if exists(time_cond_dim):
+            self.time_mlp = nn.Sequential(nn.SiLU(), nn.Linear(time_cond_dim, dim_out * 2))
+        self.cross_attn = None
+        if exists(cond_dim):
+            self.cross_attn = TokenView(CrossAttention(dim=dim_out, context_dim=cond_dim))
+        self.block1 = Block(dim, dim_out, groups=groups)
+        self.block2 = Block(dim_out, dim_out, groups=groups)
+        self.res_conv = Conv2d(dim, dim_out, 1) if dim != dim_out else Identity()
+
+    def run(self, x, time_emb=None, cond=None):
+        """x: NHWC fp32 or Cat; time_emb: [B, time_cond_dim] fp32; cond: conditioning context (see CrossAttention.run)."""
+        ops = get_ops()
+        B = x.shape[0]
+        scale_shift = None
+        if exists(self.time_mlp) and exists(time_emb):
+            lin = self.time_mlp[1]
+            scale_shift = torch.empty((B, lin.out_features), dtype=F32, device=time_emb.device)
+            # SiLU -> Linear (layers.py:396-399); chunk(2, dim=1) = (scale, shift) is read in place by gn_apply
+            ops.linear_f32(time_emb, B, lin.in_features, lin.weight, lin.bias, lin.out_features, 1, 0, None,
+                           scale_shift, None)
+        h = self.block1.run(x)
+        if exists(self.cross_attn):
+            assert exists(cond)
+            h = self.cross_attn.run(h, context=cond)      # returns attn(h) + h
+        if isinstance(self.res_conv, Identity):
+            assert not isinstance(x, Cat)
+            res = x
+        else:
+            res = self.res_conv.run(x)
+        return self.block2.run(h, scale_shift, residual=res)
+
+    def forward(self, x, time_emb=None, cond=None):
+        _no_grad_check(x)
+        ctx = Context(cond) if exists(cond) else None
+        return to_nchw(self.run(to_nhwc(x), time_emb, ctx))
+
+
+# ------------------------------------------------------------------------------------------------ attention
+class Context:
+    """Conditioning tokens c [B, m, D] (fp32) plus lazily created fp16 copy for the tensor-core k/v projections."""
+
+    def __init__(self, c_f32):
+        self.f32 = c_f32.contiguous()
+        self._f16 = None
+
+    @property
+    def f16(self):
+        if self._f16 is None:
+            B, m, D = self.f32.shape
+            self._f16 = torch.empty((B * m, D), dtype=F16, device=self.f32.device)
+            get_ops().cast_act(self.f32, D, None, 0, 1.0, 1, 1, B * m, 0, self._f16)
+        return self._f16
+
+
+class CrossAttention(nn.Module):
+    """reference: layers.py:180-251.  8 heads x 64 (defaults; the U-Net never overrides them), context is NOT normed,
+    a learned null key/value is prepended, q is scaled by dim_head**-0.5 (folded into the packed to_q weight)."""
+
+    def __init__(self, dim, *, context_dim=None, dim_head=64, heads=8, norm_context=False):
+        super().__init__()
+        assert dim_head == 64, "the fused attention kernel is specialised for dim_head = 64 (the reference's constant)"
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        inner_dim = dim_head * heads
+        context_dim = default(context_dim, dim)
+        self.norm = LayerNorm(dim)
+        self.norm_context = LayerNorm(context_dim) if norm_context else Identity()
+        self.null_kv = nn.Parameter(torch.randn(2, dim_head))
+        self.to_q = nn.Linear(dim, inner_dim, bias=False)
+        self.to_kv = nn.Linear(context_dim, inner_dim * 2, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim, bias=False), LayerNorm(dim))
+        self._pq, self._pkv, self._po = _PackCache(), _PackCache(), _PackCache()
+
+    def run(self, x, context, mask=None, residual=True):
+        """x: NHWC [B, H, W, C] (tokens = pixels); context: Context; mask: uint8 [B, m] or None.  Returns attn(x) + x
+        when `residual` (the `+ h` of ResnetBlock.forward, layers.py:435, is fused into the output LayerNorm kernel)."""
+        ops = get_ops()
+        B, H, W, C = x.shape
+        n = H * W
+        m, D = context.f32.shape[1], context.f32.shape[2]
+        inner = self.heads * 64
+        rows = x.reshape(B * n, C)
+        assert isinstance(self.norm_context, Identity)
+        # q projection
+        tc_q = _tc_linear_ok(B * n, C, inner)
+        xn = self.norm.run_rows(rows, B * n, C, out_dtype=F16 if tc_q else F32)
+        q = _linear_rows(None if tc_q else xn, xn if tc_q else None, B * n, C, self.to_q.weight, self._pq, inner,
+                         want_f16=True, scale=self.scale)
+        # k/v projection of the (un-normed) context
+        tc_kv = _tc_linear_ok(B * m, D, 2 * inner)
+        kv = _linear_rows(None if tc_kv else context.f32.reshape(B * m, D), context.f16 if tc_kv else None, B * m, D,
+                          self.to_kv.weight, self._pkv, 2 * inner, want_f16=True)
+        o = torch.empty((B * n, inner), dtype=F16, device=x.device)
+        ops.attention(q, n * inner, inner, kv, kv[:, inner:], m * 2 * inner, 2 * inner, 64, self.null_kv, mask, B,
+                      self.heads, n, m, o, n * inner, inner)
+        # output projection (K = 512 is always tensor-core shaped) + LayerNorm + residual
+        tc_o = _tc_linear_ok(B * n, inner, C)
+        if tc_o:
+            y = _linear_rows(None, o, B * n, inner, self.to_out[0].weight, self._po, C)
+        else:
+            y = _linear_rows(o.float(), None, B * n, inner, self.to_out[0].weight, self._po, C)
+        out = self.to_out[1].run_rows(y, B * n, C, residual=rows if residual else None)
+        return out.reshape(B, H, W, C)
+
+    def forward(self, x, context, mask=None):
+        """Reference calling convention: x [b, n, dim], context [b, m, context_dim] -> [b, n, dim] (no residual)."""
+        _no_grad_check(x, context)
+        B, n, C = x.shape
+        xx = x.contiguous().reshape(B, 1, n, C)
+        mk = mask.to(torch.uint8).contiguous() if exists(mask) else None
+        return self.run(xx, Context(context), mk, residual=False).reshape(B, n, C)
+
+
+class Attention(nn.Module):
+    """reference: layers.py:14-104 -- multi-query self attention: `heads` query heads share ONE key/value head
+    (to_kv: dim -> 2*64), learned null kv prepended.  `context` / `attn_bias` are never used by the U-Net."""
+
+    def __init__(self, dim, *, dim_head=64, heads=8, context_dim=None):
+        super().__init__()
+        assert dim_head == 64, "the fused attention kernel is specialised for dim_head = 64 (Unet.py:86 ATTN_DIM_HEAD)"
+        assert not exists(context_dim), "Attention(context_dim=...) is never instantiated by the U-Net"
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        inner_dim = dim_head * heads
+        self.norm = LayerNorm(dim)
+        self.null_kv = nn.Parameter(torch.randn(2, dim_head))
+        self.to_q = nn.Linear(dim, inner_dim, bias=False)
+        self.to_kv = nn.Linear(dim, dim_head * 2, bias=False)
+        self.to_context = None
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, dim, bias=False), LayerNorm(dim))
+        self._pq, self._pkv, self._po = _PackCache(), _PackCache(), _PackCache()
+
+    def run(self, x, context=None, mask=None, residual=True):
+        """x: NHWC [B, H, W, C].  Returns attn(x) (+ x when `residual`: TransformerBlock.forward layers.py:497 and the
+        mid Residual(Attention), Unet.py:273)."""
+        assert context is None
+        ops = get_ops()
+        B, H, W, C = x.shape
+        n = H * W
+        inner = self.heads * 64
+        rows = x.reshape(B * n, C)
+        tc = _tc_linear_ok(B * n, C, inner) and _tc_linear_ok(B * n, C, 128)
+        xn = self.norm.run_rows(rows, B * n, C, out_dtype=F16 if tc else F32)
+        q = _linear_rows(None if tc else xn, xn if tc else None, B * n, C, self.to_q.weight, self._pq, inner,
+                         want_f16=True, scale=self.scale)
+        kv = _linear_rows(None if tc else xn, xn if tc else None, B * n, C, self.to_kv.weight, self._pkv, 128,
+                          want_f16=True)
+        o = torch.empty((B * n, inner), dtype=F16, device=x.device)
+        ops.attention(q, n * inner, inner, kv, kv[:, 64:], n * 128, 128, 0, self.null_kv, mask, B, self.heads, n, n, o,
+                      n * inner, inner)
+        if _tc_linear_ok(B * n, inner, C):
+            y = _linear_rows(None, o, B * n, inner, self.to_out[0].weight, self._po, C)
+        else:
+            y = _linear_rows(o.float(), None, B * n, inner, self.to_out[0].weight, self._po, C)
+        out = self.to_out[1].run_rows(y, B * n, C, residual=rows if residual else None)
+        return out.reshape(B, H, W, C)
+
+    def forward(self, x, context=None, mask=None, attn_bias=None):
+        _no_grad_check(x)
+        assert context is None and attn_bias is None
+        B, n, C = x.shape
+        mk = mask.to(torch.uint8).contiguous() if exists(mask) else None
+        return self.run(x.contiguous().reshape(B, 1, n, C), mask=mk, residual=False).reshape(B, n, C)
+
+
+class _ResidualAttention(Residual):
+    """Residual(Attention) for the optional mid attention (Unet.py:272-274); keeps the `fn` key."""
+
+    def run(self, x):
+        return self.fn.run(x, residual=True)
+
+
+def ChanFeedForward(dim, mult=2):
+    """reference: layers.py:148-161 (parameter container; lowered inside TransformerBlock.run)."""
+    hidden_dim = int(dim * mult)
+    return nn.Sequential(
+        ChanLayerNorm(dim),
+        Conv2d(dim, hidden_dim, 1, bias=False),
+        nn.GELU(),
+        ChanLayerNorm(hidden_dim),
+        Conv2d(hidden_dim, dim, 1, bias=False))
+
+
+class TransformerBlock(nn.Module):
+    """reference: layers.py:468-499 -- x = attn(x) + x ; x = ff(x) + x"""
+
+    def __init__(self, dim, *, heads=8, dim_head=32, ff_mult=2, context_dim=None):
+        super().__init__()
+        self.attn = TokenView(Attention(dim=dim, heads=heads, dim_head=dim_head, context_dim=context_dim))
+        self.ff = ChanFeedForward(dim=dim, mult=ff_mult)
+
+    def run(self, x, context=None):
+        B, H, W, C = x.shape
+        R = B * H * W
+        x = self.attn.run(x, residual=True)
+        ln1, conv1, _, ln2, conv2 = self.ff
+        hid = conv1.out_channels
+        rows = x.reshape(R, C)
+        tc1 = _tc_linear_ok(R, C, hid)
+        y = ln1.run_rows(rows, R, C, out_dtype=F16 if tc1 else F32)
+        h = _linear_rows(None if tc1 else y, y if tc1 else None, R, C, conv1.weight, conv1._pack, hid)
+        tc2 = _tc_linear_ok(R, hid, C)
+        z = ln2.run_rows(h, R, hid, out_dtype=F16 if tc2 else F32, pre_gelu=True)       # GELU(erf) -> ChanLayerNorm
+        out = _linear_rows(None if tc2 else z, z if tc2 else None, R, hid, conv2.weight, conv2._pack, C, residual=rows)
+        return out.reshape(B, H, W, C)
+
+    def forward(self, x, context=None):
+        _no_grad_check(x)
+        return to_nchw(self.run(to_nhwc(x)))

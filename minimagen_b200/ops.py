@@ -1,0 +1,165 @@
+"""Tensor-level view of the C ABI: every method takes torch CUDA tensors (caller-allocated outputs), checks dtypes /
+contiguity, and makes exactly one call into libminimagen_b200.so on the current torch CUDA stream.
+
+`NativeOps` is the only implementation shipped in the package.  (tests/ carries a torch emulation of the same
+interface so that the host-side orchestration can be unit-tested on a CPU-only box; the product never uses it.)
+"""
+import torch
+
+from . import _native as N
+
+F16, F32, F64, I64, U8 = torch.float16, torch.float32, torch.float64, torch.int64, torch.uint8
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+
+
+class NativeOps:
+    name = "native-sm100a"
+
+    # ---------------------------------------------------------------- capability / weights
+    def igemm_supported(self, H, W, c_in, c_out):
+        return bool(N.load().mi_conv2d_igemm_supported(int(H), int(W), int(c_in), int(c_out)))
+
+    def pack_conv_weight(self, w, scale=1.0):
+        """w: (O, I, KH, KW) or (O, I) fp32 -> (O, KH*KW*I) fp16 tap-major / channel-minor."""
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        w = w.detach().to(F32).contiguous()
+        O, I, KH, KW = w.shape
+        out = torch.empty((O, KH * KW * I), dtype=F16, device=w.device)
+        N.call("mi_pack_conv_weight_f16", N.ptr(w), O, I, KH, KW, float(scale), N.ptr(out), N.stream())
+        return out
+
+    # ---------------------------------------------------------------- convolutions
+    def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
+                   out_strides, block_n=0):
+        _chk(act, F16, "act"); _chk(wp, F16, "wp"); _chk(bias, F32, "bias"); _chk(residual, F32, "residual")
+        _chk(out_f32, F32, "out_f32"); _chk(out_f16, F16, "out_f16")
+        sb, sh, sw = out_strides
+        N.call("mi_conv2d_igemm_f16", N.ptr(act), B, H, W, lda, c_off, c_in, N.ptr(wp), c_out, kh, kw, mode,
+               N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16), sb, sh, sw, block_n, None, N.stream())
+
+    def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
+                    out_strides):
+        _chk(inp, F32, "inp"); _chk(w, F32, "w"); _chk(bias, F32, "bias"); _chk(residual, F32, "residual")
+        if out.dtype != F32:
+            raise TypeError("out must be fp32")
+        sb, sh, sw, sc = out_strides
+        N.call("mi_conv2d_direct_f32", N.ptr(inp), B, Hin, Win, c_in, ldi, N.ptr(w), c_out, kh, kw, stride, pad,
+               N.ptr(bias), N.ptr(residual), N.ptr(out), Hout, Wout, sb, sh, sw, sc, N.stream())
+
+    # ---------------------------------------------------------------- normalisation / casts
+    def gn_stats(self, src0, c0, src1, c1, scale1, B, hw, groups, sums):
+        _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(sums, F64, "sums")
+        N.call("mi_gn_stats", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, hw, groups, N.ptr(sums), N.stream())
+
+    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, eps, out):
+        _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(sums, F64, "sums"); _chk(gamma, F32, "gamma")
+        _chk(beta, F32, "beta"); _chk(scale_shift, F32, "scale_shift")
+        N.call("mi_gn_apply_silu", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, hw, groups, N.ptr(sums),
+               N.ptr(gamma), N.ptr(beta), N.ptr(scale_shift), float(eps), N.ptr(out), int(out.dtype == F16), N.stream())
+
+    def cast_act(self, src0, c0, src1, c1, scale1, B, H, W, mode, out):
+        _chk(src0, F32, "src0"); _chk(src1, F32, "src1")
+        N.call("mi_cast_act", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, H, W, mode, N.ptr(out),
+               int(out.dtype == F16), N.stream())
+
+    def ln_rows(self, inp, rows, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16):
+        _chk(inp, F32, "inp"); _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta"); _chk(residual, F32, "residual")
+        _chk(out_f32, F32, "out_f32"); _chk(out_f16, F16, "out_f16")
+        N.call("mi_ln_rows", N.ptr(inp), rows, C, N.ptr(gamma), N.ptr(beta), float(eps), int(pre_gelu), N.ptr(residual),
+               N.ptr(out_f32), N.ptr(out_f16), N.stream())
+
+    # ---------------------------------------------------------------- conditioning
+    def linear_f32(self, inp, M, K, W, bias, Nout, in_act, out_act, addend, out_f32, out_f16, out_scale=1.0):
+        _chk(inp, F32, "inp"); _chk(W, F32, "W"); _chk(bias, F32, "bias"); _chk(addend, F32, "addend")
+        _chk(out_f32, F32, "out_f32"); _chk(out_f16, F16, "out_f16")
+        N.call("mi_linear_f32", N.ptr(inp), M, K, N.ptr(W), N.ptr(bias), Nout, in_act, out_act, N.ptr(addend),
+               N.ptr(out_f32), N.ptr(out_f16), float(out_scale), N.stream())
+
+    def posemb(self, t, B, dim, out):
+        _chk(t, I64, "t"); _chk(out, F32, "out")
+        N.call("mi_sinusoidal_posemb", N.ptr(t), B, dim, N.ptr(out), N.stream())
+
+    def text_tokens(self, proj, B, L, D, mask, keep, null_embed, max_len, c_out, m, row_off, pooled):
+        _chk(proj, F32, "proj"); _chk(mask, U8, "mask"); _chk(keep, U8, "keep"); _chk(null_embed, F32, "null_embed")
+        _chk(c_out, F32, "c_out"); _chk(pooled, F32, "pooled")
+        N.call("mi_text_tokens", N.ptr(proj), B, L, D, N.ptr(mask), N.ptr(keep), N.ptr(null_embed), max_len,
+               N.ptr(c_out), m, row_off, N.ptr(pooled), N.stream())
+
+    def place_rows(self, src, B, r, D, dst, m, row_off):
+        _chk(src, F32, "src"); _chk(dst, F32, "dst")
+        N.call("mi_place_rows", N.ptr(src), B, r, D, N.ptr(dst), m, row_off, N.stream())
+
+    def select_rows(self, a, null_row, keep, addend, B, Nn, out):
+        _chk(a, F32, "a"); _chk(null_row, F32, "null_row"); _chk(keep, U8, "keep"); _chk(addend, F32, "addend")
+        N.call("mi_select_rows", N.ptr(a), N.ptr(null_row), N.ptr(keep), N.ptr(addend), B, Nn, N.ptr(out), N.stream())
+
+    def nchw_to_nhwc(self, a, ca, b, cb, B, hw, c_pad, out):
+        _chk(a, F32, "a"); _chk(b, F32, "b"); _chk(out, F32, "out")
+        N.call("mi_nchw_to_nhwc", N.ptr(a), ca, N.ptr(b), cb, B, hw, c_pad, N.ptr(out), N.stream())
+
+    # ---------------------------------------------------------------- attention
+    def attention(self, q, q_bs, ldq, k, v, kv_bs, ldkv, kv_hs, null_kv, mask, B, heads, n, m, out, o_bs, ldo):
+        """k / v may be views (column offsets) into one projection buffer: only their data_ptr is used."""
+        if q.dtype != F16 or k.dtype != F16 or v.dtype != F16 or out.dtype != F16:
+            raise TypeError("attention operands must be fp16")
+        _chk(null_kv, F32, "null_kv"); _chk(mask, U8, "mask")
+        N.call("mi_attention_fwd", N.ptr(q), q_bs, ldq, N.ptr(k), N.ptr(v), kv_bs, ldkv, kv_hs, N.ptr(null_kv),
+               N.ptr(mask), B, heads, n, m, N.ptr(out), o_bs, ldo, N.stream())
+
+    # ---------------------------------------------------------------- DDPM step
+    def step_x0(self, x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, B, n, x0):
+        for nm, tt in (("x_t", x_t), ("eps_cond", eps_cond), ("eps_null", eps_null), ("tab_a", tab_a),
+                       ("tab_b", tab_b), ("x0", x0)):
+            _chk(tt, F32, nm)
+        _chk(t, I64, "t")
+        N.call("mi_step_x0", N.ptr(x_t), N.ptr(eps_cond), N.ptr(eps_null), float(cond_scale), N.ptr(t), N.ptr(tab_a),
+               N.ptr(tab_b), B, n, N.ptr(x0), N.stream())
+
+    def step_quantile(self, x0, B, n, rank_lo, rank_hi, weight, min_s, s):
+        _chk(x0, F32, "x0"); _chk(s, F32, "s")
+        N.call("mi_step_quantile", N.ptr(x0), B, n, int(rank_lo), int(rank_hi), float(weight), float(min_s), N.ptr(s),
+               N.stream())
+
+    def step_posterior(self, x0, x_t, noise, s, t, c1, c2, sigma, B, n, out):
+        for nm, tt in (("x0", x0), ("x_t", x_t), ("noise", noise), ("s", s), ("c1", c1), ("c2", c2), ("sigma", sigma),
+                       ("out", out)):
+            _chk(tt, F32, nm)
+        _chk(t, I64, "t")
+        N.call("mi_step_posterior", N.ptr(x0), N.ptr(x_t), N.ptr(noise), N.ptr(s), N.ptr(t), N.ptr(c1), N.ptr(c2),
+               N.ptr(sigma), B, n, N.ptr(out), N.stream())
+
+    def step_finalize(self, x, n, unnormalize, out):
+        _chk(x, F32, "x"); _chk(out, F32, "out")
+        N.call("mi_step_finalize", N.ptr(x), n, int(unnormalize), N.ptr(out), N.stream())
+
+    def q_sample(self, x0, noise, t, tab_a, tab_b, B, n, post_scale, post_shift, out):
+        _chk(x0, F32, "x0"); _chk(noise, F32, "noise"); _chk(t, I64, "t"); _chk(out, F32, "out")
+        N.call("mi_q_sample", N.ptr(x0), N.ptr(noise), N.ptr(t), N.ptr(tab_a), N.ptr(tab_b), B, n, float(post_scale),
+               float(post_shift), N.ptr(out), N.stream())
+
+
+_OPS = None
+
+
+def get_ops():
+    """The process-wide ops backend.  Loads the native library on first use (raises if it is missing)."""
+    global _OPS
+    if _OPS is None:
+        N.load()
+        _OPS = NativeOps()
+    return _OPS
+
+
+def set_ops(ops):
+    """Test hook: install another implementation of the ops interface (used by tests/ only)."""
+    global _OPS
+    _OPS = ops

@@ -1,0 +1,258 @@
+"""TEST INFRASTRUCTURE ONLY: a torch (CPU) emulation of the `minimagen_b200.ops` interface.
+
+It mirrors the CONTRACT of every C-ABI entry point (layouts, packing order, strides, fp16 operand rounding, in-place
+output semantics) with plain torch ops, so that the host-side orchestration in minimagen_b200/{layers,Unet,Imagen}.py
+can be executed -- and compared against the real reference -- on a box without a GPU.  The product never imports this
+file; on a GPU box the native library is the only backend.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+F16, F32, F64 = torch.float16, torch.float32, torch.float64
+
+
+def _strided(out, shape, strides):
+    return out.as_strided(shape, strides, out.storage_offset())
+
+
+def _cat_src(src0, c0, src1, c1, scale1, lead_shape):
+    a = src0.reshape(*lead_shape, c0)
+    if src1 is None or c1 == 0:
+        return a
+    return torch.cat((a, src1.reshape(*lead_shape, c1) * scale1), dim=-1)
+
+
+class EmuOps:
+    name = "torch-emulation (tests only)"
+
+    def __init__(self):
+        self.calls = []
+
+    def _log(self, name):
+        self.calls.append(name)
+
+    # ---------------------------------------------------------------- capability / weights
+    def igemm_supported(self, H, W, c_in, c_out):
+        def ilog2(v):
+            l = int(math.log2(v)) if v > 0 else -1
+            return l if (1 << l) == v else -1
+        if c_in <= 0 or c_in % 64 or c_out <= 0 or c_out % 16:
+            return False
+        if W >= 128:
+            return True
+        if ilog2(W) < 3:
+            return False
+        bh = 128 // W
+        if H >= bh:
+            return H % bh == 0
+        return ilog2(H) >= 0
+
+    def pack_conv_weight(self, w, scale=1.0):
+        self._log("pack")
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        O, I, KH, KW = w.shape
+        return (w.detach().float() * scale).permute(0, 2, 3, 1).reshape(O, KH * KW * I).to(F16).contiguous()
+
+    # ---------------------------------------------------------------- convolutions
+    def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
+                   out_strides, block_n=0):
+        self._log("conv_igemm")
+        assert act.dtype == F16 and wp.dtype == F16
+        P = 4 if mode == 1 else 1
+        a = act.reshape(B, P, H, W, lda)[..., c_off:c_off + c_in].float()
+        w = wp.float().reshape(c_out, kh, kw, c_in).permute(0, 3, 1, 2)           # OIHW
+        if mode == 0:
+            y = F.conv2d(a[:, 0].permute(0, 3, 1, 2), w, None, stride=1, padding=(kh // 2, kw // 2))
+        else:
+            # un-split the 4 phases back to the (2H, 2W) input: phase p = (h&1)*2 + (w&1)
+            full = torch.zeros((B, 2 * H, 2 * W, c_in))
+            for p in range(4):
+                full[:, (p >> 1)::2, (p & 1)::2] = a[:, p]
+            y = F.conv2d(full.permute(0, 3, 1, 2), w, None, stride=2, padding=1)
+        y = y.permute(0, 2, 3, 1)                                                 # B,H,W,Cout
+        if bias is not None:
+            y = y + bias
+        sb, sh, sw = out_strides
+        if residual is not None:
+            y = y + _strided(residual, (B, H, W, c_out), (sb, sh, sw, 1))
+        if out_f32 is not None:
+            _strided(out_f32, (B, H, W, c_out), (sb, sh, sw, 1)).copy_(y)
+        if out_f16 is not None:
+            _strided(out_f16, (B, H, W, c_out), (sb, sh, sw, 1)).copy_(y.to(F16))
+
+    def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
+                    out_strides):
+        self._log("conv_direct")
+        a = inp.reshape(B, Hin, Win, ldi)[..., :c_in].permute(0, 3, 1, 2)
+        y = F.conv2d(a, w.detach().reshape(c_out, c_in, kh, kw), None, stride=stride, padding=pad).permute(0, 2, 3, 1)
+        assert y.shape[1] == Hout and y.shape[2] == Wout
+        if bias is not None:
+            y = y + bias.detach()
+        if residual is not None:
+            y = y + _strided(residual, (B, Hout, Wout, c_out), out_strides)
+        _strided(out, (B, Hout, Wout, c_out), out_strides).copy_(y)
+
+    # ---------------------------------------------------------------- normalisation / casts
+    def gn_stats(self, src0, c0, src1, c1, scale1, B, hw, groups, sums):
+        self._log("gn_stats")
+        x = _cat_src(src0, c0, src1, c1, scale1, (B, hw)).double()
+        C = c0 + c1
+        xg = x.reshape(B, hw, groups, C // groups)
+        sums[:, :, 0] += xg.sum(dim=(1, 3))
+        sums[:, :, 1] += (xg * xg).sum(dim=(1, 3))
+
+    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, eps, out):
+        self._log("gn_apply_silu")
+        x = _cat_src(src0, c0, src1, c1, scale1, (B, hw))
+        C = c0 + c1
+        n = (C // groups) * hw
+        mean = sums[:, :, 0] / n
+        var = (sums[:, :, 1] / n - mean * mean).clamp(min=0)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        mean_c = mean.float().repeat_interleave(C // groups, dim=1)[:, None, :]
+        rstd_c = rstd.float().repeat_interleave(C // groups, dim=1)[:, None, :]
+        y = (x - mean_c) * rstd_c * gamma.detach() + beta.detach()
+        if scale_shift is not None:
+            y = y * (scale_shift[:, None, :C] + 1.0) + scale_shift[:, None, C:]
+        y = y * torch.sigmoid(y)
+        out.reshape(B, hw, C).copy_(y.to(out.dtype))
+
+    def cast_act(self, src0, c0, src1, c1, scale1, B, H, W, mode, out):
+        self._log("cast_act")
+        x = _cat_src(src0, c0, src1, c1, scale1, (B, H, W))
+        C = c0 + c1
+        if mode == 0:
+            out.reshape(B, H, W, C).copy_(x.to(out.dtype))
+        elif mode == 1:
+            out.reshape(B, 2 * H, 2 * W, C).copy_(
+                x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).to(out.dtype))
+        else:
+            o = out.reshape(B, 4, H // 2, W // 2, C)
+            for p in range(4):
+                o[:, p].copy_(x[:, (p >> 1)::2, (p & 1)::2].to(out.dtype))
+
+    def ln_rows(self, inp, rows, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16):
+        self._log("ln_rows")
+        x = inp.reshape(rows, C)
+        if pre_gelu:
+            x = F.gelu(x)
+        y = F.layer_norm(x, (C,), gamma.detach().reshape(C), beta.detach().reshape(C) if beta is not None else None, eps)
+        if residual is not None:
+            y = y + residual.reshape(rows, C)
+        if out_f32 is not None:
+            out_f32.reshape(rows, C).copy_(y)
+        if out_f16 is not None:
+            out_f16.reshape(rows, C).copy_(y.to(F16))
+
+    # ---------------------------------------------------------------- conditioning
+    def linear_f32(self, inp, M, K, W, bias, Nout, in_act, out_act, addend, out_f32, out_f16, out_scale=1.0):
+        self._log("linear_f32")
+        x = inp.reshape(M, K)
+        if in_act == 1:
+            x = F.silu(x)
+        y = F.linear(x, W.detach().reshape(Nout, K), bias.detach() if bias is not None else None)
+        if addend is not None:
+            y = y + addend.reshape(M, Nout)
+        if out_act == 1:
+            y = F.silu(y)
+        y = y * out_scale
+        if out_f32 is not None:
+            out_f32.reshape(M, Nout).copy_(y)
+        if out_f16 is not None:
+            out_f16.reshape(M, Nout).copy_(y.to(F16))
+
+    def posemb(self, t, B, dim, out):
+        self._log("posemb")
+        half = dim // 2
+        step = math.log(10000) / (half - 1)
+        emb = torch.exp(torch.arange(half) * -step)
+        arg = t[:, None] * emb[None, :]
+        out.copy_(torch.cat((arg.sin(), arg.cos()), dim=-1))
+
+    def text_tokens(self, proj, B, L, D, mask, keep, null_embed, max_len, c_out, m, row_off, pooled):
+        self._log("text_tokens")
+        Lc = min(L, max_len)
+        tok = torch.zeros((B, max_len, D))
+        tok[:, :Lc] = proj.reshape(B, L, D)[:, :Lc]
+        cond = keep.bool()[:, None].expand(B, max_len).clone()
+        if mask is not None:
+            mk = torch.zeros((B, max_len), dtype=torch.bool)
+            mk[:, :Lc] = mask.bool()[:, :Lc]
+            cond = cond & mk
+        o = torch.where(cond[:, :, None], tok, null_embed.detach().reshape(1, max_len, D))
+        c_out.reshape(B, m, D)[:, row_off:row_off + max_len] = o
+        pooled.copy_(o.mean(dim=1))
+
+    def place_rows(self, src, B, r, D, dst, m, row_off):
+        self._log("place_rows")
+        dst.reshape(B, m, D)[:, row_off:row_off + r] = src.reshape(B, r, D)
+
+    def select_rows(self, a, null_row, keep, addend, B, Nn, out):
+        self._log("select_rows")
+        y = torch.where(keep.bool()[:, None], a.reshape(B, Nn), null_row.detach().reshape(1, Nn))
+        if addend is not None:
+            y = y + addend.reshape(B, Nn)
+        out.copy_(y)
+
+    def nchw_to_nhwc(self, a, ca, b, cb, B, hw, c_pad, out):
+        self._log("nchw_to_nhwc")
+        o = out.reshape(B, hw, c_pad)
+        o.zero_()
+        o[:, :, :ca] = a.reshape(B, ca, hw).permute(0, 2, 1)
+        if b is not None and cb:
+            o[:, :, ca:ca + cb] = b.reshape(B, cb, hw).permute(0, 2, 1)
+
+    # ---------------------------------------------------------------- attention
+    def attention(self, q, q_bs, ldq, k, v, kv_bs, ldkv, kv_hs, null_kv, mask, B, heads, n, m, out, o_bs, ldo):
+        self._log("attention")
+        qq = q.as_strided((B, heads, n, 64), (q_bs, 64, ldq, 1), q.storage_offset()).float()
+        kk = k.as_strided((B, heads, m, 64), (kv_bs, kv_hs, ldkv, 1), k.storage_offset()).float()
+        vv = v.as_strided((B, heads, m, 64), (kv_bs, kv_hs, ldkv, 1), v.storage_offset()).float()
+        nk = null_kv.detach()[0].to(F16).float().reshape(1, 1, 1, 64).expand(B, heads, 1, 64)
+        nv = null_kv.detach()[1].to(F16).float().reshape(1, 1, 1, 64).expand(B, heads, 1, 64)
+        kk = torch.cat((nk, kk), dim=2)
+        vv = torch.cat((nv, vv), dim=2)
+        sim = qq @ kk.transpose(-1, -2)
+        if mask is not None:
+            mk = F.pad(mask.bool(), (1, 0), value=True)[:, None, None, :]
+            sim = sim.masked_fill(~mk, -torch.finfo(sim.dtype).max)
+        attn = sim.softmax(dim=-1)
+        o = attn @ vv                                                       # B,h,n,64
+        out.as_strided((B, heads, n, 64), (o_bs, 64, ldo, 1), out.storage_offset()).copy_(o.to(F16))
+
+    # ---------------------------------------------------------------- DDPM step
+    def step_x0(self, x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, B, n, x0):
+        self._log("step_x0")
+        e = eps_cond.reshape(B, n)
+        if eps_null is not None:
+            nl = eps_null.reshape(B, n)
+            e = nl + (e - nl) * cond_scale
+        x0.reshape(B, n).copy_(tab_a[t][:, None] * x_t.reshape(B, n) - tab_b[t][:, None] * e)
+
+    def step_quantile(self, x0, B, n, rank_lo, rank_hi, weight, min_s, s):
+        self._log("step_quantile")
+        srt = x0.reshape(B, n).abs().sort(dim=-1).values
+        lo, hi = srt[:, rank_lo], srt[:, rank_hi]
+        w = torch.tensor(weight, dtype=F32)
+        s.copy_(torch.lerp(lo, hi, w).clamp(min=min_s))
+
+    def step_posterior(self, x0, x_t, noise, s, t, c1, c2, sigma, B, n, out):
+        self._log("step_posterior")
+        sb = s[:, None]
+        xs = x0.reshape(B, n).clamp(-sb, sb) / sb
+        mean = c1[t][:, None] * xs + c2[t][:, None] * x_t.reshape(B, n)
+        sig = torch.where(t == 0, torch.zeros_like(sigma[t]), sigma[t])[:, None]
+        out.reshape(B, n).copy_(mean + sig * noise.reshape(B, n))
+
+    def step_finalize(self, x, n, unnormalize, out):
+        self._log("step_finalize")
+        v = x.clamp(-1., 1.)
+        out.copy_((v + 1) * 0.5 if unnormalize else v)
+
+    def q_sample(self, x0, noise, t, tab_a, tab_b, B, n, post_scale, post_shift, out):
+        self._log("q_sample")
+        v = tab_a[t][:, None] * x0.reshape(B, n) + tab_b[t][:, None] * noise.reshape(B, n)
+        out.reshape(B, n).copy_(v * post_scale + post_shift)
