@@ -1,0 +1,121 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.pt by running the UNMODIFIED reference (oracle/reference.py)
+on the CPU in this container.  Re-run with:  python oracle/make_golden.py
+The fixtures pin (a) oracle/restatement.py and (b) the CUDA path on the GPU box, where /root/reference is absent.
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import reference  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def _inputs(b, s, L, E, seed, lowres):
+    g = torch.Generator().manual_seed(seed)
+    d = dict(x=torch.randn(b, 3, s, s, generator=g), time=torch.tensor([17, 3][:b]),
+             text_embeds=torch.randn(b, L, E, generator=g))
+    mask = torch.ones(b, L, dtype=torch.bool)
+    mask[0, L // 2:] = False
+    d['text_embeds'][0, L // 2:] = 0.          # t5.py:82 zeroes padded positions
+    d['text_mask'] = mask
+    if lowres:
+        d['lowres_cond_img'] = torch.randn(b, 3, s, s, generator=g)
+        d['lowres_noise_times'] = torch.full((b,), 5)
+    return d
+
+
+def unet_case(name, cfg, s, lowres):
+    from minimagen.Unet import Unet
+    torch.manual_seed(0)
+    u = Unet(**cfg).eval()
+    inp = _inputs(2, s, 11, cfg.get('text_embed_dim', 512), 1, lowres)
+    kw = {k: v for k, v in inp.items() if k not in ('x', 'time')}
+    with torch.no_grad():
+        out_cond = u(inp['x'], inp['time'], **kw)
+        out_null = u(inp['x'], inp['time'], cond_drop_prob=1., **kw)
+        out_nomask = u(inp['x'], inp['time'], **{**kw, 'text_mask': None})
+        out_cfg = u.forward_with_cond_scale(inp['x'], inp['time'], cond_scale=3., **kw)
+    torch.save(dict(cfg=cfg, state_dict=u.state_dict(), inputs=inp, out_cond=out_cond, out_null=out_null,
+                    out_nomask=out_nomask, out_cfg3=out_cfg), os.path.join(OUT, name + ".pt"))
+    print(name, "params", sum(p.numel() for p in u.parameters()), "out std", out_cond.std().item())
+
+
+def step_case():
+    """_p_mean_variance/_p_sample on injected model output + noise, T = 25 (the shipped tiny config) and T = 1000."""
+    from minimagen.Imagen import Imagen
+    from minimagen.Unet import Unet, BaseTest
+    cases = {}
+    for T in (25, 1000):
+        torch.manual_seed(0)
+        u = Unet(**BaseTest.defaults)
+        im = Imagen(unets=u, text_encoder_name='t5_small', image_sizes=(64,), timesteps=T, cond_drop_prob=0.15)
+        sch = im.noise_schedulers[0]
+        g = torch.Generator().manual_seed(5 + T)
+        x = torch.randn(3, 3, 64, 64, generator=g)
+        eps = torch.randn(3, 3, 64, 64, generator=g) * 1.5
+        noise = torch.randn(3, 3, 64, 64, generator=g)
+        t = torch.tensor([T - 1, T // 3, 0])
+        with torch.no_grad():
+            mean, var, logvar = im._p_mean_variance(u, x=x, t=t, noise_scheduler=sch, model_output=eps)
+            x0 = sch.predict_start_from_noise(x, t=t, noise=eps)
+            s = torch.quantile(x0.flatten(1).abs(), 0.9, dim=-1)
+            nz = (1 - (t == 0).float()).reshape(3, 1, 1, 1)
+            out = mean + nz * (0.5 * logvar).exp() * noise
+        tables = {k: v.clone() for k, v in sch.named_buffers()}
+        cases[T] = dict(x=x, eps=eps, noise=noise, t=t, mean=mean, logvar=logvar, x0=x0, s_quantile=s, out=out,
+                        tables=tables)
+    # quantile rank arithmetic at the BASELINE image sizes (fp32 rank)
+    ranks = {}
+    for n in (3 * 64 * 64, 3 * 256 * 256, 3 * 1024 * 1024):
+        r = torch.tensor(0.9, dtype=torch.float32) * (n - 1)
+        ranks[n] = (int(r.floor()), int(r.ceil()), float(r - r.floor()))
+    cases['ranks'] = ranks
+    torch.save(cases, os.path.join(OUT, "ddpm_step.pt"))
+    print("ddpm_step ranks", ranks)
+
+
+def sample_case():
+    """3 iterations of Imagen._p_sample_loop (tiny base U-Net, T=25, cond_scale=3) with injected noise."""
+    import minimagen.Imagen as MI
+    from minimagen.Imagen import Imagen
+    from minimagen.Unet import Unet, BaseTest
+    torch.manual_seed(0)
+    u = Unet(**BaseTest.defaults)
+    im = Imagen(unets=u, text_encoder_name='t5_small', image_sizes=(64,), timesteps=25, cond_drop_prob=0.15).eval()
+    sd = u.state_dict()
+    g = torch.Generator().manual_seed(11)
+    inp = _inputs(2, 64, 9, 512, 2, False)
+    x_T = torch.randn(2, 3, 64, 64, generator=g)
+    noises = [torch.randn(2, 3, 64, 64, generator=g) for _ in range(3)]
+    sch = im.noise_schedulers[0]
+    img = x_T
+    traj = []
+    it = iter(noises)
+    real = MI.torch.randn_like
+    MI.torch.randn_like = lambda z: next(it)
+    try:
+        with torch.no_grad():
+            for i, t in enumerate(sch._get_sampling_timesteps(2, device='cpu')[:3]):
+                img = im._p_sample(u, img, t, text_embeds=inp['text_embeds'], text_mask=inp['text_mask'], cond_scale=3.,
+                                   noise_scheduler=sch)
+                traj.append(img)
+    finally:
+        MI.torch.randn_like = real
+    torch.save(dict(cfg=dict(BaseTest.defaults), state_dict=sd, text_embeds=inp['text_embeds'],
+                    text_mask=inp['text_mask'], x_T=x_T, noises=noises, traj=traj, timesteps=25, cond_scale=3.),
+               os.path.join(OUT, "sample_loop.pt"))
+    print("sample_loop x std", [t.std().item() for t in traj])
+
+
+if __name__ == "__main__":
+    reference.load()
+    os.makedirs(OUT, exist_ok=True)
+    from minimagen.Unet import BaseTest, SuperTest
+    unet_case("unet_tiny_base", dict(BaseTest.defaults), 64, False)
+    unet_case("unet_tiny_sr", dict(SuperTest.defaults, lowres_cond=True), 64, True)
+    step_case()
+    sample_case()

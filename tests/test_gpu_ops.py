@@ -1,0 +1,314 @@
+"""GPU parity, op by op, through the C ABI: every native kernel vs the torch restatement of its contract
+(tests/emu_ops.py) on identical seeded inputs.  Integer / index work (quantile order statistics, timestep gathers) is
+checked bit-exactly; floating point within the stated tolerances."""
+import pytest
+import torch
+
+from conftest import rel_l2
+from emu_ops import EmuOps
+
+pytestmark = pytest.mark.gpu
+F16, F32, F64 = torch.float16, torch.float32, torch.float64
+EMU = EmuOps()
+
+
+def _cu(t):
+    return None if t is None else t.cuda()
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return torch.randn(*shape, generator=g) * scale
+
+
+# ---------------------------------------------------------------------------------------------- conv (tensor cores)
+IGEMM_CASES = [
+    # B, H, W, Cin, Cout, k, mode, bias, residual, f16out
+    (2, 16, 16, 64, 128, 3, 0, True, True, False),
+    (1, 32, 32, 128, 64, 3, 0, True, False, True),
+    (3, 8, 8, 64, 64, 3, 0, False, True, False),       # tile spans two images + batch tail
+    (1, 64, 64, 64, 16, 3, 0, True, False, False),     # narrow N
+    (2, 16, 16, 256, 256, 1, 0, True, True, False),    # 1x1
+    (2, 16, 16, 64, 128, 4, 1, True, False, False),    # Downsample 4x4 s2 via phase split
+    (1, 4, 256, 64, 64, 3, 0, True, False, False),     # W > 128
+    (1, 1, 520, 128, 1024, 1, 0, False, False, True),  # GEMM with ragged M (8320-like token rows)
+    (2, 16, 16, 1024, 512, 3, 0, True, True, False),   # deep K, 2 N tiles
+]
+
+
+@pytest.mark.parametrize("case", IGEMM_CASES)
+def test_conv_igemm(native, case):
+    B, H, W, Cin, Cout, k, mode, bias, residual, f16out = case
+    assert native.igemm_supported(H, W, Cin, Cout)
+    P = 4 if mode == 1 else 1
+    act = _rand(B, P, H, W, Cin, seed=1).to(F16)
+    w = _rand(Cout, Cin, k, k, seed=2, scale=(k * k * Cin) ** -0.5)
+    b = _rand(Cout, seed=3) if bias else None
+    r = _rand(B, H, W, Cout, seed=4) if residual else None
+    strides = (H * W * Cout, W * Cout, Cout)
+    wp_e = EMU.pack_conv_weight(w)
+    wp_n = native.pack_conv_weight(w.cuda())
+    assert torch.equal(wp_n.cpu(), wp_e)
+    o_e = torch.zeros(B, H, W, Cout)
+    o16_e = torch.zeros(B, H, W, Cout, dtype=F16) if f16out else None
+    EMU.conv_igemm(act, B, H, W, Cin, 0, Cin, wp_e, Cout, k, k, mode, b, r, o_e, o16_e, strides)
+    o_n = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    o16_n = torch.zeros(B, H, W, Cout, dtype=F16, device="cuda") if f16out else None
+    native.conv_igemm(act.cuda(), B, H, W, Cin, 0, Cin, wp_n, Cout, k, k, mode, _cu(b), _cu(r), o_n, o16_n, strides)
+    torch.cuda.synchronize()
+    assert rel_l2(o_n, o_e) < 2e-5          # same fp16 operands, fp32 accumulation order differs
+    if f16out:
+        assert rel_l2(o16_n, o_e) < 1e-3
+
+
+def test_conv_igemm_channel_offset_and_strided_output(native):
+    """operand = a channel slice of a wider buffer; result written into a channel slice of a wider NHWC buffer"""
+    B, H, W, lda, c_off, Cin, Cout, ldo = 1, 16, 16, 192, 64, 128, 64, 160
+    act = _rand(B, 1, H, W, lda, seed=5).to(F16)
+    w = _rand(Cout, Cin, 3, 3, seed=6, scale=0.03)
+    wp = EMU.pack_conv_weight(w)
+    strides = (H * W * ldo, W * ldo, ldo)
+    o_e = torch.zeros(B, H, W, ldo)
+    EMU.conv_igemm(act, B, H, W, lda, c_off, Cin, wp, Cout, 3, 3, 0, None, None, o_e[..., 32:], None, strides)
+    o_n = torch.zeros(B, H, W, ldo, device="cuda")
+    native.conv_igemm(act.cuda(), B, H, W, lda, c_off, Cin, wp.cuda(), Cout, 3, 3, 0, None, None, o_n[..., 32:], None,
+                      strides)
+    assert rel_l2(o_n, o_e) < 2e-5
+    assert torch.count_nonzero(o_n[..., :32]) == 0 and torch.count_nonzero(o_n[..., 96:]) == 0
+
+
+# ---------------------------------------------------------------------------------------------- conv (direct)
+DIRECT_CASES = [
+    # B, Hin, Win, Cin, ldi, Cout, k, stride, pad, residual, nchw_out
+    (2, 32, 32, 6, 8, 32, 15, 1, 7, False, False),     # stem k=15 on 6 (padded to 8) channels
+    (2, 32, 32, 3, 4, 4, 7, 1, 3, False, False),
+    (1, 20, 20, 128, 128, 3, 3, 1, 1, False, True),    # final conv -> NCHW
+    (2, 16, 16, 24, 24, 16, 3, 1, 1, True, False),     # tiny-config style
+    (2, 16, 16, 8, 8, 16, 4, 2, 1, False, False),      # Downsample on the small-channel path
+    (1, 8, 8, 16, 16, 8, 1, 1, 0, True, False),
+]
+
+
+@pytest.mark.parametrize("case", DIRECT_CASES)
+def test_conv_direct(native, case):
+    B, Hin, Win, Cin, ldi, Cout, k, stride, pad, residual, nchw = case
+    Hout = (Hin + 2 * pad - k) // stride + 1
+    Wout = (Win + 2 * pad - k) // stride + 1
+    x = torch.zeros(B, Hin, Win, ldi)
+    x[..., :Cin] = _rand(B, Hin, Win, Cin, seed=7)
+    w = _rand(Cout, Cin, k, k, seed=8, scale=(k * k * Cin) ** -0.5)
+    b = _rand(Cout, seed=9)
+    if nchw:
+        shape, strides = (B, Cout, Hout, Wout), (Cout * Hout * Wout, Wout, 1, Hout * Wout)
+    else:
+        shape, strides = (B, Hout, Wout, Cout), (Hout * Wout * Cout, Wout * Cout, Cout, 1)
+    r = _rand(*shape, seed=10) if residual else None
+    o_e = torch.zeros(shape)
+    EMU.conv_direct(x, B, Hin, Win, Cin, ldi, w, Cout, k, k, stride, pad, b, r, o_e, Hout, Wout, strides)
+    o_n = torch.full(shape, float("nan"), device="cuda")
+    native.conv_direct(x.cuda(), B, Hin, Win, Cin, ldi, w.cuda(), Cout, k, k, stride, pad, b.cuda(), _cu(r), o_n, Hout,
+                       Wout, strides)
+    assert rel_l2(o_n, o_e) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- GroupNorm / casts / LN
+@pytest.mark.parametrize("B,HW,C0,C1,groups", [(2, 256, 128, 0, 8), (2, 1024, 256, 128, 8), (3, 100, 8, 0, 8),
+                                               (2, 64, 16, 8, 8), (1, 4096, 2048, 0, 8), (2, 256, 32, 0, 8)])
+@pytest.mark.parametrize("f16", [True, False])
+def test_groupnorm_silu(native, B, HW, C0, C1, groups, f16):
+    C = C0 + C1
+    s0 = _rand(B, HW, C0, seed=11) * 2 + 0.5
+    s1 = _rand(B, HW, C1, seed=12) if C1 else None
+    gamma, beta = _rand(C, seed=13), _rand(C, seed=14)
+    ss = _rand(B, 2 * C, seed=15, scale=0.3)
+    sums_e = torch.zeros(B, groups, 2, dtype=F64)
+    EMU.gn_stats(s0, C0, s1, C1, 0.7071, B, HW, groups, sums_e)
+    sums_n = torch.zeros(B, groups, 2, dtype=F64, device="cuda")
+    native.gn_stats(s0.cuda(), C0, _cu(s1), C1, 0.7071, B, HW, groups, sums_n)
+    assert rel_l2(sums_n, sums_e) < 1e-6
+    dt = F16 if f16 else F32
+    o_e = torch.zeros(B, HW, C, dtype=dt)
+    EMU.gn_apply_silu(s0, C0, s1, C1, 0.7071, B, HW, groups, sums_e, gamma, beta, ss, 1e-5, o_e)
+    o_n = torch.zeros(B, HW, C, dtype=dt, device="cuda")
+    native.gn_apply_silu(s0.cuda(), C0, _cu(s1), C1, 0.7071, B, HW, groups, sums_n, gamma.cuda(), beta.cuda(),
+                         ss.cuda(), 1e-5, o_n)
+    assert rel_l2(o_n, o_e) < (1e-3 if f16 else 2e-6)
+    # and against torch's own GroupNorm (the op the reference calls)
+    x = torch.cat((s0, s1 * 0.7071), dim=-1) if C1 else s0
+    gn = torch.nn.functional.group_norm(x.transpose(1, 2).reshape(B, C, HW, 1), groups, gamma, beta, 1e-5)
+    y = gn * (ss[:, :C, None, None] + 1) + ss[:, C:, None, None]
+    y = torch.nn.functional.silu(y).reshape(B, C, HW).transpose(1, 2)
+    assert rel_l2(o_n, y) < (1e-3 if f16 else 5e-6)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("f16", [True, False])
+def test_cast_act(native, mode, f16):
+    B, H, W, C0, C1 = 2, 8, 16, 64, 32
+    s0, s1 = _rand(B, H, W, C0, seed=16), _rand(B, H, W, C1, seed=17)
+    dt = F16 if f16 else F32
+    numel = B * H * W * (C0 + C1) * (4 if mode == 1 else 1)
+    o_e = torch.zeros(numel, dtype=dt)
+    EMU.cast_act(s0, C0, s1, C1, 0.5, B, H, W, mode, o_e)
+    o_n = torch.zeros(numel, dtype=dt, device="cuda")
+    native.cast_act(s0.cuda(), C0, s1.cuda(), C1, 0.5, B, H, W, mode, o_n)
+    assert torch.equal(o_n.cpu(), o_e)
+
+
+@pytest.mark.parametrize("R,C,pre_gelu,res,beta", [(100, 16, 0, True, True), (513, 1024, 1, False, False),
+                                                   (64, 2048, 0, True, False), (7, 8, 0, False, True),
+                                                   (520, 128, 0, False, True)])
+def test_ln_rows(native, R, C, pre_gelu, res, beta):
+    x = _rand(R, C, seed=18) * 3 + 1
+    gamma = _rand(C, seed=19)
+    bt = _rand(C, seed=20) if beta else None
+    r = _rand(R, C, seed=21) if res else None
+    o_e, o16_e = torch.zeros(R, C), torch.zeros(R, C, dtype=F16)
+    EMU.ln_rows(x, R, C, gamma, bt, 1e-5, pre_gelu, r, o_e, o16_e)
+    o_n, o16_n = torch.zeros(R, C, device="cuda"), torch.zeros(R, C, dtype=F16, device="cuda")
+    native.ln_rows(x.cuda(), R, C, gamma.cuda(), _cu(bt), 1e-5, pre_gelu, _cu(r), o_n, o16_n)
+    assert rel_l2(o_n, o_e) < 3e-6
+    assert rel_l2(o16_n, o_e) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- conditioning
+@pytest.mark.parametrize("M,K,N,in_act,out_act,add", [(2, 8, 32, 0, 1, False), (32, 1024, 2048, 1, 0, False),
+                                                      (32, 512, 512, 0, 0, True), (516, 8, 1024, 0, 0, False),
+                                                      (9, 768, 128, 0, 0, False)])
+def test_linear_f32(native, M, K, N, in_act, out_act, add):
+    x, w, b = _rand(M, K, seed=22), _rand(N, K, seed=23, scale=K ** -0.5), _rand(N, seed=24)
+    a = _rand(M, N, seed=25) if add else None
+    o_e = torch.zeros(M, N)
+    EMU.linear_f32(x, M, K, w, b, N, in_act, out_act, a, o_e, None, 0.125)
+    o_n = torch.zeros(M, N, device="cuda")
+    o16 = torch.zeros(M, N, dtype=F16, device="cuda")
+    native.linear_f32(x.cuda(), M, K, w.cuda(), b.cuda(), N, in_act, out_act, _cu(a), o_n, o16, 0.125)
+    assert rel_l2(o_n, o_e) < 2e-6
+    assert rel_l2(o16, o_e) < 1e-3
+
+
+def test_posemb_and_text_tokens(native):
+    t = torch.tensor([0, 1, 17, 500, 999])
+    for dim in (8, 128, 256):
+        o_e = torch.zeros(5, dim)
+        EMU.posemb(t, 5, dim, o_e)
+        o_n = torch.zeros(5, dim, device="cuda")
+        native.posemb(t.cuda(), 5, dim, o_n)
+        assert (o_n.cpu() - o_e).abs().max() < 2e-4          # sin/cos of arguments up to 999 rad, fp32
+    B, L, D, m, nt = 3, 11, 16, 260, 4
+    proj = _rand(B, L, D, seed=26)
+    mask = torch.ones(B, L, dtype=torch.uint8)
+    mask[0, 5:] = 0
+    keep = torch.tensor([1, 0, 1], dtype=torch.uint8)
+    null = _rand(256, D, seed=27)
+    for mk in (mask, None):
+        c_e, p_e = torch.zeros(B, m, D), torch.zeros(B, D)
+        EMU.text_tokens(proj, B, L, D, mk, keep, null, 256, c_e, m, nt, p_e)
+        c_n, p_n = torch.zeros(B, m, D, device="cuda"), torch.zeros(B, D, device="cuda")
+        native.text_tokens(proj.cuda(), B, L, D, _cu(mk), keep.cuda(), null.cuda(), 256, c_n, m, nt, p_n)
+        assert torch.equal(c_n.cpu(), c_e)                   # pure select: exact
+        assert rel_l2(p_n, p_e) < 1e-6
+    src = _rand(B, 2, D, seed=28)
+    d_e, d_n = torch.zeros(B, m, D), torch.zeros(B, m, D, device="cuda")
+    EMU.place_rows(src, B, 2, D, d_e, m, 2)
+    native.place_rows(src.cuda(), B, 2, D, d_n, m, 2)
+    assert torch.equal(d_n.cpu(), d_e)
+    a, nl, ad = _rand(B, 32, seed=29), _rand(32, seed=30), _rand(B, 32, seed=31)
+    s_e, s_n = torch.zeros(B, 32), torch.zeros(B, 32, device="cuda")
+    EMU.select_rows(a, nl, keep, ad, B, 32, s_e)
+    native.select_rows(a.cuda(), nl.cuda(), keep.cuda(), ad.cuda(), B, 32, s_n)
+    assert torch.equal(s_n.cpu(), s_e)
+    x, lr = _rand(2, 3, 10, 10, seed=32), _rand(2, 3, 10, 10, seed=33)
+    n_e, n_n = torch.ones(2, 100, 8), torch.ones(2, 100, 8, device="cuda")
+    EMU.nchw_to_nhwc(x, 3, lr, 3, 2, 100, 8, n_e)
+    native.nchw_to_nhwc(x.cuda(), 3, lr.cuda(), 3, 2, 100, 8, n_n)
+    assert torch.equal(n_n.cpu(), n_e)
+
+
+# ---------------------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,heads,n,m,shared,use_mask", [(2, 8, 256, 260, False, False), (2, 8, 64, 258, False, True),
+                                                         (1, 8, 1024, 1024, True, False), (2, 8, 256, 256, True, True),
+                                                         (1, 2, 100, 37, False, True)])
+def test_attention(native, B, heads, n, m, shared, use_mask):
+    inner = heads * 64
+    q = (_rand(B * n, inner, seed=34) * 0.125).to(F16)
+    ldkv = 128 if shared else 2 * inner
+    kv = _rand(B * m, ldkv, seed=35).to(F16)
+    null_kv = _rand(2, 64, seed=36)
+    mask = None
+    if use_mask:
+        mask = (torch.rand(B, m, generator=torch.Generator().manual_seed(1)) > 0.3).to(torch.uint8)
+    v_off = 64 if shared else inner
+    args = (n * inner, inner)
+    o_e = torch.zeros(B * n, inner, dtype=F16)
+    EMU.attention(q, n * inner, inner, kv, kv[:, v_off:], m * ldkv, ldkv, 0 if shared else 64, null_kv, mask, B, heads,
+                  n, m, o_e, *args)
+    qn, kvn = q.cuda(), kv.cuda()
+    o_n = torch.zeros(B * n, inner, dtype=F16, device="cuda")
+    native.attention(qn, n * inner, inner, kvn, kvn[:, v_off:], m * ldkv, ldkv, 0 if shared else 64, null_kv.cuda(),
+                     _cu(mask), B, heads, n, m, o_n, *args)
+    assert rel_l2(o_n, o_e) < 2e-3           # fp16 P / fp16 output rounding
+
+
+# ---------------------------------------------------------------------------------------------- DDPM step
+@pytest.mark.parametrize("n,B", [(3 * 64 * 64, 4), (3 * 256 * 256, 2), (1000, 3), (3 * 1024 * 1024, 1)])
+def test_quantile_is_exact(native, n, B):
+    """Order statistics are integer work: the selected elements must be bit-identical to a full sort."""
+    from minimagen_b200.Imagen import quantile_rank
+    g = torch.Generator().manual_seed(n)
+    x0 = torch.randn(B, n, generator=g) * 1.7
+    x0[0, : n // 3] = 0.75                      # long runs of equal values around / below the rank
+    if B > 1:
+        x0[1] = x0[1].round()                   # heavy ties everywhere
+    lo, hi, w = quantile_rank(n, 0.9)
+    s_n = torch.zeros(B, device="cuda")
+    native.step_quantile(x0.cuda(), B, n, lo, hi, w, 0.0, s_n)
+    srt = x0.abs().sort(dim=-1).values
+    expect = torch.lerp(srt[:, lo], srt[:, hi], torch.tensor(w))
+    assert torch.equal(s_n.cpu(), expect), (s_n.cpu(), expect)
+    assert torch.equal(s_n.cpu(), torch.quantile(x0.abs(), 0.9, dim=-1))
+    # w = 0 selects one element exactly
+    native.step_quantile(x0.cuda(), B, n, lo, lo, 0.0, 0.0, s_n)
+    assert torch.equal(s_n.cpu(), srt[:, lo])
+    native.step_quantile(x0.cuda(), B, n, n - 1, n - 1, 0.0, 0.0, s_n)
+    assert torch.equal(s_n.cpu(), srt[:, -1])
+    native.step_quantile(x0.cuda(), B, n, 0, 1, 0.5, 0.0, s_n)
+    assert torch.equal(s_n.cpu(), torch.lerp(srt[:, 0], srt[:, 1], torch.tensor(0.5)))
+
+
+@pytest.mark.parametrize("T", [25, 1000])
+def test_step_kernels_vs_golden(native, T):
+    from conftest import load_golden
+    g = load_golden("ddpm_step.pt")[T]
+    tabs = {k: v.cuda() for k, v in g["tables"].items()}
+    sigma = (0.5 * g["tables"]["posterior_log_variance_clipped"]).exp().cuda()
+    B, n = 3, 3 * 64 * 64
+    x, eps, noise, t = g["x"].cuda(), g["eps"].cuda(), g["noise"].cuda(), g["t"].cuda()
+    x0 = torch.zeros_like(x)
+    native.step_x0(x, eps, None, 1.0, t, tabs["sqrt_recip_alphas_cumprod"], tabs["sqrt_recipm1_alphas_cumprod"], B, n,
+                   x0)
+    assert torch.equal(x0.cpu(), g["x0"])                                  # un-fused fp32 ops: bit exact
+    s = torch.zeros(B, device="cuda")
+    native.step_quantile(x0, B, n, 11058, 11059, 0.2998046875, 0.0, s)
+    assert torch.equal(s.cpu(), g["s_quantile"])
+    native.step_quantile(x0, B, n, 11058, 11059, 0.2998046875, 1.0, s)
+    out = torch.zeros_like(x)
+    native.step_posterior(x0, x, noise, s, t, tabs["posterior_mean_coef1"], tabs["posterior_mean_coef2"], sigma, B, n,
+                          out)
+    assert torch.equal(out.cpu(), g["out"])
+    # CFG combine inside step_x0
+    nl = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(9))
+    native.step_x0(x, eps, nl.cuda(), 7.0, t, tabs["sqrt_recip_alphas_cumprod"], tabs["sqrt_recipm1_alphas_cumprod"],
+                   B, n, x0)
+    e = nl + (g["eps"] - nl) * 7.0
+    a = g["tables"]["sqrt_recip_alphas_cumprod"][g["t"]].reshape(3, 1, 1, 1)
+    b = g["tables"]["sqrt_recipm1_alphas_cumprod"][g["t"]].reshape(3, 1, 1, 1)
+    assert torch.equal(x0.cpu(), a * g["x"] - b * e)
+    fin = torch.zeros_like(x)
+    native.step_finalize(out, out.numel(), 1, fin)
+    assert torch.equal(fin.cpu(), (g["out"].clamp(-1, 1) + 1) * 0.5)
+    q = torch.zeros_like(x)
+    native.q_sample(x, noise, t, tabs["sqrt_alphas_cumprod"], tabs["sqrt_one_minus_alphas_cumprod"], B, n, 1.0, 0.0, q)
+    sa = g["tables"]["sqrt_alphas_cumprod"][g["t"]].reshape(3, 1, 1, 1)
+    sb = g["tables"]["sqrt_one_minus_alphas_cumprod"][g["t"]].reshape(3, 1, 1, 1)
+    assert torch.equal(q.cpu(), sa * g["x"] + sb * g["noise"])

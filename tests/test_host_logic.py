@@ -1,0 +1,161 @@
+"""Host-side logic on CPU: the class surfaces / checkpoint ABI mirror the reference, and the orchestration in
+minimagen_b200/{layers,Unet,Imagen}.py -- executed through the torch EMULATION of the ops interface (tests/emu_ops.py)
+-- reproduces the reference's outputs.  (The emulation rounds tensor-core operands to fp16 like the kernels do, hence
+the 2e-3 bound; the tiny config runs its convolutions in fp32 and lands near 2e-4.)"""
+import inspect
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_l2
+from oracle import reference, restatement as R
+
+
+def _mine(cfg, sd):
+    from minimagen_b200.Unet import Unet
+    u = Unet(**cfg).eval()
+    u.load_state_dict(sd)
+    return u
+
+
+@pytest.mark.parametrize("name", ["unet_tiny_base.pt", "unet_tiny_sr.pt"])
+def test_state_dict_abi_matches_reference_checkpoint(name):
+    from minimagen_b200.Unet import Unet
+    g = load_golden(name)
+    u = Unet(**g["cfg"])
+    mine = u.state_dict()
+    assert list(mine.keys()) == list(g["state_dict"].keys())          # same keys, same order
+    for k, v in g["state_dict"].items():
+        assert mine[k].shape == v.shape and mine[k].dtype == v.dtype, k
+    assert not u.load_state_dict(g["state_dict"]).missing_keys
+
+
+@pytest.mark.parametrize("name", ["unet_tiny_base.pt", "unet_tiny_sr.pt"])
+def test_unet_forward_orchestration_vs_golden(emu, name):
+    g = load_golden(name)
+    u = _mine(g["cfg"], g["state_dict"])
+    inp = g["inputs"]
+    kw = {k: v for k, v in inp.items() if k not in ("x", "time")}
+    with torch.no_grad():
+        assert rel_l2(u(inp["x"], inp["time"], **kw), g["out_cond"]) < 1e-3
+        assert rel_l2(u(inp["x"], inp["time"], cond_drop_prob=1., **kw), g["out_null"]) < 1e-3
+        assert rel_l2(u(inp["x"], inp["time"], **dict(kw, text_mask=None)), g["out_nomask"]) < 1e-3
+        assert rel_l2(u.forward_with_cond_scale(inp["x"], inp["time"], cond_scale=3., **kw), g["out_cfg3"]) < 1e-3
+    assert "conv_direct" in emu.calls and "attention" in emu.calls
+
+
+@pytest.mark.parametrize("cfg,s,lowres", [
+    (dict(dim=64, dim_mults=(1, 2), attend_at_middle=True, text_embed_dim=768), 32, False),
+    (dict(dim=64, dim_mults=(1, 2, 4), num_resnet_blocks=(1, 2, 2), layer_attns=(False, False, True),
+          layer_cross_attns=(False, True, True), lowres_cond=True, memory_efficient=True), 32, True),
+])
+def test_unet_forward_tensor_core_shaped_configs(emu, cfg, s, lowres):
+    """Channel counts that route through conv_igemm / fp16 operands (vs the bit-exact-pinned restatement)."""
+    from minimagen_b200.Unet import Unet
+    torch.manual_seed(0)
+    u = Unet(**cfg).eval()
+    sd = u.state_dict()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, s, s, generator=g)
+    te = torch.randn(2, 20, cfg.get("text_embed_dim", 512), generator=g)
+    tm = torch.ones(2, 20, dtype=torch.bool)
+    tm[1, 5:] = False
+    kw = dict(text_embeds=te, text_mask=tm)
+    if lowres:
+        kw.update(lowres_cond_img=torch.randn(2, 3, s, s, generator=g), lowres_noise_times=torch.tensor([200, 3]))
+    t = torch.tensor([999, 0])
+    with torch.no_grad():
+        ref_out = R.unet_forward(sd, cfg, x, t, **kw)
+        out = u(x, t, **kw)
+    assert emu.calls.count("conv_igemm") > 20
+    assert rel_l2(out, ref_out) < 3e-3
+
+
+def test_step_kernels_contract_vs_golden(emu):
+    from minimagen_b200.Imagen import Imagen
+    from minimagen_b200.Unet import Unet, BaseTest
+    for T in (25, 1000):
+        g = load_golden("ddpm_step.pt")[T]
+        im = Imagen(unets=Unet(**BaseTest.defaults), text_encoder_name="t5_small", image_sizes=(64,), timesteps=T,
+                    cond_drop_prob=0.15)
+        sch = im.noise_schedulers[0]
+        for k, v in g["tables"].items():
+            assert torch.equal(getattr(sch, k), v), k
+        with torch.no_grad():
+            out = im._step(im.unets[0], g["x"], g["t"], g["noise"], noise_scheduler=sch, text_embeds=None,
+                           text_mask=None, lowres_cond_img=None, lowres_noise_times=None, cond_scale=1.,
+                           model_output=g["eps"])
+            mean, _, logvar = im._p_mean_variance(im.unets[0], g["x"], g["t"], noise_scheduler=sch,
+                                                  model_output=g["eps"])
+        assert torch.equal(out, g["out"])
+        assert torch.equal(mean, g["mean"]) and torch.equal(logvar, g["logvar"])
+
+
+@pytest.mark.parametrize("graph", [False])
+def test_sample_loop_vs_golden(emu, graph):
+    from minimagen_b200.Imagen import Imagen
+    from minimagen_b200.Unet import Unet
+    g = load_golden("sample_loop.pt")
+    u = _mine(g["cfg"], g["state_dict"])
+    im = Imagen(unets=u, text_encoder_name="t5_small", image_sizes=(64,), timesteps=g["timesteps"],
+                cond_drop_prob=0.15).eval()
+    im.unets[0].load_state_dict(g["state_dict"])
+    im.use_cuda_graph = graph
+    draws = {"init": g["x_T"]}
+    im.noise_fn = lambda kind, shape, step: g["x_T"] if kind == "init" else g["noises"][g["timesteps"] - 1 - step]
+    out = im._p_sample_loop(im.unets[0], (2, 3, 64, 64), noise_scheduler=im.noise_schedulers[0],
+                            text_embeds=g["text_embeds"], text_mask=g["text_mask"], cond_scale=g["cond_scale"],
+                            max_steps=3)
+    expect = (g["traj"][2].clamp(-1, 1) + 1) * 0.5
+    assert rel_l2(out, expect) < 2e-3
+
+
+def test_imagen_surface_and_asserts(emu):
+    from minimagen_b200.Imagen import Imagen
+    from minimagen_b200.Unet import Unet, Base, Super, BaseTest, SuperTest
+    assert BaseTest.defaults["dim"] == 8 and SuperTest.defaults["memory_efficient"] is True
+    assert Base.defaults["dim_mults"] == (1, 2, 3, 4) and Super.defaults["num_resnet_blocks"] == (2, 4, 8, 8)
+    u0, u1 = Unet(**BaseTest.defaults), Unet(**SuperTest.defaults)
+    im = Imagen(unets=(u0, u1), text_encoder_name="t5_small", image_sizes=(32, 64), timesteps=25, cond_drop_prob=0.)
+    assert im.unets[0] is u0 and im.unets[1] is not u1 and im.unets[1].lowres_cond      # re-instantiated like the reference
+    assert len(im.noise_schedulers) == 2 and im.lowres_noise_schedule.num_timesteps == 25
+    sd = im.state_dict()
+    assert all(k.startswith("unets.") for k in sd)            # schedule buffers are non-persistent (diffusion_model.py:39)
+    with pytest.raises(AssertionError, match="text or text encodings"):
+        im.sample()
+    with pytest.raises(AssertionError, match="invalid text embedding dimension"):
+        im.sample(text_embeds=torch.zeros(1, 4, 7))
+    with pytest.raises(AssertionError, match="classifier free guidance"):
+        im._step(u0, torch.zeros(1, 3, 32, 32), torch.zeros(1, dtype=torch.long), torch.zeros(1, 3, 32, 32),
+                 noise_scheduler=im.noise_schedulers[0], text_embeds=torch.zeros(1, 4, 512), text_mask=None,
+                 lowres_cond_img=None, lowres_noise_times=None, cond_scale=3.)
+    with pytest.raises(AssertionError, match="at least 20"):
+        Imagen(unets=u0, text_encoder_name="t5_small", image_sizes=(32,), timesteps=10)
+    with pytest.raises(NotImplementedError, match="8f-2"):
+        im(torch.zeros(1, 3, 64, 64), text_embeds=torch.zeros(1, 4, 512), unet_number=1)
+
+
+@pytest.mark.skipif(not reference.available(), reason="reference tree only exists in the build container")
+def test_signatures_match_reference():
+    reference.load()
+    import minimagen.Unet as RU
+    import minimagen.Imagen as RI
+    import minimagen.diffusion_model as RD
+    import minimagen_b200.Unet as MU
+    import minimagen_b200.Imagen as MI
+    import minimagen_b200.diffusion_model as MD
+
+    def params(f):
+        return [(p.name, p.kind, p.default) for p in inspect.signature(f).parameters.values()]
+    assert params(MU.Unet.__init__) == params(RU.Unet.__init__)
+    assert params(MI.Imagen.__init__) == params(RI.Imagen.__init__)
+    assert params(MD.GaussianDiffusion.__init__) == params(RD.GaussianDiffusion.__init__)
+    assert params(MU.Unet.forward) == params(RU.Unet.forward)
+    ref_sample = [p[0] for p in params(RI.Imagen.sample)]
+    assert [p[0] for p in params(MI.Imagen.sample)][:len(ref_sample)] == ref_sample
+    for cls in ("Base", "Super", "BaseTest", "SuperTest"):
+        assert getattr(MU, cls).defaults == getattr(RU, cls).defaults
+    # training.get_default_args introspection (training.py:660-671) must see the same defaults
+    ref_defaults = {k: v.default for k, v in inspect.signature(RU.Unet.__init__).parameters.items()}
+    my_defaults = {k: v.default for k, v in inspect.signature(MU.Unet.__init__).parameters.items()}
+    assert ref_defaults == my_defaults
