@@ -20,6 +20,12 @@ def _chk(t, dtype, name):
         raise ValueError(f"{name}: tensor must be contiguous")
 
 
+def _chk_out(t, dtype, name):
+    """Outputs are addressed through explicit strides, so views (e.g. a channel slice) are fine; only the dtype is fixed."""
+    if t is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
 class NativeOps:
     name = "native-sm100a"
 
@@ -40,15 +46,15 @@ class NativeOps:
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
                    out_strides, block_n=0):
-        _chk(act, F16, "act"); _chk(wp, F16, "wp"); _chk(bias, F32, "bias"); _chk(residual, F32, "residual")
-        _chk(out_f32, F32, "out_f32"); _chk(out_f16, F16, "out_f16")
+        _chk(act, F16, "act"); _chk(wp, F16, "wp"); _chk(bias, F32, "bias"); _chk_out(residual, F32, "residual")
+        _chk_out(out_f32, F32, "out_f32"); _chk_out(out_f16, F16, "out_f16")
         sb, sh, sw = out_strides
         N.call("mi_conv2d_igemm_f16", N.ptr(act), B, H, W, lda, c_off, c_in, N.ptr(wp), c_out, kh, kw, mode,
                N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16), sb, sh, sw, block_n, None, N.stream())
 
     def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
                     out_strides):
-        _chk(inp, F32, "inp"); _chk(w, F32, "w"); _chk(bias, F32, "bias"); _chk(residual, F32, "residual")
+        _chk(inp, F32, "inp"); _chk(w, F32, "w"); _chk(bias, F32, "bias"); _chk_out(residual, F32, "residual")
         if out.dtype != F32:
             raise TypeError("out must be fp32")
         sb, sh, sw, sc = out_strides
