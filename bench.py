@@ -204,10 +204,17 @@ def main():
     torch.manual_seed(0)
     with torch.device(dev):
         unet = Unet(**wl["cfg"]).eval()
-    imagen = Imagen(unets=unet, text_encoder_name="t5_base" if wl["E"] == 768 else "t5_small",
-                    image_sizes=(wl["size"],), timesteps=wl["T"], cond_drop_prob=0.1).eval().to(dev)
-    unet = imagen.unets[0]
-    sch = imagen.noise_schedulers[0]
+        if wl["lowres"]:
+            # Imagen treats its first U-Net as the base model (Imagen.py:96-101), so the SR U-Net under test is stage 2
+            # behind a tiny stand-in base stage that is never run here
+            from minimagen_b200.Unet import BaseTest
+            stages, sizes = (Unet(**BaseTest.defaults, text_embed_dim=wl["E"]), unet), (wl["size"] // 4, wl["size"])
+        else:
+            stages, sizes = (unet,), (wl["size"],)
+    imagen = Imagen(unets=stages, text_encoder_name="t5_base" if wl["E"] == 768 else "t5_small",
+                    image_sizes=sizes, timesteps=wl["T"], cond_drop_prob=0.1).eval().to(dev)
+    assert imagen.unets[-1] is unet, "the U-Net under test was re-instantiated"
+    sch = imagen.noise_schedulers[-1]
     inp = synth_inputs(wl, B, 1000 + rank)           # each rank owns its own shard of the global batch
     text = inp["text_embeds"].to(dev)
     mask = inp["text_mask"].to(dev)
@@ -238,6 +245,7 @@ def main():
         torch.cuda.synchronize()
         launches_per_step = _native.launch_count - l0
 
+        print(f"[bench] launches/step={launches_per_step}", file=sys.stderr, flush=True)
         # per-kernel timing of the dominant kernel (tcgen05 implicit GEMM): CUDA events around every launch of one
         # eager step, on the launching stream
         conv_ms, conv_flops, conv_calls = measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev)
@@ -275,6 +283,8 @@ def main():
         if world > 1:
             dist.barrier()
         ms = e0.elapsed_time(e1)
+        print(f"[bench] device-resident: {ms / args.steps:.2f} ms/step; conv_tc {conv_ms:.2f} ms/step over {conv_calls} "
+              f"launches", file=sys.stderr, flush=True)
         clocks = sampler.stop() if sampler else None
         assert torch.isfinite(cur).all(), "non-finite output"
 
