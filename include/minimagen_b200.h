@@ -50,15 +50,18 @@ int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, in
  *             (2H x 2W) input produced by mi_cast_act(mode=2).
  *   w_f16     packed by mi_pack_conv_weight_f16, [c_out][kh*kw*c_in]
  *   bias      [c_out] fp32 or NULL;  residual: fp32 or NULL, added in the epilogue, addressed like the output
- *   out_f32 / out_f16   either or both; element (b,h,w,n) is written at  b*out_sb + h*out_sh + w*out_sw + n
+ *   out_f32 / out_f16   either or both; element (b,h,w,n) is written at  b*out_sb + h*out_sh + w*out_sw + n*out_sc
+ *             (out_sc = 1: channel-contiguous NHWC-style rows; out_sc = H*W with out_sw = 1: NCHW, used by final_conv
+ *             Unet.py:327,472); only channels n < n_valid are stored (n_valid = 0: all; lets c_out be zero-padded up
+ *             to a multiple of 16); residual requires out_sc = 1
  *   block_n   0 = auto, or one of 16/32/64/128/256 (tile width; must divide c_out)
  * Requirements: c_in % 64 == 0, c_out % 16 == 0, W a power of two >= 8 (or W >= 128), see mi_conv2d_igemm_supported.
  * A plain GEMM  out[M][N] = act[M][K] * w[N][K]^T  is the case B=1, H=1, W=M, kh=kw=1. */
 int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out);
 int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c_off, int c_in, const void* w_f16,
                         int c_out, int kh, int kw, int mode, const float* bias, const float* residual, float* out_f32,
-                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, int block_n,
-                        int* err_flag, void* stream);
+                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, long long out_sc,
+                        int n_valid, int block_n, int* err_flag, void* stream);
 
 /* Direct fp32 convolution for shapes outside the tensor-core path: the CrossEmbedLayer stem (layers.py:300, 3/6 input
  * channels, k = 3/7/15), final_conv (Unet.py:327, 3 output channels) and every conv of the tiny test config.
@@ -79,10 +82,11 @@ int mi_conv2d_direct_f32(const float* in, int B, int Hin, int Win, int c_in, int
 int mi_gn_stats(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
                 double* sums, void* stream);
 /* Block.forward (layers.py:136-144): SiLU( GroupNorm(x) * (scale + 1) + shift ) -> conv operand (fp16 or fp32).
- * scale_shift: [B][2*C] fp32 (time_mlp output, layers.py:427-429: first half scale, second half shift) or NULL. */
+ * scale_shift: fp32, row b at scale_shift + b*scale_shift_ld holds [scale(C) | shift(C)] (time_mlp output,
+ * layers.py:427-429; the rows of all ResnetBlocks live in one buffer, hence the row pitch) or NULL. */
 int mi_gn_apply_silu(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
-                     const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
-                     void* out, int out_is_f16, void* stream);
+                     const double* sums, const float* gamma, const float* beta, const float* scale_shift,
+                     int scale_shift_ld, float eps, void* out, int out_is_f16, void* stream);
 /* Raw conv operands with the skip concat folded in; mode 0 plain copy/cast, 1 nearest x2 upsample (layers.py:513),
  * 2 four-phase split for the stride-2 Downsample conv (layers.py:319). out: fp16 or fp32. */
 int mi_cast_act(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W, int mode,
@@ -115,6 +119,16 @@ int mi_select_rows(const float* a, const float* null_row, const uint8_t* keep, c
 /* torch.cat((x, lowres_cond_img), dim=1) (Unet.py:397) + NCHW -> NHWC with channels zero-padded to c_pad */
 int mi_nchw_to_nhwc(const float* a, int ca, const float* b, int cb, int B, int hw, int c_pad, float* out,
                     void* stream);
+
+/* Tensor-core operand of the CrossEmbedLayer stem (layers.py:294-305; kernels 3/7/15, stride 1, <= 8 input channels):
+ * out[b][h][w][j*8 + c] = cat(a, b)[b][c][h][w + j - 7] (zero outside the row, j = 15 and c >= ca+cb are zero), fp16,
+ * 128 values per pixel.  The three convs, zero-embedded in one 15x15 window, then run as ONE
+ * mi_conv2d_igemm_f16(kh = 15, kw = 1, c_in = 128).  a / b: NCHW fp32 (x and lowres_cond_img, Unet.py:397). */
+int mi_stem_unroll_f16(const float* a, int ca, const float* b, int cb, int B, int H, int W, void* out_f16,
+                       void* stream);
+/* out = x * sigmoid(x): the nn.SiLU in front of every ResnetBlock.time_mlp (layers.py:396-399), applied once per
+ * step to the shared time embedding instead of once per block */
+int mi_silu_f32(const float* in, long long n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------- attention
  * Fused softmax attention, dim_head 64: CrossAttention.forward (layers.py:220-251) with kv_head_stride = 64, and the

@@ -181,48 +181,71 @@ class Unet(nn.Module):
         t, c = self._text_condition(text_embeds, B, cond_drop_prob, device, text_mask, t, time_tokens)
         ctx = Context(c)
 
-        # torch.cat((x, lowres_cond_img), dim=1) + NCHW -> NHWC, channels zero-padded to a multiple of 4
-        lr = lowres_cond_img if exists(lowres_cond_img) else None
-        c_in = Cx + (lr.shape[1] if exists(lr) else 0)
-        cp = (c_in + 3) // 4 * 4
-        x_pad = torch.empty((B, H, W, cp), dtype=F32, device=device)
-        ops.nchw_to_nhwc(x.to(F32).contiguous(), Cx, lr.to(F32).contiguous() if exists(lr) else None,
-                         lr.shape[1] if exists(lr) else 0, B, H * W, cp, x_pad)
-        h = self.init_conv.run_padded(x_pad, B, H, W)
+        # every ResnetBlock's time_mlp (SiLU -> Linear, layers.py:396-399) in ONE GEMM over the shared time embedding
+        ss = self._all_scale_shifts(t)
+
+        # torch.cat((x, lowres_cond_img), dim=1) (Unet.py:397) + CrossEmbedLayer stem (Unet.py:400)
+        h = self.init_conv.run_stem(x, lowres_cond_img)
 
         hiddens = []
         for pre_downsample, init_block, resnet_blocks, attn_block, post_downsample in self.downs:
             if exists(pre_downsample):
                 h = pre_downsample.run(h)
-            h = init_block.run(h, t, ctx)
+            h = init_block.run(h, t, ctx, ss[init_block])
             for resnet_block in resnet_blocks:
-                h = resnet_block.run(h, t)
+                h = resnet_block.run(h, t, None, ss[resnet_block])
                 hiddens.append(h)
             h = attn_block.run(h)
             hiddens.append(h)
             if exists(post_downsample):
                 h = post_downsample.run(h)
 
-        h = self.mid_block1.run(h, t, ctx)
+        h = self.mid_block1.run(h, t, ctx, ss[self.mid_block1])
         if exists(self.mid_attn):
             h = self.mid_attn.run(h)
-        h = self.mid_block2.run(h, t, ctx)
+        h = self.mid_block2.run(h, t, ctx, ss[self.mid_block2])
 
         skip = lambda cur: Cat(cur, hiddens.pop(), self.skip_connect_scale)
         for init_block, resnet_blocks, attn_block, upsample in self.ups:
-            h = init_block.run(skip(h), t, ctx)
+            h = init_block.run(skip(h), t, ctx, ss[init_block])
             for resnet_block in resnet_blocks:
-                h = resnet_block.run(skip(h), t)
+                h = resnet_block.run(skip(h), t, None, ss[resnet_block])
             h = attn_block.run(h)
             h = upsample.run(h)
 
-        h = self.final_res_block.run(h, t)
+        h = self.final_res_block.run(h, t, None, ss[self.final_res_block])
 
-        # final 3x3 conv straight into the NCHW result
-        out = torch.empty((B, self.channels_out, H, W), dtype=F32, device=device)
+        # final 3x3 conv (Unet.py:472) straight into the NCHW result
         fc = self.final_conv
-        ops.conv_direct(h, B, H, W, fc.in_channels, h.shape[3], fc.weight.detach(), fc.out_channels, 3, 3, 1, 1,
-                        fc.bias, None, out, H, W, (self.channels_out * H * W, W, 1, H * W))
+        if get_ops().igemm_supported(H, W, fc.in_channels, 16):
+            a = torch.empty((B, 1, H, W, fc.in_channels), dtype=torch.float16, device=device)
+            ops.cast_act(h, fc.in_channels, None, 0, 1.0, B, H, W, 0, a)
+            return fc.run_prepared_nchw(a, B, H, W)
+        return fc.run_prepared_nchw(h, B, H, W)
+
+    def _all_scale_shifts(self, t):
+        """{ResnetBlock: view [B, 2*dim_out] (row pitch = total width)} -- the time_mlp of every ResnetBlock evaluated
+        by one fp32 GEMM  SiLU(t) @ cat(W_i)^T + cat(b_i)  (weights concatenated once and cached)."""
+        from .layers import ResnetBlock
+        ops = get_ops()
+        blocks = [m for m in self.modules() if isinstance(m, ResnetBlock) and exists(m.time_mlp)]
+        key = tuple((m.time_mlp[1].weight.data_ptr(), m.time_mlp[1].weight._version, m.time_mlp[1].bias._version)
+                    for m in blocks)
+        if getattr(self, "_tm_key", None) != key:
+            self._tm_w = torch.cat([m.time_mlp[1].weight.detach() for m in blocks], dim=0).contiguous()
+            self._tm_b = torch.cat([m.time_mlp[1].bias.detach() for m in blocks], dim=0).contiguous()
+            self._tm_key = key
+        B, tcd = t.shape
+        total = self._tm_w.shape[0]
+        st = torch.empty_like(t)
+        ops.silu(t.contiguous(), st)
+        buf = torch.empty((B, total), dtype=F32, device=t.device)
+        ops.linear_f32(st, B, tcd, self._tm_w, self._tm_b, total, 0, 0, None, buf, None)
+        out, off = {}, 0
+        for m in blocks:
+            n = m.time_mlp[1].out_features
+            out[m] = buf[:, off:off + n]
+            off += n
         return out
 
     def forward_with_cond_scale(self, *args, cond_scale: float = 1., **kwargs):

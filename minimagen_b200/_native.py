@@ -21,10 +21,10 @@ SIGNATURES = {
     "mi_device_ok": [],
     "mi_pack_conv_weight_f16": [_P, _I, _I, _I, _I, _F, _P, _P],
     "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
-    "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _L, _L, _I, _P, _P],
+    "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P, _P],
     "mi_conv2d_direct_f32": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _P],
     "mi_gn_stats": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P],
-    "mi_gn_apply_silu": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _F, _P, _I, _P],
+    "mi_gn_apply_silu": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _I, _P],
     "mi_cast_act": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _I, _P],
     "mi_ln_rows": [_P, _L, _I, _P, _P, _F, _I, _P, _P, _P, _P],
     "mi_linear_f32": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P],
@@ -33,6 +33,8 @@ SIGNATURES = {
     "mi_place_rows": [_P, _I, _I, _I, _P, _I, _I, _P],
     "mi_select_rows": [_P, _P, _P, _P, _I, _I, _P, _P],
     "mi_nchw_to_nhwc": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "mi_stem_unroll_f16": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "mi_silu_f32": [_P, _L, _P, _P],
     "mi_attention_fwd": [_P, _L, _I, _P, _P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _L, _I, _P],
     "mi_step_x0": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _P, _P],
     "mi_step_quantile": [_P, _I, _I, _I, _I, _F, _F, _P, _P],

@@ -50,13 +50,14 @@ int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out) { return mi::co
 
 int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* w, int c_out,
                         int kh, int kw, int mode, const float* bias, const float* residual, float* out_f32,
-                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, int block_n,
-                        int* err_flag, void* stream) {
+                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, long long out_sc,
+                        int n_valid, int block_n, int* err_flag, void* stream) {
     mi::ConvTcProblem p{};
     p.act = act; p.B = B; p.H = H; p.W = W; p.lda = lda; p.a_channels = lda; p.a_chan_off = c_off; p.Cin = c_in;
     p.wpacked = w; p.Cout = c_out;
     p.out_f32 = out_f32; p.out_f16 = (__half*)out_f16; p.bias = bias; p.residual = residual;
-    p.out_sb = out_sb; p.out_sh = out_sh; p.out_sw = out_sw; p.block_n_hint = block_n; p.err_flag = err_flag;
+    p.out_sb = out_sb; p.out_sh = out_sh; p.out_sw = out_sw; p.out_sc = out_sc; p.n_valid = n_valid;
+    p.block_n_hint = block_n; p.err_flag = err_flag;
     if (mode == 0) {
         if (!(kh & 1) || !(kw & 1) || kh * kw > mi::kConvMaxTaps) return fail(-4, "mi_conv2d_igemm_f16: mode 0 needs odd kh,kw with kh*kw <= 16");
         p.phases = 1; p.num_taps = kh * kw;
@@ -78,7 +79,9 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     } else {
         return fail(-4, "mi_conv2d_igemm_f16: unknown mode");
     }
-    if ((out_sw % 4) || (out_sh % 4) || (out_sb % 4)) return fail(-8, "mi_conv2d_igemm_f16: output strides must be multiples of 4 elements");
+    if (out_sc <= 1 && ((out_sw % 4) || (out_sh % 4) || (out_sb % 4)))
+        return fail(-8, "mi_conv2d_igemm_f16: channel-contiguous output strides must be multiples of 4 elements");
+    if (out_sc > 1 && residual) return fail(-8, "mi_conv2d_igemm_f16: residual needs channel-contiguous output");
     const int rc = mi::conv_tc_launch(p, S(stream));
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;
@@ -98,10 +101,10 @@ int mi_gn_stats(const float* src0, int c0, const float* src1, int c1, float scal
     return check(mi::gn_stats(src0, c0, src1, c1, scale1, B, hw, groups, sums, S(stream)), "mi_gn_stats");
 }
 int mi_gn_apply_silu(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
-                     const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
-                     void* out, int out_is_f16, void* stream) {
-    return check(mi::gn_apply_silu(src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, eps, out,
-                                   out_is_f16, S(stream)),
+                     const double* sums, const float* gamma, const float* beta, const float* scale_shift,
+                     int scale_shift_ld, float eps, void* out, int out_is_f16, void* stream) {
+    return check(mi::gn_apply_silu(src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift,
+                                   scale_shift_ld, eps, out, out_is_f16, S(stream)),
                  "mi_gn_apply_silu");
 }
 int mi_cast_act(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W, int mode,
@@ -136,6 +139,12 @@ int mi_select_rows(const float* a, const float* null_row, const uint8_t* keep, c
 }
 int mi_nchw_to_nhwc(const float* a, int ca, const float* b, int cb, int B, int hw, int c_pad, float* out, void* stream) {
     return check(mi::nchw_to_nhwc(a, ca, b, cb, B, hw, c_pad, out, S(stream)), "mi_nchw_to_nhwc");
+}
+int mi_stem_unroll_f16(const float* a, int ca, const float* b, int cb, int B, int H, int W, void* out, void* stream) {
+    return check(mi::stem_unroll(a, ca, b, cb, B, H, W, (__half*)out, S(stream)), "mi_stem_unroll_f16");
+}
+int mi_silu_f32(const float* in, long long n, float* out, void* stream) {
+    return check(mi::silu_f32(in, n, out, S(stream)), "mi_silu_f32");
 }
 int mi_attention_fwd(const void* q, long long q_bs, int ldq, const void* k, const void* v, long long kv_bs, int ldkv,
                      int kv_head_stride, const float* null_kv, const uint8_t* key_mask, int B, int heads, int n, int m,

@@ -192,7 +192,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
                         }
                     }
-                    if (args.residual) {
+                    if (args.residual && args.out_sc == 1) {
                         const float* r = args.residual + pix + n;
 #pragma unroll
                         for (int i = 0; i < 16; i += 4) {
@@ -200,22 +200,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
                         }
                     }
-                    if (args.out_f32) {
-                        float* o = args.out_f32 + pix + n;
+                    if (args.out_sc != 1 || n + 16 > args.n_valid) {
+                        // strided-channel (e.g. NCHW) or ragged-N store: scalar, coalesced across the warp's pixels
+                        if (args.out_f32) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                    }
-                    if (args.out_f16) {
-                        __half* o = args.out_f16 + pix + n;
-                        uint32_t p[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                            p[i] = *reinterpret_cast<uint32_t*>(&h2);
+                            for (int i = 0; i < 16; ++i)
+                                if (n + i < args.n_valid) args.out_f32[pix + (long long)(n + i) * args.out_sc] = f[i];
                         }
-                        *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
-                        *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+                        if (args.out_f16) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n + i < args.n_valid)
+                                    args.out_f16[pix + (long long)(n + i) * args.out_sc] = __float2half_rn(f[i]);
+                        }
+                    } else {
+                        if (args.out_f32) {
+                            float* o = args.out_f32 + pix + n;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                        }
+                        if (args.out_f16) {
+                            __half* o = args.out_f16 + pix + n;
+                            uint32_t p[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                                p[i] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+                            *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+                        }
                     }
                 }
             }
@@ -327,6 +342,8 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     a.B = p.B; a.H = p.H; a.W = p.W;
     a.a_chan_off = p.a_chan_off;
     a.out_sb = p.out_sb; a.out_sh = p.out_sh; a.out_sw = p.out_sw;
+    a.out_sc = p.out_sc > 0 ? p.out_sc : 1;
+    a.n_valid = p.n_valid > 0 ? p.n_valid : p.Cout;
     a.out_f32 = p.out_f32; a.out_f16 = p.out_f16; a.bias = p.bias; a.residual = p.residual;
     a.err_flag = p.err_flag;
     for (int t = 0; t < p.num_taps; ++t) { a.dh[t] = p.dh[t]; a.dw[t] = p.dw[t]; a.ph[t] = p.ph[t]; }

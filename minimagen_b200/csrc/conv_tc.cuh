@@ -18,6 +18,8 @@ struct ConvTcArgs {
     int B, H, W;                          // output pixel grid (== TMA pixel grid of every phase)
     int a_chan_off;                       // first input channel inside the activation buffer
     long long out_sb, out_sh, out_sw;     // output (and residual) strides in elements
+    long long out_sc;                     // channel stride (1 = NHWC-style contiguous channels; H*W for NCHW output)
+    int n_valid;                          // channels >= n_valid are computed (zero-padded weights) but not stored
     float* out_f32;                       // optional
     __half* out_f16;                      // optional
     const float* bias;                    // optional, [C_out]
@@ -41,6 +43,8 @@ struct ConvTcProblem {
     int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
     float* out_f32; __half* out_f16; const float* bias; const float* residual;
     long long out_sb, out_sh, out_sw;
+    long long out_sc;       // 0 or 1 = contiguous channels
+    int n_valid;            // 0 = all C_out channels are stored
     int block_n_hint;       // 0 = auto
     int* err_flag;
 };

@@ -36,7 +36,7 @@ __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
 // nn.GroupNorm(groups, C) statistics (layers.py:127): per (sample, group) sum and sum of squares over (C/groups)*H*W.
 // grid = (ceil(HW / kGnChunk), B); sums[b][g][0..1] accumulated with double atomics (buffer pre-zeroed by the caller).
-constexpr int kGnChunk = 64;
+constexpr int kGnChunk = 256;
 
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1, int HW,
@@ -62,7 +62,18 @@ gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict_
     for (int cv = cv0; cv < V; cv += cv_step) {
         const int c = cv << 2;
         float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int p = plane; p < npix; p += nplanes) {
+        int p = plane;
+        for (; p + 3 * nplanes < npix; p += 4 * nplanes) {     // 4 independent 16-byte loads in flight
+            const float4 v0 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p, c);
+            const float4 v1 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p + nplanes, c);
+            const float4 v2 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p + 2 * nplanes, c);
+            const float4 v3 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p + 3 * nplanes, c);
+            s[0] += (v0.x + v1.x) + (v2.x + v3.x); q[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+            s[1] += (v0.y + v1.y) + (v2.y + v3.y); q[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+            s[2] += (v0.z + v1.z) + (v2.z + v3.z); q[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+            s[3] += (v0.w + v1.w) + (v2.w + v3.w); q[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+        }
+        for (; p < npix; p += nplanes) {
             const float4 v = load_cat4(src0, C0, src1, C1, scale1, pix_base + p, c);
             s[0] += v.x; q[0] += v.x * v.x;
             s[1] += v.y; q[1] += v.y * v.y;
@@ -88,13 +99,18 @@ gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ GroupNorm apply
 // Block.forward (layers.py:138-144): y = SiLU( GN(x) * (scale + 1) + shift ), written as the conv's fp16 operand
-// (tensor-core path) or fp32 (small-channel path).  grid = (ceil(HW*C/8 / 256), B)
-template <typename OutT>
+// (tensor-core path) or fp32 (small-channel path).
+// HBM-bound (4 B read + 2 B written per element).  Each CTA first folds GroupNorm, its affine and the FiLM
+// (scale, shift) into ONE per-channel multiply-add   y = x * A[c] + Bc[c]   kept in shared memory (cost C, amortised
+// over kGnApplyPix * C elements), so the streaming loop is 2 x LDG.128 + 4 x LDS.128 + 8 FMA + 8 SiLU + 1 x STG.128.
+// grid = (ceil(HW / pix_per_cta), B)
+template <typename OutT, bool kFast>
 __global__ void __launch_bounds__(256)
 gn_apply_silu_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1,
                      int HW, int groups, const double* __restrict__ sums, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, const float* __restrict__ scale_shift, float eps,
-                     OutT* __restrict__ out) {
+                     const float* __restrict__ beta, const float* __restrict__ scale_shift, int ss_ld, float eps,
+                     OutT* __restrict__ out, int pix_per_cta) {
+    extern __shared__ float s_ab[];   // A[C], Bc[C]
     __shared__ float s_mean[32], s_rstd[32];
     const int C = C0 + C1;
     const int Cg = C / groups;
@@ -110,37 +126,49 @@ gn_apply_silu_kernel(const float* __restrict__ src0, int C0, const float* __rest
         s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
-    const int V8 = C >> 3;
-    const long long total = (long long)HW * V8;
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % V8) << 3;
-    const long long pix = (long long)b * HW + idx / V8;
-    float v[8];
-    {
-        const float4 a = load_cat4(src0, C0, src1, C1, scale1, pix, c);
-        const float4 d = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int ch = c + e;
+    float* sA = s_ab;
+    float* sB = s_ab + C;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
         const int g = ch / Cg;
-        float y = (v[e] - s_mean[g]) * s_rstd[g] * __ldg(gamma + ch) + __ldg(beta + ch);
+        float a = s_rstd[g] * gamma[ch];
+        float bb = beta[ch] - s_mean[g] * a;
         if (scale_shift) {
-            const float sc = __ldg(scale_shift + (long long)b * 2 * C + ch);
-            const float sh = __ldg(scale_shift + (long long)b * 2 * C + C + ch);
-            y = y * (sc + 1.0f) + sh;
+            const float sc = scale_shift[(long long)b * ss_ld + ch] + 1.0f;
+            const float sh = scale_shift[(long long)b * ss_ld + C + ch];
+            a *= sc;
+            bb = bb * sc + sh;
         }
-        v[e] = silu_f(y);
+        sA[ch] = a;
+        sB[ch] = bb;
     }
-    if constexpr (sizeof(OutT) == 2) {
-        const uint2 lo = pack_half4(v[0], v[1], v[2], v[3]), hi = pack_half4(v[4], v[5], v[6], v[7]);
-        *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + pix * C + c) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-    } else {
-        float* o = reinterpret_cast<float*>(out) + pix * C + c;
-        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    __syncthreads();
+    const int V8 = C >> 3;
+    const int p0 = blockIdx.x * pix_per_cta;
+    const int npix = min(pix_per_cta, HW - p0);
+    const int total = npix * V8;
+    const long long pix_base = (long long)b * HW + p0;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int c = (idx % V8) << 3;
+        const long long pix = pix_base + idx / V8;
+        const float4 x0 = load_cat4(src0, C0, src1, C1, scale1, pix, c);
+        const float4 x1 = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(sA + c), a1 = *reinterpret_cast<const float4*>(sA + c + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sB + c), b1 = *reinterpret_cast<const float4*>(sB + c + 4);
+        float v[8] = {fmaf(x0.x, a0.x, b0.x), fmaf(x0.y, a0.y, b0.y), fmaf(x0.z, a0.z, b0.z), fmaf(x0.w, a0.w, b0.w),
+                      fmaf(x1.x, a1.x, b1.x), fmaf(x1.y, a1.y, b1.y), fmaf(x1.z, a1.z, b1.z), fmaf(x1.w, a1.w, b1.w)};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            if constexpr (kFast) v[e] = __fdividef(v[e], 1.0f + __expf(-v[e]));
+            else v[e] = silu_f(v[e]);
+        }
+        if constexpr (sizeof(OutT) == 2) {
+            const uint2 lo = pack_half4(v[0], v[1], v[2], v[3]), hi = pack_half4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + pix * C + c) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+            float* o = reinterpret_cast<float*>(out) + pix * C + c;
+            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
     }
 }
 
@@ -245,8 +273,7 @@ ln_rows_kernel(const float* __restrict__ in, long long R, int C, const float* __
 // out[M][N] = act_out( act_in(in)[M][K] @ W[N][K]^T + bias + addend ).  For the conditioning MLPs (M = batch rows;
 // Unet.py:101-161, layers.py:396-399) and for projections whose K/N are not tensor-core shaped (tiny config).
 // One warp per (8-row tile, output column); lanes split K.
-constexpr int kLinRows = 8;
-
+template <int kLinRows>
 __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias,
                   int N, int in_act, int out_act, const float* __restrict__ addend, float* __restrict__ out_f32,
@@ -380,6 +407,39 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int 
     out[i] = __float2half_rn(w[((o * I + c) * KH + t / KW) * KW + t % KW] * scale);
 }
 
+// Stem operand for the tensor-core path of CrossEmbedLayer (layers.py:294-305, kernels 3/7/15, stride 1):
+// horizontally unrolled window  out[b][h][w][j*8 + c] = in_c[b][h][w + j - 7]  (j < 15, c < Ca+Cb <= 8, else 0), fp16.
+// With it the k x k convs (all zero-embedded in one 15 x 15 window) become a 15-tap (vertical) implicit GEMM over
+// 128 "channels": K = 15 * 128, N = dim.  Inputs are the NCHW fp32 images x and lowres_cond_img (torch.cat, Unet.py:397).
+__global__ void stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b2, int Cb, int B,
+                                   int H, int W, __half* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * H * W * 16;
+    if (idx >= total) return;
+    const int j = (int)(idx & 15);
+    const long long pix = idx >> 4;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const long long b = pix / ((long long)W * H);
+    const int ws = w + j - 7;
+    __half v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float f = 0.f;
+        if (j < 15 && ws >= 0 && ws < W) {
+            if (c < Ca) f = a[((b * Ca + c) * H + h) * W + ws];
+            else if (c < Ca + Cb) f = b2[((b * Cb + (c - Ca)) * H + h) * W + ws];
+        }
+        v[c] = __float2half_rn(f);
+    }
+    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
+__global__ void silu_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = silu_f(in[i]);
+}
+
 inline unsigned grid1d(long long total, int block) { return (unsigned)((total + block - 1) / block); }
 
 }  // namespace
@@ -395,17 +455,23 @@ int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1,
 }
 
 int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
-                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
-                  void* out, int out_is_f16, cudaStream_t st) {
+                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, int ss_ld,
+                  float eps, void* out, int out_is_f16, cudaStream_t st) {
     const int C = C0 + C1;
     if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
-    dim3 grid(grid1d((long long)HW * (C / 8), 256), B);
+    if (scale_shift && ss_ld < 2 * C) return -1;
+    int pix = 32768 / C;               // ~32K elements per CTA
+    if (pix < 1) pix = 1;
+    if (pix > HW) pix = HW;
+    const size_t smem = 2 * (size_t)C * sizeof(float);
+    if (smem > 48 * 1024) return -1;
+    dim3 grid((HW + pix - 1) / pix, B);
     if (out_is_f16)
-        gn_apply_silu_kernel<__half><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma, beta,
-                                                           scale_shift, eps, (__half*)out);
+        gn_apply_silu_kernel<__half, true><<<grid, 256, smem, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma,
+                                                                    beta, scale_shift, ss_ld, eps, (__half*)out, pix);
     else
-        gn_apply_silu_kernel<float><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma, beta,
-                                                          scale_shift, eps, (float*)out);
+        gn_apply_silu_kernel<float, false><<<grid, 256, smem, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma,
+                                                                    beta, scale_shift, ss_ld, eps, (float*)out, pix);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -432,8 +498,26 @@ int ln_rows(const float* in, long long R, int C, const float* gamma, const float
 int linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
                const float* addend, float* out_f32, __half* out_f16, float out_scale, cudaStream_t st) {
     if (K % 4) return -1;
-    dim3 grid((N + 7) / 8, (M + kLinRows - 1) / kLinRows);
-    linear_f32_kernel<<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16, out_scale);
+    if (M > 8) {     // 32-row tiles: every weight row is streamed once per 32 input rows
+        dim3 grid((N + 7) / 8, (M + 31) / 32);
+        linear_f32_kernel<32><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+                                                    out_scale);
+    } else {
+        dim3 grid((N + 7) / 8, 1);
+        linear_f32_kernel<8><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+                                                   out_scale);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int stem_unroll(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, __half* out, cudaStream_t st) {
+    if (Ca + Cb > 8 || Ca < 1) return -1;
+    stem_unroll_kernel<<<grid1d((long long)B * H * W * 16, 256), 256, 0, st>>>(a, Ca, b, Cb, B, H, W, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int silu_f32(const float* in, long long n, float* out, cudaStream_t st) {
+    silu_kernel<<<grid1d(n, 256), 256, 0, st>>>(in, n, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

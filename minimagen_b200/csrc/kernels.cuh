@@ -11,8 +11,8 @@ namespace mi {
 int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
              double* sums, cudaStream_t st);
 int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
-                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, float eps,
-                  void* out, int out_is_f16, cudaStream_t st);
+                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, int ss_ld,
+                  float eps, void* out, int out_is_f16, cudaStream_t st);
 int cast_act(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int H, int W, int mode,
              void* out, int out_is_f16, cudaStream_t st);
 int ln_rows(const float* in, long long R, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
@@ -27,6 +27,8 @@ int place_rows(const float* src, int B, int r, int D, float* dst, int m, int row
 int select_rows(const float* a, const float* nullv, const uint8_t* keep, const float* addend, int B, int N, float* out,
                 cudaStream_t st);
 int nchw_to_nhwc(const float* a, int Ca, const float* b, int Cb, int B, int HW, int Cp, float* out, cudaStream_t st);
+int stem_unroll(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, __half* out, cudaStream_t st);
+int silu_f32(const float* in, long long n, float* out, cudaStream_t st);
 int pack_conv_weight(const float* w, int O, int I, int KH, int KW, float scale, __half* out, cudaStream_t st);
 
 // conv_direct.cu

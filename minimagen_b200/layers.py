@@ -258,6 +258,31 @@ class Conv2d(nn.Conv2d):
                             self.padding[0], self.bias, residual, out, H, W, (*strides, 1))
         return out
 
+    def run_prepared_nchw(self, a, B, H, W):
+        """Same-padding conv whose result is written straight to an NCHW fp32 tensor [B, C_out, H, W] (the U-Net's
+        final_conv, Unet.py:327/:472).  Tensor-core path: C_out is zero-padded to a multiple of 16 in the packed
+        weight and only the real channels are stored (n_valid)."""
+        ops = get_ops()
+        Cin, Cout = self.in_channels, self.out_channels
+        kh, kw = self.kernel_size
+        out = torch.empty((B, Cout, H, W), dtype=F32, device=a.device)
+        if a.dtype == F16:
+            Np = (Cout + 15) // 16 * 16
+            key = (self.weight.data_ptr(), self.weight._version, self.bias._version if exists(self.bias) else -1)
+            if getattr(self, "_nchw_key", None) != key:
+                wp = torch.zeros((Np, kh * kw * Cin), dtype=F16, device=a.device)
+                wp[:Cout] = ops.pack_conv_weight(self.weight)
+                bp = torch.zeros((Np,), dtype=F32, device=a.device)
+                if exists(self.bias):
+                    bp[:Cout] = self.bias.detach()
+                self._nchw_w, self._nchw_b, self._nchw_key = wp, bp, key
+            ops.conv_igemm(a, B, H, W, Cin, 0, Cin, self._nchw_w, Np, kh, kw, 0, self._nchw_b, None, out, None,
+                           (Cout * H * W, W, 1), out_sc=H * W, n_valid=Cout)
+        else:
+            ops.conv_direct(a, B, H, W, Cin, a.shape[3], self.weight.detach(), Cout, kh, kw, 1, self.padding[0],
+                            self.bias, None, out, H, W, (Cout * H * W, W, 1, H * W))
+        return out
+
     def run(self, x, residual=None, upsample=False):
         """x: NHWC fp32 tensor or Cat.  `upsample` applies nn.Upsample(scale_factor=2, 'nearest') first (layers.py:513)."""
         ops = get_ops()
@@ -336,6 +361,50 @@ class CrossEmbedLayer(nn.Module):
         self.convs = nn.ModuleList([
             Conv2d(dim_in, ds, k, stride=stride, padding=(k - stride) // 2) for k, ds in zip(kernel_sizes, dim_scales)])
 
+    def stem_tc_ok(self, H, W):
+        ks = [c.kernel_size[0] for c in self.convs]
+        return (self.stride == 1 and self.dim_in <= 8 and max(ks) <= 15 and all(k % 2 == 1 for k in ks)
+                and get_ops().igemm_supported(H, W, 128, self.dim_out))
+
+    def _stem_weights(self):
+        """All convs zero-embedded in one 15x15 window over 8 (zero-padded) channels, laid out for the 15-tap vertical
+        implicit GEMM over the horizontally unrolled operand (see mi_stem_unroll_f16): [dim_out][r*128 + j*8 + c]."""
+        key = tuple((c.weight.data_ptr(), c.weight._version, c.bias._version) for c in self.convs)
+        if getattr(self, "_stem_key", None) != key:
+            dev = self.convs[0].weight.device
+            wm = torch.zeros((self.dim_out, 15, 16, 8), dtype=F32, device=dev)
+            off = 0
+            for conv in self.convs:
+                k, n = conv.kernel_size[0], conv.out_channels
+                lo = 7 - k // 2
+                wm[off:off + n, lo:lo + k, lo:lo + k, :self.dim_in] = conv.weight.detach().permute(0, 2, 3, 1)
+                off += n
+            self._stem_w = wm.reshape(self.dim_out, 15 * 128).to(F16).contiguous()
+            self._stem_b = torch.cat([c.bias.detach() for c in self.convs]).contiguous()
+            self._stem_key = key
+        return self._stem_w, self._stem_b
+
+    def run_stem(self, x, lowres=None):
+        """x (and optionally lowres_cond_img): NCHW fp32.  Returns NHWC fp32 [B, H, W, dim_out]."""
+        ops = get_ops()
+        B, Cx, H, W = x.shape
+        Cl = lowres.shape[1] if exists(lowres) else 0
+        assert Cx + Cl == self.dim_in
+        x = x.to(F32).contiguous()
+        lowres = lowres.to(F32).contiguous() if exists(lowres) else None
+        if self.stem_tc_ok(H, W):
+            a = torch.empty((B, 1, H, W, 128), dtype=F16, device=x.device)
+            ops.stem_unroll(x, Cx, lowres, Cl, B, H, W, a)
+            wp, bias = self._stem_weights()
+            C = self.dim_out
+            out = torch.empty((B, H, W, C), dtype=F32, device=x.device)
+            ops.conv_igemm(a, B, H, W, 128, 0, 128, wp, C, 15, 1, 0, bias, None, out, None, (H * W * C, W * C, C))
+            return out
+        cp = (self.dim_in + 3) // 4 * 4
+        x_pad = torch.empty((B, H, W, cp), dtype=F32, device=x.device)
+        ops.nchw_to_nhwc(x, Cx, lowres, Cl, B, H * W, cp, x_pad)
+        return self.run_padded(x_pad, B, H, W)
+
     def run_padded(self, x_pad, B, H, W):
         """x_pad: fp32 NHWC [B, H, W, ld] holding dim_in channels (zero padded to ld). stride must be 1."""
         assert self.stride == 1
@@ -352,11 +421,7 @@ class CrossEmbedLayer(nn.Module):
 
     def forward(self, x):
         _no_grad_check(x)
-        B, Cin, H, W = x.shape
-        cp = (Cin + 3) // 4 * 4
-        x_pad = torch.empty((B, H, W, cp), dtype=F32, device=x.device)
-        get_ops().nchw_to_nhwc(x.contiguous(), Cin, None, 0, B, H * W, cp, x_pad)
-        return to_nchw(self.run_padded(x_pad, B, H, W))
+        return to_nchw(self.run_stem(x))
 
 
 # ------------------------------------------------------------------------------------------------ ResNet
@@ -381,7 +446,8 @@ class Block(nn.Module):
         ops.gn_stats(s0, C0, s1, C1, sc, B, H * W, G, sums)
         tc = self.project.tc_ok(H, W)
         a = torch.empty((B, 1, H, W, C) if tc else (B, H, W, C), dtype=F16 if tc else F32, device=x.device)
-        ops.gn_apply_silu(s0, C0, s1, C1, sc, B, H * W, G, sums, gn.weight, gn.bias, scale_shift, gn.eps, a)
+        ss_ld = scale_shift.stride(0) if exists(scale_shift) else 0
+        ops.gn_apply_silu(s0, C0, s1, C1, sc, B, H * W, G, sums, gn.weight, gn.bias, scale_shift, ss_ld, gn.eps, a)
         return self.project.run_prepared(a, B, H, W, residual)
 
     def forward(self, x, scale_shift=None):
@@ -408,12 +474,13 @@ class ResnetBlock(nn.Module):
         self.block2 = Block(dim_out, dim_out, groups=groups)
         self.res_conv = Conv2d(dim, dim_out, 1) if dim != dim_out else Identity()
 
-    def run(self, x, time_emb=None, cond=None):
-        """x: NHWC fp32 or Cat; time_emb: [B, time_cond_dim] fp32; cond: conditioning context (see CrossAttention.run)."""
+    def run(self, x, time_emb=None, cond=None, scale_shift=None):
+        """x: NHWC fp32 or Cat; time_emb: [B, time_cond_dim] fp32; cond: conditioning context (see CrossAttention.run).
+        `scale_shift`: this block's time_mlp output [B, 2*dim_out] if the caller already computed it (the U-Net batches
+        the time_mlps of all its ResnetBlocks into one GEMM per step); otherwise it is computed here from `time_emb`."""
         ops = get_ops()
         B = x.shape[0]
-        scale_shift = None
-        if exists(self.time_mlp) and exists(time_emb):
+        if not exists(scale_shift) and exists(self.time_mlp) and exists(time_emb):
             lin = self.time_mlp[1]
             scale_shift = torch.empty((B, lin.out_features), dtype=F32, device=time_emb.device)
             # SiLU -> Linear (layers.py:396-399); chunk(2, dim=1) = (scale, shift) is read in place by gn_apply

@@ -45,12 +45,13 @@ class NativeOps:
 
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
-                   out_strides, block_n=0):
+                   out_strides, block_n=0, out_sc=1, n_valid=0):
         _chk(act, F16, "act"); _chk(wp, F16, "wp"); _chk(bias, F32, "bias"); _chk_out(residual, F32, "residual")
         _chk_out(out_f32, F32, "out_f32"); _chk_out(out_f16, F16, "out_f16")
         sb, sh, sw = out_strides
         N.call("mi_conv2d_igemm_f16", N.ptr(act), B, H, W, lda, c_off, c_in, N.ptr(wp), c_out, kh, kw, mode,
-               N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16), sb, sh, sw, block_n, None, N.stream())
+               N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16), sb, sh, sw, out_sc, n_valid, block_n, None,
+               N.stream())
 
     def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
                     out_strides):
@@ -66,11 +67,13 @@ class NativeOps:
         _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(sums, F64, "sums")
         N.call("mi_gn_stats", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, hw, groups, N.ptr(sums), N.stream())
 
-    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, eps, out):
+    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, ss_ld, eps, out):
+        """scale_shift: fp32 view whose row b starts at data_ptr + b*ss_ld and holds [scale(C) | shift(C)]."""
         _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(sums, F64, "sums"); _chk(gamma, F32, "gamma")
-        _chk(beta, F32, "beta"); _chk(scale_shift, F32, "scale_shift")
+        _chk(beta, F32, "beta"); _chk_out(scale_shift, F32, "scale_shift")
         N.call("mi_gn_apply_silu", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, hw, groups, N.ptr(sums),
-               N.ptr(gamma), N.ptr(beta), N.ptr(scale_shift), float(eps), N.ptr(out), int(out.dtype == F16), N.stream())
+               N.ptr(gamma), N.ptr(beta), N.ptr(scale_shift), int(ss_ld), float(eps), N.ptr(out),
+               int(out.dtype == F16), N.stream())
 
     def cast_act(self, src0, c0, src1, c1, scale1, B, H, W, mode, out):
         _chk(src0, F32, "src0"); _chk(src1, F32, "src1")
@@ -111,6 +114,14 @@ class NativeOps:
     def nchw_to_nhwc(self, a, ca, b, cb, B, hw, c_pad, out):
         _chk(a, F32, "a"); _chk(b, F32, "b"); _chk(out, F32, "out")
         N.call("mi_nchw_to_nhwc", N.ptr(a), ca, N.ptr(b), cb, B, hw, c_pad, N.ptr(out), N.stream())
+
+    def stem_unroll(self, a, ca, b, cb, B, H, W, out):
+        _chk(a, F32, "a"); _chk(b, F32, "b"); _chk(out, F16, "out")
+        N.call("mi_stem_unroll_f16", N.ptr(a), ca, N.ptr(b), cb, B, H, W, N.ptr(out), N.stream())
+
+    def silu(self, inp, out):
+        _chk(inp, F32, "inp"); _chk(out, F32, "out")
+        N.call("mi_silu_f32", N.ptr(inp), inp.numel(), N.ptr(out), N.stream())
 
     # ---------------------------------------------------------------- attention
     def attention(self, q, q_bs, ldq, k, v, kv_bs, ldkv, kv_hs, null_kv, mask, B, heads, n, m, out, o_bs, ldo):

@@ -58,7 +58,7 @@ class EmuOps:
 
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
-                   out_strides, block_n=0):
+                   out_strides, block_n=0, out_sc=1, n_valid=0):
         self._log("conv_igemm")
         assert act.dtype == F16 and wp.dtype == F16
         P = 4 if mode == 1 else 1
@@ -76,12 +76,15 @@ class EmuOps:
         if bias is not None:
             y = y + bias
         sb, sh, sw = out_strides
+        nv = n_valid if n_valid else c_out
         if residual is not None:
+            assert out_sc == 1
             y = y + _strided(residual, (B, H, W, c_out), (sb, sh, sw, 1))
+        y = y[..., :nv]
         if out_f32 is not None:
-            _strided(out_f32, (B, H, W, c_out), (sb, sh, sw, 1)).copy_(y)
+            _strided(out_f32, (B, H, W, nv), (sb, sh, sw, out_sc)).copy_(y)
         if out_f16 is not None:
-            _strided(out_f16, (B, H, W, c_out), (sb, sh, sw, 1)).copy_(y.to(F16))
+            _strided(out_f16, (B, H, W, nv), (sb, sh, sw, out_sc)).copy_(y.to(F16))
 
     def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
                     out_strides):
@@ -104,7 +107,7 @@ class EmuOps:
         sums[:, :, 0] += xg.sum(dim=(1, 3))
         sums[:, :, 1] += (xg * xg).sum(dim=(1, 3))
 
-    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, eps, out):
+    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, ss_ld, eps, out):
         self._log("gn_apply_silu")
         x = _cat_src(src0, c0, src1, c1, scale1, (B, hw))
         C = c0 + c1
@@ -116,7 +119,8 @@ class EmuOps:
         rstd_c = rstd.float().repeat_interleave(C // groups, dim=1)[:, None, :]
         y = (x - mean_c) * rstd_c * gamma.detach() + beta.detach()
         if scale_shift is not None:
-            y = y * (scale_shift[:, None, :C] + 1.0) + scale_shift[:, None, C:]
+            ss = scale_shift.as_strided((B, 2 * C), (ss_ld, 1), scale_shift.storage_offset())
+            y = y * (ss[:, None, :C] + 1.0) + ss[:, None, C:]
         y = y * torch.sigmoid(y)
         out.reshape(B, hw, C).copy_(y.to(out.dtype))
 
@@ -204,6 +208,20 @@ class EmuOps:
         o[:, :, :ca] = a.reshape(B, ca, hw).permute(0, 2, 1)
         if b is not None and cb:
             o[:, :, ca:ca + cb] = b.reshape(B, cb, hw).permute(0, 2, 1)
+
+    def stem_unroll(self, a, ca, b, cb, B, H, W, out):
+        self._log("stem_unroll")
+        x = a if b is None or cb == 0 else torch.cat((a, b), dim=1)            # B,C,H,W
+        C = x.shape[1]
+        xp = F.pad(x, (7, 8))                                                   # w + j - 7, j in [0,16)
+        o = torch.zeros((B, H, W, 16, 8))
+        for j in range(15):
+            o[:, :, :, j, :C] = xp[:, :, :, j:j + W].permute(0, 2, 3, 1)
+        out.reshape(B, H, W, 128).copy_(o.reshape(B, H, W, 128).to(F16))
+
+    def silu(self, inp, out):
+        self._log("silu")
+        out.copy_(F.silu(inp))
 
     # ---------------------------------------------------------------- attention
     def attention(self, q, q_bs, ldq, k, v, kv_bs, ldkv, kv_hs, null_kv, mask, B, heads, n, m, out, o_bs, ldo):
