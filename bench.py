@@ -117,7 +117,12 @@ def cpu_baseline(wl, sd, steps=3, warmup=1):
     """The reference's algorithm (CPU oracle port) on the host cores: U-Net forward + DDPM step at batch 1, scaled
     linearly to the workload batch (the full batch would take ~1 minute per step on 8 cores)."""
     from oracle import restatement as R
-    cores = os.cpu_count()
+    try:
+        import psutil
+        cores = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        cores = os.cpu_count()
+    # one thread per PHYSICAL core: on the 2 x 32-core (HT) B200 hosts 128 threads is ~200x slower than 64
     torch.set_num_threads(cores)
     inp = synth_inputs(wl, 1, 123)
     tabs = R.ddpm_tables(wl["T"])
