@@ -35,12 +35,12 @@ __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) 
 
 // ------------------------------------------------------------------------------------------------ GroupNorm stats
 // nn.GroupNorm(groups, C) statistics (layers.py:127): per (sample, group) sum and sum of squares over (C/groups)*H*W.
-// grid = (ceil(HW / kGnChunk), B); sums[b][g][0..1] accumulated with double atomics (buffer pre-zeroed by the caller).
-constexpr int kGnChunk = 256;
+// grid = (ceil(HW / chunk), B) with chunk ~ 32K elements / C pixels, so small images still fill the GPU;
+// sums[b][g][0..1] accumulated with double atomics (buffer pre-zeroed by the caller).
 
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1, int HW,
-                int groups, double* __restrict__ sums) {
+                int groups, double* __restrict__ sums, int kGnChunk) {
     extern __shared__ double s_acc[];   // [groups][2]
     const int C = C0 + C1;
     const int V = C >> 2;
@@ -317,6 +317,71 @@ linear_f32_kernel(const float* __restrict__ in, int M, int K, const float* __res
     }
 }
 
+// Shared-memory tiled variant for M > 8 (the batched time-MLP GEMM: 32 rows x ~66K columns x K = 1024, i.e. a 270 MB
+// weight stream that must be read exactly once).  CTA tile = 32 rows x 128 columns, K chunks of 32; thread (ty, tx)
+// owns rows 4*ty..4*ty+3 and columns tx, tx+32, tx+64, tx+96.
+constexpr int kTM = 32, kTN = 128, kTK = 32;
+
+__global__ void __launch_bounds__(256)
+linear_tiled_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias,
+                    int N, int in_act, int out_act, const float* __restrict__ addend, float* __restrict__ out_f32,
+                    __half* __restrict__ out_f16, float out_scale) {
+    __shared__ __align__(16) float xs[kTK][kTM + 4];      // [k][row]
+    __shared__ float ws[kTK][kTN + 1];                    // [k][col], +1: conflict-free transposed stores
+    const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < K; k0 += kTK) {
+        {   // x chunk: 32 rows x 32 k, one float4 per thread
+            const int row = threadIdx.x >> 3, kq = (threadIdx.x & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + row < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(in + (long long)(m0 + row) * K + k0 + kq);
+            if (in_act == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+            xs[kq][row] = v.x; xs[kq + 1][row] = v.y; xs[kq + 2][row] = v.z; xs[kq + 3][row] = v.w;
+        }
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {   // w chunk: 128 cols x 32 k, 8 threads (128 B) per column
+            const int col = pass * 32 + (threadIdx.x >> 3), kq = (threadIdx.x & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + col < N && k0 + kq < K) v = __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + col) * K + k0 + kq));
+            ws[kq][col] = v.x; ws[kq + 1][col] = v.y; ws[kq + 2][col] = v.z; ws[kq + 3][col] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kTK; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
+            const float b0 = ws[k][tx], b1 = ws[k][tx + 32], b2 = ws[k][tx + 64], b3 = ws[k][tx + 96];
+            acc[0][0] += a.x * b0; acc[0][1] += a.x * b1; acc[0][2] += a.x * b2; acc[0][3] += a.x * b3;
+            acc[1][0] += a.y * b0; acc[1][1] += a.y * b1; acc[1][2] += a.y * b2; acc[1][3] += a.y * b3;
+            acc[2][0] += a.z * b0; acc[2][1] += a.z * b1; acc[2][2] += a.z * b2; acc[2][3] += a.z * b3;
+            acc[3][0] += a.w * b0; acc[3][1] += a.w * b1; acc[3][2] += a.w * b2; acc[3][3] += a.w * b3;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx + 32 * j;
+            if (n >= N) continue;
+            const long long oi = (long long)m * N + n;
+            float y = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (addend) y += addend[oi];
+            if (out_act == 1) y = silu_f(y);
+            y *= out_scale;
+            if (out_f32) out_f32[oi] = y;
+            if (out_f16) out_f16[oi] = __float2half_rn(y);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ conditioning bits
 // SinusoidalPosEmb.forward (layers.py:461-465): emb_j = exp(j * -(ln(1e4)/(half-1))) in fp32, arg = float(t) * emb_j,
 // out = cat(sin(arg), cos(arg)).
@@ -449,8 +514,11 @@ int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1,
              double* sums, cudaStream_t st) {
     const int C = C0 + C1;
     if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
-    dim3 grid((HW + kGnChunk - 1) / kGnChunk, B);
-    gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(double), st>>>(src0, C0, src1, C1, scale1, HW, groups, sums);
+    int chunk = 32768 / C;
+    if (chunk < 4) chunk = 4;
+    if (chunk > HW) chunk = HW;
+    dim3 grid((HW + chunk - 1) / chunk, B);
+    gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(double), st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, chunk);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -460,7 +528,7 @@ int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float sc
     const int C = C0 + C1;
     if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
     if (scale_shift && ss_ld < 2 * C) return -1;
-    int pix = 32768 / C;               // ~32K elements per CTA
+    int pix = 16384 / C;               // ~16K elements per CTA
     if (pix < 1) pix = 1;
     if (pix > HW) pix = HW;
     const size_t smem = 2 * (size_t)C * sizeof(float);
@@ -498,10 +566,10 @@ int ln_rows(const float* in, long long R, int C, const float* gamma, const float
 int linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
                const float* addend, float* out_f32, __half* out_f16, float out_scale, cudaStream_t st) {
     if (K % 4) return -1;
-    if (M > 8) {     // 32-row tiles: every weight row is streamed once per 32 input rows
-        dim3 grid((N + 7) / 8, (M + 31) / 32);
-        linear_f32_kernel<32><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
-                                                    out_scale);
+    if (M > 8) {     // 32 x 128 shared-memory tiles: every weight row is streamed once per 32 input rows
+        dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
+        linear_tiled_kernel<<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+                                                  out_scale);
     } else {
         dim3 grid((N + 7) / 8, 1);
         linear_f32_kernel<8><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
