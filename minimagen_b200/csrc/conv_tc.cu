@@ -43,6 +43,70 @@ struct Cfg {
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// TMEM accumulator tile (this thread's row, BLOCK_N fp32 columns) -> +bias -> +residual -> global stores.
+template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t taddr, int n0, long long pix, bool valid) {
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 16) {
+                uint32_t v[16];
+                ptx::tmem_ld_x16(taddr + c, v);
+                ptx::tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+                    const int n = n0 + c;
+                    if (args.bias) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 bv = __ldg(reinterpret_cast<const float4*>(args.bias + n + i));
+                            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+                        }
+                    }
+                    if (args.residual && args.out_sc == 1) {
+                        const float* r = args.residual + pix + n;
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 rv = *reinterpret_cast<const float4*>(r + i);
+                            f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
+                        }
+                    }
+                    if (args.out_sc != 1 || n + 16 > args.n_valid) {
+                        // strided-channel (e.g. NCHW) or ragged-N store: scalar, coalesced across the warp's pixels
+                        if (args.out_f32) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n + i < args.n_valid) args.out_f32[pix + (long long)(n + i) * args.out_sc] = f[i];
+                        }
+                        if (args.out_f16) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (n + i < args.n_valid)
+                                    args.out_f16[pix + (long long)(n + i) * args.out_sc] = __float2half_rn(f[i]);
+                        }
+                    } else {
+                        if (args.out_f32) {
+                            float* o = args.out_f32 + pix + n;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4)
+                                *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+                        }
+                        if (args.out_f16) {
+                            __half* o = args.out_f16 + pix + n;
+                            uint32_t p[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+                                p[i] = *reinterpret_cast<uint32_t*>(&h2);
+                            }
+                            *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
+                            *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
+                        }
+                    }
+                }
+            }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -175,65 +239,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 16) {
-                uint32_t v[16];
-                ptx::tmem_ld_x16(taddr + c, v);
-                ptx::tmem_ld_wait();
-                if (valid) {
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                    const int n = n0 + c;
-                    if (args.bias) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(args.bias + n + i));
-                            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-                        }
-                    }
-                    if (args.residual && args.out_sc == 1) {
-                        const float* r = args.residual + pix + n;
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 rv = *reinterpret_cast<const float4*>(r + i);
-                            f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
-                        }
-                    }
-                    if (args.out_sc != 1 || n + 16 > args.n_valid) {
-                        // strided-channel (e.g. NCHW) or ragged-N store: scalar, coalesced across the warp's pixels
-                        if (args.out_f32) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n + i < args.n_valid) args.out_f32[pix + (long long)(n + i) * args.out_sc] = f[i];
-                        }
-                        if (args.out_f16) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n + i < args.n_valid)
-                                    args.out_f16[pix + (long long)(n + i) * args.out_sc] = __float2half_rn(f[i]);
-                        }
-                    } else {
-                        if (args.out_f32) {
-                            float* o = args.out_f32 + pix + n;
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                        }
-                        if (args.out_f16) {
-                            __half* o = args.out_f16 + pix + n;
-                            uint32_t p[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                                p[i] = *reinterpret_cast<uint32_t*>(&h2);
-                            }
-                            *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
-                            *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
@@ -244,6 +250,168 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ 2-CTA variant
+// cta_group::2: a pair of CTAs (one cluster, two SMs of a TPC) computes a 256-pixel x BLOCK_N tile.  Each CTA stages its
+// own 128-pixel A tile and HALF of the weight tile (BLOCK_N/2 rows); one tcgen05.mma issued by the leader CTA consumes
+// both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Versus the 1-CTA kernel this halves
+// the weight bytes each SM pulls from L2 and the shared-memory operand traffic per FLOP.
+template <int BLOCK_N>
+struct Cfg2 {
+    static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kConvBlockK * 2;
+    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ ConvTcArgs args) {
+    using C = Cfg2<BLOCK_N>;
+    constexpr int STAGES = C::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStageBytes);
+    uint64_t* full_bar = bars;                     // used in the leader CTA only
+    uint64_t* empty_bar = bars + STAGES;           // per CTA
+    uint64_t* tfull_bar = bars + 2 * STAGES;       // per CTA
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // used in the leader CTA only
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    int* err = args.err_flag;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            ptx::mbar_init(&full_bar[i], 2);      // leader's expect_tx arrive + peer's remote arrive
+            ptx::mbar_init(&empty_bar[i], 1);     // one multicast tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tfull_bar[i], 1);
+            ptx::mbar_init(&tempty_bar[i], 256);  // epilogue threads of both CTAs
+        }
+        ptx::fence_barrier_init();
+    }
+    ptx::cluster_sync_all();                      // barrier inits visible cluster-wide before any remote arrive / TMA
+    if (warp == 2) {
+        ptx::tmem_alloc_2sm(tmem_ptr_smem, C::kTmemCols);
+        ptx::tmem_relinquish_2sm();
+    }
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int num_kb = args.num_taps * args.chunks_per_tap;
+    const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
+    const int pairs_m = (tiles_m + 1) >> 1;
+    const int total_pairs = pairs_m * args.tiles_n;
+    const int BW = 1 << args.bw_log2, BH = 1 << args.bh_log2;
+    const int BB = kConvBlockM >> (args.bw_log2 + args.bh_log2);
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer (both CTAs) =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+                const int nt = pt % args.tiles_n;
+                const int mt = 2 * (pt / args.tiles_n) + (int)rank;      // may be == tiles_m (dummy tile: all OOB)
+                const int w0 = (mt % args.tiles_w) * BW;
+                const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
+                const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
+                const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+                int kb = 0;
+                for (int t = 0; t < args.num_taps; ++t) {
+                    const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
+                    for (int j = 0; j < args.chunks_per_tap; ++j, ++kb) {
+                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 1100 + stage);
+                        uint8_t* sa = smem + stage * C::kStageBytes;
+                        uint8_t* sb = sa + kABytes;
+                        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                        ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
+                                             h0 + dh, ph, b0);
+                        ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
+                        if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            constexpr uint32_t idesc = ptx::make_idesc_f16(256, BLOCK_N, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 1200 + as);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase, err, 1300 + stage);
+                    ptx::tc_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kConvBlockK / 16; ++k)
+                        ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    ptx::umma_commit_2sm(&empty_bar[stage], 3);               // frees this stage in BOTH CTAs
+                    if (kb == num_kb - 1) ptx::umma_commit_2sm(&tfull_bar[as], 3);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (both CTAs, own 128 rows) =====================
+        const int ew = warp & 3;
+        const int m = ew * 32 + lane;
+        const int bw = m & (BW - 1);
+        const int bh = (m >> args.bw_log2) & (BH - 1);
+        const int bb = m >> (args.bw_log2 + args.bh_log2);
+        int iter = 0;
+        for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
+            const int nt = pt % args.tiles_n;
+            const int mt = 2 * (pt / args.tiles_n) + (int)rank;
+            const int w = (mt % args.tiles_w) * BW + bw;
+            const int h = ((mt / args.tiles_w) % args.tiles_h) * BH + bh;
+            const int b = (mt / (args.tiles_w * args.tiles_h)) * BB + bb;
+            const int n0 = nt * BLOCK_N;
+            const bool valid = (mt < tiles_m) && (b < args.B) && (h < args.H) && (w < args.W);
+            const long long pix = (long long)b * args.out_sb + (long long)h * args.out_sh + (long long)w * args.out_sw;
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tfull_bar[as], aphase, err, 1400 + as);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive_cluster(&tempty_bar[as], 0);                    // the leader's barrier
+        }
+    }
+
+    ptx::tc_fence_before();
+    ptx::cluster_sync_all();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc_2sm(tmem_base, C::kTmemCols);
     }
 }
 
@@ -285,6 +453,23 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& arg
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
     conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    return cudaGetLastError() == cudaSuccess ? 0 : -11;
+}
+
+template <int BLOCK_N>
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& args, int total_pairs, int num_sms,
+            cudaStream_t stream) {
+    using C = Cfg2<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) !=
+            cudaSuccess)
+            return -10;
+        attr_set = true;
+    }
+    int clusters = num_sms / 2;
+    if (clusters > total_pairs) clusters = total_pairs;
+    conv_tc2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -358,9 +543,20 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     const int tiles_m = a.tiles_w * a.tiles_h * a.tiles_b;
     int block_n = 0;
     const int cands[5] = {256, 128, 64, 32, 16};
-    if (p.block_n_hint > 0 && p.Cout % p.block_n_hint == 0) {
+    // CTA pairs (cta_group::2, 256-pixel x block_n tiles) whenever C_out allows and there is work for every pair
+    bool pair = false;
+    if (p.cta_pair != 1 && p.block_n_hint >= 0) {
+        const int pairs_m = (tiles_m + 1) / 2;
+        int want = (p.block_n_hint == 128 || p.block_n_hint == 256) ? p.block_n_hint : (p.Cout % 256 == 0 ? 256 : 128);
+        if (p.Cout % want == 0 && (p.cta_pair == 2 || pairs_m * (p.Cout / want) >= num_sms / 4)) {
+            pair = true;
+            block_n = want;
+        }
+    }
+    const int hint = p.block_n_hint < 0 ? -p.block_n_hint : p.block_n_hint;
+    if (!pair && hint > 0 && p.Cout % hint == 0) {
         for (int i = 0; i < 5; ++i)
-            if (cands[i] == p.block_n_hint) block_n = cands[i];
+            if (cands[i] == hint) block_n = cands[i];
     }
     if (block_n == 0) {
         // largest BLOCK_N dividing C_out that still gives every SM a tile; never shrink below 64 for that reason
@@ -391,7 +587,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         const cuuint64_t K = (cuuint64_t)p.num_taps * p.Cin;
         cuuint64_t gdim[2] = {K, (cuuint64_t)p.Cout};
         cuuint64_t gstr[1] = {K * 2};
-        cuuint32_t box[2] = {kConvBlockK, (cuuint32_t)block_n};
+        cuuint32_t box[2] = {kConvBlockK, (cuuint32_t)(pair ? block_n / 2 : block_n)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.wpacked), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -399,6 +595,11 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         if (r != CUDA_SUCCESS) return -7;
     }
 
+    if (pair) {
+        const int total_pairs = ((tiles_m + 1) / 2) * a.tiles_n;
+        return block_n == 256 ? launch2<256>(tmA, tmB, a, total_pairs, num_sms, stream)
+                              : launch2<128>(tmA, tmB, a, total_pairs, num_sms, stream);
+    }
     switch (block_n) {
         case 256: return launch<256>(tmA, tmB, a, total_tiles, num_sms, stream);
         case 128: return launch<128>(tmA, tmB, a, total_tiles, num_sms, stream);

@@ -45,7 +45,8 @@ struct ConvTcProblem {
     long long out_sb, out_sh, out_sw;
     long long out_sc;       // 0 or 1 = contiguous channels
     int n_valid;            // 0 = all C_out channels are stored
-    int block_n_hint;       // 0 = auto
+    int block_n_hint;       // 0 = auto; > 0 preferred tile width; < 0: |value| with the 1-CTA kernel forced
+    int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
     int* err_flag;
 };
 

@@ -35,6 +35,7 @@ struct Case {
     int B, H, W, Cin, Cout, k, stride;   // stride 1 (k=1|3) or 2 (k=4, pad 1)
     bool bias, residual, f16out;
     int hint;
+    int pair;   // 0 auto, 1 force 1-CTA kernel, 2 force CTA-pair kernel
 };
 
 static int* g_err = nullptr;   // host-mapped
@@ -102,7 +103,7 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
         }
     p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
     p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
-    p.block_n_hint = c.hint; p.err_flag = g_err;
+    p.block_n_hint = c.hint; p.cta_pair = c.pair; p.err_flag = g_err;
 
     *g_err = 0;
     int rc = conv_tc_launch(p, 0);
@@ -191,19 +192,29 @@ int main(int argc, char** argv) {
     int failures = 0;
     if (!strcmp(mode, "check") || !strcmp(mode, "all")) {
         const Case cases[] = {
-            {"gemm1x1_n64", 1, 16, 16, 64, 64, 1, 1, false, false, false, 0},
-            {"gemm1x1_k128", 1, 16, 16, 128, 64, 1, 1, false, false, false, 0},
-            {"c3_16x16", 2, 16, 16, 64, 128, 3, 1, false, false, false, 0},
-            {"c3_32x32", 1, 32, 32, 128, 128, 3, 1, true, false, false, 0},
-            {"c3_8x8_bb2", 3, 8, 8, 64, 64, 3, 1, true, true, true, 0},
-            {"c3_w256", 1, 4, 256, 64, 64, 3, 1, false, false, false, 0},
-            {"c3_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256},
-            {"c3_n512", 2, 16, 16, 64, 512, 3, 1, true, false, false, 256},
-            {"c3_n16", 1, 16, 16, 64, 16, 3, 1, true, false, false, 0},
-            {"c3_n32", 1, 16, 16, 64, 32, 3, 1, true, false, false, 0},
-            {"c4_s2", 2, 32, 32, 64, 128, 4, 2, true, false, true, 0},
-            {"c3_persist", 8, 64, 64, 64, 64, 3, 1, true, true, false, 0},
-            {"c3_deepk", 1, 16, 16, 1024, 128, 3, 1, false, false, false, 0},
+            {"gemm1x1_n64", 1, 16, 16, 64, 64, 1, 1, false, false, false, 0, 1},
+            {"gemm1x1_k128", 1, 16, 16, 128, 64, 1, 1, false, false, false, 0, 1},
+            {"c3_16x16", 2, 16, 16, 64, 128, 3, 1, false, false, false, 0, 1},
+            {"c3_32x32", 1, 32, 32, 128, 128, 3, 1, true, false, false, 0, 1},
+            {"c3_8x8_bb2", 3, 8, 8, 64, 64, 3, 1, true, true, true, 0, 1},
+            {"c3_w256", 1, 4, 256, 64, 64, 3, 1, false, false, false, 0, 1},
+            {"c3_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256, 1},
+            {"c3_n512", 2, 16, 16, 64, 512, 3, 1, true, false, false, 256, 1},
+            {"c3_n16", 1, 16, 16, 64, 16, 3, 1, true, false, false, 0, 1},
+            {"c3_n32", 1, 16, 16, 64, 32, 3, 1, true, false, false, 0, 1},
+            {"c4_s2", 2, 32, 32, 64, 128, 4, 2, true, false, true, 0, 1},
+            {"c3_persist", 8, 64, 64, 64, 64, 3, 1, true, true, false, 0, 1},
+            {"c3_deepk", 1, 16, 16, 1024, 128, 3, 1, false, false, false, 0, 1},
+            // ---- CTA-pair (cta_group::2) kernel
+            {"p_c3_16x16_n128", 2, 16, 16, 64, 128, 3, 1, true, false, false, 128, 2},
+            {"p_c3_16x16_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256, 2},
+            {"p_c3_odd_tiles", 5, 8, 8, 64, 128, 3, 1, true, true, false, 128, 2},
+            {"p_c3_n512", 2, 32, 32, 64, 512, 3, 1, true, false, false, 256, 2},
+            {"p_gemm1x1", 1, 16, 16, 256, 256, 1, 1, false, false, false, 256, 2},
+            {"p_c4_s2", 2, 32, 32, 64, 128, 4, 2, true, false, true, 128, 2},
+            {"p_c3_persist", 8, 64, 64, 64, 128, 3, 1, true, true, false, 128, 2},
+            {"p_c3_deepk", 2, 16, 16, 1024, 256, 3, 1, false, true, false, 256, 2},
+            {"p_c3_w256", 1, 4, 256, 64, 128, 3, 1, false, false, false, 128, 2},
         };
         for (const Case& c : cases) {
             double ms = 0;
@@ -213,23 +224,33 @@ int main(int argc, char** argv) {
     }
     if (!strcmp(mode, "perf") || !strcmp(mode, "all")) {
         const Case cases[] = {
-            {"sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256},
-            {"sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 128},
-            {"sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256},
-            {"sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256},
-            {"sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 128},
-            {"sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256},
-            {"sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 128},
-            {"sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128},
-            {"sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128},
-            {"sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128},
-            {"pw_16_2048", 32, 16, 16, 2048, 1024, 1, 1, true, false, false, 256},
+            {"P sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 2},
+            {"P sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 2},
+            {"P sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 2},
+            {"P sr_32_1024", 32, 32, 32, 1024, 512, 3, 1, true, true, false, 256, 2},
+            {"P sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256, 2},
+            {"P sr_64_256 n128", 32, 64, 64, 256, 256, 3, 1, true, true, false, 128, 2},
+            {"P sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 2},
+            {"P sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128, 2},
+            {"P sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128, 2},
+            {"P pw_16_2048", 32, 16, 16, 2048, 1024, 1, 1, true, false, false, 256, 2},
+            {"sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 1},
+            {"sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 128, 1},
+            {"sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 1},
+            {"sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 1},
+            {"sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 128, 1},
+            {"sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256, 1},
+            {"sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 128, 1},
+            {"sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 1},
+            {"sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128, 1},
+            {"sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128, 1},
+            {"pw_16_2048", 32, 16, 16, 2048, 1024, 1, 1, true, false, false, 256, 1},
         };
         for (const Case& c : cases) {
             double ms = 0;
             run_case(c, false, 10, &ms);
             const double flops = 2.0 * c.B * (c.H / c.stride) * (c.W / c.stride) * (double)c.Cout * c.k * c.k * c.Cin;
-            printf("[perf %s hint=%d] B=%d %dx%d %d->%d k=%d : %.3f ms  %.1f TFLOP/s\n", c.name, c.hint, c.B, c.H, c.W,
+            printf("[perf %s hint=%d pair=%d] B=%d %dx%d %d->%d k=%d : %.3f ms  %.1f TFLOP/s\n", c.name, c.hint, c.pair, c.B, c.H, c.W,
                    c.Cin, c.Cout, c.k, ms, flops / ms * 1e-9);
             fflush(stdout);
         }
