@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--batch-streams", type=int, default=None, help="concurrent batch slices inside Unet.forward")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -219,6 +220,8 @@ def main():
     imagen = Imagen(unets=stages, text_encoder_name="t5_base" if wl["E"] == 768 else "t5_small",
                     image_sizes=sizes, timesteps=wl["T"], cond_drop_prob=0.1).eval().to(dev)
     assert imagen.unets[-1] is unet, "the U-Net under test was re-instantiated"
+    if args.batch_streams is not None:
+        unet.batch_streams = args.batch_streams
     sch = imagen.noise_schedulers[-1]
     inp = synth_inputs(wl, B, 1000 + rank)           # each rank owns its own shard of the global batch
     text = inp["text_embeds"].to(dev)
@@ -358,6 +361,7 @@ def main():
                      "kernel_share_of_step": conv_ms / (ms / args.steps) if ms else None, "peak_source": peak_src,
                      "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peak_tf},
         "clocks": clocks, "cuda_graph": use_graph, "launches_per_step": launches_per_step,
+        "batch_streams": unet.batch_streams,
     }
     if not args.no_cpu_baseline:
         sd = unet.state_dict()
@@ -384,11 +388,14 @@ def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):
             flops[0] += 2.0 * B * H * W * c_out * kh * kw_ * c_in
 
     ops_mod.set_ops(Timed())
+    streams = unet.batch_streams
+    unet.batch_streams = 1            # one stream: every launch is timed alone, not while sharing SMs with the other half
     try:
         imagen._step(unet, x, t_dev, torch.randn(shape, device=dev), **kw)
         torch.cuda.synchronize()
     finally:
         ops_mod.set_ops(real)
+        unet.batch_streams = streams
     total = sum(s.elapsed_time(e) for s, e in events)
     return total, flops[0], len(events)
 

@@ -173,19 +173,62 @@ class Unet(nn.Module):
         assert not (self.lowres_cond and not exists(lowres_noise_times)), \
             'low resolution conditioning noise time must be present'
         _no_grad_check(x, self.null_text_embed)
-        ops = get_ops()
         B, Cx, H, W = x.shape
         device = x.device
+        x = x.to(F32).contiguous()
+        lowres = lowres_cond_img.to(F32).contiguous() if exists(lowres_cond_img) else None
 
+        # conditioning for the whole batch (cheap, weight-streaming bound) on the caller's stream
         t, time_tokens = self._generate_t_tokens(time, lowres_noise_times)
         t, c = self._text_condition(text_embeds, B, cond_drop_prob, device, text_mask, t, time_tokens)
-        ctx = Context(c)
-
         # every ResnetBlock's time_mlp (SiLU -> Linear, layers.py:396-399) in ONE GEMM over the shared time embedding
         ss = self._all_scale_shifts(t)
 
+        out = torch.empty((B, self.channels_out, H, W), dtype=F32, device=device)
+        chunks = self._batch_chunks(B, x.is_cuda)
+        if len(chunks) == 1:
+            self._forward_body(x, lowres, t, c, ss, out)
+            return out
+        # The spatial body is per-sample, so batch halves are independent: run them on two streams.  Tensor-core-bound
+        # convs of one half then overlap the HBM-bound GroupNorm/cast/epilogue traffic of the other and fill each
+        # other's tile-quantisation tails (fork/join is captured as parallel branches by a CUDA graph).
+        main = torch.cuda.current_stream(device)
+        streams = self._side_streams(len(chunks), device)
+        for (b0, b1), s in zip(chunks, streams):
+            s.wait_stream(main)
+            with torch.cuda.stream(s):
+                self._forward_body(x[b0:b1], lowres[b0:b1] if exists(lowres) else None, t[b0:b1], c[b0:b1],
+                                   {k: v[b0:b1] for k, v in ss.items()}, out[b0:b1])
+        for s in streams:
+            main.wait_stream(s)
+        return out
+
+    batch_streams = 2          # number of concurrent batch slices in forward (1 = off)
+    min_chunk_batch = 8
+
+    def _batch_chunks(self, B, is_cuda):
+        n = self.batch_streams if is_cuda else 1
+        while n > 1 and (B % n != 0 or B // n < self.min_chunk_batch):
+            n -= 1
+        per = B // n
+        return [(i * per, (i + 1) * per) for i in range(n)]
+
+    def _side_streams(self, n, device):
+        key = (n, str(device))
+        if getattr(self, "_streams_key", None) != key:
+            self._streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+            self._streams_key = key
+        return self._streams
+
+    def _forward_body(self, x, lowres, t, c, ss, out):
+        """Stem -> down path -> middle -> up path -> final block/conv for a batch slice; writes NCHW into `out`."""
+        ops = get_ops()
+        B, _, H, W = x.shape
+        device = x.device
+        ctx = Context(c)
+
         # torch.cat((x, lowres_cond_img), dim=1) (Unet.py:397) + CrossEmbedLayer stem (Unet.py:400)
-        h = self.init_conv.run_stem(x, lowres_cond_img)
+        h = self.init_conv.run_stem(x, lowres)
 
         hiddens = []
         for pre_downsample, init_block, resnet_blocks, attn_block, post_downsample in self.downs:
@@ -217,11 +260,12 @@ class Unet(nn.Module):
 
         # final 3x3 conv (Unet.py:472) straight into the NCHW result
         fc = self.final_conv
-        if get_ops().igemm_supported(H, W, fc.in_channels, 16):
+        if ops.igemm_supported(H, W, fc.in_channels, 16):
             a = torch.empty((B, 1, H, W, fc.in_channels), dtype=torch.float16, device=device)
             ops.cast_act(h, fc.in_channels, None, 0, 1.0, B, H, W, 0, a)
-            return fc.run_prepared_nchw(a, B, H, W)
-        return fc.run_prepared_nchw(h, B, H, W)
+            fc.run_prepared_nchw(a, B, H, W, out)
+        else:
+            fc.run_prepared_nchw(h, B, H, W, out)
 
     def _all_scale_shifts(self, t):
         """{ResnetBlock: view [B, 2*dim_out] (row pitch = total width)} -- the time_mlp of every ResnetBlock evaluated

@@ -258,14 +258,15 @@ class Conv2d(nn.Conv2d):
                             self.padding[0], self.bias, residual, out, H, W, (*strides, 1))
         return out
 
-    def run_prepared_nchw(self, a, B, H, W):
+    def run_prepared_nchw(self, a, B, H, W, out=None):
         """Same-padding conv whose result is written straight to an NCHW fp32 tensor [B, C_out, H, W] (the U-Net's
         final_conv, Unet.py:327/:472).  Tensor-core path: C_out is zero-padded to a multiple of 16 in the packed
         weight and only the real channels are stored (n_valid)."""
         ops = get_ops()
         Cin, Cout = self.in_channels, self.out_channels
         kh, kw = self.kernel_size
-        out = torch.empty((B, Cout, H, W), dtype=F32, device=a.device)
+        if out is None:
+            out = torch.empty((B, Cout, H, W), dtype=F32, device=a.device)
         if a.dtype == F16:
             Np = (Cout + 15) // 16 * 16
             key = (self.weight.data_ptr(), self.weight._version, self.bias._version if exists(self.bias) else -1)

@@ -109,3 +109,27 @@ def test_sample_api_and_sharding_invariance(native):
         noise_fn.lo = lo
         parts.append(im.sample(text_embeds=te[lo:lo + 2], text_masks=tm[lo:lo + 2], cond_scale=3.))
     assert rel_l2(torch.cat(parts), full) < 1e-5      # GroupNorm sums use (double) atomics: order may differ
+
+
+def test_batch_streams_are_exact(native):
+    """Unet.forward runs batch halves on two streams (per-sample independence); the result must not depend on it."""
+    from minimagen_b200.Unet import Unet
+    cfg = dict(dim=64, dim_mults=(1, 2), num_resnet_blocks=1, layer_attns=(False, True), layer_cross_attns=(False, True),
+               lowres_cond=True, memory_efficient=True, text_embed_dim=768)
+    torch.manual_seed(0)
+    u = Unet(**cfg).eval().cuda()
+    g = torch.Generator().manual_seed(5)
+    B = 16
+    x = torch.randn(B, 3, 32, 32, generator=g).cuda()
+    kw = dict(text_embeds=torch.randn(B, 12, 768, generator=g).cuda(), text_mask=torch.ones(B, 12, dtype=torch.bool).cuda(),
+              lowres_cond_img=torch.randn(B, 3, 32, 32, generator=g).cuda(),
+              lowres_noise_times=torch.full((B,), 200).cuda())
+    t = torch.randint(0, 1000, (B,), generator=g).cuda()
+    with torch.no_grad():
+        u.batch_streams = 1
+        a = u(x, t, **kw)
+        u.batch_streams = 2
+        assert len(u._batch_chunks(B, True)) == 2
+        b = u(x, t, **kw)
+        torch.cuda.synchronize()
+    assert rel_l2(b, a) < 1e-6
