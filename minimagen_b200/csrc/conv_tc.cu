@@ -30,81 +30,114 @@ namespace mi {
 
 namespace {
 
-constexpr int kNumThreads = 256;
+constexpr int kNumThreads = 128 + 32 * 8;   // warps 0-3: TMA / MMA / TMEM-alloc / spare, warps 4-11: epilogue
 constexpr uint32_t kABytes = kConvBlockM * kConvBlockK * 2;   // 16 KiB per stage
+constexpr int kEpiWarps = 8;                                   // two warps per TMEM lane quarter, each owning half the columns
+constexpr uint32_t kEpiBytes = kEpiWarps * 32 * 32 * 4;        // epilogue transpose patches (4 KB per warp)
+constexpr uint32_t kRingBudget = 192 * 1024;                   // shared memory for the operand rings (+ patches + barriers <= 227 KB)
 
 template <int BLOCK_N>
 struct Cfg {
     static constexpr uint32_t kBBytes = BLOCK_N * kConvBlockK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     // fill ~192 KiB with stages
-    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr int kStages = (kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes);
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);   // powers of two for our BLOCK_Ns
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
 };
 
-// TMEM accumulator tile (this thread's row, BLOCK_N fp32 columns) -> +bias -> +residual -> global stores.
+// TMEM accumulator tile -> +bias -> +residual -> global stores.
+// tcgen05.ld hands every thread one accumulator ROW; storing rows directly makes each warp-wide store touch 32 different
+// lines with 16 B each.  So each warp transposes 32 x 32 slabs through a private shared-memory patch: rows go in, and
+// come back out as (4 rows x 8 lanes x float4) so that every warp-wide load of the residual and store of the result
+// covers four full 128-byte lines.  All eight residual loads of a slab are issued before the accumulator is read, to
+// overlap their latency.  Strided-channel / ragged-N outputs (final_conv -> NCHW) keep the simple per-row path.
+constexpr int kEpiLd = 32;   // floats per staged row; 16-byte chunks are XOR-swizzled with the row index (conflict-free)
+
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t taddr, int n0, long long pix, bool valid) {
+__device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t taddr, int n0, long long pix, bool valid,
+                                              float* stage /* this warp's [32][kEpiLd] patch */, int c_begin, int c_end) {
+    const int lane = threadIdx.x & 31;
+    if (args.out_sc != 1 || n0 + BLOCK_N > args.n_valid || (BLOCK_N % 32) != 0) {
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 16) {
-                uint32_t v[16];
-                ptx::tmem_ld_x16(taddr + c, v);
-                ptx::tmem_ld_wait();
-                if (valid) {
-                    float f[16];
+        for (int c = c_begin; c < c_end; c += 16) {
+            uint32_t v[16];
+            ptx::tmem_ld_x16(taddr + c, v);
+            ptx::tmem_ld_wait();
+            if (valid) {
+                const int n = n0 + c;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                    const int n = n0 + c;
-                    if (args.bias) {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 bv = __ldg(reinterpret_cast<const float4*>(args.bias + n + i));
-                            f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-                        }
-                    }
-                    if (args.residual && args.out_sc == 1) {
-                        const float* r = args.residual + pix + n;
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 rv = *reinterpret_cast<const float4*>(r + i);
-                            f[i] += rv.x; f[i + 1] += rv.y; f[i + 2] += rv.z; f[i + 3] += rv.w;
-                        }
-                    }
-                    if (args.out_sc != 1 || n + 16 > args.n_valid) {
-                        // strided-channel (e.g. NCHW) or ragged-N store: scalar, coalesced across the warp's pixels
-                        if (args.out_f32) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n + i < args.n_valid) args.out_f32[pix + (long long)(n + i) * args.out_sc] = f[i];
-                        }
-                        if (args.out_f16) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (n + i < args.n_valid)
-                                    args.out_f16[pix + (long long)(n + i) * args.out_sc] = __float2half_rn(f[i]);
-                        }
-                    } else {
-                        if (args.out_f32) {
-                            float* o = args.out_f32 + pix + n;
-#pragma unroll
-                            for (int i = 0; i < 16; i += 4)
-                                *reinterpret_cast<float4*>(o + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-                        }
-                        if (args.out_f16) {
-                            __half* o = args.out_f16 + pix + n;
-                            uint32_t p[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                __half2 h2 = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
-                                p[i] = *reinterpret_cast<uint32_t*>(&h2);
-                            }
-                            *reinterpret_cast<uint4*>(o) = make_uint4(p[0], p[1], p[2], p[3]);
-                            *reinterpret_cast<uint4*>(o + 8) = make_uint4(p[4], p[5], p[6], p[7]);
-                        }
+                for (int i = 0; i < 16; ++i) {
+                    if (n + i < args.n_valid) {
+                        float f = __uint_as_float(v[i]) + (args.bias ? __ldg(args.bias + n + i) : 0.f);
+                        const long long o = pix + (long long)(n + i) * args.out_sc;
+                        if (args.residual && args.out_sc == 1) f += args.residual[o];
+                        if (args.out_f32) args.out_f32[o] = f;
+                        if (args.out_f16) args.out_f16[o] = __float2half_rn(f);
                     }
                 }
             }
+        }
+        return;
+    }
+    const int sub = lane >> 3;            // which of the 4 rows a quarter-warp handles per step
+    const int cv = (lane & 7) * 4;        // its 4 columns inside the 32-column slab
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const int pix_lo = (int)(pix & 0xffffffffLL), pix_hi = (int)(pix >> 32);
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+        const int n = n0 + c;
+        float4 res[8];
+        if (args.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i * 4 + sub;
+                const long long p = ((long long)__shfl_sync(0xffffffffu, pix_hi, r) << 32) |
+                                    (unsigned)__shfl_sync(0xffffffffu, pix_lo, r);
+                res[i] = ((vmask >> r) & 1u) ? *reinterpret_cast<const float4*>(args.residual + p + n + cv)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        uint32_t v0[16], v1[16];
+        ptx::tmem_ld_x16(taddr + c, v0);
+        ptx::tmem_ld_x16(taddr + c + 16, v1);
+        ptx::tmem_ld_wait();
+        float* srow = stage + lane * kEpiLd;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (args.bias) {
+                b0 = __ldg(reinterpret_cast<const float4*>(args.bias + n + i));
+                b1 = __ldg(reinterpret_cast<const float4*>(args.bias + n + 16 + i));
+            }
+            *reinterpret_cast<float4*>(srow + ((((i >> 2)) ^ (lane & 7)) << 2)) =
+                make_float4(__uint_as_float(v0[i]) + b0.x, __uint_as_float(v0[i + 1]) + b0.y,
+                            __uint_as_float(v0[i + 2]) + b0.z, __uint_as_float(v0[i + 3]) + b0.w);
+            *reinterpret_cast<float4*>(srow + ((((i >> 2) + 4) ^ (lane & 7)) << 2)) =
+                make_float4(__uint_as_float(v1[i]) + b1.x, __uint_as_float(v1[i + 1]) + b1.y,
+                            __uint_as_float(v1[i + 2]) + b1.z, __uint_as_float(v1[i + 3]) + b1.w);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + sub;
+            float4 f = *reinterpret_cast<const float4*>(stage + r * kEpiLd + (((lane & 7) ^ (r & 7)) << 2));
+            const long long p = ((long long)__shfl_sync(0xffffffffu, pix_hi, r) << 32) |
+                                (unsigned)__shfl_sync(0xffffffffu, pix_lo, r);
+            if ((vmask >> r) & 1u) {
+                if (args.residual) { f.x += res[i].x; f.y += res[i].y; f.z += res[i].z; f.w += res[i].w; }
+                if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + p + n + cv) = f;
+                if (args.out_f16) {
+                    __half2 lo = __floats2half2_rn(f.x, f.y), hi = __floats2half2_rn(f.z, f.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+                    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(args.out_f16 + p + n + cv) = pk;
+                }
+            }
+        }
+        __syncwarp();
+    }
 }
 
 template <int BLOCK_N>
@@ -123,6 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = bars + 2 * STAGES;      // [2]       MMA -> epilogue
     uint64_t* tempty_bar = bars + 2 * STAGES + 2; // [2]       epilogue -> MMA
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256) + (((threadIdx.x >> 5) + 4) & 7) * 32 * kEpiLd;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -139,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 128);
+            ptx::mbar_init(&tempty_bar[i], 32 * kEpiWarps);
         }
         ptx::fence_barrier_init();
     }
@@ -177,10 +211,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
                         uint8_t* sa = smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
+                        if ((args.dbg & 1) && (tile != (int)blockIdx.x || kb >= STAGES)) {
+                            ptx::mbar_arrive(&full_bar[stage]);      // DEBUG: no data movement, MMA reuses stale smem
+                        } else {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
                         ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
                                          h0 + dh, ph, b0);
                         ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -219,6 +257,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         // ===================== epilogue =====================
         const int ew = warp & 3;                 // TMEM lane quarter this warp may access
+        const int c_half = (BLOCK_N >= 64) ? BLOCK_N / 2 : BLOCK_N;   // warps 4-7: first half of the columns, 8-11: second
+        const int c_begin = (BLOCK_N >= 64 && warp >= 8) ? c_half : 0;
+        const int c_end = (BLOCK_N >= 64) ? c_begin + c_half : (warp >= 8 ? 0 : BLOCK_N);
         const int m = ew * 32 + lane;            // row of the tile == TMEM lane
         const int bw = m & (BW - 1);
         const int bh = (m >> args.bw_log2) & (BH - 1);
@@ -239,7 +280,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid);
+            if (!(args.dbg & 2)) epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end);   // DEBUG bit 1: skip the epilogue
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
@@ -263,9 +304,9 @@ template <int BLOCK_N>
 struct Cfg2 {
     static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kConvBlockK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr int kStages = (kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes);
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiBytes;
 };
 
 template <int BLOCK_N>
@@ -282,6 +323,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint64_t* tfull_bar = bars + 2 * STAGES;       // per CTA
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // used in the leader CTA only
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256) + (((threadIdx.x >> 5) + 4) & 7) * 32 * kEpiLd;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -300,7 +342,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tfull_bar[i], 1);
-            ptx::mbar_init(&tempty_bar[i], 256);  // epilogue threads of both CTAs
+            ptx::mbar_init(&tempty_bar[i], 2 * 32 * kEpiWarps);  // epilogue threads of both CTAs
         }
         ptx::fence_barrier_init();
     }
@@ -382,6 +424,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs, own 128 rows) =====================
         const int ew = warp & 3;
+        const int c_half = BLOCK_N / 2;
+        const int c_begin = warp >= 8 ? c_half : 0;
+        const int c_end = c_begin + c_half;
         const int m = ew * 32 + lane;
         const int bw = m & (BW - 1);
         const int bh = (m >> args.bw_log2) & (BH - 1);
@@ -401,7 +446,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 1400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid);
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end);
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(&tempty_bar[as], 0);                    // the leader's barrier
         }
@@ -412,6 +457,179 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ 3x3 halo variant
+// 3x3 / stride 1 / pad 1 only (92 % of the SR U-Net's FLOPs).  Instead of fetching nine shifted 128-pixel A tiles per
+// 64-channel chunk, ONE (16+2) x (8+2) pixel halo tile is fetched (TMA box 64 x 10 x 18, zero-filled outside the image)
+// and the nine taps are nine tcgen05.mma descriptor windows into it: output tile = 16 rows x 8 columns, so each 8-pixel
+// row segment of a window is exactly one 8 x 128 B swizzle atom, consecutive segments are one halo row (10 x 128 B =
+// 1280 B = the descriptor's stride-byte-offset) apart, and tap (r, s) starts (r*10 + s) * 128 B into the tile.  The
+// 128B swizzle is a function of the shared-memory address bits, so TMA's write pattern and the shifted MMA reads agree.
+// A traffic per chunk drops from 9 x 16 KB to 22.5 KB.
+constexpr int kHaloTH = 16, kHaloTW = 8, kHaloW = kHaloTW + 2, kHaloH = kHaloTH + 2;
+constexpr uint32_t kHaloABytes = kHaloH * kHaloW * 128;                       // 23040
+constexpr uint32_t kHaloAStride = (kHaloABytes + 1023) & ~1023u;              // 23552
+
+template <int BLOCK_N>
+struct CfgH {
+    static constexpr uint32_t kBBytes = BLOCK_N * kConvBlockK * 2;
+    static constexpr int kAStages = 3;
+    static constexpr int kBStages = (kRingBudget - kAStages * kHaloAStride) / kBBytes > 8 ? 8 : (kRingBudget - kAStages * kHaloAStride) / kBBytes;
+    static constexpr uint32_t kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+    static constexpr uint32_t kSmemBytes = kAStages * kHaloAStride + kBStages * kBBytes + 1024 + 256 + kEpiBytes;
+};
+
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((kHaloW * 128u) >> 4) << 32;   // SBO: one halo row between 8-pixel row segments
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ ConvTcArgs args) {
+    using C = CfgH<BLOCK_N>;
+    constexpr int NA = C::kAStages, NB = C::kBStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_b = smem + NA * kHaloAStride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + NB * C::kBBytes);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = bars + NA;
+    uint64_t* fullB = bars + 2 * NA;
+    uint64_t* emptyB = bars + 2 * NA + NB;
+    uint64_t* tfull_bar = bars + 2 * NA + 2 * NB;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256) + (((threadIdx.x >> 5) + 4) & 7) * 32 * kEpiLd;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int* err = args.err_flag;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NA; ++i) { ptx::mbar_init(&fullA[i], 1); ptx::mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < NB; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 32 * kEpiWarps); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int chunks = args.chunks_per_tap;
+    const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
+    const int total_tiles = tiles_m * args.tiles_n;
+    const int Cin = chunks * kConvBlockK;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % args.tiles_n;
+                const int mt = tile / args.tiles_n;
+                const int w0 = (mt % args.tiles_w) * kHaloTW;
+                const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHaloTH;
+                const int b0 = mt / (args.tiles_w * args.tiles_h);
+                const int n0 = nt * BLOCK_N;
+                for (int j = 0; j < chunks; ++j) {
+                    ptx::mbar_wait(&emptyA[sa], pa ^ 1, err, 2100 + sa);
+                    ptx::mbar_arrive_expect_tx(&fullA[sa], kHaloABytes);
+                    ptx::tma_load_5d(&tmA, &fullA[sa], smem + sa * kHaloAStride, args.a_chan_off + j * kConvBlockK,
+                                     w0 - 1, h0 - 1, 0, b0);
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                    for (int t = 0; t < 9; ++t) {
+                        ptx::mbar_wait(&emptyB[sb], pb ^ 1, err, 2200 + sb);
+                        ptx::mbar_arrive_expect_tx(&fullB[sb], C::kBBytes);
+                        ptx::tma_load_2d(&tmB, &fullB[sb], smem_b + sb * C::kBBytes, t * Cin + j * kConvBlockK, n0);
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0);
+            int sa = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            int iter = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+                const int as = iter & 1;
+                const uint32_t aphase = (iter >> 1) & 1;
+                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 2300 + as);
+                ptx::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                for (int j = 0; j < chunks; ++j) {
+                    ptx::mbar_wait(&fullA[sa], pa, err, 2400 + sa);
+                    const uint32_t a_base = ptx::smem_u32(smem + sa * kHaloAStride);
+                    for (int t = 0; t < 9; ++t) {
+                        ptx::mbar_wait(&fullB[sb], pb, err, 2500 + sb);
+                        ptx::tc_fence_after();
+                        const uint32_t a_win = a_base + ((t / 3) * kHaloW + (t % 3)) * 128;
+                        const uint64_t da = make_halo_desc(a_win);
+                        const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_b + sb * C::kBBytes));
+#pragma unroll
+                        for (int k = 0; k < kConvBlockK / 16; ++k)
+                            ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | t | k) != 0);
+                        ptx::umma_commit(&emptyB[sb]);
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    }
+                    ptx::umma_commit(&emptyA[sa]);
+                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                }
+                ptx::umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        const int c_half = BLOCK_N / 2;
+        const int c_begin = warp >= 8 ? c_half : 0;
+        const int c_end = c_begin + c_half;
+        const int m = ew * 32 + lane;
+        const int bw = m & (kHaloTW - 1);
+        const int bh = m >> 3;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int nt = tile % args.tiles_n;
+            const int mt = tile / args.tiles_n;
+            const int w = (mt % args.tiles_w) * kHaloTW + bw;
+            const int h = ((mt / args.tiles_w) % args.tiles_h) * kHaloTH + bh;
+            const int b = mt / (args.tiles_w * args.tiles_h);
+            const int n0 = nt * BLOCK_N;
+            const bool valid = (b < args.B) && (h < args.H) && (w < args.W);
+            const long long pix = (long long)b * args.out_sb + (long long)h * args.out_sh + (long long)w * args.out_sw;
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tfull_bar[as], aphase, err, 2600 + as);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
     }
 }
 
@@ -473,6 +691,22 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& ar
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
+template <int BLOCK_N>
+int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& args, int total_tiles, int num_sms,
+                cudaStream_t stream) {
+    using C = CfgH<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3x3_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::kSmemBytes) != cudaSuccess)
+            return -10;
+        attr_set = true;
+    }
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    conv3x3_halo_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    return cudaGetLastError() == cudaSuccess ? 0 : -11;
+}
+
 }  // namespace
 
 const char* conv_tc_strerror(int code) {
@@ -512,6 +746,48 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -5;
 
+    // ---- 3x3 halo kernel (opt-in via p.halo): needs the canonical 3x3 tap order, H % 16 == 0, W % 8 == 0
+    if (p.halo && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 && p.Cout % 128 == 0) {
+        bool canon = true;
+        for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
+        if (canon) {
+            ConvTcArgs h{};
+            h.num_taps = 9; h.chunks_per_tap = p.Cin / kConvBlockK;
+            h.tiles_w = p.W / kHaloTW; h.tiles_h = p.H / kHaloTH; h.tiles_b = p.B;
+            h.B = p.B; h.H = p.H; h.W = p.W; h.a_chan_off = p.a_chan_off;
+            h.out_sb = p.out_sb; h.out_sh = p.out_sh; h.out_sw = p.out_sw;
+            h.out_sc = p.out_sc > 0 ? p.out_sc : 1; h.n_valid = p.n_valid > 0 ? p.n_valid : p.Cout;
+            h.out_f32 = p.out_f32; h.out_f16 = p.out_f16; h.bias = p.bias; h.residual = p.residual; h.err_flag = p.err_flag;
+            int dev = 0, num_sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            const int bn = (p.Cout % 256 == 0 && p.block_n_hint != 128) ? 256 : 128;
+            h.tiles_n = p.Cout / bn;
+            CUtensorMap tmA, tmB;
+            cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
+            cuuint64_t gstr[4] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.W * p.lda * 2, (cuuint64_t)p.H * p.W * p.lda * 2,
+                                  (cuuint64_t)p.H * p.W * p.lda * 2};
+            cuuint32_t box[5] = {kConvBlockK, kHaloW, kHaloH, 1, 1};
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(p.act), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return -6;
+            const cuuint64_t K = (cuuint64_t)9 * p.Cin;
+            cuuint64_t wdim[2] = {K, (cuuint64_t)p.Cout};
+            cuuint64_t wstr[1] = {K * 2};
+            cuuint32_t wbox[2] = {kConvBlockK, (cuuint32_t)bn};
+            cuuint32_t westr[2] = {1, 1};
+            if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.wpacked), wdim, wstr, wbox, westr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return -7;
+            const int total = h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n;
+            return bn == 256 ? launch_halo<256>(tmA, tmB, h, total, num_sms, stream)
+                             : launch_halo<128>(tmA, tmB, h, total, num_sms, stream);
+        }
+    }
+
     ConvTcArgs a{};
     a.num_taps = p.num_taps;
     a.chunks_per_tap = p.Cin / kConvBlockK;
@@ -531,6 +807,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     a.n_valid = p.n_valid > 0 ? p.n_valid : p.Cout;
     a.out_f32 = p.out_f32; a.out_f16 = p.out_f16; a.bias = p.bias; a.residual = p.residual;
     a.err_flag = p.err_flag;
+    a.dbg = p.dbg;
     for (int t = 0; t < p.num_taps; ++t) { a.dh[t] = p.dh[t]; a.dw[t] = p.dw[t]; a.ph[t] = p.ph[t]; }
 
     // BLOCK_N: largest of {256,128,64,32,16} dividing C_out that still yields >= 1 wave of tiles if possible

@@ -25,6 +25,7 @@ struct ConvTcArgs {
     const float* bias;                    // optional, [C_out]
     const float* residual;                // optional, fp32, same strides as the output
     int* err_flag;                        // optional: pipeline-timeout code is written here before trapping
+    int dbg;                              // profiling experiments only (bit 0: no TMA after warm-up, bit 1: no epilogue)
     int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
 };
 
@@ -47,6 +48,8 @@ struct ConvTcProblem {
     int n_valid;            // 0 = all C_out channels are stored
     int block_n_hint;       // 0 = auto; > 0 preferred tile width; < 0: |value| with the 1-CTA kernel forced
     int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
+    int halo;               // 1 = use the 3x3 halo-tile kernel when the geometry allows
+    int dbg;                // profiling experiments only
     int* err_flag;
 };
 
