@@ -54,14 +54,22 @@ int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, in
  *             (out_sc = 1: channel-contiguous NHWC-style rows; out_sc = H*W with out_sw = 1: NCHW, used by final_conv
  *             Unet.py:327,472); only channels n < n_valid are stored (n_valid = 0: all; lets c_out be zero-padded up
  *             to a multiple of 16); residual requires out_sc = 1
+ *   act2_f16  optional second activation tensor [B][phases][H][W][lda2]: the input is then the VIRTUAL channel concat
+ *             cat(act[c_off : c_off+c_in1], act2[c_off2 : c_off2+c_in-c_in1]) of every tap -- the up-path skip connection
+ *             torch.cat((x, skip * 2**-0.5), dim=1) (Unet.py:445) without materialising it (the 2**-0.5 is folded into the
+ *             packed weight columns); NULL otherwise (then c_in1 is ignored)
+ *   out_stats optional [B][c_out/16][2] doubles, zero on entry: per (image, 16-channel block) sum and sum of squares of
+ *             the OUTPUT (after bias/residual), accumulated in the epilogue -- the GroupNorm statistics of the next
+ *             Block (layers.py:136) for free; needs out_sc = 1
  *   block_n   0 = auto, or one of 16/32/64/128/256 (tile width; must divide c_out)
  * Requirements: c_in % 64 == 0, c_out % 16 == 0, W a power of two >= 8 (or W >= 128), see mi_conv2d_igemm_supported.
  * A plain GEMM  out[M][N] = act[M][K] * w[N][K]^T  is the case B=1, H=1, W=M, kh=kw=1. */
 int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out);
-int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c_off, int c_in, const void* w_f16,
-                        int c_out, int kh, int kw, int mode, const float* bias, const float* residual, float* out_f32,
-                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, long long out_sc,
-                        int n_valid, int block_n, int* err_flag, void* stream);
+int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c_off, int c_in, const void* act2_f16,
+                        int lda2, int c_off2, int c_in1, const void* w_f16, int c_out, int kh, int kw, int mode,
+                        const float* bias, const float* residual, float* out_f32, void* out_f16, double* out_stats,
+                        long long out_sb, long long out_sh, long long out_sw, long long out_sc, int n_valid,
+                        int block_n, int* err_flag, void* stream);
 
 /* Direct fp32 convolution for shapes outside the tensor-core path: the CrossEmbedLayer stem (layers.py:300, 3/6 input
  * channels, k = 3/7/15), final_conv (Unet.py:327, 3 output channels) and every conv of the tiny test config.
@@ -78,19 +86,24 @@ int mi_conv2d_direct_f32(const float* in, int B, int Hin, int Win, int c_in, int
 /* ------------------------------------------------------------------------------------------------- normalisation
  * nn.GroupNorm statistics (layers.py:127,136): per (sample, group) sum / sum-of-squares of the virtual concatenation
  * cat(src0[.., C0], src1[.., C1] * scale1) (skip connection, Unet.py:445; pass src1 = NULL, C1 = 0 otherwise).
- * sums: [B][groups][2] double, MUST be zero on entry (accumulated with atomics). */
-int mi_gn_stats(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
-                double* sums, void* stream);
+ * sums: [B][groups][2] double, MUST be zero on entry (accumulated with atomics).  src: fp32 or (in_is_f16) fp16.
+ * Called with groups = C/16 it produces the same per-16-channel block statistics as mi_conv2d_igemm_f16's out_stats. */
+int mi_gn_stats(const void* src0, int c0, const void* src1, int c1, float scale1, int in_is_f16, int B, int hw,
+                int groups, double* sums, void* stream);
 /* Block.forward (layers.py:136-144): SiLU( GroupNorm(x) * (scale + 1) + shift ) -> conv operand (fp16 or fp32).
+ * src0/src1: fp32 or (in_is_f16) fp16.  Statistics: stats0_block = 0 -> stats0 is [B][groups][2] from mi_gn_stats over the
+ * whole concat; stats0_block = k > 0 -> stats0 is [B][c0/k][2] and stats1 [B][c1/stats1_block][2]: per-source block sums
+ * written by the producing conv epilogues (mi_conv2d_igemm_f16 out_stats, k = 16); src1's are scaled by scale1 here.
  * scale_shift: fp32, row b at scale_shift + b*scale_shift_ld holds [scale(C) | shift(C)] (time_mlp output,
  * layers.py:427-429; the rows of all ResnetBlocks live in one buffer, hence the row pitch) or NULL. */
-int mi_gn_apply_silu(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
-                     const double* sums, const float* gamma, const float* beta, const float* scale_shift,
-                     int scale_shift_ld, float eps, void* out, int out_is_f16, void* stream);
+int mi_gn_apply_silu(const void* src0, int c0, const void* src1, int c1, float scale1, int in_is_f16, int B, int hw,
+                     int groups, const double* stats0, int stats0_block, const double* stats1, int stats1_block,
+                     const float* gamma, const float* beta, const float* scale_shift, int scale_shift_ld, float eps,
+                     void* out, int out_is_f16, void* stream);
 /* Raw conv operands with the skip concat folded in; mode 0 plain copy/cast, 1 nearest x2 upsample (layers.py:513),
  * 2 four-phase split for the stride-2 Downsample conv (layers.py:319). out: fp16 or fp32. */
-int mi_cast_act(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W, int mode,
-                void* out, int out_is_f16, void* stream);
+int mi_cast_act(const void* src0, int c0, const void* src1, int c1, float scale1, int in_is_f16, int B, int H, int W,
+                int mode, void* out, int out_is_f16, void* stream);
 /* Row LayerNorm over the last dim: layers.py:342 (LayerNorm, gamma + zero beta), layers.py:174-177 (ChanLayerNorm ==
  * per-pixel LN in NHWC), Unet.py:142,632 (nn.LayerNorm).  pre_gelu applies the exact-erf GELU of ChanFeedForward
  * (layers.py:158) to the input first; residual (fp32 [R][C]) is added after (layers.py:435,497-498). */

@@ -256,16 +256,14 @@ class Unet(nn.Module):
             h = attn_block.run(h)
             h = upsample.run(h)
 
-        h = self.final_res_block.run(h, t, None, ss[self.final_res_block])
+        h = self.final_res_block.run(h, t, None, ss[self.final_res_block], out_f32=False)
 
         # final 3x3 conv (Unet.py:472) straight into the NCHW result
         fc = self.final_conv
         if ops.igemm_supported(H, W, fc.in_channels, 16):
-            a = torch.empty((B, 1, H, W, fc.in_channels), dtype=torch.float16, device=device)
-            ops.cast_act(h, fc.in_channels, None, 0, 1.0, B, H, W, 0, a)
-            fc.run_prepared_nchw(a, B, H, W, out)
+            fc.run_prepared_nchw(h.need_f16(), B, H, W, out)
         else:
-            fc.run_prepared_nchw(h, B, H, W, out)
+            fc.run_prepared_nchw(h.need_f32(), B, H, W, out)
 
     def _all_scale_shifts(self, t):
         """{ResnetBlock: view [B, 2*dim_out] (row pitch = total width)} -- the time_mlp of every ResnetBlock evaluated

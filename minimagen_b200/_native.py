@@ -21,11 +21,12 @@ SIGNATURES = {
     "mi_device_ok": [],
     "mi_pack_conv_weight_f16": [_P, _I, _I, _I, _I, _F, _P, _P],
     "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
-    "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _L, _L, _L, _L, _I, _I, _P, _P],
+    "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _L, _L,
+                            _I, _I, _P, _P],
     "mi_conv2d_direct_f32": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _P],
-    "mi_gn_stats": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P],
-    "mi_gn_apply_silu": [_P, _I, _P, _I, _F, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _I, _P],
-    "mi_cast_act": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _I, _P],
+    "mi_gn_stats": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P],
+    "mi_gn_apply_silu": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _I, _F, _P, _I, _P],
+    "mi_cast_act": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _I, _P, _I, _P],
     "mi_ln_rows": [_P, _L, _I, _P, _P, _F, _I, _P, _P, _P, _P],
     "mi_linear_f32": [_P, _I, _I, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P],
     "mi_sinusoidal_posemb": [_P, _I, _I, _P, _P],

@@ -48,13 +48,16 @@ int mi_pack_conv_weight_f16(const float* w, int c_out, int c_in, int kh, int kw,
 
 int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out) { return mi::conv_tc_supported(H, W, c_in, c_out) ? 1 : 0; }
 
-int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* w, int c_out,
-                        int kh, int kw, int mode, const float* bias, const float* residual, float* out_f32,
-                        void* out_f16, long long out_sb, long long out_sh, long long out_sw, long long out_sc,
-                        int n_valid, int block_n, int* err_flag, void* stream) {
+int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* act2, int lda2,
+                        int c_off2, int c_in1, const void* w, int c_out, int kh, int kw, int mode, const float* bias,
+                        const float* residual, float* out_f32, void* out_f16, double* out_stats, long long out_sb,
+                        long long out_sh, long long out_sw, long long out_sc, int n_valid, int block_n, int* err_flag,
+                        void* stream) {
     mi::ConvTcProblem p{};
     p.act = act; p.B = B; p.H = H; p.W = W; p.lda = lda; p.a_channels = lda; p.a_chan_off = c_off; p.Cin = c_in;
     p.wpacked = w; p.Cout = c_out;
+    p.act2 = act2; p.lda2 = lda2; p.a_chan_off2 = c_off2; p.Cin1 = c_in1; p.stats = out_stats;
+    if (out_stats && (out_sc > 1 || (c_out % 32) != 0)) return fail(-8, "mi_conv2d_igemm_f16: out_stats needs channel-contiguous output and c_out % 32 == 0");
     p.out_f32 = out_f32; p.out_f16 = (__half*)out_f16; p.bias = bias; p.residual = residual;
     p.out_sb = out_sb; p.out_sh = out_sh; p.out_sw = out_sw; p.out_sc = out_sc; p.n_valid = n_valid;
     p.block_n_hint = block_n; p.err_flag = err_flag;
@@ -99,20 +102,23 @@ int mi_conv2d_direct_f32(const float* in, int B, int Hin, int Win, int c_in, int
                  "mi_conv2d_direct_f32");
 }
 
-int mi_gn_stats(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
-                double* sums, void* stream) {
-    return check(mi::gn_stats(src0, c0, src1, c1, scale1, B, hw, groups, sums, S(stream)), "mi_gn_stats");
+int mi_gn_stats(const void* src0, int c0, const void* src1, int c1, float scale1, int in_is_f16, int B, int hw,
+                int groups, double* sums, void* stream) {
+    return check(mi::gn_stats(src0, c0, src1, c1, scale1, in_is_f16, B, hw, groups, sums, S(stream)), "mi_gn_stats");
 }
-int mi_gn_apply_silu(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int hw, int groups,
-                     const double* sums, const float* gamma, const float* beta, const float* scale_shift,
-                     int scale_shift_ld, float eps, void* out, int out_is_f16, void* stream) {
-    return check(mi::gn_apply_silu(src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift,
-                                   scale_shift_ld, eps, out, out_is_f16, S(stream)),
+int mi_gn_apply_silu(const void* src0, int c0, const void* src1, int c1, float scale1, int in_is_f16, int B, int hw,
+                     int groups, const double* stats0, int stats0_block, const double* stats1, int stats1_block,
+                     const float* gamma, const float* beta, const float* scale_shift, int scale_shift_ld, float eps,
+                     void* out, int out_is_f16, void* stream) {
+    return check(mi::gn_apply_silu(src0, c0, src1, c1, scale1, in_is_f16, B, hw, groups, stats0, stats0_block, stats1,
+                                   stats1_block, gamma, beta, scale_shift, scale_shift_ld, eps, out, out_is_f16,
+                                   S(stream)),
                  "mi_gn_apply_silu");
 }
-int mi_cast_act(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W, int mode,
-                void* out, int out_is_f16, void* stream) {
-    return check(mi::cast_act(src0, c0, src1, c1, scale1, B, H, W, mode, out, out_is_f16, S(stream)), "mi_cast_act");
+int mi_cast_act(const void* src0, int c0, const void* src1, int c1, float scale1, int in_is_f16, int B, int H, int W,
+                int mode, void* out, int out_is_f16, void* stream) {
+    return check(mi::cast_act(src0, c0, src1, c1, scale1, in_is_f16, B, H, W, mode, out, out_is_f16, S(stream)),
+                 "mi_cast_act");
 }
 int mi_ln_rows(const float* in, long long rows, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
                const float* residual, float* out_f32, void* out_f16, void* stream) {

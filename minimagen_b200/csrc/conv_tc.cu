@@ -56,7 +56,8 @@ constexpr int kEpiLd = 32;   // floats per staged row; 16-byte chunks are XOR-sw
 
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t taddr, int n0, long long pix, bool valid,
-                                              float* stage /* this warp's [32][kEpiLd] patch */, int c_begin, int c_end) {
+                                              float* stage /* this warp's [32][kEpiLd] patch */, int c_begin, int c_end,
+                                              int b_img) {
     const int lane = threadIdx.x & 31;
     if (args.out_sc != 1 || n0 + BLOCK_N > args.n_valid || (BLOCK_N % 32) != 0) {
 #pragma unroll 1
@@ -118,6 +119,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
                             __uint_as_float(v1[i + 2]) + b1.z, __uint_as_float(v1[i + 3]) + b1.w);
         }
         __syncwarp();
+        float st_s = 0.f, st_q = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + sub;
@@ -126,6 +128,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
                                 (unsigned)__shfl_sync(0xffffffffu, pix_lo, r);
             if ((vmask >> r) & 1u) {
                 if (args.residual) { f.x += res[i].x; f.y += res[i].y; f.z += res[i].z; f.w += res[i].w; }
+                st_s += (f.x + f.y) + (f.z + f.w);
+                st_q += (f.x * f.x + f.y * f.y) + (f.z * f.z + f.w * f.w);
                 if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + p + n + cv) = f;
                 if (args.out_f16) {
                     __half2 lo = __floats2half2_rn(f.x, f.y), hi = __floats2half2_rn(f.z, f.w);
@@ -136,14 +140,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
                 }
             }
         }
+        if (args.stats) {
+            // GroupNorm statistics of the tensor being written, per (image, 16-channel block): this warp's 32 rows x 32
+            // columns reduce to two (sum, sum of squares) pairs -- lanes with bit 2 clear hold block 0, set: block 1
+#pragma unroll
+            for (int o = 1; o <= 16; o <<= 1) {
+                if (o == 4) continue;
+                st_s += __shfl_xor_sync(0xffffffffu, st_s, o);
+                st_q += __shfl_xor_sync(0xffffffffu, st_q, o);
+            }
+            const int b0 = __shfl_sync(0xffffffffu, b_img, vmask ? (__ffs(vmask) - 1) : 0);
+            if ((lane == 0 || lane == 4) && vmask != 0u) {
+                double* dst = args.stats + ((long long)b0 * args.stats_blocks + (n >> 4) + (lane >> 2)) * 2;
+                atomicAdd(dst, (double)st_s);
+                atomicAdd(dst + 1, (double)st_q);
+            }
+        }
         __syncwarp();
     }
 }
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ ConvTcArgs args) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
     using C = Cfg<BLOCK_N>;
     constexpr int STAGES = C::kStages;
 
@@ -164,6 +184,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmA2);
         ptx::prefetch_tensormap(&tmB);
     }
     if (warp == 1 && lane == 0) {
@@ -215,8 +236,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ptx::mbar_arrive(&full_bar[stage]);      // DEBUG: no data movement, MMA reuses stale smem
                         } else {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-                        ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
-                                         h0 + dh, ph, b0);
+                        if (j < args.a_split)
+                            ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
+                                             h0 + dh, ph, b0);
+                        else   // second half of a virtual channel concat (skip connection)
+                            ptx::tma_load_5d(&tmA2, &full_bar[stage], sa,
+                                             args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 + dw, h0 + dh, ph, b0);
                         ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -280,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            if (!(args.dbg & 2)) epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end);   // DEBUG bit 1: skip the epilogue
+            if (!(args.dbg & 2)) epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b);   // DEBUG bit 1: skip the epilogue
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
@@ -311,8 +336,8 @@ struct Cfg2 {
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
-conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ ConvTcArgs args) {
+conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
     using C = Cfg2<BLOCK_N>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -384,8 +409,13 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         uint8_t* sa = smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
                         if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-                        ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
-                                             h0 + dh, ph, b0);
+                        if (j < args.a_split)
+                            ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
+                                                 h0 + dh, ph, b0);
+                        else
+                            ptx::tma_load_5d_2sm(&tmA2, &full_bar[stage], sa,
+                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 + dw, h0 + dh, ph,
+                                                 b0);
                         ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
                         if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -446,7 +476,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 1400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end);
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b);
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(&tempty_bar[as], 0);                    // the leader's barrier
         }
@@ -620,7 +650,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 2600 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end);
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b);
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
@@ -659,8 +689,8 @@ int ilog2_exact(int v) {
 }
 
 template <int BLOCK_N>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& args, int total_tiles, int num_sms,
-           cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
+           int total_tiles, int num_sms, cudaStream_t stream) {
     using C = Cfg<BLOCK_N>;
     static bool attr_set = false;   // per-template-instance; benign race (idempotent call)
     if (!attr_set) {
@@ -670,13 +700,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& arg
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
 template <int BLOCK_N>
-int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& args, int total_pairs, int num_sms,
-            cudaStream_t stream) {
+int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
+            int total_pairs, int num_sms, cudaStream_t stream) {
     using C = Cfg2<BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -687,7 +717,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& ar
     }
     int clusters = num_sms / 2;
     if (clusters > total_pairs) clusters = total_pairs;
-    conv_tc2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    conv_tc2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -747,7 +777,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     if (!enc) return -5;
 
     // ---- 3x3 halo kernel (opt-in via p.halo): needs the canonical 3x3 tap order, H % 16 == 0, W % 8 == 0
-    if (p.halo && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 && p.Cout % 128 == 0) {
+    if (p.halo && !p.act2 && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 && p.Cout % 128 == 0) {
         bool canon = true;
         for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
         if (canon) {
@@ -758,6 +788,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
             h.out_sb = p.out_sb; h.out_sh = p.out_sh; h.out_sw = p.out_sw;
             h.out_sc = p.out_sc > 0 ? p.out_sc : 1; h.n_valid = p.n_valid > 0 ? p.n_valid : p.Cout;
             h.out_f32 = p.out_f32; h.out_f16 = p.out_f16; h.bias = p.bias; h.residual = p.residual; h.err_flag = p.err_flag;
+            h.stats = p.stats; h.stats_blocks = p.Cout / 16;
             int dev = 0, num_sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -808,6 +839,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     a.out_f32 = p.out_f32; a.out_f16 = p.out_f16; a.bias = p.bias; a.residual = p.residual;
     a.err_flag = p.err_flag;
     a.dbg = p.dbg;
+    a.stats = p.stats; a.stats_blocks = p.Cout / 16;
     for (int t = 0; t < p.num_taps; ++t) { a.dh[t] = p.dh[t]; a.dw[t] = p.dw[t]; a.ph[t] = p.ph[t]; }
 
     // BLOCK_N: largest of {256,128,64,32,16} dividing C_out that still yields >= 1 wave of tiles if possible
@@ -847,7 +879,22 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     const int total_tiles = tiles_m * a.tiles_n;
 
     // activation map: (C, W, H, P, B), fp16, box (64, BW, BH, 1, BB), 128B swizzle, OOB -> zeros
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmA2, tmB;
+    a.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK;
+    a.a_chan_off2 = p.a_chan_off2;
+    if (p.act2) {
+        if (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) || (reinterpret_cast<uintptr_t>(p.act2) & 15))
+            return -8;
+        cuuint64_t gdim[5] = {(cuuint64_t)p.lda2, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.phases, (cuuint64_t)p.B};
+        cuuint64_t gstr[4] = {(cuuint64_t)p.lda2 * 2, (cuuint64_t)p.W * p.lda2 * 2, (cuuint64_t)p.H * p.W * p.lda2 * 2,
+                              (cuuint64_t)p.phases * p.H * p.W * p.lda2 * 2};
+        cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)BW, (cuuint32_t)BH, 1, (cuuint32_t)BB};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        if (enc(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(p.act2), gdim, gstr, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -6;
+    }
     {
         cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.phases,
                               (cuuint64_t)p.B};
@@ -859,6 +906,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return -6;
+        if (!p.act2) tmA2 = tmA;
     }
     {
         const cuuint64_t K = (cuuint64_t)p.num_taps * p.Cin;
@@ -874,15 +922,15 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
 
     if (pair) {
         const int total_pairs = ((tiles_m + 1) / 2) * a.tiles_n;
-        return block_n == 256 ? launch2<256>(tmA, tmB, a, total_pairs, num_sms, stream)
-                              : launch2<128>(tmA, tmB, a, total_pairs, num_sms, stream);
+        return block_n == 256 ? launch2<256>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
+                              : launch2<128>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
     }
     switch (block_n) {
-        case 256: return launch<256>(tmA, tmB, a, total_tiles, num_sms, stream);
-        case 128: return launch<128>(tmA, tmB, a, total_tiles, num_sms, stream);
-        case 64: return launch<64>(tmA, tmB, a, total_tiles, num_sms, stream);
-        case 32: return launch<32>(tmA, tmB, a, total_tiles, num_sms, stream);
-        default: return launch<16>(tmA, tmB, a, total_tiles, num_sms, stream);
+        case 256: return launch<256>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);
+        case 128: return launch<128>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);
+        case 64: return launch<64>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);
+        case 32: return launch<32>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);
+        default: return launch<16>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);
     }
 }
 

@@ -17,6 +17,7 @@ struct ConvTcArgs {
     int tiles_w, tiles_h, tiles_b, tiles_n;
     int B, H, W;                          // output pixel grid (== TMA pixel grid of every phase)
     int a_chan_off;                       // first input channel inside the activation buffer
+    int a_split, a_chan_off2;             // k-chunks >= a_split come from the second activation tensor (virtual concat)
     long long out_sb, out_sh, out_sw;     // output (and residual) strides in elements
     long long out_sc;                     // channel stride (1 = NHWC-style contiguous channels; H*W for NCHW output)
     int n_valid;                          // channels >= n_valid are computed (zero-padded weights) but not stored
@@ -26,6 +27,8 @@ struct ConvTcArgs {
     const float* residual;                // optional, fp32, same strides as the output
     int* err_flag;                        // optional: pipeline-timeout code is written here before trapping
     int dbg;                              // profiling experiments only (bit 0: no TMA after warm-up, bit 1: no epilogue)
+    double* stats;                        // optional [B][C_out/16][2]: (sum, sum of squares) of the output per 16-channel block
+    int stats_blocks;                     // C_out / 16
     int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
 };
 
@@ -38,6 +41,8 @@ struct ConvTcProblem {
     int a_channels;         // channel extent visible to TMA (usually lda)
     int a_chan_off;         // first channel used
     int Cin;                // channels per tap
+    const void* act2;       // optional second activation tensor: channels [Cin1, Cin) of every tap come from it
+    int lda2, a_chan_off2, Cin1;
     const void* wpacked;    // fp16 [Cout][num_taps*Cin]
     int Cout;
     int num_taps;
@@ -50,6 +55,7 @@ struct ConvTcProblem {
     int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
     int halo;               // 1 = use the 3x3 halo-tile kernel when the geometry allows
     int dbg;                // profiling experiments only
+    double* stats;          // optional GroupNorm block statistics of the output (pre-zeroed), see ConvTcArgs
     int* err_flag;
 };
 

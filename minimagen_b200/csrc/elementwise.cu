@@ -25,6 +25,29 @@ __device__ __forceinline__ float4 load_cat4(const float* __restrict__ src0, int 
     return v;
 }
 
+// 8 consecutive channels [c, c+8) of the virtual concat, from fp32 or fp16 sources (C0 % 8 == 0 for fp16)
+template <typename T>
+__device__ __forceinline__ void load_cat8(const T* __restrict__ src0, int C0, const T* __restrict__ src1, int C1,
+                                          float scale1, long long pix, int c, float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 a = load_cat4(src0, C0, src1, C1, scale1, pix, c);
+        const float4 d = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
+    } else {
+        const bool first = c < C0;
+        const uint4 raw = first ? *reinterpret_cast<const uint4*>(src0 + pix * C0 + c)
+                                : *reinterpret_cast<const uint4*>(src1 + pix * C1 + (c - C0));
+        const __half2* h = reinterpret_cast<const __half2*>(&raw);
+        const float sc = first ? 1.0f : scale1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            v[2 * i] = f.x * sc;
+            v[2 * i + 1] = f.y * sc;
+        }
+    }
+}
+
 __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
     __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
     uint2 r;
@@ -38,16 +61,17 @@ __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) 
 // grid = (ceil(HW / chunk), B) with chunk ~ 32K elements / C pixels, so small images still fill the GPU;
 // sums[b][g][0..1] accumulated with double atomics (buffer pre-zeroed by the caller).
 
+template <typename InT>
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1, int HW,
-                int groups, double* __restrict__ sums, int kGnChunk) {
+gn_stats_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ src1, int C1, float scale1, int HW,
+                int groups, double* __restrict__ sums, int chunk) {
     extern __shared__ double s_acc[];   // [groups][2]
     const int C = C0 + C1;
-    const int V = C >> 2;
+    const int V = C >> 3;               // 8-channel vectors
     const int Cg = C / groups;
     const int b = blockIdx.y;
-    const int p0 = blockIdx.x * kGnChunk;
-    const int npix = min(kGnChunk, HW - p0);
+    const int p0 = blockIdx.x * chunk;
+    const int npix = min(chunk, HW - p0);
     for (int i = threadIdx.x; i < 2 * groups; i += blockDim.x) s_acc[i] = 0.0;
     __syncthreads();
 
@@ -60,33 +84,34 @@ gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict_
     }
     const long long pix_base = (long long)b * HW + p0;
     for (int cv = cv0; cv < V; cv += cv_step) {
-        const int c = cv << 2;
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+        const int c = cv << 3;
+        float s[8], q[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
         int p = plane;
-        for (; p + 3 * nplanes < npix; p += 4 * nplanes) {     // 4 independent 16-byte loads in flight
-            const float4 v0 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p, c);
-            const float4 v1 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p + nplanes, c);
-            const float4 v2 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p + 2 * nplanes, c);
-            const float4 v3 = load_cat4(src0, C0, src1, C1, scale1, pix_base + p + 3 * nplanes, c);
-            s[0] += (v0.x + v1.x) + (v2.x + v3.x); q[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
-            s[1] += (v0.y + v1.y) + (v2.y + v3.y); q[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
-            s[2] += (v0.z + v1.z) + (v2.z + v3.z); q[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
-            s[3] += (v0.w + v1.w) + (v2.w + v3.w); q[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+        for (; p + nplanes < npix; p += 2 * nplanes) {         // two independent vector loads in flight
+            float v0[8], v1[8];
+            load_cat8<InT>(src0, C0, src1, C1, scale1, pix_base + p, c, v0);
+            load_cat8<InT>(src0, C0, src1, C1, scale1, pix_base + p + nplanes, c, v1);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += v0[e] + v1[e]; q[e] += v0[e] * v0[e] + v1[e] * v1[e]; }
         }
         for (; p < npix; p += nplanes) {
-            const float4 v = load_cat4(src0, C0, src1, C1, scale1, pix_base + p, c);
-            s[0] += v.x; q[0] += v.x * v.x;
-            s[1] += v.y; q[1] += v.y * v.y;
-            s[2] += v.z; q[2] += v.z * v.z;
-            s[3] += v.w; q[3] += v.w * v.w;
+            float v0[8];
+            load_cat8<InT>(src0, C0, src1, C1, scale1, pix_base + p, c, v0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] += v0[e]; q[e] += v0[e] * v0[e]; }
         }
-        const int g0 = c / Cg, g3 = (c + 3) / Cg;
-        if (g0 == g3) {
-            atomicAdd(&s_acc[2 * g0], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
-            atomicAdd(&s_acc[2 * g0 + 1], (double)q[0] + (double)q[1] + (double)q[2] + (double)q[3]);
+        const int g0 = c / Cg, g7 = (c + 7) / Cg;
+        if (g0 == g7) {
+            double ds = 0.0, dq = 0.0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { ds += (double)s[e]; dq += (double)q[e]; }
+            atomicAdd(&s_acc[2 * g0], ds);
+            atomicAdd(&s_acc[2 * g0 + 1], dq);
         } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
+            for (int e = 0; e < 8; ++e) {
                 const int g = (c + e) / Cg;
                 atomicAdd(&s_acc[2 * g], (double)s[e]);
                 atomicAdd(&s_acc[2 * g + 1], (double)q[e]);
@@ -104,26 +129,45 @@ gn_stats_kernel(const float* __restrict__ src0, int C0, const float* __restrict_
 // (scale, shift) into ONE per-channel multiply-add   y = x * A[c] + Bc[c]   kept in shared memory (cost C, amortised
 // over kGnApplyPix * C elements), so the streaming loop is 2 x LDG.128 + 4 x LDS.128 + 8 FMA + 8 SiLU + 1 x STG.128.
 // grid = (ceil(HW / pix_per_cta), B)
-template <typename OutT, bool kFast>
+template <typename InT, typename OutT, bool kFast>
 __global__ void __launch_bounds__(256)
-gn_apply_silu_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1,
-                     int HW, int groups, const double* __restrict__ sums, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, const float* __restrict__ scale_shift, int ss_ld, float eps,
-                     OutT* __restrict__ out, int pix_per_cta) {
+gn_apply_silu_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ src1, int C1, float scale1,
+                     int HW, int groups, const double* __restrict__ stats0, int sb0, const double* __restrict__ stats1,
+                     int sb1, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ scale_shift, int ss_ld, float eps, OutT* __restrict__ out,
+                     int pix_per_cta) {
     extern __shared__ float s_ab[];   // A[C], Bc[C]
     __shared__ float s_mean[32], s_rstd[32];
     const int C = C0 + C1;
     const int Cg = C / groups;
     const int b = blockIdx.y;
     if (threadIdx.x < groups) {
+        const int g = threadIdx.x;
+        double su = 0.0, sq = 0.0;
+        if (sb0 == 0) {
+            // statistics were reduced per (image, group) over the whole virtual concat (mi_gn_stats)
+            su = stats0[((long long)b * groups + g) * 2];
+            sq = stats0[((long long)b * groups + g) * 2 + 1];
+        } else {
+            // per-source block statistics written by the producing conv epilogues: gather the blocks of this group
+            const int lo = g * Cg, hi = lo + Cg;
+            const int lo0 = min(lo, C0), hi0 = min(hi, C0);
+            for (int e = lo0 / sb0; e < hi0 / sb0; ++e) {
+                su += stats0[((long long)b * (C0 / sb0) + e) * 2];
+                sq += stats0[((long long)b * (C0 / sb0) + e) * 2 + 1];
+            }
+            const int lo1 = max(lo, C0) - C0, hi1 = max(hi, C0) - C0;
+            for (int e = lo1 / max(sb1, 1); e < hi1 / max(sb1, 1); ++e) {
+                su += (double)scale1 * stats1[((long long)b * (C1 / sb1) + e) * 2];
+                sq += (double)scale1 * (double)scale1 * stats1[((long long)b * (C1 / sb1) + e) * 2 + 1];
+            }
+        }
         const double n = (double)Cg * HW;
-        const double su = sums[((long long)b * groups + threadIdx.x) * 2];
-        const double sq = sums[((long long)b * groups + threadIdx.x) * 2 + 1];
         const double mean = su / n;
         double var = sq / n - mean * mean;
         if (var < 0) var = 0;
-        s_mean[threadIdx.x] = (float)mean;
-        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+        s_mean[g] = (float)mean;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
     float* sA = s_ab;
@@ -150,12 +194,12 @@ gn_apply_silu_kernel(const float* __restrict__ src0, int C0, const float* __rest
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int c = (idx % V8) << 3;
         const long long pix = pix_base + idx / V8;
-        const float4 x0 = load_cat4(src0, C0, src1, C1, scale1, pix, c);
-        const float4 x1 = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
+        float v[8];
+        load_cat8<InT>(src0, C0, src1, C1, scale1, pix, c, v);
         const float4 a0 = *reinterpret_cast<const float4*>(sA + c), a1 = *reinterpret_cast<const float4*>(sA + c + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(sB + c), b1 = *reinterpret_cast<const float4*>(sB + c + 4);
-        float v[8] = {fmaf(x0.x, a0.x, b0.x), fmaf(x0.y, a0.y, b0.y), fmaf(x0.z, a0.z, b0.z), fmaf(x0.w, a0.w, b0.w),
-                      fmaf(x1.x, a1.x, b1.x), fmaf(x1.y, a1.y, b1.y), fmaf(x1.z, a1.z, b1.z), fmaf(x1.w, a1.w, b1.w)};
+        v[0] = fmaf(v[0], a0.x, b0.x); v[1] = fmaf(v[1], a0.y, b0.y); v[2] = fmaf(v[2], a0.z, b0.z); v[3] = fmaf(v[3], a0.w, b0.w);
+        v[4] = fmaf(v[4], a1.x, b1.x); v[5] = fmaf(v[5], a1.y, b1.y); v[6] = fmaf(v[6], a1.z, b1.z); v[7] = fmaf(v[7], a1.w, b1.w);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             if constexpr (kFast) v[e] = __fdividef(v[e], 1.0f + __expf(-v[e]));
@@ -178,9 +222,9 @@ gn_apply_silu_kernel(const float* __restrict__ src0, int C0, const float* __rest
 //   mode 0: out[b][h][w][c]                     = in[b][h][w][c]
 //   mode 1: out[b][2h+i][2w+j][c]               = in[b][h][w][c]                  (nearest x2)
 //   mode 2: out[b][(h&1)*2+(w&1)][h/2][w/2][c]  = in[b][h][w][c]                  (phase split for 4x4 s2 convs)
-template <typename OutT>
+template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
-cast_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ src1, int C1, float scale1, int B, int H,
+cast_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ src1, int C1, float scale1, int B, int H,
             int W, int mode, OutT* __restrict__ out) {
     const int C = C0 + C1;
     const int V8 = C >> 3;
@@ -189,8 +233,10 @@ cast_kernel(const float* __restrict__ src0, int C0, const float* __restrict__ sr
     if (idx >= total) return;
     const int c = (int)(idx % V8) << 3;
     const long long pix = idx / V8;
-    const float4 a = load_cat4(src0, C0, src1, C1, scale1, pix, c);
-    const float4 d = load_cat4(src0, C0, src1, C1, scale1, pix, c + 4);
+    float v8[8];
+    load_cat8<InT>(src0, C0, src1, C1, scale1, pix, c, v8);
+    const float4 a = make_float4(v8[0], v8[1], v8[2], v8[3]);
+    const float4 d = make_float4(v8[4], v8[5], v8[6], v8[7]);
     const int w = (int)(pix % W);
     const int h = (int)((pix / W) % H);
     const long long b = pix / ((long long)W * H);
@@ -510,49 +556,71 @@ inline unsigned grid1d(long long total, int block) { return (unsigned)((total + 
 }  // namespace
 
 // ================================================================================================ launchers
-int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
+int gn_stats(const void* src0, int C0, const void* src1, int C1, float scale1, int in_is_f16, int B, int HW, int groups,
              double* sums, cudaStream_t st) {
     const int C = C0 + C1;
-    if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
+    if (C % 8 || C0 % 4 || groups < 1 || groups > 256 || C % groups) return -1;
+    if (in_is_f16 && (C0 % 8)) return -1;
     int chunk = 32768 / C;
     if (chunk < 4) chunk = 4;
     if (chunk > HW) chunk = HW;
     dim3 grid((HW + chunk - 1) / chunk, B);
-    gn_stats_kernel<<<grid, 256, 2 * groups * sizeof(double), st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, chunk);
+    const size_t smem = 2 * groups * sizeof(double);
+    if (in_is_f16)
+        gn_stats_kernel<__half><<<grid, 256, smem, st>>>((const __half*)src0, C0, (const __half*)src1, C1, scale1, HW,
+                                                         groups, sums, chunk);
+    else
+        gn_stats_kernel<float><<<grid, 256, smem, st>>>((const float*)src0, C0, (const float*)src1, C1, scale1, HW,
+                                                        groups, sums, chunk);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
-                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, int ss_ld,
-                  float eps, void* out, int out_is_f16, cudaStream_t st) {
+int gn_apply_silu(const void* src0, int C0, const void* src1, int C1, float scale1, int in_is_f16, int B, int HW,
+                  int groups, const double* stats0, int sb0, const double* stats1, int sb1, const float* gamma,
+                  const float* beta, const float* scale_shift, int ss_ld, float eps, void* out, int out_is_f16,
+                  cudaStream_t st) {
     const int C = C0 + C1;
     if (C % 8 || C0 % 4 || groups > 32 || C % groups) return -1;
+    if (in_is_f16 && (C0 % 8)) return -1;
     if (scale_shift && ss_ld < 2 * C) return -1;
+    const int Cg = C / groups;
+    if (sb0 > 0) {   // block statistics: every group boundary must fall on block boundaries of the source it lies in
+        if (C0 % sb0 || Cg % sb0 || (C1 && (sb1 <= 0 || C1 % sb1 || Cg % sb1 || !stats1))) return -1;
+        if (C1 && (C0 % sb1)) return -1;
+    }
     int pix = 16384 / C;               // ~16K elements per CTA
     if (pix < 1) pix = 1;
     if (pix > HW) pix = HW;
     const size_t smem = 2 * (size_t)C * sizeof(float);
     if (smem > 48 * 1024) return -1;
     dim3 grid((HW + pix - 1) / pix, B);
-    if (out_is_f16)
-        gn_apply_silu_kernel<__half, true><<<grid, 256, smem, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma,
-                                                                    beta, scale_shift, ss_ld, eps, (__half*)out, pix);
-    else
-        gn_apply_silu_kernel<float, false><<<grid, 256, smem, st>>>(src0, C0, src1, C1, scale1, HW, groups, sums, gamma,
-                                                                    beta, scale_shift, ss_ld, eps, (float*)out, pix);
+#define MI_GN_LAUNCH(IN, OUT, FAST)                                                                                 \
+    gn_apply_silu_kernel<IN, OUT, FAST><<<grid, 256, smem, st>>>((const IN*)src0, C0, (const IN*)src1, C1, scale1, HW, \
+                                                                 groups, stats0, sb0, stats1, sb1, gamma, beta,      \
+                                                                 scale_shift, ss_ld, eps, (OUT*)out, pix)
+    if (in_is_f16) {
+        if (out_is_f16) MI_GN_LAUNCH(__half, __half, true); else MI_GN_LAUNCH(__half, float, false);
+    } else {
+        if (out_is_f16) MI_GN_LAUNCH(float, __half, true); else MI_GN_LAUNCH(float, float, false);
+    }
+#undef MI_GN_LAUNCH
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
-int cast_act(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int H, int W, int mode,
-             void* out, int out_is_f16, cudaStream_t st) {
+int cast_act(const void* src0, int C0, const void* src1, int C1, float scale1, int in_is_f16, int B, int H, int W,
+             int mode, void* out, int out_is_f16, cudaStream_t st) {
     const int C = C0 + C1;
     if (C % 8 || C0 % 4 || mode < 0 || mode > 2) return -1;
+    if (in_is_f16 && (C0 % 8)) return -1;
     if (mode == 2 && ((H | W) & 1)) return -1;
     const unsigned grid = grid1d((long long)B * H * W * (C / 8), 256);
-    if (out_is_f16)
-        cast_kernel<__half><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, B, H, W, mode, (__half*)out);
-    else
-        cast_kernel<float><<<grid, 256, 0, st>>>(src0, C0, src1, C1, scale1, B, H, W, mode, (float*)out);
+    if (in_is_f16) {
+        if (out_is_f16) cast_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)src0, C0, (const __half*)src1, C1, scale1, B, H, W, mode, (__half*)out);
+        else cast_kernel<__half, float><<<grid, 256, 0, st>>>((const __half*)src0, C0, (const __half*)src1, C1, scale1, B, H, W, mode, (float*)out);
+    } else {
+        if (out_is_f16) cast_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)src0, C0, (const float*)src1, C1, scale1, B, H, W, mode, (__half*)out);
+        else cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src0, C0, (const float*)src1, C1, scale1, B, H, W, mode, (float*)out);
+    }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -8,13 +8,14 @@
 namespace mi {
 
 // elementwise.cu
-int gn_stats(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
+int gn_stats(const void* src0, int C0, const void* src1, int C1, float scale1, int in_is_f16, int B, int HW, int groups,
              double* sums, cudaStream_t st);
-int gn_apply_silu(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int HW, int groups,
-                  const double* sums, const float* gamma, const float* beta, const float* scale_shift, int ss_ld,
-                  float eps, void* out, int out_is_f16, cudaStream_t st);
-int cast_act(const float* src0, int C0, const float* src1, int C1, float scale1, int B, int H, int W, int mode,
-             void* out, int out_is_f16, cudaStream_t st);
+int gn_apply_silu(const void* src0, int C0, const void* src1, int C1, float scale1, int in_is_f16, int B, int HW,
+                  int groups, const double* stats0, int sb0, const double* stats1, int sb1, const float* gamma,
+                  const float* beta, const float* scale_shift, int ss_ld, float eps, void* out, int out_is_f16,
+                  cudaStream_t st);
+int cast_act(const void* src0, int C0, const void* src1, int C1, float scale1, int in_is_f16, int B, int H, int W,
+             int mode, void* out, int out_is_f16, cudaStream_t st);
 int ln_rows(const float* in, long long R, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
             const float* residual, float* out_f32, __half* out_f16, cudaStream_t st);
 int linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,

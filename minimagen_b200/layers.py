@@ -20,11 +20,67 @@ F16, F32, F64 = torch.float16, torch.float32, torch.float64
 
 
 # ------------------------------------------------------------------------------------------------ plumbing
+STATS_BLOCK = 16   # channels per GroupNorm block-statistics entry written by the conv epilogues
+
+
+class Act:
+    """One NHWC activation [B, H, W, C] of the U-Net: an fp32 copy (residual stream precision, only kept where an
+    identity residual or a LayerNorm needs it), an fp16 copy (tensor-core / GroupNorm-apply operand) -- at least one of
+    the two -- and optionally the GroupNorm block statistics [B, C/16, 2] (sum, sum of squares per 16 channels) that
+    the producing conv epilogue accumulated."""
+    __slots__ = ("f32", "f16", "stats")
+
+    def __init__(self, f32=None, f16=None, stats=None):
+        assert f32 is not None or f16 is not None
+        self.f32, self.f16, self.stats = f32, f16, stats
+
+    @property
+    def any(self):
+        return self.f32 if self.f32 is not None else self.f16
+
+    @property
+    def shape(self):
+        sh = self.any.shape
+        return (sh[0], sh[-3], sh[-2], sh[-1])
+
+    @property
+    def device(self):
+        return self.any.device
+
+    def need_f32(self):
+        if self.f32 is None:
+            B, H, W, C = self.shape
+            self.f32 = torch.empty((B, H, W, C), dtype=F32, device=self.device)
+            get_ops().cast_act(self.f16, C, None, 0, 1.0, B, H, W, 0, self.f32)
+        return self.f32
+
+    def need_f16(self):
+        if self.f16 is None:
+            B, H, W, C = self.shape
+            self.f16 = torch.empty((B, 1, H, W, C), dtype=F16, device=self.device)
+            get_ops().cast_act(self.f32, C, None, 0, 1.0, B, H, W, 0, self.f16)
+        return self.f16
+
+    def need_stats(self):
+        """Block statistics by a stand-alone pass (tensors not produced by a conv epilogue, e.g. attention outputs)."""
+        if self.stats is None:
+            B, H, W, C = self.shape
+            self.stats = torch.zeros((B, C // STATS_BLOCK, 2), dtype=F64, device=self.device)
+            get_ops().gn_stats(self.any, C, None, 0, 1.0, B, H * W, C // STATS_BLOCK, self.stats)
+        return self.stats
+
+
+def as_act(x):
+    return x if isinstance(x, (Act, Cat)) else Act(f32=x)
+
+
 class Cat:
-    """Virtual channel concatenation cat(a, b * scale) of two NHWC tensors (the up-path skip connection,
-    reference Unet.py:445).  Never materialised in fp32: the GroupNorm / cast kernels read both sources."""
+    """Virtual channel concatenation cat(a, b * scale) of two activations (the up-path skip connection, reference
+    Unet.py:445).  Never materialised in fp32: GroupNorm statistics combine the two sources' block statistics, the
+    GroupNorm-apply / cast kernels read both sources, and 1x1 / 3x3 convs read them as two TMA sources."""
 
     def __init__(self, a, b, scale):
+        a, b = as_act(a), as_act(b)
         assert a.shape[:3] == b.shape[:3]
         self.a, self.b, self.scale = a, b, float(scale)
 
@@ -37,11 +93,19 @@ class Cat:
         return self.a.device
 
 
-def _srcs(x):
-    """-> (src0, C0, src1, C1, scale1)"""
+def _srcs(x, prefer_f16):
+    """-> (src0, C0, src1, C1, scale1) with both sources in ONE dtype (fp16 if every source has it and it is preferred)"""
+    parts = [x.a, x.b] if isinstance(x, Cat) else [x]
+    use16 = prefer_f16 and all(p.f16 is not None for p in parts)
+    if not use16 and not all(p.f32 is not None for p in parts):
+        use16 = all(p.f16 is not None for p in parts)
+        if not use16:
+            for p in parts:
+                p.need_f32()
+    t = [(p.f16 if use16 else p.f32) for p in parts]
     if isinstance(x, Cat):
-        return x.a, x.a.shape[3], x.b, x.b.shape[3], x.scale
-    return x, x.shape[3], None, 0, 1.0
+        return t[0], x.a.shape[3], t[1], x.b.shape[3], x.scale
+    return t[0], x.shape[3], None, 0, 1.0
 
 
 def _no_grad_check(*tensors):
@@ -117,11 +181,12 @@ class LayerNorm(nn.Module):
         self.gamma = nn.Parameter(torch.ones(dim))
         self.register_buffer('beta', torch.zeros(dim))
 
-    def run_rows(self, rows_f32, R, C, residual=None, out_dtype=F32, pre_gelu=False):
-        out = torch.empty((R, C), dtype=out_dtype, device=rows_f32.device)
-        get_ops().ln_rows(rows_f32, R, C, self.gamma, self.beta, 1e-5, pre_gelu, residual,
-                          out if out_dtype == F32 else None, out if out_dtype == F16 else None)
-        return out
+    def run_rows(self, rows_f32, R, C, residual=None, out_dtype=F32, pre_gelu=False, both=False):
+        """-> fp32 or fp16 [R, C]; with `both` -> (fp32, fp16)."""
+        o32 = torch.empty((R, C), dtype=F32, device=rows_f32.device) if (both or out_dtype == F32) else None
+        o16 = torch.empty((R, C), dtype=F16, device=rows_f32.device) if (both or out_dtype == F16) else None
+        get_ops().ln_rows(rows_f32, R, C, self.gamma, self.beta, 1e-5, pre_gelu, residual, o32, o16)
+        return (o32, o16) if both else (o32 if out_dtype == F32 else o16)
 
     def forward(self, x):
         _no_grad_check(x, self.gamma)
@@ -184,14 +249,16 @@ class Parallel(nn.Module):
         self.fns = nn.ModuleList(fns)
 
     def run(self, x):
+        x = as_act(x)
         out = None
-        for fn in self.fns:
-            out = fn.run(x, residual=out)
+        for i, fn in enumerate(self.fns):
+            last = i == len(self.fns) - 1
+            out = fn.run(x, residual=out.f32 if exists(out) else None, f32=True, f16=last, stats=last)
         return out
 
     def forward(self, x):
         _no_grad_check(x)
-        return to_nchw(self.run(to_nhwc(x)))
+        return to_nchw(self.run(to_nhwc(x)).need_f32())
 
 
 class TokenView(nn.Module):
@@ -208,7 +275,9 @@ class TokenView(nn.Module):
 
     def forward(self, x, **kwargs):
         _no_grad_check(x)
-        return to_nchw(self.run(to_nhwc(x), **kwargs))
+        if "context" in kwargs and not isinstance(kwargs["context"], Context):
+            kwargs["context"] = Context(kwargs["context"])
+        return to_nchw(self.run(as_act(to_nhwc(x)), **kwargs).need_f32())
 
 
 # ------------------------------------------------------------------------------------------------ convolutions
@@ -238,25 +307,45 @@ class Conv2d(nn.Conv2d):
         kh, kw = self.kernel_size
         return kh * kw <= 16 and get_ops().igemm_supported(H, W, self.in_channels, self.out_channels)
 
-    def run_prepared(self, a, B, H, W, residual=None):
+    def run_prepared(self, a, B, H, W, residual=None, f32=True, f16=False, stats=False, a2=None, c_in1=0, wp=None):
         """Conv over an already prepared operand `a`:
-           tensor-core path: fp16 [B, P, H, W, C_in] (P = 4 phases for the stride-2 geometry), (H, W) = output grid;
+           tensor-core path: fp16 [B, P, H, W, C] (P = 4 phases for the stride-2 geometry), (H, W) = output grid;
+                             optional second source `a2` (virtual concat: channels [c_in1, C_in) come from it);
            direct path:      fp32 [B, H_in, W_in, C_in].
-        Returns fp32 NHWC [B, H, W, C_out] (bias added, `residual` fp32 NHWC added if given)."""
+        Returns an Act [B, H, W, C_out] (bias added, fp32 NHWC `residual` added) holding the requested copies; `stats`
+        additionally accumulates the output's GroupNorm block statistics in the epilogue (tensor-core path only)."""
         ops = get_ops()
         Cin, Cout = self.in_channels, self.out_channels
         kh, kw = self.kernel_size
-        out = torch.empty((B, H, W, Cout), dtype=F32, device=a.device)
         strides = (H * W * Cout, W * Cout, Cout)
+        dev = a.device
         if a.dtype == F16:
             mode = 1 if self._geom == 'down' else 0
-            ops.conv_igemm(a, B, H, W, Cin, 0, Cin, self._pack.get(self.weight), Cout, kh, kw, mode, self.bias,
-                           residual, out, None, strides)
-        else:
-            Hin, Win = a.shape[1], a.shape[2]
-            ops.conv_direct(a, B, Hin, Win, Cin, a.shape[3], self.weight.detach(), Cout, kh, kw, self.stride[0],
-                            self.padding[0], self.bias, residual, out, H, W, (*strides, 1))
-        return out
+            st = torch.zeros((B, Cout // STATS_BLOCK, 2), dtype=F64, device=dev) if (stats and Cout % 32 == 0) else None
+            if not f32 and not f16:
+                f32 = True
+            o32 = torch.empty((B, H, W, Cout), dtype=F32, device=dev) if f32 else None
+            o16 = torch.empty((B, 1, H, W, Cout), dtype=F16, device=dev) if f16 else None
+            lda = a.shape[-1]
+            ops.conv_igemm(a, B, H, W, lda, 0, Cin, wp if exists(wp) else self._pack.get(self.weight), Cout, kh, kw, mode,
+                           self.bias, residual, o32, o16, strides, act2=a2, lda2=a2.shape[-1] if exists(a2) else 0,
+                           c_in1=c_in1, out_stats=st)
+            return Act(o32, o16, st)
+        out = torch.empty((B, H, W, Cout), dtype=F32, device=dev)
+        Hin, Win = a.shape[1], a.shape[2]
+        ops.conv_direct(a, B, Hin, Win, Cin, a.shape[3], self.weight.detach(), Cout, kh, kw, self.stride[0],
+                        self.padding[0], self.bias, residual, out, H, W, (*strides, 1))
+        return Act(f32=out)
+
+    def _pack_cat(self, c0, scale):
+        """Packed weight whose input-channel columns >= c0 (of every tap) carry the skip-connection scale."""
+        key = (self.weight.data_ptr(), self.weight._version, c0, float(scale))
+        if getattr(self, "_cat_key", None) != key:
+            w = self.weight.detach().clone()
+            w[:, c0:] *= scale
+            self._cat_w = get_ops().pack_conv_weight(w)
+            self._cat_key = key
+        return self._cat_w
 
     def run_prepared_nchw(self, a, B, H, W, out=None):
         """Same-padding conv whose result is written straight to an NCHW fp32 tensor [B, C_out, H, W] (the U-Net's
@@ -284,10 +373,11 @@ class Conv2d(nn.Conv2d):
                             self.bias, None, out, H, W, (Cout * H * W, W, 1, H * W))
         return out
 
-    def run(self, x, residual=None, upsample=False):
-        """x: NHWC fp32 tensor or Cat.  `upsample` applies nn.Upsample(scale_factor=2, 'nearest') first (layers.py:513)."""
+    def run(self, x, residual=None, upsample=False, f32=True, f16=False, stats=False):
+        """x: Act / Cat (or a bare fp32 NHWC tensor).  `upsample` applies nn.Upsample(scale_factor=2, 'nearest') first
+        (layers.py:513).  Returns an Act."""
         ops = get_ops()
-        s0, C0, s1, C1, sc = _srcs(x)
+        x = as_act(x)
         B, H, W, C = x.shape
         assert C == self.in_channels, (C, self.in_channels)
         geom = self._geom
@@ -298,30 +388,32 @@ class Conv2d(nn.Conv2d):
             Ho, Wo = H // 2, W // 2
         else:
             Ho, Wo = H, W
+        kw = dict(residual=residual, f32=f32, f16=f16, stats=stats)
         if self.tc_ok(Ho, Wo):
-            if upsample:
-                a = torch.empty((B, 1, Ho, Wo, C), dtype=F16, device=x.device)
-                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 1, a)
-            elif geom == 'down':
-                a = torch.empty((B, 4, Ho, Wo, C), dtype=F16, device=x.device)
-                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 2, a)
-            else:
-                a = torch.empty((B, 1, H, W, C), dtype=F16, device=x.device)
-                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 0, a)
+            if not upsample and geom == 'same':
+                if isinstance(x, Cat):
+                    c0 = x.a.shape[3]
+                    if c0 % 64 == 0:      # two TMA sources, skip scale folded into the packed weight
+                        return self.run_prepared(x.a.need_f16(), B, H, W, a2=x.b.need_f16(), c_in1=c0,
+                                                 wp=self._pack_cat(c0, x.scale), **kw)
+                else:
+                    return self.run_prepared(x.need_f16(), B, H, W, **kw)
+            s0, C0, s1, C1, sc = _srcs(x, True)
+            mode = 1 if upsample else (2 if geom == 'down' else 0)
+            a = torch.empty((B, 4 if mode == 2 else 1, Ho, Wo, C), dtype=F16, device=x.device)
+            ops.cast_act(s0, C0, s1, C1, sc, B, H, W, mode, a)
+            return self.run_prepared(a, B, Ho, Wo, **kw)
+        if upsample or isinstance(x, Cat):
+            s0, C0, s1, C1, sc = _srcs(x, False)
+            a = torch.empty((B, Ho if upsample else H, Wo if upsample else W, C), dtype=F32, device=x.device)
+            ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 1 if upsample else 0, a)
         else:
-            if upsample:
-                a = torch.empty((B, Ho, Wo, C), dtype=F32, device=x.device)
-                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 1, a)
-            elif isinstance(x, Cat):
-                a = torch.empty((B, H, W, C), dtype=F32, device=x.device)
-                ops.cast_act(s0, C0, s1, C1, sc, B, H, W, 0, a)
-            else:
-                a = x
-        return self.run_prepared(a, B, Ho, Wo, residual)
+            a = x.need_f32()
+        return self.run_prepared(a, B, Ho, Wo, **kw)
 
     def forward(self, x):
         _no_grad_check(x, self.weight)
-        return to_nchw(self.run(to_nhwc(x)))
+        return to_nchw(self.run(to_nhwc(x)).need_f32())
 
 
 def Downsample(dim, dim_out=None):
@@ -334,11 +426,12 @@ class _UpsampleSeq(nn.Sequential):
     lowered as ONE cast kernel (nearest x2 fused into the operand preparation) + one conv."""
 
     def run(self, x):
-        return self[1].run(x, upsample=True)
+        # consumed only through the next up block's virtual concat: fp16 + statistics suffice on the tensor-core path
+        return self[1].run(x, upsample=True, f32=False, f16=True, stats=True)
 
     def forward(self, x):
         _no_grad_check(x)
-        return to_nchw(self.run(to_nhwc(x)))
+        return to_nchw(self.run(to_nhwc(x)).need_f32())
 
 
 def Upsample(dim, dim_out=None):
@@ -399,12 +492,15 @@ class CrossEmbedLayer(nn.Module):
             wp, bias = self._stem_weights()
             C = self.dim_out
             out = torch.empty((B, H, W, C), dtype=F32, device=x.device)
-            ops.conv_igemm(a, B, H, W, 128, 0, 128, wp, C, 15, 1, 0, bias, None, out, None, (H * W * C, W * C, C))
-            return out
+            out16 = torch.empty((B, 1, H, W, C), dtype=F16, device=x.device)
+            st = torch.zeros((B, C // STATS_BLOCK, 2), dtype=F64, device=x.device) if C % 32 == 0 else None
+            ops.conv_igemm(a, B, H, W, 128, 0, 128, wp, C, 15, 1, 0, bias, None, out, out16, (H * W * C, W * C, C),
+                           out_stats=st)
+            return Act(out, out16, st)
         cp = (self.dim_in + 3) // 4 * 4
         x_pad = torch.empty((B, H, W, cp), dtype=F32, device=x.device)
         ops.nchw_to_nhwc(x, Cx, lowres, Cl, B, H * W, cp, x_pad)
-        return self.run_padded(x_pad, B, H, W)
+        return Act(f32=self.run_padded(x_pad, B, H, W))
 
     def run_padded(self, x_pad, B, H, W):
         """x_pad: fp32 NHWC [B, H, W, ld] holding dim_in channels (zero padded to ld). stride must be 1."""
@@ -422,7 +518,7 @@ class CrossEmbedLayer(nn.Module):
 
     def forward(self, x):
         _no_grad_check(x)
-        return to_nchw(self.run_stem(x))
+        return to_nchw(self.run_stem(x).need_f32())
 
 
 # ------------------------------------------------------------------------------------------------ ResNet
@@ -436,20 +532,32 @@ class Block(nn.Module):
         self.activation = nn.SiLU()
         self.project = Conv2d(dim, dim_out, 3, padding=1)
 
-    def run(self, x, scale_shift=None, residual=None):
+    def run(self, x, scale_shift=None, residual=None, f32=True, f16=False, stats=False):
+        """x: Act / Cat.  GroupNorm statistics come from the producers' epilogue block statistics when every source has
+        (or can cheaply get) them and the groups are unions of 16-channel blocks; otherwise from one mi_gn_stats pass."""
         ops = get_ops()
-        s0, C0, s1, C1, sc = _srcs(x)
+        x = as_act(x)
         B, H, W, C = x.shape
         gn = self.groupnorm
         assert isinstance(gn, nn.GroupNorm), "Block(norm=False) is never instantiated by the U-Net"
         G = gn.num_groups
-        sums = torch.zeros((B, G, 2), dtype=F64, device=x.device)
-        ops.gn_stats(s0, C0, s1, C1, sc, B, H * W, G, sums)
+        Cg = C // G
         tc = self.project.tc_ok(H, W)
+        parts = [x.a, x.b] if isinstance(x, Cat) else [x]
+        block_mode = tc and Cg % STATS_BLOCK == 0 and all(p.shape[3] % STATS_BLOCK == 0 for p in parts)
+        s0, C0, s1, C1, sc = _srcs(x, tc)
+        if block_mode:
+            st0, sb0 = parts[0].need_stats(), STATS_BLOCK
+            st1, sb1 = (parts[1].need_stats(), STATS_BLOCK) if len(parts) > 1 else (None, 0)
+        else:
+            st0 = torch.zeros((B, G, 2), dtype=F64, device=x.device)
+            ops.gn_stats(s0, C0, s1, C1, sc, B, H * W, G, st0)
+            sb0, st1, sb1 = 0, None, 0
         a = torch.empty((B, 1, H, W, C) if tc else (B, H, W, C), dtype=F16 if tc else F32, device=x.device)
         ss_ld = scale_shift.stride(0) if exists(scale_shift) else 0
-        ops.gn_apply_silu(s0, C0, s1, C1, sc, B, H * W, G, sums, gn.weight, gn.bias, scale_shift, ss_ld, gn.eps, a)
-        return self.project.run_prepared(a, B, H, W, residual)
+        ops.gn_apply_silu(s0, C0, s1, C1, sc, B, H * W, G, st0, sb0, st1, sb1, gn.weight, gn.bias, scale_shift, ss_ld,
+                          gn.eps, a)
+        return self.project.run_prepared(a, B, H, W, residual, f32=f32, f16=f16, stats=stats)
 
     def forward(self, x, scale_shift=None):
         _no_grad_check(x)
@@ -457,7 +565,7 @@ class Block(nn.Module):
         if exists(scale_shift):
             scale, shift = scale_shift
             ss = torch.cat((scale.reshape(x.shape[0], -1), shift.reshape(x.shape[0], -1)), dim=1).contiguous()
-        return to_nchw(self.run(to_nhwc(x), ss))
+        return to_nchw(self.run(to_nhwc(x), ss).need_f32())
 
 
 class ResnetBlock(nn.Module):
@@ -475,8 +583,9 @@ class ResnetBlock(nn.Module):
         self.block2 = Block(dim_out, dim_out, groups=groups)
         self.res_conv = Conv2d(dim, dim_out, 1) if dim != dim_out else Identity()
 
-    def run(self, x, time_emb=None, cond=None, scale_shift=None):
-        """x: NHWC fp32 or Cat; time_emb: [B, time_cond_dim] fp32; cond: conditioning context (see CrossAttention.run).
+    def run(self, x, time_emb=None, cond=None, scale_shift=None, out_f32=True):
+        """x: Act / Cat; returns an Act (fp32 copy only if `out_f32`, needed when the consumer adds it as an identity
+        residual or runs a LayerNorm on it); time_emb: [B, time_cond_dim] fp32; cond: conditioning context (see CrossAttention.run).
         `scale_shift`: this block's time_mlp output [B, 2*dim_out] if the caller already computed it (the U-Net batches
         the time_mlps of all its ResnetBlocks into one GEMM per step); otherwise it is computed here from `time_emb`."""
         ops = get_ops()
@@ -487,21 +596,25 @@ class ResnetBlock(nn.Module):
             # SiLU -> Linear (layers.py:396-399); chunk(2, dim=1) = (scale, shift) is read in place by gn_apply
             ops.linear_f32(time_emb, B, lin.in_features, lin.weight, lin.bias, lin.out_features, 1, 0, None,
                            scale_shift, None)
-        h = self.block1.run(x)
-        if exists(self.cross_attn):
+        x = as_act(x)
+        tc = self.block1.project.tc_ok(x.shape[1], x.shape[2]) and self.block2.project.tc_ok(x.shape[1], x.shape[2])
+        attn = exists(self.cross_attn)
+        # conv1's output feeds only GroupNorm 2 (fp16 + epilogue statistics) unless cross-attention reads it (fp32)
+        h = self.block1.run(x, f32=attn or not tc, f16=tc and not attn, stats=tc and not attn)
+        if attn:
             assert exists(cond)
-            h = self.cross_attn.run(h, context=cond)      # returns attn(h) + h
+            h = self.cross_attn.run(h, context=cond)      # attn(h) + h
         if isinstance(self.res_conv, Identity):
             assert not isinstance(x, Cat)
-            res = x
+            res = x.need_f32()
         else:
-            res = self.res_conv.run(x)
-        return self.block2.run(h, scale_shift, residual=res)
+            res = self.res_conv.run(x, f32=True).f32
+        return self.block2.run(h, scale_shift, residual=res, f32=out_f32 or not tc, f16=tc, stats=tc)
 
     def forward(self, x, time_emb=None, cond=None):
         _no_grad_check(x)
         ctx = Context(cond) if exists(cond) else None
-        return to_nchw(self.run(to_nhwc(x), time_emb, ctx))
+        return to_nchw(self.run(to_nhwc(x), time_emb, ctx).need_f32())
 
 
 # ------------------------------------------------------------------------------------------------ attention
@@ -544,11 +657,12 @@ class CrossAttention(nn.Module):
         """x: NHWC [B, H, W, C] (tokens = pixels); context: Context; mask: uint8 [B, m] or None.  Returns attn(x) + x
         when `residual` (the `+ h` of ResnetBlock.forward, layers.py:435, is fused into the output LayerNorm kernel)."""
         ops = get_ops()
+        x = as_act(x)
         B, H, W, C = x.shape
         n = H * W
         m, D = context.f32.shape[1], context.f32.shape[2]
         inner = self.heads * 64
-        rows = x.reshape(B * n, C)
+        rows = x.need_f32().reshape(B * n, C)
         assert isinstance(self.norm_context, Identity)
         # q projection
         tc_q = _tc_linear_ok(B * n, C, inner)
@@ -568,8 +682,8 @@ class CrossAttention(nn.Module):
             y = _linear_rows(None, o, B * n, inner, self.to_out[0].weight, self._po, C)
         else:
             y = _linear_rows(o.float(), None, B * n, inner, self.to_out[0].weight, self._po, C)
-        out = self.to_out[1].run_rows(y, B * n, C, residual=rows if residual else None)
-        return out.reshape(B, H, W, C)
+        o32, o16 = self.to_out[1].run_rows(y, B * n, C, residual=rows if residual else None, both=True)
+        return Act(o32.reshape(B, H, W, C), o16.reshape(B, 1, H, W, C))
 
     def forward(self, x, context, mask=None):
         """Reference calling convention: x [b, n, dim], context [b, m, context_dim] -> [b, n, dim] (no residual)."""
@@ -577,7 +691,7 @@ class CrossAttention(nn.Module):
         B, n, C = x.shape
         xx = x.contiguous().reshape(B, 1, n, C)
         mk = mask.to(torch.uint8).contiguous() if exists(mask) else None
-        return self.run(xx, Context(context), mk, residual=False).reshape(B, n, C)
+        return self.run(xx, Context(context), mk, residual=False).f32.reshape(B, n, C)
 
 
 class Attention(nn.Module):
@@ -604,10 +718,11 @@ class Attention(nn.Module):
         mid Residual(Attention), Unet.py:273)."""
         assert context is None
         ops = get_ops()
+        x = as_act(x)
         B, H, W, C = x.shape
         n = H * W
         inner = self.heads * 64
-        rows = x.reshape(B * n, C)
+        rows = x.need_f32().reshape(B * n, C)
         tc = _tc_linear_ok(B * n, C, inner) and _tc_linear_ok(B * n, C, 128)
         xn = self.norm.run_rows(rows, B * n, C, out_dtype=F16 if tc else F32)
         q = _linear_rows(None if tc else xn, xn if tc else None, B * n, C, self.to_q.weight, self._pq, inner,
@@ -621,15 +736,15 @@ class Attention(nn.Module):
             y = _linear_rows(None, o, B * n, inner, self.to_out[0].weight, self._po, C)
         else:
             y = _linear_rows(o.float(), None, B * n, inner, self.to_out[0].weight, self._po, C)
-        out = self.to_out[1].run_rows(y, B * n, C, residual=rows if residual else None)
-        return out.reshape(B, H, W, C)
+        o32, o16 = self.to_out[1].run_rows(y, B * n, C, residual=rows if residual else None, both=True)
+        return Act(o32.reshape(B, H, W, C), o16.reshape(B, 1, H, W, C))
 
     def forward(self, x, context=None, mask=None, attn_bias=None):
         _no_grad_check(x)
         assert context is None and attn_bias is None
         B, n, C = x.shape
         mk = mask.to(torch.uint8).contiguous() if exists(mask) else None
-        return self.run(x.contiguous().reshape(B, 1, n, C), mask=mk, residual=False).reshape(B, n, C)
+        return self.run(x.contiguous().reshape(B, 1, n, C), mask=mk, residual=False).f32.reshape(B, n, C)
 
 
 class _ResidualAttention(Residual):
@@ -659,20 +774,23 @@ class TransformerBlock(nn.Module):
         self.ff = ChanFeedForward(dim=dim, mult=ff_mult)
 
     def run(self, x, context=None):
+        x = as_act(x)
         B, H, W, C = x.shape
         R = B * H * W
         x = self.attn.run(x, residual=True)
         ln1, conv1, _, ln2, conv2 = self.ff
         hid = conv1.out_channels
-        rows = x.reshape(R, C)
+        rows = x.f32.reshape(R, C)
         tc1 = _tc_linear_ok(R, C, hid)
         y = ln1.run_rows(rows, R, C, out_dtype=F16 if tc1 else F32)
         h = _linear_rows(None if tc1 else y, y if tc1 else None, R, C, conv1.weight, conv1._pack, hid)
-        tc2 = _tc_linear_ok(R, hid, C)
+        tc2 = _tc_linear_ok(R, hid, C) and conv2.tc_ok(H, W)
         z = ln2.run_rows(h, R, hid, out_dtype=F16 if tc2 else F32, pre_gelu=True)       # GELU(erf) -> ChanLayerNorm
-        out = _linear_rows(None if tc2 else z, z if tc2 else None, R, hid, conv2.weight, conv2._pack, C, residual=rows)
-        return out.reshape(B, H, W, C)
+        if tc2:   # 1x1 conv in image geometry: fp32 + fp16 copies and GroupNorm statistics from the epilogue
+            return conv2.run_prepared(z.reshape(B, 1, H, W, hid), B, H, W, residual=x.f32, f32=True, f16=True, stats=True)
+        out = _linear_rows(z, None, R, hid, conv2.weight, conv2._pack, C, residual=rows)
+        return Act(f32=out.reshape(B, H, W, C))
 
     def forward(self, x, context=None):
         _no_grad_check(x)
-        return to_nchw(self.run(to_nhwc(x)))
+        return to_nchw(self.run(to_nhwc(x)).need_f32())

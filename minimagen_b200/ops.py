@@ -45,13 +45,16 @@ class NativeOps:
 
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
-                   out_strides, block_n=0, out_sc=1, n_valid=0):
-        _chk(act, F16, "act"); _chk(wp, F16, "wp"); _chk(bias, F32, "bias"); _chk_out(residual, F32, "residual")
-        _chk_out(out_f32, F32, "out_f32"); _chk_out(out_f16, F16, "out_f16")
+                   out_strides, block_n=0, out_sc=1, n_valid=0, act2=None, lda2=0, c_off2=0, c_in1=0, out_stats=None):
+        """act2 (optional): second fp16 activation tensor; channels [c_in1, c_in) of every tap are read from it.
+        out_stats (optional): zeroed fp64 [B, c_out/16, 2] receiving per-block (sum, sum of squares) of the output."""
+        _chk(act, F16, "act"); _chk(act2, F16, "act2"); _chk(wp, F16, "wp"); _chk(bias, F32, "bias")
+        _chk_out(residual, F32, "residual"); _chk_out(out_f32, F32, "out_f32"); _chk_out(out_f16, F16, "out_f16")
+        _chk(out_stats, F64, "out_stats")
         sb, sh, sw = out_strides
-        N.call("mi_conv2d_igemm_f16", N.ptr(act), B, H, W, lda, c_off, c_in, N.ptr(wp), c_out, kh, kw, mode,
-               N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16), sb, sh, sw, out_sc, n_valid, block_n, None,
-               N.stream())
+        N.call("mi_conv2d_igemm_f16", N.ptr(act), B, H, W, lda, c_off, c_in, N.ptr(act2), lda2, c_off2, c_in1,
+               N.ptr(wp), c_out, kh, kw, mode, N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16),
+               N.ptr(out_stats), sb, sh, sw, out_sc, n_valid, block_n, None, N.stream())
 
     def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
                     out_strides):
@@ -64,21 +67,26 @@ class NativeOps:
 
     # ---------------------------------------------------------------- normalisation / casts
     def gn_stats(self, src0, c0, src1, c1, scale1, B, hw, groups, sums):
-        _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(sums, F64, "sums")
-        N.call("mi_gn_stats", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, hw, groups, N.ptr(sums), N.stream())
+        _chk(src0, src0.dtype, "src0"); _chk(src1, src0.dtype, "src1"); _chk(sums, F64, "sums")
+        N.call("mi_gn_stats", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), int(src0.dtype == F16), B, hw, groups,
+               N.ptr(sums), N.stream())
 
-    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, ss_ld, eps, out):
-        """scale_shift: fp32 view whose row b starts at data_ptr + b*ss_ld and holds [scale(C) | shift(C)]."""
-        _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(sums, F64, "sums"); _chk(gamma, F32, "gamma")
-        _chk(beta, F32, "beta"); _chk_out(scale_shift, F32, "scale_shift")
-        N.call("mi_gn_apply_silu", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, hw, groups, N.ptr(sums),
-               N.ptr(gamma), N.ptr(beta), N.ptr(scale_shift), int(ss_ld), float(eps), N.ptr(out),
-               int(out.dtype == F16), N.stream())
+    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, stats0, sb0, stats1, sb1, gamma, beta,
+                      scale_shift, ss_ld, eps, out):
+        """src0/src1: both fp32 or both fp16.  sb0 == 0: stats0 = [B, groups, 2] group sums over the concat (gn_stats);
+        sb0 > 0: per-source block sums [B, c/sb, 2].  scale_shift: fp32 view, row b at data_ptr + b*ss_ld = [scale | shift]."""
+        in16 = src0.dtype == F16
+        _chk(src0, src0.dtype, "src0"); _chk(src1, src0.dtype, "src1"); _chk(stats0, F64, "stats0")
+        _chk(stats1, F64, "stats1"); _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta")
+        _chk_out(scale_shift, F32, "scale_shift")
+        N.call("mi_gn_apply_silu", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), int(in16), B, hw, groups,
+               N.ptr(stats0), int(sb0), N.ptr(stats1), int(sb1), N.ptr(gamma), N.ptr(beta), N.ptr(scale_shift),
+               int(ss_ld), float(eps), N.ptr(out), int(out.dtype == F16), N.stream())
 
     def cast_act(self, src0, c0, src1, c1, scale1, B, H, W, mode, out):
-        _chk(src0, F32, "src0"); _chk(src1, F32, "src1")
-        N.call("mi_cast_act", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, H, W, mode, N.ptr(out),
-               int(out.dtype == F16), N.stream())
+        _chk(src0, src0.dtype, "src0"); _chk(src1, src0.dtype, "src1")
+        N.call("mi_cast_act", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), int(src0.dtype == F16), B, H, W, mode,
+               N.ptr(out), int(out.dtype == F16), N.stream())
 
     def ln_rows(self, inp, rows, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16):
         _chk(inp, F32, "inp"); _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta"); _chk(residual, F32, "residual")

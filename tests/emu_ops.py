@@ -58,11 +58,15 @@ class EmuOps:
 
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
-                   out_strides, block_n=0, out_sc=1, n_valid=0):
+                   out_strides, block_n=0, out_sc=1, n_valid=0, act2=None, lda2=0, c_off2=0, c_in1=0, out_stats=None):
         self._log("conv_igemm")
         assert act.dtype == F16 and wp.dtype == F16
         P = 4 if mode == 1 else 1
-        a = act.reshape(B, P, H, W, lda)[..., c_off:c_off + c_in].float()
+        if act2 is None:
+            a = act.reshape(B, P, H, W, lda)[..., c_off:c_off + c_in].float()
+        else:
+            a = torch.cat((act.reshape(B, P, H, W, lda)[..., c_off:c_off + c_in1].float(),
+                           act2.reshape(B, P, H, W, lda2)[..., c_off2:c_off2 + (c_in - c_in1)].float()), dim=-1)
         w = wp.float().reshape(c_out, kh, kw, c_in).permute(0, 3, 1, 2)           # OIHW
         if mode == 0:
             y = F.conv2d(a[:, 0].permute(0, 3, 1, 2), w, None, stride=1, padding=(kh // 2, kw // 2))
@@ -80,6 +84,10 @@ class EmuOps:
         if residual is not None:
             assert out_sc == 1
             y = y + _strided(residual, (B, H, W, c_out), (sb, sh, sw, 1))
+        if out_stats is not None:
+            yb = y.double().reshape(B, H * W, c_out // 16, 16)
+            out_stats[:, :, 0] += yb.sum(dim=(1, 3))
+            out_stats[:, :, 1] += (yb * yb).sum(dim=(1, 3))
         y = y[..., :nv]
         if out_f32 is not None:
             _strided(out_f32, (B, H, W, nv), (sb, sh, sw, out_sc)).copy_(y)
@@ -101,17 +109,30 @@ class EmuOps:
     # ---------------------------------------------------------------- normalisation / casts
     def gn_stats(self, src0, c0, src1, c1, scale1, B, hw, groups, sums):
         self._log("gn_stats")
-        x = _cat_src(src0, c0, src1, c1, scale1, (B, hw)).double()
+        x = _cat_src(src0.float(), c0, src1.float() if src1 is not None else None, c1, scale1, (B, hw)).double()
         C = c0 + c1
         xg = x.reshape(B, hw, groups, C // groups)
         sums[:, :, 0] += xg.sum(dim=(1, 3))
         sums[:, :, 1] += (xg * xg).sum(dim=(1, 3))
 
-    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, sums, gamma, beta, scale_shift, ss_ld, eps, out):
+    def gn_apply_silu(self, src0, c0, src1, c1, scale1, B, hw, groups, stats0, sb0, stats1, sb1, gamma, beta,
+                      scale_shift, ss_ld, eps, out):
         self._log("gn_apply_silu")
-        x = _cat_src(src0, c0, src1, c1, scale1, (B, hw))
+        x = _cat_src(src0.float(), c0, src1.float() if src1 is not None else None, c1, scale1, (B, hw))
         C = c0 + c1
         n = (C // groups) * hw
+        if sb0 == 0:
+            sums = stats0
+        else:
+            # per-channel-block sums of both sources -> per-channel-range sums of the concat -> groups
+            parts = [stats0.reshape(B, c0 // sb0, 1, 2).expand(B, c0 // sb0, sb0, 2).reshape(B, c0, 2) / sb0]
+            if c1:
+                s1 = stats1.clone().reshape(B, c1 // sb1, 2)
+                s1[..., 0] *= scale1
+                s1[..., 1] *= scale1 * scale1
+                parts.append(s1.reshape(B, c1 // sb1, 1, 2).expand(B, c1 // sb1, sb1, 2).reshape(B, c1, 2) / sb1)
+            per_ch = torch.cat(parts, dim=1)                               # [B, C, 2] (block sums spread evenly)
+            sums = per_ch.reshape(B, groups, C // groups, 2).sum(dim=2)
         mean = sums[:, :, 0] / n
         var = (sums[:, :, 1] / n - mean * mean).clamp(min=0)
         rstd = 1.0 / torch.sqrt(var + eps)
@@ -126,7 +147,7 @@ class EmuOps:
 
     def cast_act(self, src0, c0, src1, c1, scale1, B, H, W, mode, out):
         self._log("cast_act")
-        x = _cat_src(src0, c0, src1, c1, scale1, (B, H, W))
+        x = _cat_src(src0.float(), c0, src1.float() if src1 is not None else None, c1, scale1, (B, H, W))
         C = c0 + c1
         if mode == 0:
             out.reshape(B, H, W, C).copy_(x.to(out.dtype))

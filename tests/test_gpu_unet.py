@@ -133,3 +133,27 @@ def test_batch_streams_are_exact(native):
         b = u(x, t, **kw)
         torch.cuda.synchronize()
     assert rel_l2(b, a) < 1e-6
+
+
+def test_cfg3_structure_error_budget(native):
+    """The BASELINE cfg-3 network itself (Super.defaults, lowres_cond, t5-base width; 715.8 M parameters) at a reduced
+    64x64 / batch-2 input so that the CPU oracle finishes in seconds: rel-L2 of the predicted noise vs the fp32 oracle.
+    This is the figure the north star bounds by 1e-3 for the fp32 reference; tensor-core operands are fp16."""
+    from minimagen_b200.Unet import Unet, Super
+    cfg = dict(Super.defaults, lowres_cond=True, text_embed_dim=768)
+    torch.manual_seed(0)
+    u = Unet(**cfg).eval()
+    sd = {k: v for k, v in u.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    b, s = 2, 64
+    x = torch.randn(b, 3, s, s, generator=g)
+    kw = dict(text_embeds=torch.randn(b, 20, 768, generator=g), text_mask=torch.ones(b, 20, dtype=torch.bool),
+              lowres_cond_img=torch.randn(b, 3, s, s, generator=g), lowres_noise_times=torch.full((b,), 200))
+    t = torch.tensor([500, 37])
+    with torch.no_grad():
+        ref_out = R.unet_forward(sd, cfg, x, t, **kw)
+        u = u.cuda()
+        out = u(x.cuda(), t.cuda(), **{k: v.cuda() for k, v in kw.items()})
+    err = rel_l2(out, ref_out)
+    print(f"cfg3 structure @64x64 b=2: rel-L2 = {err:.3e}")
+    assert err < 2e-3
