@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--batch-streams", type=int, default=None, help="concurrent batch slices inside Unet.forward")
+    ap.add_argument("--gn-f16", action="store_true", help="GroupNorm inputs in fp16 (faster, 1.05e-3 instead of 9e-4 rel-L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -202,10 +203,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from minimagen_b200 import _native
+    from minimagen_b200 import _native, layers
     from minimagen_b200.Imagen import Imagen
     from minimagen_b200.Unet import Unet
     _native.load()
+    if args.gn_f16:
+        layers.GN_INPUT_F32 = False
 
     torch.manual_seed(0)
     with torch.device(dev):
@@ -361,7 +364,7 @@ def main():
                      "kernel_share_of_step": conv_ms / (ms / args.steps) if ms else None, "peak_source": peak_src,
                      "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peak_tf},
         "clocks": clocks, "cuda_graph": use_graph, "launches_per_step": launches_per_step,
-        "batch_streams": unet.batch_streams,
+        "batch_streams": unet.batch_streams, "gn_input": "f32" if layers.GN_INPUT_F32 else "f16",
     }
     if not args.no_cpu_baseline:
         sd = unet.state_dict()

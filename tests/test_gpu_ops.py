@@ -116,7 +116,7 @@ def test_stem_tensor_core_path(native, Ca, Cb, dim):
     assert layer.stem_tc_ok(H, W)
     with torch.no_grad():
         out = layer.run_stem(x.cuda(), _cu(lr))
-    assert rel_l2(out.permute(0, 3, 1, 2), ref) < 1e-3          # fp16 operands, one layer
+    assert rel_l2(out.need_f32().permute(0, 3, 1, 2), ref) < 1e-3          # fp16 operands, one layer
 
 
 def test_silu(native):
@@ -164,10 +164,14 @@ def test_conv_direct(native, case):
 @pytest.mark.parametrize("B,HW,C0,C1,groups", [(2, 256, 128, 0, 8), (2, 1024, 256, 128, 8), (3, 100, 8, 0, 8),
                                                (2, 64, 16, 8, 8), (1, 4096, 2048, 0, 8), (2, 256, 32, 0, 8)])
 @pytest.mark.parametrize("f16", [True, False])
-def test_groupnorm_silu(native, B, HW, C0, C1, groups, f16):
+@pytest.mark.parametrize("in16", [False, True])
+def test_groupnorm_silu(native, B, HW, C0, C1, groups, f16, in16):
+    if in16 and (C0 % 8 or (C1 and C1 % 8)):
+        pytest.skip("fp16 sources need 8-channel alignment")
     C = C0 + C1
-    s0 = _rand(B, HW, C0, seed=11) * 2 + 0.5
-    s1 = _rand(B, HW, C1, seed=12) if C1 else None
+    dt_in = F16 if in16 else F32
+    s0 = (_rand(B, HW, C0, seed=11) * 2 + 0.5).to(dt_in)
+    s1 = _rand(B, HW, C1, seed=12).to(dt_in) if C1 else None
     gamma, beta = _rand(C, seed=13), _rand(C, seed=14)
     ss = _rand(B, 2 * C, seed=15, scale=0.3)
     sums_e = torch.zeros(B, groups, 2, dtype=F64)
@@ -176,29 +180,86 @@ def test_groupnorm_silu(native, B, HW, C0, C1, groups, f16):
     native.gn_stats(s0.cuda(), C0, _cu(s1), C1, 0.7071, B, HW, groups, sums_n)
     assert rel_l2(sums_n, sums_e) < 1e-6
     dt = F16 if f16 else F32
-    o_e = torch.zeros(B, HW, C, dtype=dt)
     big = torch.zeros(B, 2 * C + 24)
     big[:, 8:8 + 2 * C] = ss
     ssv_e = big[:, 8:8 + 2 * C]                 # a column slice of a wider buffer (row pitch != 2C)
-    EMU.gn_apply_silu(s0, C0, s1, C1, 0.7071, B, HW, groups, sums_e, gamma, beta, ssv_e, big.stride(0), 1e-5, o_e)
+    o_e = torch.zeros(B, HW, C, dtype=dt)
+    EMU.gn_apply_silu(s0, C0, s1, C1, 0.7071, B, HW, groups, sums_e, 0, None, 0, gamma, beta, ssv_e, big.stride(0),
+                      1e-5, o_e)
     o_n = torch.zeros(B, HW, C, dtype=dt, device="cuda")
     big_n = big.cuda()
-    native.gn_apply_silu(s0.cuda(), C0, _cu(s1), C1, 0.7071, B, HW, groups, sums_n, gamma.cuda(), beta.cuda(),
-                         big_n[:, 8:8 + 2 * C], big_n.stride(0), 1e-5, o_n)
+    native.gn_apply_silu(s0.cuda(), C0, _cu(s1), C1, 0.7071, B, HW, groups, sums_n, 0, None, 0, gamma.cuda(),
+                         beta.cuda(), big_n[:, 8:8 + 2 * C], big_n.stride(0), 1e-5, o_n)
     assert rel_l2(o_n, o_e) < (1e-3 if f16 else 5e-6)
     # and against torch's own GroupNorm (the op the reference calls)
-    x = torch.cat((s0, s1 * 0.7071), dim=-1) if C1 else s0
+    x = torch.cat((s0.float(), s1.float() * 0.7071), dim=-1) if C1 else s0.float()
     gn = torch.nn.functional.group_norm(x.transpose(1, 2).reshape(B, C, HW, 1), groups, gamma, beta, 1e-5)
     y = gn * (ss[:, :C, None, None] + 1) + ss[:, C:, None, None]
     y = torch.nn.functional.silu(y).reshape(B, C, HW).transpose(1, 2)
     assert rel_l2(o_n, y) < (1e-3 if f16 else 1e-5)
 
 
+def test_groupnorm_block_statistics_from_conv_epilogue(native):
+    """conv epilogue block statistics (per 16 channels) of two producers -> GroupNorm over their virtual concat"""
+    B, H, W, Cin = 2, 16, 16, 64
+    C0, C1, G = 256, 128, 8                      # concat of 384 channels: groups of 48 straddle the two sources
+    outs = []
+    for i, Cout in enumerate((C0, C1)):
+        act = _rand(B, 1, H, W, Cin, seed=50 + i).to(F16)
+        w = _rand(Cout, Cin, 3, 3, seed=52 + i, scale=0.05)
+        wp = EMU.pack_conv_weight(w)
+        strides = (H * W * Cout, W * Cout, Cout)
+        o16 = torch.zeros(B, 1, H, W, Cout, dtype=F16, device="cuda")
+        o32 = torch.zeros(B, H, W, Cout, device="cuda")
+        st = torch.zeros(B, Cout // 16, 2, dtype=F64, device="cuda")
+        native.conv_igemm(act.cuda(), B, H, W, Cin, 0, Cin, wp.cuda(), Cout, 3, 3, 0, None, None, o32, o16, strides,
+                          out_stats=st)
+        blk = o32.double().reshape(B, H * W, Cout // 16, 16)
+        assert rel_l2(st[:, :, 0], blk.sum(dim=(1, 3))) < 1e-6
+        assert rel_l2(st[:, :, 1], (blk * blk).sum(dim=(1, 3))) < 1e-6
+        # stand-alone pass with groups = C/16 yields the same block statistics
+        st2 = torch.zeros_like(st)
+        native.gn_stats(o32, Cout, None, 0, 1.0, B, H * W, Cout // 16, st2)
+        assert rel_l2(st2, st) < 1e-6
+        outs.append((o32, o16, st))
+    gamma, beta = _rand(C0 + C1, seed=60), _rand(C0 + C1, seed=61)
+    a = torch.zeros(B, H * W, C0 + C1, dtype=F16, device="cuda")
+    native.gn_apply_silu(outs[0][1], C0, outs[1][1], C1, 0.7071, B, H * W, G, outs[0][2], 16, outs[1][2], 16,
+                         gamma.cuda(), beta.cuda(), None, 0, 1e-5, a)
+    x = torch.cat((outs[0][0].cpu(), outs[1][0].cpu() * 0.7071), dim=-1).reshape(B, H * W, C0 + C1)
+    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(x.transpose(1, 2), G, gamma, beta, 1e-5)).transpose(1, 2)
+    assert rel_l2(a, ref) < 2e-3              # fp16 inputs and outputs
+
+
+def test_conv_igemm_two_sources(native):
+    """virtual concat as two TMA sources (skip connection), skip scale folded into the packed weight"""
+    B, H, W, C0, C1, Cout = 2, 16, 16, 128, 64, 128
+    a0, a1 = _rand(B, 1, H, W, C0, seed=70).to(F16), _rand(B, 1, H, W, C1, seed=71).to(F16)
+    for k in (1, 3):
+        w = _rand(Cout, C0 + C1, k, k, seed=72 + k, scale=0.05)
+        wsc = w.clone()
+        wsc[:, C0:] *= 0.7071
+        wp = EMU.pack_conv_weight(wsc)
+        strides = (H * W * Cout, W * Cout, Cout)
+        o_e = torch.zeros(B, H, W, Cout)
+        EMU.conv_igemm(a0, B, H, W, C0, 0, C0 + C1, wp, Cout, k, k, 0, None, None, o_e, None, strides, act2=a1, lda2=C1,
+                       c_in1=C0)
+        ref = torch.nn.functional.conv2d(torch.cat((a0[:, 0].float(), a1[:, 0].float()), dim=-1).permute(0, 3, 1, 2),
+                                         wsc.half().float(), None, padding=k // 2).permute(0, 2, 3, 1)
+        assert rel_l2(o_e, ref) < 1e-6
+        o_n = torch.zeros(B, H, W, Cout, device="cuda")
+        native.conv_igemm(a0.cuda(), B, H, W, C0, 0, C0 + C1, wp.cuda(), Cout, k, k, 0, None, None, o_n, None, strides,
+                          act2=a1.cuda(), lda2=C1, c_in1=C0)
+        assert rel_l2(o_n, o_e) < 2e-5
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("f16", [True, False])
-def test_cast_act(native, mode, f16):
+@pytest.mark.parametrize("in16", [False, True])
+def test_cast_act(native, mode, f16, in16):
     B, H, W, C0, C1 = 2, 8, 16, 64, 32
-    s0, s1 = _rand(B, H, W, C0, seed=16), _rand(B, H, W, C1, seed=17)
+    dt_in = F16 if in16 else F32
+    s0, s1 = _rand(B, H, W, C0, seed=16).to(dt_in), _rand(B, H, W, C1, seed=17).to(dt_in)
     dt = F16 if f16 else F32
     numel = B * H * W * (C0 + C1) * (4 if mode == 1 else 1)
     o_e = torch.zeros(numel, dtype=dt)
