@@ -222,10 +222,24 @@ class Unet(nn.Module):
 
     def _forward_body(self, x, lowres, t, c, ss, out):
         """Stem -> down path -> middle -> up path -> final block/conv for a batch slice; writes NCHW into `out`."""
+        from . import layers as _layers
         ops = get_ops()
         B, _, H, W = x.shape
         device = x.device
         ctx = Context(c)
+        # all GroupNorm statistics accumulators of this pass come out of one zero-filled buffer (one fill, not ~180)
+        n_res = sum(1 for m in self.modules() if isinstance(m, ResnetBlock))
+        if x.is_cuda:
+            _layers._ARENA = _layers.ZeroArena(device, B * (self.dim * max(8, 1)) // 8 * 4 * (2 * n_res + 8))
+        try:
+            return self._forward_body_impl(x, lowres, t, c, ss, out, ctx)
+        finally:
+            _layers._ARENA = None
+
+    def _forward_body_impl(self, x, lowres, t, c, ss, out, ctx):
+        ops = get_ops()
+        B, _, H, W = x.shape
+        device = x.device
 
         # torch.cat((x, lowres_cond_img), dim=1) (Unet.py:397) + CrossEmbedLayer stem (Unet.py:400)
         h = self.init_conv.run_stem(x, lowres)

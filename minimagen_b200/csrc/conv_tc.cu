@@ -325,20 +325,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // own 128-pixel A tile and HALF of the weight tile (BLOCK_N/2 rows); one tcgen05.mma issued by the leader CTA consumes
 // both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Versus the 1-CTA kernel this halves
 // the weight bytes each SM pulls from L2 and the shared-memory operand traffic per FLOP.
-template <int BLOCK_N>
+template <int BLOCK_N, int KC>
 struct Cfg2 {
-    static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kConvBlockK * 2;
-    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kConvBlockK * 2;       // one 64-channel atom of the half weight tile
+    static constexpr uint32_t kStageBytes = KC * (kABytes + kBBytes);          // KC 64-channel k-chunks per pipeline stage
     static constexpr int kStages = (kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes);
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiBytes;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
-    using C = Cfg2<BLOCK_N>;
+    using C = Cfg2<BLOCK_N, KC>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -404,19 +404,23 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 int kb = 0;
                 for (int t = 0; t < args.num_taps; ++t) {
                     const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
-                    for (int j = 0; j < args.chunks_per_tap; ++j, ++kb) {
+                    for (int j = 0; j < args.chunks_per_tap; j += KC, kb += KC) {
                         ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 1100 + stage);
                         uint8_t* sa = smem + stage * C::kStageBytes;
-                        uint8_t* sb = sa + kABytes;
+                        uint8_t* sb = sa + KC * kABytes;
                         if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-                        if (j < args.a_split)
-                            ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
-                                                 h0 + dh, ph, b0);
-                        else
-                            ptx::tma_load_5d_2sm(&tmA2, &full_bar[stage], sa,
-                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 + dw, h0 + dh, ph,
-                                                 b0);
-                        ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
+#pragma unroll
+                        for (int kc = 0; kc < KC; ++kc) {
+                            const int jj = j + kc;
+                            if (jj < args.a_split)
+                                ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa + kc * kABytes,
+                                                     args.a_chan_off + jj * kConvBlockK, w0 + dw, h0 + dh, ph, b0);
+                            else
+                                ptx::tma_load_5d_2sm(&tmA2, &full_bar[stage], sa + kc * kABytes,
+                                                     args.a_chan_off2 + (jj - args.a_split) * kConvBlockK, w0 + dw, h0 + dh,
+                                                     ph, b0);
+                            ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb + kc * C::kBBytes, (kb + kc) * kConvBlockK, n0);
+                        }
                         if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -436,17 +440,20 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 1200 + as);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
+                for (int kb = 0; kb < num_kb; kb += KC) {
                     ptx::mbar_wait(&full_bar[stage], phase, err, 1300 + stage);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
 #pragma unroll
-                    for (int k = 0; k < kConvBlockK / 16; ++k)
-                        ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(sa + kc * kABytes);
+                        const uint64_t db = ptx::make_kmajor_sw128_desc(sa + KC * kABytes + kc * C::kBBytes);
+#pragma unroll
+                        for (int k = 0; k < kConvBlockK / 16; ++k)
+                            ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | kc | k) != 0);
+                    }
                     ptx::umma_commit_2sm(&empty_bar[stage], 3);               // frees this stage in BOTH CTAs
-                    if (kb == num_kb - 1) ptx::umma_commit_2sm(&tfull_bar[as], 3);
+                    if (kb + KC >= num_kb) ptx::umma_commit_2sm(&tfull_bar[as], 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -704,20 +711,20 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& t
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int KC>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
             int total_pairs, int num_sms, cudaStream_t stream) {
-    using C = Cfg2<BLOCK_N>;
+    using C = Cfg2<BLOCK_N, KC>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) !=
+        if (cudaFuncSetAttribute(conv_tc2_kernel<BLOCK_N, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes) !=
             cudaSuccess)
             return -10;
         attr_set = true;
     }
     int clusters = num_sms / 2;
     if (clusters > total_pairs) clusters = total_pairs;
-    conv_tc2_kernel<BLOCK_N><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
+    conv_tc2_kernel<BLOCK_N, KC><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -777,7 +784,8 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     if (!enc) return -5;
 
     // ---- 3x3 halo kernel (opt-in via p.halo): needs the canonical 3x3 tap order, H % 16 == 0, W % 8 == 0
-    if (p.halo && !p.act2 && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 && p.Cout % 128 == 0) {
+    if (p.halo && !p.act2 && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 &&
+        (p.Cout % 128 == 0 || p.Cout == 16)) {
         bool canon = true;
         for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
         if (canon) {
@@ -792,7 +800,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
             int dev = 0, num_sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            const int bn = (p.Cout % 256 == 0 && p.block_n_hint != 128) ? 256 : 128;
+            const int bn = p.Cout == 16 ? 16 : ((p.Cout % 256 == 0 && p.block_n_hint != 128) ? 256 : 128);
             h.tiles_n = p.Cout / bn;
             CUtensorMap tmA, tmB;
             cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
@@ -814,6 +822,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return -7;
             const int total = h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n;
+            if (bn == 16) return launch_halo<16>(tmA, tmB, h, total, num_sms, stream);
             return bn == 256 ? launch_halo<256>(tmA, tmB, h, total, num_sms, stream)
                              : launch_halo<128>(tmA, tmB, h, total, num_sms, stream);
         }
@@ -922,8 +931,13 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
 
     if (pair) {
         const int total_pairs = ((tiles_m + 1) / 2) * a.tiles_n;
-        return block_n == 256 ? launch2<256>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
-                              : launch2<128>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
+        // two 64-channel k-chunks per pipeline stage (half the barrier round trips) when the channel counts allow
+        const bool kc2 = p.kmerge != 1 && (a.chunks_per_tap % 2 == 0) && (a.a_split % 2 == 0);
+        if (block_n == 256)
+            return kc2 ? launch2<256, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
+                       : launch2<256, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
+        return kc2 ? launch2<128, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
+                   : launch2<128, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
     }
     switch (block_n) {
         case 256: return launch<256>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);

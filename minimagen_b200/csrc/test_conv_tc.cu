@@ -103,7 +103,7 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
         }
     p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
     p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
-    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3); p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair >= 10) p.cta_pair = 1; p.err_flag = g_err;
+    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3); p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
 
     *g_err = 0;
     int rc = conv_tc_launch(p, 0);
@@ -212,6 +212,7 @@ int main(int argc, char** argv) {
             {"h_c3_persist", 8, 64, 64, 64, 128, 3, 1, true, true, false, 128, 3},
             {"h_c3_deepk", 2, 16, 16, 1024, 256, 3, 1, false, true, false, 256, 3},
             {"h_c3_w256", 1, 16, 256, 64, 128, 3, 1, false, false, false, 128, 3},
+            {"h_c3_n16", 2, 32, 32, 128, 16, 3, 1, true, false, false, 0, 3},
             // ---- CTA-pair (cta_group::2) kernel
             {"p_c3_16x16_n128", 2, 16, 16, 64, 128, 3, 1, true, false, false, 128, 2},
             {"p_c3_16x16_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256, 2},
@@ -247,6 +248,10 @@ int main(int argc, char** argv) {
             {"H sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 3},
             {"H sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128, 3},
             {"H sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128, 3},
+            {"P(kc1) sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 4},
+            {"P(kc1) sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 4},
+            {"P(kc1) sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256, 4},
+            {"P(kc1) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 4},
             {"P sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 2},
             {"P sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 2},
             {"P sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 2},

@@ -29,6 +29,36 @@ STATS_BLOCK = 16   # channels per GroupNorm block-statistics entry written by th
 GN_INPUT_F32 = True
 
 
+class ZeroArena:
+    """One zero-filled fp64 buffer per forward pass from which the (many, tiny) GroupNorm statistics accumulators are
+    carved, instead of one fill kernel per accumulator."""
+
+    def __init__(self, device, n_doubles):
+        self.buf = torch.zeros((n_doubles,), dtype=F64, device=device)
+        self.off = 0
+
+    def take(self, shape):
+        n = 1
+        for d in shape:
+            n *= d
+        if self.off + n > self.buf.numel():
+            return None
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += (n + 1) // 2 * 2      # keep 16-byte alignment
+        return out
+
+
+_ARENA = None
+
+
+def stats_zeros(shape, device):
+    if _ARENA is not None and _ARENA.buf.device == device:
+        t = _ARENA.take(shape)
+        if t is not None:
+            return t
+    return torch.zeros(shape, dtype=F64, device=device)
+
+
 class Act:
     """One NHWC activation [B, H, W, C] of the U-Net: an fp32 copy (residual stream precision, only kept where an
     identity residual or a LayerNorm needs it), an fp16 copy (tensor-core / GroupNorm-apply operand) -- at least one of
@@ -71,7 +101,7 @@ class Act:
         """Block statistics by a stand-alone pass (tensors not produced by a conv epilogue, e.g. attention outputs)."""
         if self.stats is None:
             B, H, W, C = self.shape
-            self.stats = torch.zeros((B, C // STATS_BLOCK, 2), dtype=F64, device=self.device)
+            self.stats = stats_zeros((B, C // STATS_BLOCK, 2), self.device)
             get_ops().gn_stats(self.any, C, None, 0, 1.0, B, H * W, C // STATS_BLOCK, self.stats)
         return self.stats
 
@@ -327,7 +357,7 @@ class Conv2d(nn.Conv2d):
         dev = a.device
         if a.dtype == F16:
             mode = 1 if self._geom == 'down' else 0
-            st = torch.zeros((B, Cout // STATS_BLOCK, 2), dtype=F64, device=dev) if (stats and Cout % 32 == 0) else None
+            st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0) else None
             if not f32 and not f16:
                 f32 = True
             o32 = torch.empty((B, H, W, Cout), dtype=F32, device=dev) if f32 else None
@@ -499,7 +529,7 @@ class CrossEmbedLayer(nn.Module):
             C = self.dim_out
             out = torch.empty((B, H, W, C), dtype=F32, device=x.device)
             out16 = torch.empty((B, 1, H, W, C), dtype=F16, device=x.device)
-            st = torch.zeros((B, C // STATS_BLOCK, 2), dtype=F64, device=x.device) if C % 32 == 0 else None
+            st = stats_zeros((B, C // STATS_BLOCK, 2), x.device) if C % 32 == 0 else None
             ops.conv_igemm(a, B, H, W, 128, 0, 128, wp, C, 15, 1, 0, bias, None, out, out16, (H * W * C, W * C, C),
                            out_stats=st)
             return Act(out, out16, st)
@@ -556,7 +586,7 @@ class Block(nn.Module):
             st0, sb0 = parts[0].need_stats(), STATS_BLOCK
             st1, sb1 = (parts[1].need_stats(), STATS_BLOCK) if len(parts) > 1 else (None, 0)
         else:
-            st0 = torch.zeros((B, G, 2), dtype=F64, device=x.device)
+            st0 = stats_zeros((B, G, 2), x.device)
             ops.gn_stats(s0, C0, s1, C1, sc, B, H * W, G, st0)
             sb0, st1, sb1 = 0, None, 0
         a = torch.empty((B, 1, H, W, C) if tc else (B, H, W, C), dtype=F16 if tc else F32, device=x.device)
