@@ -71,6 +71,20 @@ int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c
                         long long out_sb, long long out_sh, long long out_sw, long long out_sc, int n_valid,
                         int block_n, int* err_flag, void* stream);
 
+/* Fused Block.forward (layers.py:131-145): GroupNorm -> (scale + 1, shift) -> SiLU -> Conv2d 3x3 in ONE kernel; the
+ * normalised tensor never exists in HBM.  The raw fp32 NHWC input (optionally the virtual concat cat(src0, src1*scale1),
+ * Unet.py:445) is fetched as halo tiles by TMA, transformed to the fp16 tensor-core operand in shared memory
+ * (GroupNorm mean/rstd from the producers' 16-channel block statistics stats0/stats1 = out_stats of the convs that wrote
+ * src0/src1), and convolved on tcgen05.  Epilogue as mi_conv2d_igemm_f16 (bias, fp32 residual, fp32/fp16 outputs
+ * [B][H][W][c_out] contiguous, out_stats).  Requirements: mi_conv3x3_gn_supported (H % 16 == 0, W % 8 == 0,
+ * c0 % 64 == 0, c1 % 64 == 0, c_out % 128 == 0, (c0+c1)/groups % 16 == 0). */
+int mi_conv3x3_gn_supported(int H, int W, int c0, int c1, int c_out, int groups);
+int mi_conv3x3_gn_silu_f16(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W,
+                           int groups, const double* stats0, const double* stats1, const float* gamma,
+                           const float* beta, const float* scale_shift, int scale_shift_ld, float eps,
+                           const void* w_f16, int c_out, const float* bias, const float* residual, float* out_f32,
+                           void* out_f16, double* out_stats, int* err_flag, void* stream);
+
 /* Direct fp32 convolution for shapes outside the tensor-core path: the CrossEmbedLayer stem (layers.py:300, 3/6 input
  * channels, k = 3/7/15), final_conv (Unet.py:327, 3 output channels) and every conv of the tiny test config.
  *   in        [B][Hin][Win][ldi] fp32 (channel-contiguous, ldi % 4 == 0, channels >= c_in up to the next multiple of 4

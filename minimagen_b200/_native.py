@@ -23,6 +23,9 @@ SIGNATURES = {
     "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
     "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _L, _L,
                             _I, _I, _P, _P],
+    "mi_conv3x3_gn_supported": [_I, _I, _I, _I, _I, _I],
+    "mi_conv3x3_gn_silu_f16": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P,
+                               _P],
     "mi_conv2d_direct_f32": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _I, _L, _L, _L, _L, _P],
     "mi_gn_stats": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P],
     "mi_gn_apply_silu": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _I, _P, _I, _P, _P, _P, _I, _F, _P, _I, _P],

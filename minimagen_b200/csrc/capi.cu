@@ -93,6 +93,27 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     return 0;
 }
 
+int mi_conv3x3_gn_supported(int H, int W, int c0, int c1, int c_out, int groups) {
+    return mi::conv_gn_supported(H, W, c0, c1, c_out, groups) ? 1 : 0;
+}
+
+int mi_conv3x3_gn_silu_f16(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W,
+                           int groups, const double* stats0, const double* stats1, const float* gamma,
+                           const float* beta, const float* scale_shift, int scale_shift_ld, float eps, const void* w,
+                           int c_out, const float* bias, const float* residual, float* out_f32, void* out_f16,
+                           double* out_stats, int* err_flag, void* stream) {
+    mi::ConvGnProblem p{};
+    p.src0 = src0; p.C0 = c0; p.src1 = src1; p.C1 = c1; p.scale1 = scale1; p.B = B; p.H = H; p.W = W; p.groups = groups;
+    p.stats0 = stats0; p.stats1 = stats1; p.gamma = gamma; p.beta = beta; p.scale_shift = scale_shift;
+    p.ss_ld = scale_shift_ld; p.eps = eps; p.wpacked = w; p.Cout = c_out; p.bias = bias; p.residual = residual;
+    p.out_f32 = out_f32; p.out_f16 = (__half*)out_f16; p.out_stats = out_stats; p.err_flag = err_flag;
+    if (scale_shift && scale_shift_ld < 2 * (c0 + c1)) return fail(-8, "mi_conv3x3_gn_silu_f16: scale_shift_ld < 2*C");
+    const int rc = mi::conv_gn_launch(p, S(stream));
+    if (rc != 0) return fail(rc, rc == -3 ? "mi_conv3x3_gn_silu_f16: unsupported geometry (see mi_conv3x3_gn_supported)"
+                                          : mi::conv_tc_strerror(rc));
+    return 0;
+}
+
 int mi_conv2d_direct_f32(const float* in, int B, int Hin, int Win, int c_in, int ldi, const float* w, int c_out, int kh,
                          int kw, int stride, int pad, const float* bias, const float* residual, float* out, int Hout,
                          int Wout, long long out_sb, long long out_sh, long long out_sw, long long out_sc,

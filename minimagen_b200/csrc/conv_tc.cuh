@@ -60,6 +60,34 @@ struct ConvTcProblem {
     int* err_flag;
 };
 
+// GroupNorm / FiLM / SiLU prologue of the fused Block kernel (conv_gn.cu)
+struct GnPrologueArgs {
+    int C0, C1, groups;           // channels of source 0 / source 1 (virtual concat), GroupNorm groups
+    float scale1, eps;            // source-1 scale (skip connection 2^-1/2), GroupNorm eps
+    const double* stats0;         // [B][C0/16][2] block statistics of source 0
+    const double* stats1;         // [B][C1/16][2] block statistics of source 1 (unscaled) or null
+    const float* gamma;           // [C0+C1]
+    const float* beta;            // [C0+C1]
+    const float* scale_shift;     // optional: row b at scale_shift + b*ss_ld = [scale(C) | shift(C)]
+    int ss_ld;
+};
+
+struct ConvGnProblem {
+    const float* src0; int C0;    // fp32 NHWC [B][H][W][C0]
+    const float* src1; int C1;    // optional second source [B][H][W][C1]
+    float scale1;
+    int B, H, W, groups;
+    const double* stats0; const double* stats1;
+    const float* gamma; const float* beta; const float* scale_shift; int ss_ld; float eps;
+    const void* wpacked; int Cout;          // fp16 [Cout][9*(C0+C1)]
+    const float* bias; const float* residual;
+    float* out_f32; __half* out_f16; double* out_stats;
+    int* err_flag;
+};
+
+bool conv_gn_supported(int H, int W, int C0, int C1, int Cout, int groups);
+int conv_gn_launch(const ConvGnProblem& p, cudaStream_t stream);
+
 bool conv_tc_supported(int H, int W, int Cin, int Cout);
 int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream);
 const char* conv_tc_strerror(int code);

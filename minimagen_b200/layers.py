@@ -28,6 +28,9 @@ STATS_BLOCK = 16   # channels per GroupNorm block-statistics entry written by th
 # element written and re-read; ~5 % faster steps) at 1.05e-3 rel-L2.
 GN_INPUT_F32 = True
 
+# Block.forward as ONE kernel (GroupNorm/FiLM/SiLU in the conv's shared-memory prologue) where the geometry allows
+FUSE_GN_CONV = True
+
 
 class ZeroArena:
     """One zero-filled fp64 buffer per forward pass from which the (many, tiny) GroupNorm statistics accumulators are
@@ -581,6 +584,24 @@ class Block(nn.Module):
         tc = self.project.tc_ok(H, W)
         parts = [x.a, x.b] if isinstance(x, Cat) else [x]
         block_mode = tc and Cg % STATS_BLOCK == 0 and all(p.shape[3] % STATS_BLOCK == 0 for p in parts)
+        if (block_mode and FUSE_GN_CONV and all(p.f32 is not None for p in parts)
+                and ops.conv_gn_supported(H, W, parts[0].shape[3], parts[1].shape[3] if len(parts) > 1 else 0,
+                                          self.project.out_channels, G)):
+            # one kernel: GroupNorm/FiLM/SiLU as the conv's shared-memory prologue (mi_conv3x3_gn_silu_f16)
+            conv = self.project
+            Cout = conv.out_channels
+            dev = x.device
+            if not f32 and not f16:
+                f32 = True
+            o32 = torch.empty((B, H, W, Cout), dtype=F32, device=dev) if f32 else None
+            o16 = torch.empty((B, 1, H, W, Cout), dtype=F16, device=dev) if f16 else None
+            st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if stats else None
+            p1 = parts[1] if len(parts) > 1 else None
+            ops.conv_gn(parts[0].f32, parts[0].shape[3], p1.f32 if p1 else None, p1.shape[3] if p1 else 0,
+                        x.scale if p1 else 1.0, B, H, W, G, parts[0].need_stats(), p1.need_stats() if p1 else None,
+                        gn.weight, gn.bias, scale_shift, scale_shift.stride(0) if exists(scale_shift) else 0, gn.eps,
+                        conv._pack.get(conv.weight), Cout, conv.bias, residual, o32, o16, st)
+            return Act(o32, o16, st)
         s0, C0, s1, C1, sc = _srcs(x, tc and not GN_INPUT_F32)
         if block_mode:
             st0, sb0 = parts[0].need_stats(), STATS_BLOCK

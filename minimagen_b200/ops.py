@@ -56,6 +56,21 @@ class NativeOps:
                N.ptr(wp), c_out, kh, kw, mode, N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16),
                N.ptr(out_stats), sb, sh, sw, out_sc, n_valid, block_n, None, N.stream())
 
+    def conv_gn_supported(self, H, W, c0, c1, c_out, groups):
+        return bool(N.load().mi_conv3x3_gn_supported(int(H), int(W), int(c0), int(c1), int(c_out), int(groups)))
+
+    def conv_gn(self, src0, c0, src1, c1, scale1, B, H, W, groups, stats0, stats1, gamma, beta, scale_shift, ss_ld, eps,
+                wp, c_out, bias, residual, out_f32, out_f16, out_stats):
+        """Fused GroupNorm -> FiLM -> SiLU -> 3x3 conv (Block.forward) over fp32 NHWC source(s)."""
+        _chk(src0, F32, "src0"); _chk(src1, F32, "src1"); _chk(stats0, F64, "stats0"); _chk(stats1, F64, "stats1")
+        _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta"); _chk_out(scale_shift, F32, "scale_shift"); _chk(wp, F16, "wp")
+        _chk(bias, F32, "bias"); _chk(residual, F32, "residual"); _chk(out_f32, F32, "out_f32")
+        _chk(out_f16, F16, "out_f16"); _chk(out_stats, F64, "out_stats")
+        N.call("mi_conv3x3_gn_silu_f16", N.ptr(src0), c0, N.ptr(src1), c1, float(scale1), B, H, W, groups,
+               N.ptr(stats0), N.ptr(stats1), N.ptr(gamma), N.ptr(beta), N.ptr(scale_shift), int(ss_ld), float(eps),
+               N.ptr(wp), c_out, N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16), N.ptr(out_stats), None,
+               N.stream())
+
     def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
                     out_strides):
         _chk(inp, F32, "inp"); _chk(w, F32, "w"); _chk(bias, F32, "bias"); _chk_out(residual, F32, "residual")

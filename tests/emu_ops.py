@@ -94,6 +94,23 @@ class EmuOps:
         if out_f16 is not None:
             _strided(out_f16, (B, H, W, nv), (sb, sh, sw, out_sc)).copy_(y.to(F16))
 
+    def conv_gn_supported(self, H, W, c0, c1, c_out, groups):
+        C = c0 + c1
+        return (H % 16 == 0 and W % 8 == 0 and c0 % 64 == 0 and c1 % 64 == 0 and C > 0 and c_out % 128 == 0
+                and 1 <= groups <= 32 and C % groups == 0 and (C // groups) % 16 == 0)
+
+    def conv_gn(self, src0, c0, src1, c1, scale1, B, H, W, groups, stats0, stats1, gamma, beta, scale_shift, ss_ld, eps,
+                wp, c_out, bias, residual, out_f32, out_f16, out_stats):
+        self._log("conv_gn")
+        C = c0 + c1
+        a = torch.zeros((B, 1, H, W, C), dtype=F16)
+        self.gn_apply_silu(src0, c0, src1, c1, scale1, B, H * W, groups, stats0, 16, stats1, 16, gamma, beta, scale_shift,
+                           ss_ld, eps, a)
+        self.calls.pop()
+        self.conv_igemm(a, B, H, W, C, 0, C, wp, c_out, 3, 3, 0, bias, residual, out_f32, out_f16,
+                        (H * W * c_out, W * c_out, c_out), out_stats=out_stats)
+        self.calls.pop()
+
     def conv_direct(self, inp, B, Hin, Win, c_in, ldi, w, c_out, kh, kw, stride, pad, bias, residual, out, Hout, Wout,
                     out_strides):
         self._log("conv_direct")

@@ -231,6 +231,50 @@ def test_groupnorm_block_statistics_from_conv_epilogue(native):
     assert rel_l2(a, ref) < 2e-3              # fp16 inputs and outputs
 
 
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout,res,ss", [(2, 16, 16, 128, 0, 128, False, False), (2, 32, 16, 256, 128, 256, True, True),
+                                                     (3, 16, 8, 128, 128, 128, True, True), (1, 64, 64, 128, 0, 256, False, True)])
+def test_fused_groupnorm_conv(native, B, H, W, C0, C1, Cout, res, ss):
+    """mi_conv3x3_gn_silu_f16 == mi_gn_apply_silu (block statistics) followed by mi_conv2d_igemm_f16"""
+    G, C = 8, C0 + C1
+    assert native.conv_gn_supported(H, W, C0, C1, Cout, G)
+    x0 = _rand(B, H, W, C0, seed=80) * 1.5 + 0.3
+    x1 = _rand(B, H, W, C1, seed=81) if C1 else None
+    gamma, beta = _rand(C, seed=82), _rand(C, seed=83)
+    ssv = _rand(B, 2 * C, seed=84, scale=0.3) if ss else None
+    w = _rand(Cout, C, 3, 3, seed=85, scale=(9 * C) ** -0.5)
+    bias = _rand(Cout, seed=86)
+    r = _rand(B, H, W, Cout, seed=87) if res else None
+    wp = EMU.pack_conv_weight(w)
+
+    def blockstats(t, Cc):
+        st = torch.zeros(B, Cc // 16, 2, dtype=F64)
+        EMU.gn_stats(t, Cc, None, 0, 1.0, B, H * W, Cc // 16, st)
+        return st
+    st0, st1 = blockstats(x0, C0), (blockstats(x1, C1) if C1 else None)
+    o_e, o16_e = torch.zeros(B, H, W, Cout), torch.zeros(B, 1, H, W, Cout, dtype=F16)
+    os_e = torch.zeros(B, Cout // 16, 2, dtype=F64)
+    EMU.conv_gn(x0, C0, x1, C1, 0.7071, B, H, W, G, st0, st1, gamma, beta, ssv, 2 * C, 1e-5, wp, Cout, bias, r, o_e, o16_e,
+                os_e)
+    o_n = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    o16_n = torch.zeros(B, 1, H, W, Cout, dtype=F16, device="cuda")
+    os_n = torch.zeros(B, Cout // 16, 2, dtype=F64, device="cuda")
+    native.conv_gn(x0.cuda(), C0, _cu(x1), C1, 0.7071, B, H, W, G, st0.cuda(), _cu(st1), gamma.cuda(), beta.cuda(), _cu(ssv),
+                   2 * C, 1e-5, wp.cuda(), Cout, bias.cuda(), _cu(r), o_n, o16_n, os_n)
+    torch.cuda.synchronize()
+    assert rel_l2(o_n, o_e) < 5e-4          # the fp16 rounding of the activated operand can differ in the last bit
+    assert rel_l2(o16_n, o_e) < 1.5e-3
+    assert rel_l2(os_n, os_e) < 1e-3
+    # and against the reference ops in fp32 (GroupNorm -> FiLM -> SiLU -> conv2d)
+    x = torch.cat((x0, x1 * 0.7071), dim=-1) if C1 else x0
+    y = torch.nn.functional.group_norm(x.permute(0, 3, 1, 2), G, gamma, beta, 1e-5)
+    if ss:
+        y = y * (ssv[:, :C, None, None] + 1) + ssv[:, C:, None, None]
+    y = torch.nn.functional.conv2d(torch.nn.functional.silu(y), w, bias, padding=1).permute(0, 2, 3, 1)
+    if res:
+        y = y + r
+    assert rel_l2(o_n, y) < 1.5e-3
+
+
 def test_conv_igemm_two_sources(native):
     """virtual concat as two TMA sources (skip connection), skip scale folded into the packed weight"""
     B, H, W, C0, C1, Cout = 2, 16, 16, 128, 64, 128
