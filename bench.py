@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--batch-streams", type=int, default=None, help="concurrent batch slices inside Unet.forward")
+    ap.add_argument("--fuse", default=None, choices=["off", "n128", "all"], help="fused GroupNorm+conv kernel usage")
     ap.add_argument("--gn-f16", action="store_true", help="GroupNorm inputs in fp16 (faster, 1.05e-3 instead of 9e-4 rel-L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -209,6 +210,8 @@ def main():
     _native.load()
     if args.gn_f16:
         layers.GN_INPUT_F32 = False
+    if args.fuse is not None:
+        layers.FUSE_GN_CONV = {"off": False, "n128": True, "all": "all"}[args.fuse]
 
     torch.manual_seed(0)
     with torch.device(dev):

@@ -38,10 +38,11 @@ constexpr int kOpStages = 2;
 template <int BLOCK_N>
 struct CfgG {
     static constexpr uint32_t kBBytes = BLOCK_N * kConvBlockK * 2;
-    static constexpr int kBStages = BLOCK_N == 256 ? 3 : 5;
+    static constexpr int kBStages = BLOCK_N == 256 ? 3 : 3;
+    static constexpr int kRawStages = BLOCK_N == 256 ? 1 : 2;       // the raw fp32 staging ring
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     static constexpr uint32_t kAux = 2048;   // barriers, tmem ptr, group stats, coefficients
-    static constexpr uint32_t kSmemBytes = kRawStride + kOpStages * kOpStride + kBStages * kBBytes + kEpiBytes + kAux + 1024;
+    static constexpr uint32_t kSmemBytes = kRawStages * kRawStride + kOpStages * kOpStride + kBStages * kBBytes + kEpiBytes + kAux + 1024;
 };
 
 __device__ __forceinline__ uint64_t make_halo_desc_g(uint32_t smem_addr) {
@@ -64,19 +65,20 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
                   const __grid_constant__ GnPrologueArgs gn) {
     using C = CfgG<BLOCK_N>;
     constexpr int NB = C::kBStages;
+    constexpr int NR = C::kRawStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* s_rawbuf = smem;
-    uint8_t* s_op = smem + kRawStride;
+    uint8_t* s_op = smem + NR * kRawStride;
     uint8_t* s_b = s_op + kOpStages * kOpStride;
     float* epi_base = reinterpret_cast<float*>(s_b + NB * C::kBBytes);
     uint8_t* aux = reinterpret_cast<uint8_t*>(epi_base) + kEpiBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(aux);
-    uint64_t* fullRaw = bars;                      // [1]  TMA -> transform
-    uint64_t* emptyRaw = bars + 1;                 // [1]  transform -> TMA
-    uint64_t* xformed = bars + 2;                  // [kOpStages] transform -> MMA
-    uint64_t* emptyOp = bars + 2 + kOpStages;      // [kOpStages] MMA -> transform
-    uint64_t* fullB = bars + 2 + 2 * kOpStages;    // [NB]
+    uint64_t* fullRaw = bars;                      // [NR] TMA -> transform
+    uint64_t* emptyRaw = bars + 2;                 // [NR] transform -> TMA
+    uint64_t* xformed = bars + 4;                  // [kOpStages] transform -> MMA
+    uint64_t* emptyOp = bars + 4 + kOpStages;      // [kOpStages] MMA -> transform
+    uint64_t* fullB = bars + 4 + 2 * kOpStages;    // [NB]
     uint64_t* emptyB = fullB + NB;                 // [NB]
     uint64_t* tfull_bar = emptyB + NB;             // [2]
     uint64_t* tempty_bar = tfull_bar + 2;          // [2]
@@ -95,8 +97,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
         ptx::prefetch_tensormap(&tmB);
     }
     if (warp == 1 && lane == 0) {
-        ptx::mbar_init(fullRaw, 1);
-        ptx::mbar_init(emptyRaw, 128);
+        for (int i = 0; i < NR; ++i) { ptx::mbar_init(&fullRaw[i], 1); ptx::mbar_init(&emptyRaw[i], 128); }
         for (int i = 0; i < kOpStages; ++i) { ptx::mbar_init(&xformed[i], 128); ptx::mbar_init(&emptyOp[i], 1); }
         for (int i = 0; i < NB; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 32 * kEpiWarps); }
@@ -119,7 +120,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             // ===================== TMA producer =====================
-            int sb = 0;
+            int sb = 0, sr = 0;
             uint32_t praw = 0, pb = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % args.tiles_n;
@@ -129,14 +130,15 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
                 const int b0 = mt / (args.tiles_w * args.tiles_h);
                 const int n0 = nt * BLOCK_N;
                 for (int j = 0; j < chunks; ++j) {
-                    ptx::mbar_wait(emptyRaw, praw ^ 1, err, 3100);
-                    ptx::mbar_arrive_expect_tx(fullRaw, kRawBytes);
+                    ptx::mbar_wait(&emptyRaw[sr], praw ^ 1, err, 3100 + sr);
+                    ptx::mbar_arrive_expect_tx(&fullRaw[sr], kRawBytes);
                     const bool first = j < args.a_split;
                     const CUtensorMap* tm = first ? &tmR0 : &tmR1;
                     const int c0 = (first ? j : j - args.a_split) * kConvBlockK;
-                    ptx::tma_load_5d(tm, fullRaw, s_rawbuf, c0, w0 - 1, h0 - 1, 0, b0);
-                    ptx::tma_load_5d(tm, fullRaw, s_rawbuf + kRawHalf, c0 + 32, w0 - 1, h0 - 1, 0, b0);
-                    praw ^= 1;
+                    uint8_t* rb = s_rawbuf + sr * kRawStride;
+                    ptx::tma_load_5d(tm, &fullRaw[sr], rb, c0, w0 - 1, h0 - 1, 0, b0);
+                    ptx::tma_load_5d(tm, &fullRaw[sr], rb + kRawHalf, c0 + 32, w0 - 1, h0 - 1, 0, b0);
+                    if (++sr == NR) { sr = 0; praw ^= 1; }
                     for (int t = 0; t < 9; ++t) {
                         ptx::mbar_wait(&emptyB[sb], pb ^ 1, err, 3200 + sb);
                         ptx::mbar_arrive_expect_tx(&fullB[sb], C::kBBytes);
@@ -186,7 +188,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
         const int p0 = (tt >> 3) & 7;                  // rows p == p0 (mod 8)  ->  the swizzle phase is fixed per thread
         const int lq = qo ^ p0;                        // logical chunk: channels [8*lq, 8*lq + 8) of the 64-channel chunk
         const int half = tt >> 6;                      // two thread halves interleave the rows
-        int so = 0;
+        int so = 0, sr = 0;
         uint32_t po = 0, praw = 0;
         const int C0 = gn.C0, Ctot = gn.C0 + gn.C1, Cg = Ctot / gn.groups;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -242,10 +244,10 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { ca[e] = cA[lq * 8 + e]; cb[e] = cB[lq * 8 + e]; }
 
-                ptx::mbar_wait(fullRaw, praw, err, 3600);               // raw tile landed
+                ptx::mbar_wait(&fullRaw[sr], praw, err, 3600 + sr);     // raw tile landed
                 ptx::mbar_wait(&emptyOp[so], po ^ 1, err, 3700 + so);   // operand slot free (its MMAs retired)
                 uint8_t* op = s_op + so * kOpStride;
-                const uint8_t* rawp = s_rawbuf + (lq >> 2) * kRawHalf + (lq & 3) * 32;   // 8 fp32 = 32 B inside the 128-B row
+                const uint8_t* rawp = s_rawbuf + sr * kRawStride + (lq >> 2) * kRawHalf + (lq & 3) * 32;   // 8 fp32 = 32 B
                 for (int p = p0 + 8 * half; p < kHaloPix; p += 16) {
                     const int ph = p / kHW, pw = p - ph * kHW;
                     const int gh = h0 - 1 + ph, gw = w0 - 1 + pw;
@@ -267,8 +269,8 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
                 }
                 ptx::fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core (async proxy)
                 ptx::mbar_arrive(&xformed[so]);
-                ptx::mbar_arrive(emptyRaw);
-                praw ^= 1;
+                ptx::mbar_arrive(&emptyRaw[sr]);
+                if (++sr == NR) { sr = 0; praw ^= 1; }
                 if (++so == kOpStages) { so = 0; po ^= 1; }
             }
         }
