@@ -278,7 +278,13 @@ def main():
                 cur = step_fn(cur, t_dev, torch.randn(shape, device=dev))
             return cur
 
-        run_steps(args.warmup, x, T - 1)
+        warm = run_steps(args.warmup, x, T - 1)
+        if world > 1:
+            # warm the collective too (NCCL builds channels / registers buffers on first use)
+            fin = torch.empty_like(warm)
+            ops.step_finalize(warm, warm.numel(), 1, fin)
+            gathered = torch.empty((world * B, *shape[1:]), device=dev)
+            dist.all_gather_into_tensor(gathered, fin)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
