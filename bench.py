@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--batch-streams", type=int, default=None, help="concurrent batch slices inside Unet.forward")
     ap.add_argument("--fuse", default=None, choices=["off", "n128", "all"], help="fused GroupNorm+conv kernel usage")
+    ap.add_argument("--kernel-table", default=None, help="write a CUPTI per-kernel time table of 3 steps to this path")
     ap.add_argument("--gn-f16", action="store_true", help="GroupNorm inputs in fp16 (faster, 1.05e-3 instead of 9e-4 rel-L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -308,6 +309,9 @@ def main():
         clocks = sampler.stop() if sampler else None
         assert torch.isfinite(cur).all(), "non-finite output"
 
+        if args.kernel_table and rank == 0:
+            kernel_table(lambda: run_steps(3, x, T - 1), 3, args.kernel_table)
+
         # end-to-end: public API call per step with host buffers (pinned) in, result out
         out_host = torch.empty(shape, dtype=torch.float32).pin_memory()
         noise_host = torch.randn(shape).pin_memory()
@@ -382,6 +386,26 @@ def main():
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def kernel_table(fn, steps, path):
+    """Diagnostics only (never a bench value): CUPTI kernel records of `steps` un-serialised steps, summed per kernel."""
+    import collections
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type is not None and str(ev.device_type).endswith("CUDA"):
+            a = agg[ev.name[:110]]
+            a[0] += 1
+            a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+    tot = sum(t for _, t in agg.values())
+    with open(path, "w") as f:
+        f.write(f"# per-step kernel time (CUPTI, {steps} steps averaged), total {tot / steps / 1e3:.3f} ms/step\n")
+        for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{t / steps / 1e3:9.3f} ms {c / steps:7.1f} launches  {name}\n")
 
 
 def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):

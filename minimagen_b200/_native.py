@@ -22,7 +22,8 @@ SIGNATURES = {
     "mi_pack_conv_weight_f16": [_P, _I, _I, _I, _I, _F, _P, _P],
     "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
     "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _L, _L,
-                            _I, _I, _P, _P],
+                            _I, _I, _P, _P, _L, _P],
+    "mi_conv2d_igemm_workspace_bytes": [],
     "mi_conv3x3_gn_supported": [_I, _I, _I, _I, _I, _I],
     "mi_conv3x3_gn_silu_f16": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P,
                                _P],
@@ -46,7 +47,7 @@ SIGNATURES = {
     "mi_step_finalize": [_P, _L, _I, _P, _P],
     "mi_q_sample": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
 }
-_RESTYPES = {"mi_last_error": c_char_p}
+_RESTYPES = {"mi_last_error": c_char_p, "mi_conv2d_igemm_workspace_bytes": c_longlong}
 
 _lib = None
 launch_count = 0   # number of kernel launches issued through this binding (bench.py reports it)

@@ -52,8 +52,10 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
                         int c_off2, int c_in1, const void* w, int c_out, int kh, int kw, int mode, const float* bias,
                         const float* residual, float* out_f32, void* out_f16, double* out_stats, long long out_sb,
                         long long out_sh, long long out_sw, long long out_sc, int n_valid, int block_n, int* err_flag,
-                        void* stream) {
+                        void* workspace, long long workspace_bytes, void* stream) {
     mi::ConvTcProblem p{};
+    p.splitk_ws = workspace; p.splitk_ws_bytes = workspace ? workspace_bytes : 0;
+    if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15)) return fail(-8, "mi_conv2d_igemm_f16: workspace must be 16-byte aligned");
     p.act = act; p.B = B; p.H = H; p.W = W; p.lda = lda; p.a_channels = lda; p.a_chan_off = c_off; p.Cin = c_in;
     p.wpacked = w; p.Cout = c_out;
     p.act2 = act2; p.lda2 = lda2; p.a_chan_off2 = c_off2; p.Cin1 = c_in1; p.stats = out_stats;
@@ -92,6 +94,8 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;
 }
+
+long long mi_conv2d_igemm_workspace_bytes(void) { return mi::conv_tc_splitk_bytes(); }
 
 int mi_conv3x3_gn_supported(int H, int W, int c0, int c1, int c_out, int groups) {
     return mi::conv_gn_supported(H, W, c0, c1, c_out, groups) ? 1 : 0;

@@ -156,7 +156,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < kConvBlockK / 16; ++k) {
                         // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in the (addr >> 4) field
-                        ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        // profiling bit 3: odd k-steps accumulate into the OTHER TMEM buffer (two independent chains)
+                        const uint32_t d = ((args.dbg & 8) && (k & 1)) ? tmem_base + (as ^ 1) * BLOCK_N : tmem_d;
+                        ptx::umma_f16(d, da + 2 * k, db + 2 * k, idesc, (kb | (k >> ((args.dbg & 8) ? 1 : 0))) != 0);
                     }
                     ptx::umma_commit(&empty_bar[stage]);             // frees the smem slot when these MMAs retire
                     if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[as]);   // accumulator complete
@@ -210,6 +212,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // own 128-pixel A tile and HALF of the weight tile (BLOCK_N/2 rows); one tcgen05.mma issued by the leader CTA consumes
 // both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Versus the 1-CTA kernel this halves
 // the weight bytes each SM pulls from L2 and the shared-memory operand traffic per FLOP.
+// Work walk of one cluster.  Normal mode: whole tiles cluster_id, cluster_id + NC, ...  Stream-K mode (args.stream_k): the
+// S pipeline-stage units of all tiles are laid end to end and cut into NC equal ranges, so every cluster does the same
+// number of MMA stages even when tiles % NC != 0 (1.73 waves would otherwise cost 2).  A range of >= S units starts with
+// at most one tile TAIL (s0 > 0: the head belongs to the previous cluster) and ends with at most one tile HEAD (s1 < S).
+struct SegWalk {
+    int cur, end, S, nc;
+    bool sk;
+    __device__ SegWalk(bool stream_k, int S_, int total_pairs, int cid, int nc_) : S(S_), nc(nc_), sk(stream_k) {
+        if (sk) {
+            const long long U = (long long)total_pairs * S;
+            cur = (int)(U * cid / nc);
+            end = (int)(U * (cid + 1) / nc);
+        } else {
+            cur = cid;
+            end = total_pairs;
+        }
+    }
+    __device__ bool next(int& pt, int& s0, int& s1) {
+        if (cur >= end) return false;
+        if (sk) {
+            pt = cur / S;
+            s0 = cur - pt * S;
+            s1 = min(S, s0 + (end - cur));
+            cur += s1 - s0;
+        } else {
+            pt = cur; s0 = 0; s1 = S;
+            cur += nc;
+        }
+        return true;
+    }
+};
+
 template <int BLOCK_N, int KC>
 struct Cfg2 {
     static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kConvBlockK * 2;       // one 64-channel atom of the half weight tile
@@ -266,7 +300,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
-    const int num_kb = args.num_taps * args.chunks_per_tap;
+    const int num_st = args.num_taps * args.chunks_per_tap / KC;      // pipeline stages (KC k-chunks each) per tile
     const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
     const int pairs_m = (tiles_m + 1) >> 1;
     const int total_pairs = pairs_m * args.tiles_n;
@@ -279,36 +313,40 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             // ===================== TMA producer (both CTAs) =====================
             int stage = 0;
             uint32_t phase = 0;
-            for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+            SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
+            int pt, s0, s1;
+            while (walk.next(pt, s0, s1)) {
                 const int nt = pt % args.tiles_n;
                 const int mt = 2 * (pt / args.tiles_n) + (int)rank;      // may be == tiles_m (dummy tile: all OOB)
                 const int w0 = (mt % args.tiles_w) * BW;
                 const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
                 const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
                 const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-                int kb = 0;
-                for (int t = 0; t < args.num_taps; ++t) {
+                int kb = s0 * KC;
+                int t = kb / args.chunks_per_tap;
+                int j = kb - t * args.chunks_per_tap;
+                for (int s = s0; s < s1; ++s, kb += KC) {
                     const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
-                    for (int j = 0; j < args.chunks_per_tap; j += KC, kb += KC) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 1100 + stage);
-                        uint8_t* sa = smem + stage * C::kStageBytes;
-                        uint8_t* sb = sa + KC * kABytes;
-                        if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 1100 + stage);
+                    uint8_t* sa = smem + stage * C::kStageBytes;
+                    uint8_t* sb = sa + KC * kABytes;
+                    if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
 #pragma unroll
-                        for (int kc = 0; kc < KC; ++kc) {
-                            const int jj = j + kc;
-                            if (jj < args.a_split)
-                                ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa + kc * kABytes,
-                                                     args.a_chan_off + jj * kConvBlockK, w0 + dw, h0 + dh, ph, b0);
-                            else
-                                ptx::tma_load_5d_2sm(&tmA2, &full_bar[stage], sa + kc * kABytes,
-                                                     args.a_chan_off2 + (jj - args.a_split) * kConvBlockK, w0 + dw, h0 + dh,
-                                                     ph, b0);
-                            ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb + kc * C::kBBytes, (kb + kc) * kConvBlockK, n0);
-                        }
-                        if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const int jj = j + kc;
+                        if (jj < args.a_split)
+                            ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa + kc * kABytes,
+                                                 args.a_chan_off + jj * kConvBlockK, w0 + dw, h0 + dh, ph, b0);
+                        else
+                            ptx::tma_load_5d_2sm(&tmA2, &full_bar[stage], sa + kc * kABytes,
+                                                 args.a_chan_off2 + (jj - args.a_split) * kConvBlockK, w0 + dw, h0 + dh,
+                                                 ph, b0);
+                        ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb + kc * C::kBBytes, (kb + kc) * kConvBlockK, n0);
                     }
+                    if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    j += KC;
+                    if (j >= args.chunks_per_tap) { j = 0; ++t; }
                 }
             }
         }
@@ -319,13 +357,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
+            SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
+            int pt, s0, s1;
+            for (; walk.next(pt, s0, s1); ++iter) {
                 const int as = iter & 1;
                 const uint32_t aphase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 1200 + as);
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < num_kb; kb += KC) {
+                for (int s = s0; s < s1; ++s) {
                     ptx::mbar_wait(&full_bar[stage], phase, err, 1300 + stage);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
@@ -335,10 +375,10 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const uint64_t db = ptx::make_kmajor_sw128_desc(sa + KC * kABytes + kc * C::kBBytes);
 #pragma unroll
                         for (int k = 0; k < kConvBlockK / 16; ++k)
-                            ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | kc | k) != 0);
+                            ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, ((s - s0) | kc | k) != 0);
                     }
                     ptx::umma_commit_2sm(&empty_bar[stage], 3);               // frees this stage in BOTH CTAs
-                    if (kb + KC >= num_kb) ptx::umma_commit_2sm(&tfull_bar[as], 3);
+                    if (s + 1 == s1) ptx::umma_commit_2sm(&tfull_bar[as], 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -354,7 +394,9 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int bh = (m >> args.bw_log2) & (BH - 1);
         const int bb = m >> (args.bw_log2 + args.bh_log2);
         int iter = 0;
-        for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
+        SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
+        int pt, s0, s1;
+        for (; walk.next(pt, s0, s1); ++iter) {
             const int nt = pt % args.tiles_n;
             const int mt = 2 * (pt / args.tiles_n) + (int)rank;
             const int w = (mt % args.tiles_w) * BW + bw;
@@ -368,7 +410,45 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 1400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b);
+            if (s0 > 0 && (args.dbg & 4)) {
+                // profiling: stream-K schedule without the partial-tile exchange (results are wrong)
+            } else if (s0 > 0) {
+                // stream-K tail of a tile owned by the previous cluster: park the raw fp32 partial sums in this cluster's
+                // workspace slot ([rank][column][row], row-contiguous) and raise its ready counter
+                const int slot = cluster_id * 2 + (int)rank;
+                float* ws = args.sk_ws + (size_t)slot * BLOCK_N * kConvBlockM + m;
+                epilogue_park<BLOCK_N>(taddr, c_begin, c_end, ws);
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicAdd(args.sk_flags + 2 * slot, 1);
+            } else {
+                const float* partial = nullptr;
+                int* fl = nullptr;
+                if (s1 < num_st && !(args.dbg & 4)) {
+                    // stream-K head: the next cluster computed the rest of the k range as ITS first segment
+                    const int slot = (cluster_id + 1) * 2 + (int)rank;
+                    fl = args.sk_flags + 2 * slot;
+                    if (lane == 0) {
+                        const long long t0 = clock64();
+                        while (ptx::ld_acquire_gpu(fl) < kEpiWarps) {
+                            if (clock64() - t0 > 4000000000LL) {
+                                if (err) { atomicExch(err, 1500); __threadfence_system(); }
+                                __trap();
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    partial = args.sk_ws + (size_t)slot * BLOCK_N * kConvBlockM + m;
+                }
+                epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b, partial);
+                if (fl) {
+                    __syncwarp();
+                    if (lane == 0 && atomicAdd(fl + 1, 1) == kEpiWarps - 1) {   // last consumer re-arms the slot
+                        atomicExch(fl + 1, 0);
+                        atomicExch(fl, 0);
+                    }
+                }
+            }
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(&tempty_bar[as], 0);                    // the leader's barrier
         }
@@ -395,11 +475,17 @@ constexpr int kHaloTH = 16, kHaloTW = 8, kHaloW = kHaloTW + 2, kHaloH = kHaloTH 
 constexpr uint32_t kHaloABytes = kHaloH * kHaloW * 128;                       // 23040
 constexpr uint32_t kHaloAStride = (kHaloABytes + 1023) & ~1023u;              // 23552
 
+// BLOCK_N == 16 (final_conv, C_out = 3 padded to 16): the whole weight matrix (9 taps x <= 4 chunks x 2 KB) stays RESIDENT
+// in shared memory -- it is loaded once per CTA, the B pipeline (18 small TMA round trips per 128-pixel tile, which made
+// this layer latency-bound at 15 % of HBM speed) disappears and the freed barriers/stages deepen the A ring.
+constexpr int kHaloResChunks = 4;
 template <int BLOCK_N>
 struct CfgH {
+    static constexpr bool kBRes = BLOCK_N == 16;
     static constexpr uint32_t kBBytes = BLOCK_N * kConvBlockK * 2;
-    static constexpr int kAStages = 3;
-    static constexpr int kBStages = (kRingBudget - kAStages * kHaloAStride) / kBBytes > 8 ? 8 : (kRingBudget - kAStages * kHaloAStride) / kBBytes;
+    static constexpr int kAStages = kBRes ? 5 : 3;
+    static constexpr int kBStages = kBRes ? 9 * kHaloResChunks
+        : ((kRingBudget - kAStages * kHaloAStride) / kBBytes > 8 ? 8 : (kRingBudget - kAStages * kHaloAStride) / kBBytes);
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
     static constexpr uint32_t kSmemBytes = kAStages * kHaloAStride + kBStages * kBBytes + 1024 + 256 + kEpiBytes;
 };
@@ -425,9 +511,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + NB * C::kBBytes);
     uint64_t* fullA = bars;
     uint64_t* emptyA = bars + NA;
+    constexpr int NBB = C::kBRes ? 1 : NB;          // barriers of the B ring (resident weights: one "loaded" barrier)
     uint64_t* fullB = bars + 2 * NA;
-    uint64_t* emptyB = bars + 2 * NA + NB;
-    uint64_t* tfull_bar = bars + 2 * NA + 2 * NB;
+    uint64_t* emptyB = bars + 2 * NA + NBB;
+    uint64_t* tfull_bar = bars + 2 * NA + 2 * NBB;
+    static_assert((2 * NA + 2 * NBB + 4) * 8 + 8 <= 256, "barrier block overlaps the epilogue patches");
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
     float* epi_stage = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256) + (((threadIdx.x >> 5) + 4) & 7) * 32 * kEpiLd;
@@ -442,7 +530,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NA; ++i) { ptx::mbar_init(&fullA[i], 1); ptx::mbar_init(&emptyA[i], 1); }
-        for (int i = 0; i < NB; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < NBB; ++i) { ptx::mbar_init(&fullB[i], 1); ptx::mbar_init(&emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 32 * kEpiWarps); }
         ptx::fence_barrier_init();
     }
@@ -464,6 +552,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (lane == 0) {
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
+            if constexpr (C::kBRes) {
+                // resident weights: tile (j, t) at slot j*9 + t, all on one barrier (tiles_n == 1)
+                ptx::mbar_arrive_expect_tx(&fullB[0], 9 * chunks * C::kBBytes);
+                for (int j = 0; j < chunks; ++j)
+                    for (int t = 0; t < 9; ++t)
+                        ptx::tma_load_2d(&tmB, &fullB[0], smem_b + (j * 9 + t) * C::kBBytes, t * Cin + j * kConvBlockK, 0);
+            }
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % args.tiles_n;
                 const int mt = tile / args.tiles_n;
@@ -477,11 +572,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     ptx::tma_load_5d(&tmA, &fullA[sa], smem + sa * kHaloAStride, args.a_chan_off + j * kConvBlockK,
                                      w0 - 1, h0 - 1, 0, b0);
                     if (++sa == NA) { sa = 0; pa ^= 1; }
-                    for (int t = 0; t < 9; ++t) {
-                        ptx::mbar_wait(&emptyB[sb], pb ^ 1, err, 2200 + sb);
-                        ptx::mbar_arrive_expect_tx(&fullB[sb], C::kBBytes);
-                        ptx::tma_load_2d(&tmB, &fullB[sb], smem_b + sb * C::kBBytes, t * Cin + j * kConvBlockK, n0);
-                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    if constexpr (!C::kBRes) {
+                        for (int t = 0; t < 9; ++t) {
+                            ptx::mbar_wait(&emptyB[sb], pb ^ 1, err, 2200 + sb);
+                            ptx::mbar_arrive_expect_tx(&fullB[sb], C::kBBytes);
+                            ptx::tma_load_2d(&tmB, &fullB[sb], smem_b + sb * C::kBBytes, t * Cin + j * kConvBlockK, n0);
+                            if (++sb == NB) { sb = 0; pb ^= 1; }
+                        }
                     }
                 }
             }
@@ -492,6 +589,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int sa = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             int iter = 0;
+            if constexpr (C::kBRes) ptx::mbar_wait(&fullB[0], 0, err, 2500);     // resident weights have landed
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
                 const int as = iter & 1;
                 const uint32_t aphase = (iter >> 1) & 1;
@@ -502,7 +600,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     ptx::mbar_wait(&fullA[sa], pa, err, 2400 + sa);
                     const uint32_t a_base = ptx::smem_u32(smem + sa * kHaloAStride);
                     for (int t = 0; t < 9; ++t) {
-                        ptx::mbar_wait(&fullB[sb], pb, err, 2500 + sb);
+                        if constexpr (C::kBRes) sb = j * 9 + t;
+                        else ptx::mbar_wait(&fullB[sb], pb, err, 2500 + sb);
                         ptx::tc_fence_after();
                         const uint32_t a_win = a_base + ((t / 3) * kHaloW + (t % 3)) * 128;
                         const uint64_t da = make_halo_desc(a_win);
@@ -510,8 +609,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                         for (int k = 0; k < kConvBlockK / 16; ++k)
                             ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | t | k) != 0);
-                        ptx::umma_commit(&emptyB[sb]);
-                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                        if constexpr (!C::kBRes) {
+                            ptx::umma_commit(&emptyB[sb]);
+                            if (++sb == NB) { sb = 0; pb ^= 1; }
+                        }
                     }
                     ptx::umma_commit(&emptyA[sa]);
                     if (++sa == NA) { sa = 0; pa ^= 1; }
@@ -598,7 +699,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& t
 
 template <int BLOCK_N, int KC>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
-            int total_pairs, int num_sms, cudaStream_t stream) {
+            int total_pairs, int num_sms, void* sk_ws, long long sk_bytes, int sk_mode, cudaStream_t stream) {
     using C = Cfg2<BLOCK_N, KC>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -609,7 +710,21 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& 
     }
     int clusters = num_sms / 2;
     if (clusters > total_pairs) clusters = total_pairs;
-    conv_tc2_kernel<BLOCK_N, KC><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
+    ConvTcArgs a = args;
+    // stream-K when whole tiles would leave the last wave mostly empty (e.g. 128 tiles on 74 clusters = 1.73 waves)
+    a.stream_k = 0;
+    if (sk_ws && args.out_sc == 1 && args.n_valid == args.tiles_n * BLOCK_N && (BLOCK_N % 32) == 0 && (args.dbg & 3) == 0 &&
+        total_pairs > clusters && total_pairs % clusters != 0) {
+        const int waves = (total_pairs + clusters - 1) / clusters;
+        const size_t need = kSkFlagBytes + (size_t)2 * clusters * BLOCK_N * kConvBlockM * sizeof(float);
+        if ((sk_mode == 2 || (double)total_pairs / ((double)waves * clusters) < 0.93) && sk_mode != 1 &&
+            (size_t)sk_bytes >= need) {
+            a.stream_k = 1;
+            a.sk_flags = reinterpret_cast<int*>(sk_ws);
+            a.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sk_ws) + kSkFlagBytes);
+        }
+    }
+    conv_tc2_kernel<BLOCK_N, KC><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -648,6 +763,13 @@ const char* conv_tc_strerror(int code) {
     }
 }
 
+long long conv_tc_splitk_bytes() {
+    int dev = 0, num_sms = 148;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
+    return kSkFlagBytes + (long long)num_sms * 256 * kConvBlockM * (long long)sizeof(float);
+}
+
 bool conv_tc_supported(int H, int W, int Cin, int Cout) {
     if (Cin <= 0 || Cin % kConvBlockK != 0 || Cout <= 0 || Cout % 16 != 0) return false;
     if (W >= 128) return true;                            // BW = 128, BH = 1, BB = 1; ragged tail rows are masked
@@ -670,7 +792,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
 
     // ---- 3x3 halo kernel (opt-in via p.halo): needs the canonical 3x3 tap order, H % 16 == 0, W % 8 == 0
     if (p.halo && !p.act2 && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 &&
-        (p.Cout % 128 == 0 || p.Cout == 16)) {
+        (p.Cout % 128 == 0 || (p.Cout == 16 && p.Cin <= kHaloResChunks * kConvBlockK))) {
         bool canon = true;
         for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
         if (canon) {
@@ -819,10 +941,10 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         // two 64-channel k-chunks per pipeline stage (half the barrier round trips) when the channel counts allow
         const bool kc2 = p.kmerge != 1 && (a.chunks_per_tap % 2 == 0) && (a.a_split % 2 == 0);
         if (block_n == 256)
-            return kc2 ? launch2<256, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
-                       : launch2<256, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
-        return kc2 ? launch2<128, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
-                   : launch2<128, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
+            return kc2 ? launch2<256, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream)
+                       : launch2<256, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream);
+        return kc2 ? launch2<128, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream)
+                   : launch2<128, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream);
     }
     switch (block_n) {
         case 256: return launch<256>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);

@@ -382,22 +382,34 @@ linear_tiled_kernel(const float* __restrict__ in, int M, int K, const float* __r
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-    for (int k0 = 0; k0 < K; k0 += kTK) {
-        {   // x chunk: 32 rows x 32 k, one float4 per thread
-            const int row = threadIdx.x >> 3, kq = (threadIdx.x & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (m0 + row < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(in + (long long)(m0 + row) * K + k0 + kq);
-            if (in_act == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
-            xs[kq][row] = v.x; xs[kq + 1][row] = v.y; xs[kq + 2][row] = v.z; xs[kq + 3][row] = v.w;
-        }
+    // software pipeline: the next chunk's global loads are issued before the current chunk's FMAs
+    const int xrow = threadIdx.x >> 3, kq = (threadIdx.x & 7) * 4;
+    float4 xr, wr[4];
+    auto fetch = [&](int k0) {
+        xr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + xrow < M && k0 + kq < K) xr = *reinterpret_cast<const float4*>(in + (long long)(m0 + xrow) * K + k0 + kq);
 #pragma unroll
         for (int pass = 0; pass < 4; ++pass) {   // w chunk: 128 cols x 32 k, 8 threads (128 B) per column
-            const int col = pass * 32 + (threadIdx.x >> 3), kq = (threadIdx.x & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n0 + col < N && k0 + kq < K) v = __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + col) * K + k0 + kq));
-            ws[kq][col] = v.x; ws[kq + 1][col] = v.y; ws[kq + 2][col] = v.z; ws[kq + 3][col] = v.w;
+            const int col = pass * 32 + (threadIdx.x >> 3);
+            wr[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n0 + col < N && k0 + kq < K)
+                wr[pass] = __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + col) * K + k0 + kq));
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += kTK) {
+        {
+            float4 v = xr;
+            if (in_act == 1) { v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w); }
+            xs[kq][xrow] = v.x; xs[kq + 1][xrow] = v.y; xs[kq + 2][xrow] = v.z; xs[kq + 3][xrow] = v.w;
+        }
+#pragma unroll
+        for (int pass = 0; pass < 4; ++pass) {
+            const int col = pass * 32 + (threadIdx.x >> 3);
+            ws[kq][col] = wr[pass].x; ws[kq + 1][col] = wr[pass].y; ws[kq + 2][col] = wr[pass].z; ws[kq + 3][col] = wr[pass].w;
         }
         __syncthreads();
+        if (k0 + kTK < K) fetch(k0 + kTK);
 #pragma unroll
         for (int k = 0; k < kTK; ++k) {
             const float4 a = *reinterpret_cast<const float4*>(&xs[k][ty * 4]);
@@ -522,28 +534,42 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int 
 // horizontally unrolled window  out[b][h][w][j*8 + c] = in_c[b][h][w + j - 7]  (j < 15, c < Ca+Cb <= 8, else 0), fp16.
 // With it the k x k convs (all zero-embedded in one 15 x 15 window) become a 15-tap (vertical) implicit GEMM over
 // 128 "channels": K = 15 * 128, N = dim.  Inputs are the NCHW fp32 images x and lowres_cond_img (torch.cat, Unet.py:397).
-__global__ void stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b2, int Cb, int B,
-                                   int H, int W, __half* __restrict__ out) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)B * H * W * 16;
-    if (idx >= total) return;
-    const int j = (int)(idx & 15);
-    const long long pix = idx >> 4;
-    const int w = (int)(pix % W);
-    const int h = (int)((pix / W) % H);
-    const long long b = pix / ((long long)W * H);
-    const int ws = w + j - 7;
-    __half v[8];
+// One CTA = kStemRows image rows x 64 columns: the 6 (<= 8) input channels of the (64 + 14)-pixel source window are read
+// once (coalesced per channel), packed to one 16-byte fp16 pixel each in shared memory, and the 16 x replicated
+// operand rows go out as consecutive 16-byte stores (LDS.128 + STG.128 per thread, 100 % write-coalesced).
+constexpr int kStemRows = 4, kStemCols = 64, kStemWin = kStemCols + 14;
+__global__ void __launch_bounds__(256)
+stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b2, int Cb, int B, int H, int W,
+                   __half* __restrict__ out) {
+    __shared__ uint4 s_px[kStemRows][kStemWin + 2];
+    const int w0 = blockIdx.x * kStemCols;
+    const int h0 = blockIdx.y * kStemRows;
+    const long long b = blockIdx.z;
+    for (int i = threadIdx.x; i < kStemRows * kStemWin; i += blockDim.x) {
+        const int r = i / kStemWin, t = i - r * kStemWin;
+        const int h = h0 + r, ws = w0 + t - 7;
+        __half v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float f = 0.f;
-        if (j < 15 && ws >= 0 && ws < W) {
-            if (c < Ca) f = a[((b * Ca + c) * H + h) * W + ws];
-            else if (c < Ca + Cb) f = b2[((b * Cb + (c - Ca)) * H + h) * W + ws];
+        for (int c = 0; c < 8; ++c) {
+            float f = 0.f;
+            if (h < H && ws >= 0 && ws < W) {
+                if (c < Ca) f = a[((b * Ca + c) * H + h) * W + ws];
+                else if (c < Ca + Cb) f = b2[((b * Cb + (c - Ca)) * H + h) * W + ws];
+            }
+            v[c] = __float2half_rn(f);
         }
-        v[c] = __float2half_rn(f);
+        s_px[r][t] = *reinterpret_cast<const uint4*>(v);
     }
-    *reinterpret_cast<uint4*>(out + idx * 8) = *reinterpret_cast<const uint4*>(v);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kStemRows * kStemCols * 16; i += blockDim.x) {
+        const int j = i & 15;
+        const int p = (i >> 4) & (kStemCols - 1);
+        const int r = i >> 10;                         // / (16 * kStemCols)
+        const int h = h0 + r, w = w0 + p;
+        if (h >= H || w >= W) continue;
+        const uint4 v = j < 15 ? s_px[r][p + j] : make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(out + (((b * H + h) * W + w) * 16 + j) * 8) = v;
+    }
 }
 
 __global__ void silu_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
@@ -634,7 +660,13 @@ int ln_rows(const float* in, long long R, int C, const float* gamma, const float
 int linear_f32(const float* in, int M, int K, const float* W, const float* bias, int N, int in_act, int out_act,
                const float* addend, float* out_f32, __half* out_f16, float out_scale, cudaStream_t st) {
     if (K % 4) return -1;
-    if (M > 8) {     // 32 x 128 shared-memory tiles: every weight row is streamed once per 32 input rows
+    if (M > 8 && M <= 64 && (long long)N * K <= (4LL << 20)) {
+        // small weight matrices (text / time conditioning MLPs at batch 32): latency-bound, so spread them over many
+        // warps -- one warp per (8-row group, output column) with the whole weight row in flight at once
+        dim3 grid((N + 7) / 8, (M + 7) / 8);
+        linear_f32_kernel<8><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+                                                   out_scale);
+    } else if (M > 8) {     // 32 x 128 shared-memory tiles: every weight row is streamed once per 32 input rows
         dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
         linear_tiled_kernel<<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
                                                   out_scale);
@@ -648,7 +680,8 @@ int linear_f32(const float* in, int M, int K, const float* W, const float* bias,
 
 int stem_unroll(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, __half* out, cudaStream_t st) {
     if (Ca + Cb > 8 || Ca < 1) return -1;
-    stem_unroll_kernel<<<grid1d((long long)B * H * W * 16, 256), 256, 0, st>>>(a, Ca, b, Cb, B, H, W, out);
+    dim3 grid((W + kStemCols - 1) / kStemCols, (H + kStemRows - 1) / kStemRows, B);
+    stem_unroll_kernel<<<grid, 256, 0, st>>>(a, Ca, b, Cb, B, H, W, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

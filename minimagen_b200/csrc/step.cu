@@ -12,6 +12,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace mi {
@@ -116,6 +118,122 @@ quantile_kernel(const float* __restrict__ x0, int n, int rank_lo, int rank_hi, f
     }
 }
 
+// Cluster variant: 8 CTAs (one thread-block cluster) per image, every CTA keeps its n/8 keys in REGISTERS, so the image
+// is read from memory once instead of four to five times by a single SM; the per-pass 256-bin histograms are summed
+// across the cluster through distributed shared memory.  Same radix select, same result bits.
+constexpr int kSelCluster = 8, kSelPerThread = 24;
+
+__global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
+quantile_cluster_kernel(const float* __restrict__ x0, int n, int rank_lo, int rank_hi, float weight, float min_s,
+                        float* __restrict__ s_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ unsigned hist[256];       // this CTA's histogram of the current pass (read remotely by the peers)
+    __shared__ unsigned ghist[256];      // cluster-wide histogram
+    __shared__ uint32_t sh_prefix, sh_k, sh_eq, sh_cta_min;
+    __shared__ uint32_t sh_min[32];
+    const int img = blockIdx.x / kSelCluster;
+    const unsigned rank = cluster.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int chunk = (n + kSelCluster - 1) / kSelCluster;
+    const int beg = rank * chunk;
+    const int cnt = max(0, min(chunk, n - beg));
+    const float* x = x0 + (long long)img * n + beg;
+
+    uint32_t keys[kSelPerThread];
+#pragma unroll
+    for (int j = 0; j < kSelPerThread; ++j) {
+        const int i = tid + j * kSelThreads;
+        keys[j] = i < cnt ? absbits(x[i]) : 0xFFFFFFFFu;          // sentinel: never matches a prefix of a finite |x|
+    }
+    uint32_t prefix = 0, maskbits = 0, k = (uint32_t)rank_lo;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j) {
+            const bool live = (tid + j * kSelThreads < cnt) && ((keys[j] & maskbits) == prefix);
+            const unsigned bin = live ? ((keys[j] >> shift) & 0xFF) : 256u;
+            const unsigned peers = __match_any_sync(0xffffffffu, bin);
+            if (live && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+        }
+        cluster.sync();                                            // every CTA's histogram is complete
+        if (tid < 256) {
+            unsigned t = 0;
+#pragma unroll
+            for (int r = 0; r < kSelCluster; ++r) t += *cluster.map_shared_rank(&hist[tid], r);
+            ghist[tid] = t;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // digit select: lane owns bins [8*lane, 8*lane+8); warp scan of the lane totals, then a scan inside one lane
+            unsigned loc[8], tot = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { loc[e] = ghist[8 * lane + e]; tot += loc[e]; }
+            unsigned incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned excl = incl - tot;
+            const bool mine = k >= excl && k < incl;               // exactly one lane (k < total count)
+            if (mine) {
+                unsigned cum = excl;
+                int d = 0;
+                for (; d < 8; ++d) {
+                    if (k < cum + loc[d]) break;
+                    cum += loc[d];
+                }
+                sh_prefix = prefix | ((uint32_t)(8 * lane + d) << shift);
+                sh_k = k - cum;
+                sh_eq = loc[d];
+            }
+        }
+        __syncthreads();
+        prefix = sh_prefix;
+        k = sh_k;
+        maskbits |= 0xFFu << shift;
+        cluster.sync();                                            // peers are done reading hist before it is re-zeroed
+    }
+    const uint32_t v_lo = prefix;
+    uint32_t v_hi = v_lo;
+    if (rank_hi > rank_lo && k + 1 >= sh_eq) {                      // uniform over the cluster (same k, same sh_eq)
+        uint32_t mn = 0xFFFFFFFFu;
+#pragma unroll
+        for (int j = 0; j < kSelPerThread; ++j)
+            if ((tid + j * kSelThreads < cnt) && keys[j] > v_lo && keys[j] < mn) mn = keys[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) sh_min[tid >> 5] = mn;
+        __syncthreads();
+        if (tid < 32) {
+            mn = sh_min[tid];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+            if (tid == 0) sh_cta_min = mn;
+        }
+        cluster.sync();
+        if (rank == 0 && tid == 0) {
+            uint32_t m = 0xFFFFFFFFu;
+            for (int r = 0; r < kSelCluster; ++r) m = min(m, *cluster.map_shared_rank(&sh_cta_min, r));
+            sh_min[0] = m;
+        }
+        cluster.sync();                                            // peers keep their smem alive until rank 0 has read it
+        if (rank == 0 && tid == 0) {
+            v_hi = sh_min[0];
+            if (v_hi == 0xFFFFFFFFu) v_hi = v_lo;
+        }
+    }
+    if (rank == 0 && tid == 0) {
+        const float lo = __uint_as_float(v_lo), hi = __uint_as_float(v_hi);
+        const float diff = __fsub_rn(hi, lo);
+        const float s = (weight < 0.5f) ? fmaf(weight, diff, lo) : fmaf(__fsub_rn(weight, 1.0f), diff, hi);
+        s_out[img] = fmaxf(s, min_s);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 posterior_kernel(const float* __restrict__ x0, const float* __restrict__ x_t, const float* __restrict__ noise,
                  const float* __restrict__ s, const long long* __restrict__ t, const float* __restrict__ tab_c1,
@@ -173,7 +291,11 @@ int step_x0(const float* x_t, const float* eps_cond, const float* eps_null, floa
 int step_quantile(const float* x0, int B, int n_per_img, int rank_lo, int rank_hi, float weight, float min_s,
                   float* s_out, cudaStream_t st) {
     if (rank_lo < 0 || rank_hi < rank_lo || rank_hi >= n_per_img) return -1;
-    quantile_kernel<<<B, kSelThreads, 0, st>>>(x0, n_per_img, rank_lo, rank_hi, weight, min_s, s_out);
+    if ((n_per_img + kSelCluster - 1) / kSelCluster <= kSelThreads * kSelPerThread)
+        quantile_cluster_kernel<<<B * kSelCluster, kSelThreads, 0, st>>>(x0, n_per_img, rank_lo, rank_hi, weight, min_s,
+                                                                        s_out);
+    else
+        quantile_kernel<<<B, kSelThreads, 0, st>>>(x0, n_per_img, rank_lo, rank_hi, weight, min_s, s_out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

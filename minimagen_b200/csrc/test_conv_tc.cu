@@ -35,10 +35,13 @@ struct Case {
     int B, H, W, Cin, Cout, k, stride;   // stride 1 (k=1|3) or 2 (k=4, pad 1)
     bool bias, residual, f16out;
     int hint;
-    int pair;   // 0 auto, 1 force 1-CTA kernel, 2 force CTA-pair kernel
+    int pair;   // 0 auto, 1 force 1-CTA kernel, 2 force CTA-pair kernel (stream-K auto), 3 halo kernel, 4 pair with one
+                // k-chunk per stage, 5 pair + stream-K forced, 6 pair without stream-K, 11..13 profiling switches
 };
 
 static int* g_err = nullptr;   // host-mapped
+static void* g_ws = nullptr;   // stream-K workspace (flags zeroed once; the kernels re-arm them)
+static long long g_ws_bytes = 0;
 
 // returns max abs error (or -1 on failure)
 static double run_case(const Case& c, bool check, int reps, double* ms_out) {
@@ -103,7 +106,11 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
         }
     p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
     p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
-    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3); p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
+    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3); p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair == 7) p.cta_pair = 2; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
+    p.splitk_ws = g_ws; p.splitk_ws_bytes = g_ws_bytes;
+    if (c.pair == 5) { p.cta_pair = 2; p.stream_k = 2; }
+    if (c.pair == 6) { p.cta_pair = 2; p.stream_k = 1; }
+    if (c.pair == 7) { p.cta_pair = 2; p.stream_k = 2; p.dbg = 4; }
 
     *g_err = 0;
     int rc = conv_tc_launch(p, 0);
@@ -185,6 +192,10 @@ int main(int argc, char** argv) {
     const char* mode = argc > 1 ? argv[1] : "all";
     CK(cudaSetDeviceFlags(cudaDeviceMapHost));
     CK(cudaHostAlloc(&g_err, sizeof(int), cudaHostAllocMapped));
+    g_ws_bytes = conv_tc_splitk_bytes();
+    CK(cudaMalloc(&g_ws, g_ws_bytes));
+    CK(cudaMemset(g_ws, 0xFF, g_ws_bytes));          // NaN partials: a read-before-write shows up in the check
+    CK(cudaMemset(g_ws, 0, kSkFlagBytes));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
@@ -213,6 +224,8 @@ int main(int argc, char** argv) {
             {"h_c3_deepk", 2, 16, 16, 1024, 256, 3, 1, false, true, false, 256, 3},
             {"h_c3_w256", 1, 16, 256, 64, 128, 3, 1, false, false, false, 128, 3},
             {"h_c3_n16", 2, 32, 32, 128, 16, 3, 1, true, false, false, 0, 3},
+            {"h_c3_n16_k256", 3, 32, 64, 256, 16, 3, 1, true, false, false, 0, 3},
+            {"h_c3_n16_persist", 4, 128, 128, 64, 16, 3, 1, false, false, false, 0, 3},
             // ---- CTA-pair (cta_group::2) kernel
             {"p_c3_16x16_n128", 2, 16, 16, 64, 128, 3, 1, true, false, false, 128, 2},
             {"p_c3_16x16_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256, 2},
@@ -223,11 +236,26 @@ int main(int argc, char** argv) {
             {"p_c3_persist", 8, 64, 64, 64, 128, 3, 1, true, true, false, 128, 2},
             {"p_c3_deepk", 2, 16, 16, 1024, 256, 3, 1, false, true, false, 256, 2},
             {"p_c3_w256", 1, 4, 256, 64, 128, 3, 1, false, false, false, 128, 2},
+            // ---- CTA-pair kernel, stream-K forced (tiles > clusters, not a multiple)
+            {"sk_c3_n256_kc1", 5, 64, 64, 64, 256, 3, 1, true, true, true, 256, 5},
+            {"sk_c3_n256_kc2", 5, 64, 64, 128, 256, 3, 1, true, true, false, 256, 5},
+            {"sk_c3_n128", 5, 64, 64, 128, 128, 3, 1, true, false, true, 128, 5},
+            {"sk_c3_n512", 3, 64, 64, 64, 512, 3, 1, false, true, false, 256, 5},
+            {"sk_gemm1x1", 10, 64, 64, 256, 256, 1, 1, true, false, false, 256, 5},
+            {"sk_c4_s2", 5, 128, 128, 64, 128, 4, 2, true, false, true, 128, 5},
         };
         for (const Case& c : cases) {
             double ms = 0;
             double err = run_case(c, true, 0, &ms);
             if (err < 0) ++failures;
+        }
+        {   // every stream-K slot must have been re-armed (ready == done == 0)
+            std::vector<int> fl(kSkFlagBytes / sizeof(int));
+            CK(cudaMemcpy(fl.data(), g_ws, kSkFlagBytes, cudaMemcpyDeviceToHost));
+            int bad = 0;
+            for (int v : fl) bad += v != 0;
+            printf("stream-K flags after the checks: %d non-zero%s\n", bad, bad ? "  **MISMATCH**" : "  OK");
+            if (bad) ++failures;
         }
     }
     if (!strcmp(mode, "perf") || !strcmp(mode, "all")) {
@@ -237,9 +265,15 @@ int main(int argc, char** argv) {
             {"D3(neither) sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 13},
             {"D1(noTMA) sr_16_1024 n128", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 128, 11},
             {"D3(neither) sr_16_1024 n128", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 128, 13},
+            {"D3alt(2 chains) sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 21},
+            {"D3alt(2 chains) sr_16_1024 n128", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 128, 21},
+            {"D3alt(2 chains) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 21},
+            {"D3alt(2 chains) sr_16_1024 n64", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 64, 21},
+            {"D3(neither) sr_16_1024 n64", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 64, 13},
             {"D1(noTMA) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 11},
             {"D2(noEpi) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 12},
             {"D3(neither) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 13},
+            {"H final_256_128_16", 32, 256, 256, 128, 16, 3, 1, true, false, false, 0, 3},
             {"H sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 3},
             {"H sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 3},
             {"H sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 3},
@@ -252,6 +286,16 @@ int main(int argc, char** argv) {
             {"P(kc1) sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 4},
             {"P(kc1) sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256, 4},
             {"P(kc1) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 4},
+            {"Pnosk 148tiles_16_1024", 37, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 6},
+            {"Pnosk 74tiles_16_1024", 37, 16, 16, 1024, 512, 3, 1, true, true, false, 256, 6},
+            {"Pnosk 64tiles_16_1024", 32, 16, 16, 1024, 512, 3, 1, true, true, false, 256, 6},
+            {"SKnoexch sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 7},
+            {"SKnoexch sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 7},
+            {"Pnosk sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 6},
+            {"Pnosk sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 6},
+            {"Pnosk sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 6},
+            {"Pnosk sr_32_1024", 32, 32, 32, 1024, 512, 3, 1, true, true, false, 256, 6},
+            {"Pnosk pw_16_2048", 32, 16, 16, 2048, 1024, 1, 1, true, false, false, 256, 6},
             {"P sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 2},
             {"P sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 2},
             {"P sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 2},
