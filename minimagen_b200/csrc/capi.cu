@@ -87,9 +87,10 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     if (out_sc <= 1 && ((out_sw % 4) || (out_sh % 4) || (out_sb % 4)))
         return fail(-8, "mi_conv2d_igemm_f16: channel-contiguous output strides must be multiples of 4 elements");
     if (out_sc > 1 && residual) return fail(-8, "mi_conv2d_igemm_f16: residual needs channel-contiguous output");
-    // kernel selection (measured on B200, profiles/r01_conv_tc_selftest_v3.log): C_out = 128 3x3 layers are fastest on the
-    // halo-tile kernel, wider outputs on the CTA-pair kernel (chosen inside conv_tc_launch)
-    p.halo = (mode == 0 && kh == 3 && kw == 3 && (c_out % 256) != 0) ? 1 : 0;
+    // kernel selection (measured on B200, profiles/r01_conv_tc_selftest_v9.log): 3x3 layers run fastest on the swapped-operand
+    // halo kernel (needs C_out % 128 == 0, H % 32 == 0), C_out = 128 / 16 layers it cannot take on the pixel-major halo
+    // kernel, everything else on the CTA-pair kernel (all chosen inside conv_tc_launch)
+    p.halo = (mode == 0 && kh == 3 && kw == 3) ? 1 : 0;
     const int rc = mi::conv_tc_launch(p, S(stream));
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;

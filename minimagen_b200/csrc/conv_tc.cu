@@ -99,57 +99,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int BB = kConvBlockM >> (args.bw_log2 + args.bh_log2);
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % args.tiles_n;
-                const int mt = tile / args.tiles_n;
-                const int w0 = (mt % args.tiles_w) * BW;
-                const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
-                const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
-                const int n0 = nt * BLOCK_N;
-                int kb = 0;
-                for (int t = 0; t < args.num_taps; ++t) {
-                    const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
-                    for (int j = 0; j < args.chunks_per_tap; ++j, ++kb) {
-                        ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
+        // ===================== TMA producer (warp stays converged, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % args.tiles_n;
+            const int mt = tile / args.tiles_n;
+            const int w0 = (mt % args.tiles_w) * BW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
+            const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
+            const int n0 = nt * BLOCK_N;
+            int kb = 0;
+            for (int t = 0; t < args.num_taps; ++t) {
+                const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
+                for (int j = 0; j < args.chunks_per_tap; ++j, ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 100 + stage);
+                    if (ptx::elect_one()) {
                         uint8_t* sa = smem + stage * C::kStageBytes;
                         uint8_t* sb = sa + kABytes;
                         if ((args.dbg & 1) && (tile != (int)blockIdx.x || kb >= STAGES)) {
                             ptx::mbar_arrive(&full_bar[stage]);      // DEBUG: no data movement, MMA reuses stale smem
                         } else {
-                        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-                        if (j < args.a_split)
-                            ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
-                                             h0 + dh, ph, b0);
-                        else   // second half of a virtual channel concat (skip connection)
-                            ptx::tma_load_5d(&tmA2, &full_bar[stage], sa,
-                                             args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 + dw, h0 + dh, ph, b0);
-                        ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                            if (j < args.a_split)
+                                ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
+                                                 h0 + dh, ph, b0);
+                            else   // second half of a virtual channel concat (skip connection)
+                                ptx::tma_load_5d(&tmA2, &full_bar[stage], sa,
+                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 + dw, h0 + dh, ph,
+                                                 b0);
+                            ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
                         }
-                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0 /*fp16*/);
-            int stage = 0;
-            uint32_t phase = 0;
-            int iter = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-                const int as = iter & 1;
-                const uint32_t aphase = (iter >> 1) & 1;
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+        // ===================== MMA issuer (warp stays converged, one elected lane issues) =====================
+        constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0 /*fp16*/);
+        int stage = 0;
+        uint32_t phase = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 200 + as);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(&full_bar[stage], phase, err, 300 + stage);
                 ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    ptx::mbar_wait(&full_bar[stage], phase, err, 300 + stage);
-                    ptx::tc_fence_after();
+                if (ptx::elect_one()) {
                     const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
                     const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
                     const uint64_t db = ptx::make_kmajor_sw128_desc(sa + kABytes);
@@ -162,8 +163,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     ptx::umma_commit(&empty_bar[stage]);             // frees the smem slot when these MMAs retire
                     if (kb == num_kb - 1) ptx::umma_commit(&tfull_bar[as]);   // accumulator complete
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -309,25 +310,25 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer (both CTAs) =====================
-            int stage = 0;
-            uint32_t phase = 0;
-            SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
-            int pt, s0, s1;
-            while (walk.next(pt, s0, s1)) {
-                const int nt = pt % args.tiles_n;
-                const int mt = 2 * (pt / args.tiles_n) + (int)rank;      // may be == tiles_m (dummy tile: all OOB)
-                const int w0 = (mt % args.tiles_w) * BW;
-                const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
-                const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
-                const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
-                int kb = s0 * KC;
-                int t = kb / args.chunks_per_tap;
-                int j = kb - t * args.chunks_per_tap;
-                for (int s = s0; s < s1; ++s, kb += KC) {
-                    const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
-                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 1100 + stage);
+        // ===================== TMA producer (both CTAs; converged warp, one elected lane issues) =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
+        int pt, s0, s1;
+        while (walk.next(pt, s0, s1)) {
+            const int nt = pt % args.tiles_n;
+            const int mt = 2 * (pt / args.tiles_n) + (int)rank;      // may be == tiles_m (dummy tile: all OOB)
+            const int w0 = (mt % args.tiles_w) * BW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * BH;
+            const int b0 = (mt / (args.tiles_w * args.tiles_h)) * BB;
+            const int n0 = nt * BLOCK_N + (int)rank * (BLOCK_N / 2);
+            int kb = s0 * KC;
+            int t = kb / args.chunks_per_tap;
+            int j = kb - t * args.chunks_per_tap;
+            for (int s = s0; s < s1; ++s, kb += KC) {
+                const int dh = args.dh[t], dw = args.dw[t], ph = args.ph[t];
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1, err, 1100 + stage);
+                if (ptx::elect_one()) {
                     uint8_t* sa = smem + stage * C::kStageBytes;
                     uint8_t* sb = sa + KC * kABytes;
                     if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
@@ -344,15 +345,15 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb + kc * C::kBBytes, (kb + kc) * kConvBlockK, n0);
                     }
                     if (!leader) ptx::mbar_arrive_cluster(&full_bar[stage], 0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
-                    j += KC;
-                    if (j >= args.chunks_per_tap) { j = 0; ++t; }
                 }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                j += KC;
+                if (j >= args.chunks_per_tap) { j = 0; ++t; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && leader) {
-            // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
             constexpr uint32_t idesc = ptx::make_idesc_f16(256, BLOCK_N, 0);
             int stage = 0;
             uint32_t phase = 0;
@@ -368,17 +369,19 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int s = s0; s < s1; ++s) {
                     ptx::mbar_wait(&full_bar[stage], phase, err, 1300 + stage);
                     ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
+                    if (ptx::elect_one()) {
+                        const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
 #pragma unroll
-                    for (int kc = 0; kc < KC; ++kc) {
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(sa + kc * kABytes);
-                        const uint64_t db = ptx::make_kmajor_sw128_desc(sa + KC * kABytes + kc * C::kBBytes);
+                        for (int kc = 0; kc < KC; ++kc) {
+                            const uint64_t da = ptx::make_kmajor_sw128_desc(sa + kc * kABytes);
+                            const uint64_t db = ptx::make_kmajor_sw128_desc(sa + KC * kABytes + kc * C::kBBytes);
 #pragma unroll
-                        for (int k = 0; k < kConvBlockK / 16; ++k)
-                            ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, ((s - s0) | kc | k) != 0);
+                            for (int k = 0; k < kConvBlockK / 16; ++k)
+                                ptx::umma_f16_2sm(tmem_d, da + 2 * k, db + 2 * k, idesc, ((s - s0) | kc | k) != 0);
+                        }
+                        ptx::umma_commit_2sm(&empty_bar[stage], 3);               // frees this stage in BOTH CTAs
+                        if (s + 1 == s1) ptx::umma_commit_2sm(&tfull_bar[as], 3);
                     }
-                    ptx::umma_commit_2sm(&empty_bar[stage], 3);               // frees this stage in BOTH CTAs
-                    if (s + 1 == s1) ptx::umma_commit_2sm(&tfull_bar[as], 3);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -549,76 +552,82 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int Cin = chunks * kConvBlockK;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            if constexpr (C::kBRes) {
-                // resident weights: tile (j, t) at slot j*9 + t, all on one barrier (tiles_n == 1)
+        // ===================== TMA producer (converged warp, one elected lane issues) =====================
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        if constexpr (C::kBRes) {
+            // resident weights: tile (j, t) at slot j*9 + t, all on one barrier (tiles_n == 1)
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&fullB[0], 9 * chunks * C::kBBytes);
                 for (int j = 0; j < chunks; ++j)
                     for (int t = 0; t < 9; ++t)
                         ptx::tma_load_2d(&tmB, &fullB[0], smem_b + (j * 9 + t) * C::kBBytes, t * Cin + j * kConvBlockK, 0);
             }
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % args.tiles_n;
-                const int mt = tile / args.tiles_n;
-                const int w0 = (mt % args.tiles_w) * kHaloTW;
-                const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHaloTH;
-                const int b0 = mt / (args.tiles_w * args.tiles_h);
-                const int n0 = nt * BLOCK_N;
-                for (int j = 0; j < chunks; ++j) {
-                    ptx::mbar_wait(&emptyA[sa], pa ^ 1, err, 2100 + sa);
+        }
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % args.tiles_n;
+            const int mt = tile / args.tiles_n;
+            const int w0 = (mt % args.tiles_w) * kHaloTW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHaloTH;
+            const int b0 = mt / (args.tiles_w * args.tiles_h);
+            const int n0 = nt * BLOCK_N;
+            for (int j = 0; j < chunks; ++j) {
+                ptx::mbar_wait(&emptyA[sa], pa ^ 1, err, 2100 + sa);
+                if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&fullA[sa], kHaloABytes);
                     ptx::tma_load_5d(&tmA, &fullA[sa], smem + sa * kHaloAStride, args.a_chan_off + j * kConvBlockK,
                                      w0 - 1, h0 - 1, 0, b0);
-                    if (++sa == NA) { sa = 0; pa ^= 1; }
-                    if constexpr (!C::kBRes) {
-                        for (int t = 0; t < 9; ++t) {
-                            ptx::mbar_wait(&emptyB[sb], pb ^ 1, err, 2200 + sb);
+                }
+                if (++sa == NA) { sa = 0; pa ^= 1; }
+                if constexpr (!C::kBRes) {
+                    for (int t = 0; t < 9; ++t) {
+                        ptx::mbar_wait(&emptyB[sb], pb ^ 1, err, 2200 + sb);
+                        if (ptx::elect_one()) {
                             ptx::mbar_arrive_expect_tx(&fullB[sb], C::kBBytes);
                             ptx::tma_load_2d(&tmB, &fullB[sb], smem_b + sb * C::kBBytes, t * Cin + j * kConvBlockK, n0);
-                            if (++sb == NB) { sb = 0; pb ^= 1; }
                         }
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0);
-            int sa = 0, sb = 0;
-            uint32_t pa = 0, pb = 0;
-            int iter = 0;
-            if constexpr (C::kBRes) ptx::mbar_wait(&fullB[0], 0, err, 2500);     // resident weights have landed
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
-                const int as = iter & 1;
-                const uint32_t aphase = (iter >> 1) & 1;
-                ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 2300 + as);
-                ptx::tc_fence_after();
-                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-                for (int j = 0; j < chunks; ++j) {
-                    ptx::mbar_wait(&fullA[sa], pa, err, 2400 + sa);
-                    const uint32_t a_base = ptx::smem_u32(smem + sa * kHaloAStride);
-                    for (int t = 0; t < 9; ++t) {
-                        if constexpr (C::kBRes) sb = j * 9 + t;
-                        else ptx::mbar_wait(&fullB[sb], pb, err, 2500 + sb);
-                        ptx::tc_fence_after();
+        // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+        constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0);
+        int sa = 0, sb = 0;
+        uint32_t pa = 0, pb = 0;
+        int iter = 0;
+        if constexpr (C::kBRes) ptx::mbar_wait(&fullB[0], 0, err, 2500);     // resident weights have landed
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 2300 + as);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+            for (int j = 0; j < chunks; ++j) {
+                ptx::mbar_wait(&fullA[sa], pa, err, 2400 + sa);
+                const uint32_t a_base = ptx::smem_u32(smem + sa * kHaloAStride);
+                for (int t = 0; t < 9; ++t) {
+                    if constexpr (C::kBRes) sb = j * 9 + t;
+                    else ptx::mbar_wait(&fullB[sb], pb, err, 2500 + sb);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
                         const uint32_t a_win = a_base + ((t / 3) * kHaloW + (t % 3)) * 128;
                         const uint64_t da = make_halo_desc(a_win);
                         const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_b + sb * C::kBBytes));
 #pragma unroll
                         for (int k = 0; k < kConvBlockK / 16; ++k)
                             ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | t | k) != 0);
-                        if constexpr (!C::kBRes) {
-                            ptx::umma_commit(&emptyB[sb]);
-                            if (++sb == NB) { sb = 0; pb ^= 1; }
-                        }
+                        if constexpr (!C::kBRes) ptx::umma_commit(&emptyB[sb]);
                     }
-                    ptx::umma_commit(&emptyA[sa]);
-                    if (++sa == NA) { sa = 0; pa ^= 1; }
+                    if constexpr (!C::kBRes) {
+                        if (++sb == NB) { sb = 0; pb ^= 1; }
+                    }
                 }
-                ptx::umma_commit(&tfull_bar[as]);
+                if (ptx::elect_one()) ptx::umma_commit(&emptyA[sa]);
+                if (++sa == NA) { sa = 0; pa ^= 1; }
             }
+            if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
         const int ew = warp & 3;
@@ -644,6 +653,220 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
             epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b);
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 halo, swapped operands
+// For 128-channel outputs the GEMM above is M = 128 pixels x N = 128 channels per instruction, and a tcgen05.mma costs
+// ~100 clk + 0.35 clk per N column on this part (profiles/r01_conv_tc_bottleneck_study.md): N = 128 tops out near 1.0
+// PFLOP/s.  So this variant computes the TRANSPOSED tile  D^T[128 channels][256 pixels] = W[128][K] x Act^T :
+//   * the "A" operand (M = 128 rows) is the 128 x 64 weight tile of one (tap, chunk),
+//   * the "B" operand (N = 256 rows) is a window of a (32+2) x (8+2)-pixel halo tile: 32 row segments of 8 pixels, one
+//     halo row (1280 B) apart -- the same shifted-descriptor trick as conv3x3_halo_kernel, now with N = 256,
+//   * the accumulator holds channels in TMEM lanes and pixels in columns, which is exactly what an NHWC store wants: a
+//     warp-wide tcgen05.ld hands lane c the value of channel c for 32 pixels, so every global access of the epilogue is one
+//     pixel's 32 consecutive channels (128 B) -- no shared-memory transposition at all.
+// The virtual concat (two activation tensors) is supported: chunk j >= a_split comes from the second tensor map.
+constexpr int kHtTH = 32, kHtTW = 8, kHtW = kHtTW + 2, kHtH = kHtTH + 2;
+constexpr uint32_t kHtHaloBytes = kHtH * kHtW * 128;                          // 43520
+constexpr uint32_t kHtHaloStride = (kHtHaloBytes + 1023) & ~1023u;            // 44032
+constexpr int kHtPix = kHtTH * kHtTW;                                         // 256 = UMMA N
+struct CfgT {
+    static constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                // one (tap, chunk) weight tile
+    static constexpr int kHStages = 2;
+    static constexpr int kWStages = (kRingBudget - kHStages * kHtHaloStride) / kWBytes;   // 6
+    static constexpr uint32_t kTmemCols = 2 * kHtPix;                         // 512: two accumulator stages
+    static constexpr uint32_t kSmemBytes = kHStages * kHtHaloStride + kWStages * kWBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((kHtW * 128u) >> 4) << 32;     // SBO: one halo row between 8-pixel row segments
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
+    using C = CfgT;
+    constexpr int NH = C::kHStages, NW = C::kWStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_w = smem + NH * kHtHaloStride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + NW * C::kWBytes);
+    uint64_t* fullH = bars;
+    uint64_t* emptyH = bars + NH;
+    uint64_t* fullW = bars + 2 * NH;
+    uint64_t* emptyW = bars + 2 * NH + NW;
+    uint64_t* tfull_bar = bars + 2 * NH + 2 * NW;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    static_assert((2 * NH + 2 * NW + 4) * 8 + 8 <= 256, "barrier block too large");
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int* err = args.err_flag;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < NH; ++i) { ptx::mbar_init(&fullH[i], 1); ptx::mbar_init(&emptyH[i], 1); }
+        for (int i = 0; i < NW; ++i) { ptx::mbar_init(&fullW[i], 1); ptx::mbar_init(&emptyW[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 32 * kEpiWarps); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    const int chunks = args.chunks_per_tap;
+    const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
+    const int total_tiles = tiles_m * args.tiles_n;
+    const int Cin = chunks * kConvBlockK;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int sh = 0, sw = 0;
+        uint32_t ph = 0, pw = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % args.tiles_n;
+            const int mt = tile / args.tiles_n;
+            const int w0 = (mt % args.tiles_w) * kHtTW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHtTH;
+            const int b0 = mt / (args.tiles_w * args.tiles_h);
+            const int n0 = nt * 128;
+            for (int j = 0; j < chunks; ++j) {
+                ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 3100 + sh);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&fullH[sh], kHtHaloBytes);
+                    if (j < args.a_split)
+                        ptx::tma_load_5d(&tmA, &fullH[sh], smem + sh * kHtHaloStride, args.a_chan_off + j * kConvBlockK,
+                                         w0 - 1, h0 - 1, 0, b0);
+                    else
+                        ptx::tma_load_5d(&tmA2, &fullH[sh], smem + sh * kHtHaloStride,
+                                         args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 - 1, h0 - 1, 0, b0);
+                }
+                if (++sh == NH) { sh = 0; ph ^= 1; }
+                for (int t = 0; t < 9; ++t) {
+                    ptx::mbar_wait(&emptyW[sw], pw ^ 1, err, 3200 + sw);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&fullW[sw], C::kWBytes);
+                        ptx::tma_load_2d(&tmB, &fullW[sw], smem_w + sw * C::kWBytes, t * Cin + j * kConvBlockK, n0);
+                    }
+                    if (++sw == NW) { sw = 0; pw ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: D^T[128 ch][256 px] += W_tile[128][64] x window^T =====================
+        constexpr uint32_t idesc = ptx::make_idesc_f16(128, kHtPix, 0);
+        int sh = 0, sw = 0;
+        uint32_t ph = 0, pw = 0;
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 3300 + as);
+            ptx::tc_fence_after();
+            const uint32_t tmem_d = tmem_base + as * kHtPix;
+            for (int j = 0; j < chunks; ++j) {
+                ptx::mbar_wait(&fullH[sh], ph, err, 3400 + sh);
+                const uint32_t h_base = ptx::smem_u32(smem + sh * kHtHaloStride);
+                for (int t = 0; t < 9; ++t) {
+                    ptx::mbar_wait(&fullW[sw], pw, err, 3500 + sw);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_w + sw * C::kWBytes));
+                        const uint64_t db = make_halo_t_desc(h_base + ((t / 3) * kHtW + (t % 3)) * 128);
+#pragma unroll
+                        for (int k = 0; k < kConvBlockK / 16; ++k)
+                            ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | t | k) != 0);
+                        ptx::umma_commit(&emptyW[sw]);
+                    }
+                    if (++sw == NW) { sw = 0; pw ^= 1; }
+                }
+                if (ptx::elect_one()) ptx::umma_commit(&emptyH[sh]);
+                if (++sh == NH) { sh = 0; ph ^= 1; }
+            }
+            if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: lane = channel, columns = pixels =====================
+        const int q = warp & 3;                       // TMEM lane quarter -> channels [32q, 32q + 32) of the tile
+        const int half = warp >= 8 ? 1 : 0;           // pixel columns [128*half, 128*half + 128)
+        int iter = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+            const int nt = tile % args.tiles_n;
+            const int mt = tile / args.tiles_n;
+            const int w0 = (mt % args.tiles_w) * kHtTW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHtTH;
+            const int b = mt / (args.tiles_w * args.tiles_h);
+            const int n = nt * 128 + q * 32 + lane;   // this thread's output channel
+            const float bias_v = args.bias ? __ldg(args.bias + n) : 0.f;
+            const long long base = (long long)b * args.out_sb + (long long)(h0 + half * 16) * args.out_sh +
+                                   (long long)w0 * args.out_sw + n;
+            const int as = iter & 1;
+            const uint32_t aphase = (iter >> 1) & 1;
+            ptx::mbar_wait(&tfull_bar[as], aphase, err, 3600 + as);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kHtPix + half * 128;
+            float st_s = 0.f, st_q = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 128; c += 32) {       // 32 pixels = 4 tile rows per step
+                uint32_t v0[16], v1[16];
+                ptx::tmem_ld_x16(taddr + c, v0);
+                ptx::tmem_ld_x16(taddr + c + 16, v1);
+                const long long rowb = base + (long long)(c >> 3) * args.out_sh;
+                float r[32];
+                if (args.residual) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        r[i] = args.residual[rowb + (long long)(i >> 3) * args.out_sh + (long long)(i & 7) * args.out_sw];
+                }
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float f = __uint_as_float(i < 16 ? v0[i] : v1[i - 16]) + bias_v;
+                    if (args.residual) f += r[i];
+                    st_s += f;
+                    st_q += f * f;
+                    const long long o = rowb + (long long)(i >> 3) * args.out_sh + (long long)(i & 7) * args.out_sw;
+                    if (args.out_f32) args.out_f32[o] = f;
+                    if (args.out_f16) args.out_f16[o] = __float2half_rn(f);
+                }
+            }
+            if (args.stats) {
+                // 16-channel blocks = half warps: lanes 0-15 and 16-31
+#pragma unroll
+                for (int o = 1; o <= 8; o <<= 1) {
+                    st_s += __shfl_xor_sync(0xffffffffu, st_s, o);
+                    st_q += __shfl_xor_sync(0xffffffffu, st_q, o);
+                }
+                if ((lane & 15) == 0) {
+                    double* dst = args.stats + ((long long)b * args.stats_blocks + (n >> 4)) * 2;
+                    atomicAdd(dst, (double)st_s);
+                    atomicAdd(dst + 1, (double)st_q);
+                }
+            }
             ptx::tc_fence_before();
             ptx::mbar_arrive(&tempty_bar[as]);
         }
@@ -744,6 +967,20 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
+int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
+                  int total_tiles, int num_sms, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3x3_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes) !=
+            cudaSuccess)
+            return -10;
+        attr_set = true;
+    }
+    const int grid = total_tiles < num_sms ? total_tiles : num_sms;
+    conv3x3_halo_t_kernel<<<grid, kNumThreads, CfgT::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
+    return cudaGetLastError() == cudaSuccess ? 0 : -11;
+}
+
 }  // namespace
 
 const char* conv_tc_strerror(int code) {
@@ -790,9 +1027,65 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -5;
 
+    // ---- 3x3 halo kernel with swapped operands (channels in TMEM lanes): 128-wide channel tiles, H % 32 == 0, W % 8 == 0
+    if (p.halo && p.halo != 2 && p.num_taps == 9 && p.phases == 1 && p.H % kHtTH == 0 && p.W % kHtTW == 0 &&
+        p.Cout % 128 == 0 && p.out_sc <= 1 && (p.n_valid == 0 || p.n_valid == p.Cout) && p.dbg == 0) {
+        bool canon = true;
+        for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
+        if (p.act2 && (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) ||
+                       (reinterpret_cast<uintptr_t>(p.act2) & 15)))
+            return -8;
+        if (canon) {
+            ConvTcArgs h{};
+            h.num_taps = 9; h.chunks_per_tap = p.Cin / kConvBlockK;
+            h.tiles_w = p.W / kHtTW; h.tiles_h = p.H / kHtTH; h.tiles_b = p.B; h.tiles_n = p.Cout / 128;
+            h.B = p.B; h.H = p.H; h.W = p.W; h.a_chan_off = p.a_chan_off;
+            h.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK; h.a_chan_off2 = p.a_chan_off2;
+            h.out_sb = p.out_sb; h.out_sh = p.out_sh; h.out_sw = p.out_sw; h.out_sc = 1; h.n_valid = p.Cout;
+            h.out_f32 = p.out_f32; h.out_f16 = p.out_f16; h.bias = p.bias; h.residual = p.residual; h.err_flag = p.err_flag;
+            h.stats = p.stats; h.stats_blocks = p.Cout / 16;
+            int dev = 0, num_sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            CUtensorMap tmA, tmA2, tmB;
+            cuuint32_t box[5] = {kConvBlockK, kHtW, kHtH, 1, 1};
+            cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+            {
+                cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
+                cuuint64_t gstr[4] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.W * p.lda * 2, (cuuint64_t)p.H * p.W * p.lda * 2,
+                                      (cuuint64_t)p.H * p.W * p.lda * 2};
+                if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(p.act), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return -6;
+            }
+            tmA2 = tmA;
+            if (p.act2) {
+                cuuint64_t gdim[5] = {(cuuint64_t)p.lda2, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
+                cuuint64_t gstr[4] = {(cuuint64_t)p.lda2 * 2, (cuuint64_t)p.W * p.lda2 * 2, (cuuint64_t)p.H * p.W * p.lda2 * 2,
+                                      (cuuint64_t)p.H * p.W * p.lda2 * 2};
+                if (enc(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(p.act2), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return -6;
+            }
+            const cuuint64_t K = (cuuint64_t)9 * p.Cin;
+            cuuint64_t wdim[2] = {K, (cuuint64_t)p.Cout};
+            cuuint64_t wstr[1] = {K * 2};
+            cuuint32_t wbox[2] = {kConvBlockK, 128};
+            cuuint32_t westr[2] = {1, 1};
+            if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.wpacked), wdim, wstr, wbox, westr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return -7;
+            return launch_halo_t(tmA, tmA2, tmB, h, h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n, num_sms, stream);
+        }
+    }
+
     // ---- 3x3 halo kernel (opt-in via p.halo): needs the canonical 3x3 tap order, H % 16 == 0, W % 8 == 0
     if (p.halo && !p.act2 && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 &&
-        (p.Cout % 128 == 0 || (p.Cout == 16 && p.Cin <= kHaloResChunks * kConvBlockK))) {
+        ((p.Cout % 128 == 0 && (p.halo == 2 || p.Cout % 256 != 0)) ||
+         (p.Cout == 16 && p.Cin <= kHaloResChunks * kConvBlockK))) {
         bool canon = true;
         for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
         if (canon) {

@@ -56,7 +56,8 @@ struct ConvTcProblem {
     int n_valid;            // 0 = all C_out channels are stored
     int block_n_hint;       // 0 = auto; > 0 preferred tile width; < 0: |value| with the 1-CTA kernel forced
     int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
-    int halo;               // 1 = use the 3x3 halo-tile kernel when the geometry allows
+    int halo;               // 1 = use a 3x3 halo-tile kernel when the geometry allows (swapped-operand form preferred),
+                            // 2 = only the pixel-major halo kernel
     int kmerge;             // 0 = auto (two k-chunks per stage when possible), 1 = one k-chunk per stage
     int dbg;                // profiling experiments only
     double* stats;          // optional GroupNorm block statistics of the output (pre-zeroed), see ConvTcArgs

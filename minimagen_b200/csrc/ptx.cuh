@@ -55,6 +55,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* e
     }
 }
 
+// One lane of a fully converged warp (elect.sync).  Issuing TMA / tcgen05 instructions under this predicate -- instead of
+// under `lane == 0` -- lets the compiler keep their operands in uniform registers; with a plain lane test it wraps every
+// UTCHMMA / UTMALDG in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop, which made the MMA issue rate the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

@@ -106,7 +106,7 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
         }
     p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
     p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
-    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3); p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair == 7) p.cta_pair = 2; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
+    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3) ? 2 : (c.pair == 8 ? 1 : 0); if (c.pair == 8) p.cta_pair = 1; p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair == 7) p.cta_pair = 2; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
     p.splitk_ws = g_ws; p.splitk_ws_bytes = g_ws_bytes;
     if (c.pair == 5) { p.cta_pair = 2; p.stream_k = 2; }
     if (c.pair == 6) { p.cta_pair = 2; p.stream_k = 1; }
@@ -226,6 +226,12 @@ int main(int argc, char** argv) {
             {"h_c3_n16", 2, 32, 32, 128, 16, 3, 1, true, false, false, 0, 3},
             {"h_c3_n16_k256", 3, 32, 64, 256, 16, 3, 1, true, false, false, 0, 3},
             {"h_c3_n16_persist", 4, 128, 128, 64, 16, 3, 1, false, false, false, 0, 3},
+            // ---- 3x3 halo kernel with swapped operands (pair == 8)
+            {"t_c3_32x32", 1, 32, 32, 128, 128, 3, 1, true, false, false, 0, 8},
+            {"t_c3_32x8_k64", 3, 32, 8, 64, 128, 3, 1, false, false, true, 0, 8},
+            {"t_c3_persist", 8, 64, 64, 64, 128, 3, 1, true, true, true, 0, 8},
+            {"t_c3_n256", 2, 32, 32, 128, 256, 3, 1, true, true, false, 0, 8},
+            {"t_c3_w256", 1, 32, 256, 64, 128, 3, 1, false, false, false, 0, 8},
             // ---- CTA-pair (cta_group::2) kernel
             {"p_c3_16x16_n128", 2, 16, 16, 64, 128, 3, 1, true, false, false, 128, 2},
             {"p_c3_16x16_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256, 2},
@@ -273,6 +279,15 @@ int main(int argc, char** argv) {
             {"D1(noTMA) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 11},
             {"D2(noEpi) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 12},
             {"D3(neither) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 13},
+            {"T sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 8},
+            {"T sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128, 8},
+            {"T sr_128_256to128", 32, 128, 128, 256, 128, 3, 1, true, true, false, 128, 8},
+            {"T sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128, 8},
+            {"T sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256, 8},
+            {"T sr_64_512to256", 32, 64, 64, 512, 256, 3, 1, true, false, false, 256, 8},
+            {"T sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 8},
+            {"T sr_32_1024", 32, 32, 32, 1024, 512, 3, 1, true, false, false, 256, 8},
+            {"P sr_64_512to256", 32, 64, 64, 512, 256, 3, 1, true, false, false, 256, 2},
             {"H final_256_128_16", 32, 256, 256, 128, 16, 3, 1, true, false, false, 0, 3},
             {"H sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 3},
             {"H sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, true, false, 256, 3},
