@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--batch-streams", type=int, default=None, help="concurrent batch slices inside Unet.forward")
     ap.add_argument("--fuse", default=None, choices=["off", "n128", "all"], help="fused GroupNorm+conv kernel usage")
     ap.add_argument("--kernel-table", default=None, help="write a CUPTI per-kernel time table of 3 steps to this path")
+    ap.add_argument("--pdl", type=int, default=None, help="programmatic dependent launch on (1) / off (0)")
     ap.add_argument("--gn-f16", action="store_true", help="GroupNorm inputs in fp16 (faster, 1.05e-3 instead of 9e-4 rel-L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -209,6 +210,8 @@ def main():
     from minimagen_b200.Imagen import Imagen
     from minimagen_b200.Unet import Unet
     _native.load()
+    if args.pdl is not None:
+        _native.load().mi_set_launch_mode(int(args.pdl))
     if args.gn_f16:
         layers.GN_INPUT_F32 = False
     if args.fuse is not None:

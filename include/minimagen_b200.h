@@ -29,6 +29,10 @@ int mi_abi_version(void);
 const char* mi_last_error(void);
 /* 1 if the current device is compute capability 10.x (the only target), else 0 */
 int mi_device_ok(void);
+/* Process-wide launch mode.  programmatic_dependent_launch != 0: every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so its prologue overlaps the tail of the kernel before it on the
+ * same stream (each kernel still waits for its predecessor before touching global memory).  Default 0. */
+int mi_set_launch_mode(int programmatic_dependent_launch);
 
 /* ------------------------------------------------------------------------------------------------- weights
  * One-time repack of a conv / linear weight from the reference's checkpoint layout (C_out, C_in, KH, KW) fp32

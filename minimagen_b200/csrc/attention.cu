@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace mi {
 
@@ -39,6 +40,8 @@ __global__ void __launch_bounds__(128)
 attn_fwd_kernel(const __half* __restrict__ q, long long q_bs, int ldq, const __half* __restrict__ k,
                 const __half* __restrict__ v, long long kv_bs, int ldkv, int kv_hs, const float* __restrict__ null_kv,
                 const uint8_t* __restrict__ mask, int n, int m, __half* __restrict__ out, long long o_bs, int ldo) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ __align__(16) __half Ks[kBK][kD + kPad];    // [key][dim]
     __shared__ __align__(16) __half Vt[kD][kBK + kPad];    // [dim][key]
     __shared__ float s_maskadd[kBK];                       // 0, -FLT_MAX (masked) or -inf (beyond the last key)
@@ -197,7 +200,7 @@ int attention_fwd(const __half* q, long long q_bs, int ldq, const __half* k, con
     if ((ldq % 8) || (ldkv % 8) || (ldo % 2) || (kv_hs % 8)) return -1;
     if ((reinterpret_cast<uintptr_t>(k) & 15) || (reinterpret_cast<uintptr_t>(v) & 15) || (kv_bs % 8)) return -1;
     dim3 grid((n + kBQ - 1) / kBQ, heads, B);
-    attn_fwd_kernel<<<grid, 128, 0, st>>>(q, q_bs, ldq, k, v, kv_bs, ldkv, kv_hs, null_kv, mask, n, m, out, o_bs, ldo);
+    launch_k(attn_fwd_kernel, grid, 128, 0, st, q, q_bs, ldq, k, v, kv_bs, ldkv, kv_hs, null_kv, mask, n, m, out, o_bs, ldo);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -30,9 +30,18 @@ inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace
 
+namespace mi {
+static bool g_pdl = false;
+bool pdl_enabled() { return g_pdl; }
+}  // namespace mi
+
 extern "C" {
 
 int mi_abi_version(void) { return MI_ABI_VERSION; }
+int mi_set_launch_mode(int programmatic_dependent_launch) {
+    mi::g_pdl = programmatic_dependent_launch != 0;
+    return 0;
+}
 const char* mi_last_error(void) { return g_err; }
 
 int mi_device_ok(void) {

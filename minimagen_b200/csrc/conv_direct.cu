@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace mi {
 
@@ -22,6 +23,8 @@ conv_direct_kernel(const float* __restrict__ in, int B, int Hin, int Win, int Ci
                    const float* __restrict__ w, int Cout, int KH, int KW, int stride, int pad,
                    const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ out,
                    int Hout, int Wout, long long osb, long long osh, long long osw, long long osc, int ci_chunk) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float w_s[];   // [KH*KW][ci_chunk][kCoT]
     const int co0 = blockIdx.y * kCoT;
     const int taps = KH * KW;
@@ -109,7 +112,7 @@ int conv_direct_f32(const float* in, int B, int Hin, int Win, int Cin, int ldi, 
     }
     const long long npix = (long long)B * Hout * Wout;
     dim3 grid((unsigned)((npix + 255) / 256), (Cout + kCoT - 1) / kCoT);
-    conv_direct_kernel<<<grid, 256, smem, st>>>(in, B, Hin, Win, Cin, ldi, w, Cout, KH, KW, stride, pad, bias, residual,
+    launch_k(conv_direct_kernel, grid, 256, smem, st, in, B, Hin, Win, Cin, ldi, w, Cout, KH, KW, stride, pad, bias, residual,
                                                 out, Hout, Wout, osb, osh, osw, osc, ci_chunk);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }

@@ -21,6 +21,7 @@
 
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
+#include "launch.cuh"
 
 namespace mi {
 
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(kGnThreads, 1)
 conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args,
                   const __grid_constant__ GnPrologueArgs gn) {
+    pdl_trigger();
     using C = CfgG<BLOCK_N>;
     constexpr int NB = C::kBStages;
     constexpr int NR = C::kRawStages;
@@ -111,6 +113,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap tmR0, const __grid_constan
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();      // everything above is independent of the previous kernel's output
 
     const int chunks = args.chunks_per_tap;             // 64-channel chunks of the (concatenated) input
     const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
@@ -341,7 +344,7 @@ int launch_gn(const CUtensorMap& r0, const CUtensorMap& r1, const CUtensorMap& t
         attr_set = true;
     }
     const int grid = total < num_sms ? total : num_sms;
-    conv3x3_gn_kernel<BLOCK_N><<<grid, kGnThreads, C::kSmemBytes, st>>>(r0, r1, tmB, a, g);
+    launch_k(conv3x3_gn_kernel<BLOCK_N>, grid, kGnThreads, C::kSmemBytes, st, r0, r1, tmB, a, g);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 

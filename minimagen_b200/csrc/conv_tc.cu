@@ -26,6 +26,7 @@
 
 #include "conv_epilogue.cuh"
 #include "ptx.cuh"
+#include "launch.cuh"
 
 namespace mi {
 
@@ -49,6 +50,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
+    pdl_trigger();
     using C = Cfg<BLOCK_N>;
     constexpr int STAGES = C::kStages;
 
@@ -91,6 +93,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();      // everything above is independent of the previous kernel's output
 
     const int num_kb = args.num_taps * args.chunks_per_tap;
     const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
@@ -258,6 +261,7 @@ template <int BLOCK_N, int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
+    pdl_trigger();
     using C = Cfg2<BLOCK_N, KC>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -300,6 +304,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     ptx::cluster_sync_all();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();      // everything above is independent of the previous kernel's output
 
     const int num_st = args.num_taps * args.chunks_per_tap / KC;      // pipeline stages (KC k-chunks each) per tile
     const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
@@ -506,6 +511,7 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ ConvTcArgs args) {
+    pdl_trigger();
     using C = CfgH<BLOCK_N>;
     constexpr int NA = C::kAStages, NB = C::kBStages;
     extern __shared__ uint8_t smem_raw[];
@@ -545,6 +551,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();      // everything above is independent of the previous kernel's output
 
     const int chunks = args.chunks_per_tap;
     const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
@@ -700,6 +707,7 @@ __device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t smem_addr) {
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
+    pdl_trigger();
     using C = CfgT;
     constexpr int NH = C::kHStages, NW = C::kWStages;
     extern __shared__ uint8_t smem_raw[];
@@ -737,6 +745,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();      // everything above is independent of the previous kernel's output
 
     const int chunks = args.chunks_per_tap;
     const int tiles_m = args.tiles_w * args.tiles_h * args.tiles_b;
@@ -916,7 +925,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& t
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    conv_tc_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
+    launch_k(conv_tc_kernel<BLOCK_N>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -947,7 +956,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& 
             a.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sk_ws) + kSkFlagBytes);
         }
     }
-    conv_tc2_kernel<BLOCK_N, KC><<<2 * clusters, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmA2, tmB, a);
+    launch_k(conv_tc2_kernel<BLOCK_N, KC>, 2 * clusters, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -963,7 +972,7 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    conv3x3_halo_kernel<BLOCK_N><<<grid, kNumThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    launch_k(conv3x3_halo_kernel<BLOCK_N>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -977,7 +986,7 @@ int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    conv3x3_halo_t_kernel<<<grid, kNumThreads, CfgT::kSmemBytes, stream>>>(tmA, tmA2, tmB, args);
+    launch_k(conv3x3_halo_t_kernel, grid, kNumThreads, CfgT::kSmemBytes, stream, tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 

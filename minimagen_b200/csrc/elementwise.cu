@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace mi {
 
@@ -65,6 +66,8 @@ template <typename InT>
 __global__ void __launch_bounds__(256)
 gn_stats_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ src1, int C1, float scale1, int HW,
                 int groups, double* __restrict__ sums, int chunk) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ double s_acc[];   // [groups][2]
     const int C = C0 + C1;
     const int V = C >> 3;               // 8-channel vectors
@@ -136,6 +139,8 @@ gn_apply_silu_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict
                      int sb1, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* __restrict__ scale_shift, int ss_ld, float eps, OutT* __restrict__ out,
                      int pix_per_cta) {
+    pdl_wait();
+    pdl_trigger();
     extern __shared__ float s_ab[];   // A[C], Bc[C]
     __shared__ float s_mean[32], s_rstd[32];
     const int C = C0 + C1;
@@ -226,6 +231,8 @@ template <typename InT, typename OutT>
 __global__ void __launch_bounds__(256)
 cast_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ src1, int C1, float scale1, int B, int H,
             int W, int mode, OutT* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int C = C0 + C1;
     const int V8 = C >> 3;
     const long long total = (long long)B * H * W * V8;
@@ -272,6 +279,8 @@ __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ in, long long R, int C, const float* __restrict__ gamma,
                const float* __restrict__ beta, float eps, int pre_gelu, const float* __restrict__ residual,
                float* __restrict__ out_f32, __half* __restrict__ out_f16) {
+    pdl_wait();
+    pdl_trigger();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= R) return;
     const int lane = threadIdx.x & 31;
@@ -324,6 +333,8 @@ __global__ void __launch_bounds__(256)
 linear_f32_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias,
                   int N, int in_act, int out_act, const float* __restrict__ addend, float* __restrict__ out_f32,
                   __half* __restrict__ out_f16, float out_scale) {
+    pdl_wait();
+    pdl_trigger();
     const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int m0 = blockIdx.y * kLinRows;
     if (n >= N) return;
@@ -372,6 +383,8 @@ __global__ void __launch_bounds__(256)
 linear_tiled_kernel(const float* __restrict__ in, int M, int K, const float* __restrict__ W, const float* __restrict__ bias,
                     int N, int in_act, int out_act, const float* __restrict__ addend, float* __restrict__ out_f32,
                     __half* __restrict__ out_f16, float out_scale) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ __align__(16) float xs[kTK][kTM + 4];      // [k][row]
     __shared__ float ws[kTK][kTN + 1];                    // [k][col], +1: conflict-free transposed stores
     const int n0 = blockIdx.x * kTN, m0 = blockIdx.y * kTM;
@@ -445,6 +458,8 @@ linear_tiled_kernel(const float* __restrict__ in, int M, int K, const float* __r
 // out = cat(sin(arg), cos(arg)).
 __global__ void posemb_kernel(const long long* __restrict__ t, int B, int dim, float neg_log_step,
                               float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int half = dim >> 1;
     if (i >= B * half) return;
@@ -463,6 +478,8 @@ __global__ void text_tokens_kernel(const float* __restrict__ proj /*[B][L][D]*/,
                                    const uint8_t* __restrict__ keep /*[B]*/, const float* __restrict__ null_embed,
                                    int max_len, float* __restrict__ c_out /*[B][m][D]*/, int m, int row_off,
                                    float* __restrict__ pooled /*[B][D]*/) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.x;
     const bool kp = keep[b] != 0;
     const int Lc = min(L, max_len);
@@ -483,6 +500,8 @@ __global__ void text_tokens_kernel(const float* __restrict__ proj /*[B][L][D]*/,
 // copy rows [B][r][D] into the conditioning sequence [B][m][D] at row offset (time tokens, Unet.py:534/:629)
 __global__ void place_rows_kernel(const float* __restrict__ src, int B, int r, int D, float* __restrict__ dst, int m,
                                   int row_off) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * r * D) return;
     const int d = (int)(i % D);
@@ -495,6 +514,8 @@ __global__ void place_rows_kernel(const float* __restrict__ src, int B, int r, i
 __global__ void select_rows_kernel(const float* __restrict__ a, const float* __restrict__ nullv,
                                    const uint8_t* __restrict__ keep, const float* __restrict__ addend, int B, int N,
                                    float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * N) return;
     const int n = (int)(i % N);
@@ -507,6 +528,8 @@ __global__ void select_rows_kernel(const float* __restrict__ a, const float* __r
 // NCHW fp32 (two sources, e.g. x and lowres_cond_img: torch.cat(dim=1), Unet.py:397) -> NHWC fp32 with C padded to Cp
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b2, int Cb, int B,
                                     int HW, int Cp, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * HW * Cp) return;
     const int c = (int)(i % Cp);
@@ -521,6 +544,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ a, int Ca, const f
 // weight packing: OIHW fp32 -> [O][(r*KW+s)*I + c] fp16 (* scale)  (one-time, on load_state_dict)
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int I, int KH, int KW, float scale,
                                         __half* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)O * I * KH * KW;
     if (i >= total) return;
@@ -541,6 +566,8 @@ constexpr int kStemRows = 4, kStemCols = 64, kStemWin = kStemCols + 14;
 __global__ void __launch_bounds__(256)
 stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict__ b2, int Cb, int B, int H, int W,
                    __half* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ uint4 s_px[kStemRows][kStemWin + 2];
     const int w0 = blockIdx.x * kStemCols;
     const int h0 = blockIdx.y * kStemRows;
@@ -573,6 +600,8 @@ stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict_
 }
 
 __global__ void silu_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = silu_f(in[i]);
 }
@@ -593,10 +622,10 @@ int gn_stats(const void* src0, int C0, const void* src1, int C1, float scale1, i
     dim3 grid((HW + chunk - 1) / chunk, B);
     const size_t smem = 2 * groups * sizeof(double);
     if (in_is_f16)
-        gn_stats_kernel<__half><<<grid, 256, smem, st>>>((const __half*)src0, C0, (const __half*)src1, C1, scale1, HW,
+        launch_k(gn_stats_kernel<__half>, grid, 256, smem, st, (const __half*)src0, C0, (const __half*)src1, C1, scale1, HW,
                                                          groups, sums, chunk);
     else
-        gn_stats_kernel<float><<<grid, 256, smem, st>>>((const float*)src0, C0, (const float*)src1, C1, scale1, HW,
+        launch_k(gn_stats_kernel<float>, grid, 256, smem, st, (const float*)src0, C0, (const float*)src1, C1, scale1, HW,
                                                         groups, sums, chunk);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -621,7 +650,7 @@ int gn_apply_silu(const void* src0, int C0, const void* src1, int C1, float scal
     if (smem > 48 * 1024) return -1;
     dim3 grid((HW + pix - 1) / pix, B);
 #define MI_GN_LAUNCH(IN, OUT, FAST)                                                                                 \
-    gn_apply_silu_kernel<IN, OUT, FAST><<<grid, 256, smem, st>>>((const IN*)src0, C0, (const IN*)src1, C1, scale1, HW, \
+    launch_k(gn_apply_silu_kernel<IN, OUT, FAST>, grid, 256, smem, st, (const IN*)src0, C0, (const IN*)src1, C1, scale1, HW, \
                                                                  groups, stats0, sb0, stats1, sb1, gamma, beta,      \
                                                                  scale_shift, ss_ld, eps, (OUT*)out, pix)
     if (in_is_f16) {
@@ -641,11 +670,11 @@ int cast_act(const void* src0, int C0, const void* src1, int C1, float scale1, i
     if (mode == 2 && ((H | W) & 1)) return -1;
     const unsigned grid = grid1d((long long)B * H * W * (C / 8), 256);
     if (in_is_f16) {
-        if (out_is_f16) cast_kernel<__half, __half><<<grid, 256, 0, st>>>((const __half*)src0, C0, (const __half*)src1, C1, scale1, B, H, W, mode, (__half*)out);
-        else cast_kernel<__half, float><<<grid, 256, 0, st>>>((const __half*)src0, C0, (const __half*)src1, C1, scale1, B, H, W, mode, (float*)out);
+        if (out_is_f16) launch_k(cast_kernel<__half, __half>, grid, 256, 0, st, (const __half*)src0, C0, (const __half*)src1, C1, scale1, B, H, W, mode, (__half*)out);
+        else launch_k(cast_kernel<__half, float>, grid, 256, 0, st, (const __half*)src0, C0, (const __half*)src1, C1, scale1, B, H, W, mode, (float*)out);
     } else {
-        if (out_is_f16) cast_kernel<float, __half><<<grid, 256, 0, st>>>((const float*)src0, C0, (const float*)src1, C1, scale1, B, H, W, mode, (__half*)out);
-        else cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src0, C0, (const float*)src1, C1, scale1, B, H, W, mode, (float*)out);
+        if (out_is_f16) launch_k(cast_kernel<float, __half>, grid, 256, 0, st, (const float*)src0, C0, (const float*)src1, C1, scale1, B, H, W, mode, (__half*)out);
+        else launch_k(cast_kernel<float, float>, grid, 256, 0, st, (const float*)src0, C0, (const float*)src1, C1, scale1, B, H, W, mode, (float*)out);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
@@ -653,7 +682,7 @@ int cast_act(const void* src0, int C0, const void* src1, int C1, float scale1, i
 int ln_rows(const float* in, long long R, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
             const float* residual, float* out_f32, __half* out_f16, cudaStream_t st) {
     if (C % 4) return -1;
-    ln_rows_kernel<<<grid1d(R, 8), 256, 0, st>>>(in, R, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    launch_k(ln_rows_kernel, grid1d(R, 8), 256, 0, st, in, R, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -664,15 +693,15 @@ int linear_f32(const float* in, int M, int K, const float* W, const float* bias,
         // small weight matrices (text / time conditioning MLPs at batch 32): latency-bound, so spread them over many
         // warps -- one warp per (8-row group, output column) with the whole weight row in flight at once
         dim3 grid((N + 7) / 8, (M + 7) / 8);
-        linear_f32_kernel<8><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+        launch_k(linear_f32_kernel<8>, grid, 256, 0, st, in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
                                                    out_scale);
     } else if (M > 8) {     // 32 x 128 shared-memory tiles: every weight row is streamed once per 32 input rows
         dim3 grid((N + kTN - 1) / kTN, (M + kTM - 1) / kTM);
-        linear_tiled_kernel<<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+        launch_k(linear_tiled_kernel, grid, 256, 0, st, in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
                                                   out_scale);
     } else {
         dim3 grid((N + 7) / 8, 1);
-        linear_f32_kernel<8><<<grid, 256, 0, st>>>(in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
+        launch_k(linear_f32_kernel<8>, grid, 256, 0, st, in, M, K, W, bias, N, in_act, out_act, addend, out_f32, out_f16,
                                                    out_scale);
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
@@ -681,12 +710,12 @@ int linear_f32(const float* in, int M, int K, const float* W, const float* bias,
 int stem_unroll(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, __half* out, cudaStream_t st) {
     if (Ca + Cb > 8 || Ca < 1) return -1;
     dim3 grid((W + kStemCols - 1) / kStemCols, (H + kStemRows - 1) / kStemRows, B);
-    stem_unroll_kernel<<<grid, 256, 0, st>>>(a, Ca, b, Cb, B, H, W, out);
+    launch_k(stem_unroll_kernel, grid, 256, 0, st, a, Ca, b, Cb, B, H, W, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int silu_f32(const float* in, long long n, float* out, cudaStream_t st) {
-    silu_kernel<<<grid1d(n, 256), 256, 0, st>>>(in, n, out);
+    launch_k(silu_kernel, grid1d(n, 256), 256, 0, st, in, n, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -694,36 +723,36 @@ int posemb(const long long* t, int B, int dim, float* out, cudaStream_t st) {
     const int half = dim / 2;
     // reference: emb = math.log(10000) / (half_dim - 1) in double, multiplied into an fp32 tensor
     const float neg_log_step = (float)(-(log(10000.0) / (double)(half - 1)));
-    posemb_kernel<<<grid1d((long long)B * half, 128), 128, 0, st>>>(t, B, dim, neg_log_step, out);
+    launch_k(posemb_kernel, grid1d((long long)B * half, 128), 128, 0, st, t, B, dim, neg_log_step, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int text_tokens(const float* proj, int B, int L, int D, const uint8_t* mask, const uint8_t* keep,
                 const float* null_embed, int max_len, float* c_out, int m, int row_off, float* pooled,
                 cudaStream_t st) {
-    text_tokens_kernel<<<B, D < 256 ? D : 256, 0, st>>>(proj, L, D, mask, keep, null_embed, max_len, c_out, m, row_off,
+    launch_k(text_tokens_kernel, B, D < 256 ? D : 256, 0, st, proj, L, D, mask, keep, null_embed, max_len, c_out, m, row_off,
                                                         pooled);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int place_rows(const float* src, int B, int r, int D, float* dst, int m, int row_off, cudaStream_t st) {
-    place_rows_kernel<<<grid1d((long long)B * r * D, 256), 256, 0, st>>>(src, B, r, D, dst, m, row_off);
+    launch_k(place_rows_kernel, grid1d((long long)B * r * D, 256), 256, 0, st, src, B, r, D, dst, m, row_off);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int select_rows(const float* a, const float* nullv, const uint8_t* keep, const float* addend, int B, int N, float* out,
                 cudaStream_t st) {
-    select_rows_kernel<<<grid1d((long long)B * N, 256), 256, 0, st>>>(a, nullv, keep, addend, B, N, out);
+    launch_k(select_rows_kernel, grid1d((long long)B * N, 256), 256, 0, st, a, nullv, keep, addend, B, N, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int nchw_to_nhwc(const float* a, int Ca, const float* b, int Cb, int B, int HW, int Cp, float* out, cudaStream_t st) {
-    nchw_to_nhwc_kernel<<<grid1d((long long)B * HW * Cp, 256), 256, 0, st>>>(a, Ca, b, Cb, B, HW, Cp, out);
+    launch_k(nchw_to_nhwc_kernel, grid1d((long long)B * HW * Cp, 256), 256, 0, st, a, Ca, b, Cb, B, HW, Cp, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int pack_conv_weight(const float* w, int O, int I, int KH, int KW, float scale, __half* out, cudaStream_t st) {
-    pack_conv_weight_kernel<<<grid1d((long long)O * I * KH * KW, 256), 256, 0, st>>>(w, O, I, KH, KW, scale, out);
+    launch_k(pack_conv_weight_kernel, grid1d((long long)O * I * KH * KW, 256), 256, 0, st, w, O, I, KH, KW, scale, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

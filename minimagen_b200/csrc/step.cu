@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 
 #include "kernels.cuh"
+#include "launch.cuh"
 
 namespace mi {
 
@@ -24,6 +25,8 @@ __global__ void __launch_bounds__(256)
 x0_kernel(const float* __restrict__ x_t, const float* __restrict__ eps_cond, const float* __restrict__ eps_null,
           float cond_scale, const long long* __restrict__ t, const float* __restrict__ tab_recip,
           const float* __restrict__ tab_recipm1, int n_per_img, float* __restrict__ x0) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_per_img) return;
@@ -46,6 +49,8 @@ __device__ __forceinline__ uint32_t absbits(float v) { return __float_as_uint(v)
 __global__ void __launch_bounds__(kSelThreads)
 quantile_kernel(const float* __restrict__ x0, int n, int rank_lo, int rank_hi, float weight, float min_s,
                 float* __restrict__ s_out) {
+    pdl_wait();
+    pdl_trigger();
     __shared__ unsigned hist[257];
     __shared__ uint32_t sh_prefix, sh_k, sh_eq;
     __shared__ uint32_t sh_min[32];
@@ -126,6 +131,8 @@ constexpr int kSelCluster = 8, kSelPerThread = 24;
 __global__ void __cluster_dims__(kSelCluster, 1, 1) __launch_bounds__(kSelThreads)
 quantile_cluster_kernel(const float* __restrict__ x0, int n, int rank_lo, int rank_hi, float weight, float min_s,
                         float* __restrict__ s_out) {
+    pdl_wait();
+    pdl_trigger();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ unsigned hist[256];       // this CTA's histogram of the current pass (read remotely by the peers)
@@ -239,6 +246,8 @@ posterior_kernel(const float* __restrict__ x0, const float* __restrict__ x_t, co
                  const float* __restrict__ s, const long long* __restrict__ t, const float* __restrict__ tab_c1,
                  const float* __restrict__ tab_c2, const float* __restrict__ tab_sigma, int n_per_img,
                  float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_per_img) return;
@@ -256,6 +265,8 @@ posterior_kernel(const float* __restrict__ x0, const float* __restrict__ x_t, co
 
 // img.clamp_(-1, 1); (img + 1) * 0.5      (Imagen.py:418-419, helpers.py:183)
 __global__ void finalize_kernel(const float* __restrict__ x, long long n, int unnormalize, float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float v = fminf(fmaxf(x[i], -1.f), 1.f);
@@ -269,6 +280,8 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
                                 const long long* __restrict__ t, const float* __restrict__ tab_a,
                                 const float* __restrict__ tab_b, int n_per_img, float post_scale, float post_shift,
                                 float* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_per_img) return;
@@ -284,7 +297,7 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const float* __res
 int step_x0(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
             const float* tab_recip, const float* tab_recipm1, int B, int n_per_img, float* x0, cudaStream_t st) {
     dim3 grid((n_per_img + 255) / 256, B);
-    x0_kernel<<<grid, 256, 0, st>>>(x_t, eps_cond, eps_null, cond_scale, t, tab_recip, tab_recipm1, n_per_img, x0);
+    launch_k(x0_kernel, grid, 256, 0, st, x_t, eps_cond, eps_null, cond_scale, t, tab_recip, tab_recipm1, n_per_img, x0);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -292,10 +305,10 @@ int step_quantile(const float* x0, int B, int n_per_img, int rank_lo, int rank_h
                   float* s_out, cudaStream_t st) {
     if (rank_lo < 0 || rank_hi < rank_lo || rank_hi >= n_per_img) return -1;
     if ((n_per_img + kSelCluster - 1) / kSelCluster <= kSelThreads * kSelPerThread)
-        quantile_cluster_kernel<<<B * kSelCluster, kSelThreads, 0, st>>>(x0, n_per_img, rank_lo, rank_hi, weight, min_s,
+        launch_k(quantile_cluster_kernel, B * kSelCluster, kSelThreads, 0, st, x0, n_per_img, rank_lo, rank_hi, weight, min_s,
                                                                         s_out);
     else
-        quantile_kernel<<<B, kSelThreads, 0, st>>>(x0, n_per_img, rank_lo, rank_hi, weight, min_s, s_out);
+        launch_k(quantile_kernel, B, kSelThreads, 0, st, x0, n_per_img, rank_lo, rank_hi, weight, min_s, s_out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -303,19 +316,19 @@ int step_posterior(const float* x0, const float* x_t, const float* noise, const 
                    const float* tab_c1, const float* tab_c2, const float* tab_sigma, int B, int n_per_img, float* out,
                    cudaStream_t st) {
     dim3 grid((n_per_img + 255) / 256, B);
-    posterior_kernel<<<grid, 256, 0, st>>>(x0, x_t, noise, s, t, tab_c1, tab_c2, tab_sigma, n_per_img, out);
+    launch_k(posterior_kernel, grid, 256, 0, st, x0, x_t, noise, s, t, tab_c1, tab_c2, tab_sigma, n_per_img, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int step_finalize(const float* x, long long n, int unnormalize, float* out, cudaStream_t st) {
-    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, unnormalize, out);
+    launch_k(finalize_kernel, (unsigned)((n + 255) / 256), 256, 0, st, x, n, unnormalize, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_b, int B,
              int n_per_img, float post_scale, float post_shift, float* out, cudaStream_t st) {
     dim3 grid((n_per_img + 255) / 256, B);
-    q_sample_kernel<<<grid, 256, 0, st>>>(x0, noise, t, tab_a, tab_b, n_per_img, post_scale, post_shift, out);
+    launch_k(q_sample_kernel, grid, 256, 0, st, x0, noise, t, tab_a, tab_b, n_per_img, post_scale, post_shift, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

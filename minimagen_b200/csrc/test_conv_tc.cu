@@ -13,6 +13,7 @@
 #include "conv_tc.cuh"
 
 using namespace mi;
+namespace mi { bool pdl_enabled() { return getenv("MI_PDL") != nullptr; } }   // launch.cuh hook (capi.cu in the library)
 
 #define CK(x)                                                                                   \
     do {                                                                                        \

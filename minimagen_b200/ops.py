@@ -36,6 +36,10 @@ class NativeOps:
     def __init__(self):
         self._ws = {}        # (device index, stream handle) -> uint8 workspace
 
+    def set_launch_mode(self, pdl):
+        """Programmatic dependent launch for every kernel of the library (mi_set_launch_mode)."""
+        N.load().mi_set_launch_mode(int(bool(pdl)))
+
     def _workspace(self, dev):
         """One stream-K scratch buffer per (device, stream): convs on different streams may run concurrently."""
         key = (dev.index, N.stream())
