@@ -683,36 +683,46 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 //     warp-wide tcgen05.ld hands lane c the value of channel c for 32 pixels, so every global access of the epilogue is one
 //     pixel's 32 consecutive channels (128 B) -- no shared-memory transposition at all.
 // The virtual concat (two activation tensors) is supported: chunk j >= a_split comes from the second tensor map.
-constexpr int kHtTH = 32, kHtTW = 8, kHtW = kHtTW + 2, kHtH = kHtTH + 2;
-constexpr uint32_t kHtHaloBytes = kHtH * kHtW * 128;                          // 43520
-constexpr uint32_t kHtHaloStride = (kHtHaloBytes + 1023) & ~1023u;            // 44032
-constexpr int kHtPix = kHtTH * kHtTW;                                         // 256 = UMMA N
+// Geometry G32x8: 32 x 8 output pixels from one (34 x 10)-pixel halo tile per chunk (SBO = one halo row).
+// Geometry G16x16 (16-pixel-wide images): a halo row is then 18 pixels, not a whole number of 8-pixel segments, so the
+// tile is fetched three times per chunk -- shifted by dw = -1 / 0 / +1 pixel, 18 rows x exactly 16 pixels each (TMA
+// zero-fills the out-of-image column) -- and tap (dh, dw) reads rows dh.. of the dw copy: 32 segments at the standard
+// 1024-byte stride.  2.5x the activation bytes into shared memory, still less L2 traffic than pixel-major tiles.
+constexpr int kHtPix = 256;                                                   // UMMA N
+template <bool kW16>
 struct CfgT {
+    static constexpr int kTH = kW16 ? 16 : 32, kTW = kW16 ? 16 : 8;           // output tile
+    static constexpr int kBoxH = kTH + 2, kBoxW = kW16 ? 16 : 10;             // TMA box (pixels)
+    static constexpr uint32_t kHaloBytes = kBoxH * kBoxW * 128;               // 36864 / 43520
+    static constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;     // 36864 / 44032
     static constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                // one (tap, chunk) weight tile
-    static constexpr int kHStages = 2;
-    static constexpr int kWStages = (kRingBudget - kHStages * kHtHaloStride) / kWBytes;   // 6
+    static constexpr int kHStages = kW16 ? 3 : 2;
+    static constexpr int kWStages = (kRingBudget - kHStages * kHaloStride) / kWBytes;   // 5 / 6
     static constexpr uint32_t kTmemCols = 2 * kHtPix;                         // 512: two accumulator stages
-    static constexpr uint32_t kSmemBytes = kHStages * kHtHaloStride + kWStages * kWBytes + 1024 + 256;
+    static constexpr uint32_t kSmemBytes = kHStages * kHaloStride + kWStages * kWBytes + 1024 + 256;
 };
 
-__device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-    d |= static_cast<uint64_t>((kHtW * 128u) >> 4) << 32;     // SBO: one halo row between 8-pixel row segments
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;        // stride between 8-pixel row segments
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(2) << 61;
     return d;
 }
 
+template <bool kW16>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
     pdl_trigger();
-    using C = CfgT;
+    using C = CfgT<kW16>;
     constexpr int NH = C::kHStages, NW = C::kWStages;
+    constexpr int kLoads = kW16 ? 3 : 1;           // activation tile loads per 64-channel chunk
+    constexpr int kTapsPerLoad = 9 / kLoads;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_w = smem + NH * kHtHaloStride;
+    uint8_t* smem_w = smem + NH * C::kHaloStride;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + NW * C::kWBytes);
     uint64_t* fullH = bars;
     uint64_t* emptyH = bars + NH;
@@ -759,29 +769,33 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int nt = tile % args.tiles_n;
             const int mt = tile / args.tiles_n;
-            const int w0 = (mt % args.tiles_w) * kHtTW;
-            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHtTH;
+            const int w0 = (mt % args.tiles_w) * C::kTW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * C::kTH;
             const int b0 = mt / (args.tiles_w * args.tiles_h);
             const int n0 = nt * 128;
             for (int j = 0; j < chunks; ++j) {
-                ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 3100 + sh);
-                if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx(&fullH[sh], kHtHaloBytes);
-                    if (j < args.a_split)
-                        ptx::tma_load_5d(&tmA, &fullH[sh], smem + sh * kHtHaloStride, args.a_chan_off + j * kConvBlockK,
-                                         w0 - 1, h0 - 1, 0, b0);
-                    else
-                        ptx::tma_load_5d(&tmA2, &fullH[sh], smem + sh * kHtHaloStride,
-                                         args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 - 1, h0 - 1, 0, b0);
-                }
-                if (++sh == NH) { sh = 0; ph ^= 1; }
-                for (int t = 0; t < 9; ++t) {
-                    ptx::mbar_wait(&emptyW[sw], pw ^ 1, err, 3200 + sw);
+                for (int l = 0; l < kLoads; ++l) {
+                    ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 3100 + sh);
                     if (ptx::elect_one()) {
-                        ptx::mbar_arrive_expect_tx(&fullW[sw], C::kWBytes);
-                        ptx::tma_load_2d(&tmB, &fullW[sw], smem_w + sw * C::kWBytes, t * Cin + j * kConvBlockK, n0);
+                        const int wc = kW16 ? w0 + l - 1 : w0 - 1;      // G16x16: copy l is shifted by dw = l - 1
+                        ptx::mbar_arrive_expect_tx(&fullH[sh], C::kHaloBytes);
+                        if (j < args.a_split)
+                            ptx::tma_load_5d(&tmA, &fullH[sh], smem + sh * C::kHaloStride,
+                                             args.a_chan_off + j * kConvBlockK, wc, h0 - 1, 0, b0);
+                        else
+                            ptx::tma_load_5d(&tmA2, &fullH[sh], smem + sh * C::kHaloStride,
+                                             args.a_chan_off2 + (j - args.a_split) * kConvBlockK, wc, h0 - 1, 0, b0);
                     }
-                    if (++sw == NW) { sw = 0; pw ^= 1; }
+                    if (++sh == NH) { sh = 0; ph ^= 1; }
+                    for (int u = 0; u < kTapsPerLoad; ++u) {
+                        const int t = kW16 ? u * 3 + l : u;             // tap index in the packed weights (dh*3 + dw)
+                        ptx::mbar_wait(&emptyW[sw], pw ^ 1, err, 3200 + sw);
+                        if (ptx::elect_one()) {
+                            ptx::mbar_arrive_expect_tx(&fullW[sw], C::kWBytes);
+                            ptx::tma_load_2d(&tmB, &fullW[sw], smem_w + sw * C::kWBytes, t * Cin + j * kConvBlockK, n0);
+                        }
+                        if (++sw == NW) { sw = 0; pw ^= 1; }
+                    }
                 }
             }
         }
@@ -798,40 +812,47 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * kHtPix;
             for (int j = 0; j < chunks; ++j) {
-                ptx::mbar_wait(&fullH[sh], ph, err, 3400 + sh);
-                const uint32_t h_base = ptx::smem_u32(smem + sh * kHtHaloStride);
-                for (int t = 0; t < 9; ++t) {
-                    ptx::mbar_wait(&fullW[sw], pw, err, 3500 + sw);
-                    ptx::tc_fence_after();
-                    if (ptx::elect_one()) {
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_w + sw * C::kWBytes));
-                        const uint64_t db = make_halo_t_desc(h_base + ((t / 3) * kHtW + (t % 3)) * 128);
+                for (int l = 0; l < kLoads; ++l) {
+                    ptx::mbar_wait(&fullH[sh], ph, err, 3400 + sh);
+                    const uint32_t h_base = ptx::smem_u32(smem + sh * C::kHaloStride);
+                    for (int u = 0; u < kTapsPerLoad; ++u) {
+                        ptx::mbar_wait(&fullW[sw], pw, err, 3500 + sw);
+                        ptx::tc_fence_after();
+                        if (ptx::elect_one()) {
+                            const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_w + sw * C::kWBytes));
+                            // G32x8: tap u = dh*3 + dw starts (dh*10 + dw) pixels into the halo tile, segments one halo
+                            // row apart; G16x16: tap (dh = u) of copy dw = l starts dh rows in, segments 1024 B apart
+                            const uint64_t db = kW16 ? make_halo_t_desc(h_base + u * 16 * 128, 1024)
+                                                     : make_halo_t_desc(h_base + ((u / 3) * C::kBoxW + (u % 3)) * 128,
+                                                                        C::kBoxW * 128);
 #pragma unroll
-                        for (int k = 0; k < kConvBlockK / 16; ++k)
-                            ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | t | k) != 0);
-                        ptx::umma_commit(&emptyW[sw]);
+                            for (int k = 0; k < kConvBlockK / 16; ++k)
+                                ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | l | u | k) != 0);
+                            ptx::umma_commit(&emptyW[sw]);
+                        }
+                        if (++sw == NW) { sw = 0; pw ^= 1; }
                     }
-                    if (++sw == NW) { sw = 0; pw ^= 1; }
+                    if (ptx::elect_one()) ptx::umma_commit(&emptyH[sh]);
+                    if (++sh == NH) { sh = 0; ph ^= 1; }
                 }
-                if (ptx::elect_one()) ptx::umma_commit(&emptyH[sh]);
-                if (++sh == NH) { sh = 0; ph ^= 1; }
             }
             if (ptx::elect_one()) ptx::umma_commit(&tfull_bar[as]);
         }
     } else if (warp >= 4) {
         // ===================== epilogue: lane = channel, columns = pixels =====================
+        constexpr int kTwLog2 = kW16 ? 4 : 3;
         const int q = warp & 3;                       // TMEM lane quarter -> channels [32q, 32q + 32) of the tile
         const int half = warp >= 8 ? 1 : 0;           // pixel columns [128*half, 128*half + 128)
         int iter = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
             const int nt = tile % args.tiles_n;
             const int mt = tile / args.tiles_n;
-            const int w0 = (mt % args.tiles_w) * kHtTW;
-            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kHtTH;
+            const int w0 = (mt % args.tiles_w) * C::kTW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * C::kTH;
             const int b = mt / (args.tiles_w * args.tiles_h);
             const int n = nt * 128 + q * 32 + lane;   // this thread's output channel
             const float bias_v = args.bias ? __ldg(args.bias + n) : 0.f;
-            const long long base = (long long)b * args.out_sb + (long long)(h0 + half * 16) * args.out_sh +
+            const long long base = (long long)b * args.out_sb + (long long)(h0 + half * (C::kTH / 2)) * args.out_sh +
                                    (long long)w0 * args.out_sw + n;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
@@ -840,16 +861,17 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kHtPix + half * 128;
             float st_s = 0.f, st_q = 0.f;
 #pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {       // 32 pixels = 4 tile rows per step
+            for (int c = 0; c < 128; c += 32) {       // 32 pixels per step
                 uint32_t v0[16], v1[16];
                 ptx::tmem_ld_x16(taddr + c, v0);
                 ptx::tmem_ld_x16(taddr + c + 16, v1);
-                const long long rowb = base + (long long)(c >> 3) * args.out_sh;
+                const long long rowb = base + (long long)(c >> kTwLog2) * args.out_sh;
                 float r[32];
                 if (args.residual) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        r[i] = args.residual[rowb + (long long)(i >> 3) * args.out_sh + (long long)(i & 7) * args.out_sw];
+                        r[i] = args.residual[rowb + (long long)(i >> kTwLog2) * args.out_sh +
+                                             (long long)(i & (C::kTW - 1)) * args.out_sw];
                 }
                 ptx::tmem_ld_wait();
 #pragma unroll
@@ -858,7 +880,8 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (args.residual) f += r[i];
                     st_s += f;
                     st_q += f * f;
-                    const long long o = rowb + (long long)(i >> 3) * args.out_sh + (long long)(i & 7) * args.out_sw;
+                    const long long o = rowb + (long long)(i >> kTwLog2) * args.out_sh +
+                                        (long long)(i & (C::kTW - 1)) * args.out_sw;
                     if (args.out_f32) args.out_f32[o] = f;
                     if (args.out_f16) args.out_f16[o] = __float2half_rn(f);
                 }
@@ -976,17 +999,19 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
+template <bool kW16>
 int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
                   int total_tiles, int num_sms, cudaStream_t stream) {
+    using C = CfgT<kW16>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv3x3_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CfgT::kSmemBytes) !=
-            cudaSuccess)
+        if (cudaFuncSetAttribute(conv3x3_halo_t_kernel<kW16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 C::kSmemBytes) != cudaSuccess)
             return -10;
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    launch_k(conv3x3_halo_t_kernel, grid, kNumThreads, CfgT::kSmemBytes, stream, tmA, tmA2, tmB, args);
+    launch_k(conv3x3_halo_t_kernel<kW16>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -1037,7 +1062,9 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     if (!enc) return -5;
 
     // ---- 3x3 halo kernel with swapped operands (channels in TMEM lanes): 128-wide channel tiles, H % 32 == 0, W % 8 == 0
-    if (p.halo && p.halo != 2 && p.num_taps == 9 && p.phases == 1 && p.H % kHtTH == 0 && p.W % kHtTW == 0 &&
+    const bool t16 = p.W == 16 && p.H % 16 == 0;                       // G16x16: one 16 x 16 tile per image (row block)
+    const bool t32 = !t16 && p.H % 32 == 0 && p.W % 8 == 0;            // G32x8
+    if (p.halo && p.halo != 2 && p.num_taps == 9 && p.phases == 1 && (t16 || t32) &&
         p.Cout % 128 == 0 && p.out_sc <= 1 && (p.n_valid == 0 || p.n_valid == p.Cout) && p.dbg == 0) {
         bool canon = true;
         for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
@@ -1047,7 +1074,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         if (canon) {
             ConvTcArgs h{};
             h.num_taps = 9; h.chunks_per_tap = p.Cin / kConvBlockK;
-            h.tiles_w = p.W / kHtTW; h.tiles_h = p.H / kHtTH; h.tiles_b = p.B; h.tiles_n = p.Cout / 128;
+            h.tiles_w = t16 ? 1 : p.W / 8; h.tiles_h = t16 ? p.H / 16 : p.H / 32; h.tiles_b = p.B; h.tiles_n = p.Cout / 128;
             h.B = p.B; h.H = p.H; h.W = p.W; h.a_chan_off = p.a_chan_off;
             h.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK; h.a_chan_off2 = p.a_chan_off2;
             h.out_sb = p.out_sb; h.out_sh = p.out_sh; h.out_sw = p.out_sw; h.out_sc = 1; h.n_valid = p.Cout;
@@ -1057,7 +1084,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             CUtensorMap tmA, tmA2, tmB;
-            cuuint32_t box[5] = {kConvBlockK, kHtW, kHtH, 1, 1};
+            cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)(t16 ? 16 : 10), (cuuint32_t)(t16 ? 18 : 34), 1, 1};
             cuuint32_t estr[5] = {1, 1, 1, 1, 1};
             {
                 cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
@@ -1087,7 +1114,9 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return -7;
-            return launch_halo_t(tmA, tmA2, tmB, h, h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n, num_sms, stream);
+            const int total = h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n;
+            return t16 ? launch_halo_t<true>(tmA, tmA2, tmB, h, total, num_sms, stream)
+                       : launch_halo_t<false>(tmA, tmA2, tmB, h, total, num_sms, stream);
         }
     }
 
@@ -1175,7 +1204,9 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     if (p.cta_pair != 1 && p.block_n_hint >= 0) {
         const int pairs_m = (tiles_m + 1) / 2;
         int want = (p.block_n_hint == 128 || p.block_n_hint == 256) ? p.block_n_hint : (p.Cout % 256 == 0 ? 256 : 128);
-        if (p.Cout % want == 0 && (p.cta_pair == 2 || pairs_m * (p.Cout / want) >= num_sms / 4)) {
+        // 1x1 convs / linears (one tap): the short K loop does not amortise the pair's cluster hand-shakes -- measured
+        // 0.033 ms (1-CTA) vs 0.047 ms (pair) on 16x16 2048->1024 -- so they stay on the 1-CTA kernel
+        if (p.Cout % want == 0 && (p.cta_pair == 2 || (p.num_taps > 1 && pairs_m * (p.Cout / want) >= num_sms / 4))) {
             pair = true;
             block_n = want;
         }

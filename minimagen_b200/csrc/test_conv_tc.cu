@@ -233,6 +233,9 @@ int main(int argc, char** argv) {
             {"t_c3_persist", 8, 64, 64, 64, 128, 3, 1, true, true, true, 0, 8},
             {"t_c3_n256", 2, 32, 32, 128, 256, 3, 1, true, true, false, 0, 8},
             {"t_c3_w256", 1, 32, 256, 64, 128, 3, 1, false, false, false, 0, 8},
+            {"t16_c3", 3, 16, 16, 128, 128, 3, 1, true, true, true, 0, 8},
+            {"t16_c3_h32_n256", 2, 32, 16, 64, 256, 3, 1, true, false, false, 0, 8},
+            {"t16_c3_persist", 160, 16, 16, 64, 128, 3, 1, false, true, false, 0, 8},
             // ---- CTA-pair (cta_group::2) kernel
             {"p_c3_16x16_n128", 2, 16, 16, 64, 128, 3, 1, true, false, false, 128, 2},
             {"p_c3_16x16_n256", 2, 16, 16, 128, 256, 3, 1, true, true, true, 256, 2},
@@ -285,6 +288,8 @@ int main(int argc, char** argv) {
             {"T sr_128_256to128", 32, 128, 128, 256, 128, 3, 1, true, true, false, 128, 8},
             {"T sr_256_128", 16, 256, 256, 128, 128, 3, 1, true, true, false, 128, 8},
             {"T sr_64_256", 32, 64, 64, 256, 256, 3, 1, true, true, false, 256, 8},
+            {"T16 sr_16_1024", 32, 16, 16, 1024, 1024, 3, 1, true, true, false, 256, 8},
+            {"T16 sr_16_2048", 32, 16, 16, 2048, 1024, 3, 1, true, false, false, 256, 8},
             {"T sr_64_512to256", 32, 64, 64, 512, 256, 3, 1, true, false, false, 256, 8},
             {"T sr_32_512", 32, 32, 32, 512, 512, 3, 1, true, true, false, 256, 8},
             {"T sr_32_1024", 32, 32, 32, 1024, 512, 3, 1, true, false, false, 256, 8},
