@@ -52,6 +52,13 @@ int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, in
  *   (H, W)    OUTPUT pixel grid.  mode 0: stride 1, "same" zero padding, kh x kw odd taps, phases = 1.
  *             mode 1: the reference's Downsample (4x4, stride 2, pad 1); act is the 4-phase split of the
  *             (2H x 2W) input produced by mi_cast_act(mode=2).
+ *             mode 2+p (p = 2a+b in 0..3), kh = kw = 2: sub-pixel phase (a, b) of the reference's Upsample
+ *             (nn.Upsample(scale_factor=2, 'nearest') followed by Conv2d 3x3 pad 1, layers.py:513-514): the outputs
+ *             (2y+a, 2x+b) depend only on the LOW-RES pixels (y+a-1+r, x+b-1+s), r,s in {0,1}, through the 3x3 weights
+ *             summed over the taps that land on the same low-res pixel (w_f16 = that 2x2 kernel, packed as usual).
+ *             (H, W) is the low-res grid; the caller points out_* at output pixel (a, b) and passes the strides of the
+ *             2H x 2W output (out_sh = 2 rows, out_sw = 2 pixels).  4 launches replace upsample copy + 3x3 conv at
+ *             4/9 of the FLOPs.
  *   w_f16     packed by mi_pack_conv_weight_f16, [c_out][kh*kw*c_in]
  *   bias      [c_out] fp32 or NULL;  residual: fp32 or NULL, added in the epilogue, addressed like the output
  *   out_f32 / out_f16   either or both; element (b,h,w,n) is written at  b*out_sb + h*out_sh + w*out_sw + n*out_sc

@@ -90,6 +90,17 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
                 p.dh[t] = (int8_t)(rr < 0 ? -1 : (rr >> 1)); p.dw[t] = (int8_t)(ss < 0 ? -1 : (ss >> 1));
                 p.ph[t] = (int8_t)((rr & 1) * 2 + (ss & 1));
             }
+    } else if (mode >= 2 && mode <= 5) {
+        // sub-pixel phase (a, b) = ((mode-2) >> 1, (mode-2) & 1) of "nearest x2 upsample, then 3x3 conv": output pixel
+        // (2y+a, 2x+b) only sees the low-res pixels (y + a-1 + r, x + b-1 + s), r,s in {0,1}, with 3x3 weights pre-summed
+        if (kh != 2 || kw != 2) return fail(-4, "mi_conv2d_igemm_f16: modes 2..5 take the 2x2 phase kernel");
+        const int a = (mode - 2) >> 1, b = (mode - 2) & 1;
+        p.phases = 1; p.num_taps = 4;
+        for (int r = 0; r < 2; ++r)
+            for (int s = 0; s < 2; ++s) {
+                const int t = r * 2 + s;
+                p.dh[t] = (int8_t)(a - 1 + r); p.dw[t] = (int8_t)(b - 1 + s); p.ph[t] = 0;
+            }
     } else {
         return fail(-4, "mi_conv2d_igemm_f16: unknown mode");
     }

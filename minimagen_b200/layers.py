@@ -29,9 +29,12 @@ STATS_BLOCK = 16   # channels per GroupNorm block-statistics entry written by th
 GN_INPUT_F32 = True
 
 # Block.forward as ONE kernel (GroupNorm/FiLM/SiLU in the conv's shared-memory prologue) where the geometry allows
-FUSE_GN_CONV = False     # False: never; True: only where C_out is not a multiple of 256 (N=128 tiles); 'all': everywhere.
+FUSE_GN_CONV = False         # False: never; True: only where C_out is not a multiple of 256 (N=128 tiles); 'all': everywhere.
 #                          Measured on cfg 3 (B200, ms/step): off 32.9, N=128 layers 34.4, all 38.4 -- the 4 transform warps
 #                          and the single-CTA halo main loop do not yet beat the CTA-pair conv + stand-alone apply kernel.
+
+# nearest-x2 upsample + 3x3 conv as four 2x2 sub-pixel convs on the low-res tensor (4/9 of the FLOPs, no upsampled copy)
+SUBPIXEL_UPSAMPLE = True
 
 
 class ZeroArena:
@@ -378,6 +381,39 @@ class Conv2d(nn.Conv2d):
                         self.padding[0], self.bias, residual, out, H, W, (*strides, 1))
         return Act(f32=out)
 
+    def _run_subpixel(self, x, B, H, W, f32, f16, stats):
+        """nn.Upsample(x2, nearest) + 3x3 conv (layers.py:513-514) as four 2x2 convs on the LOW-RES tensor: output pixel
+        (2y+a, 2x+b) sees each low-res neighbour through the sum of the 3x3 taps that land on it.  No upsampled copy is
+        ever written and the GEMM shrinks to 4/9 of the FLOPs; the four launches write the interleaved output directly."""
+        ops = get_ops()
+        Cin, Cout = self.in_channels, self.out_channels
+        key = (self.weight.data_ptr(), self.weight._version)
+        if getattr(self, "_sub_key", None) != key:
+            w = self.weight.detach().to(F32)                                   # (O, I, 3, 3)
+            rows = ((slice(0, 1), slice(1, 3)), (slice(0, 2), slice(2, 3)))    # phase a -> 3x3 rows folded onto r = 0 / 1
+            self._sub_w = []
+            for a in range(2):
+                for b in range(2):
+                    k = torch.stack([torch.stack([w[:, :, rows[a][r], rows[b][s]].sum(dim=(2, 3)) for s in range(2)], dim=-1)
+                                     for r in range(2)], dim=-2)              # (O, I, 2, 2)
+                    self._sub_w.append(ops.pack_conv_weight(k))
+            self._sub_key = key
+        dev = x.device
+        Ho, Wo = 2 * H, 2 * W
+        if not f32 and not f16:
+            f32 = True
+        st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0) else None
+        o32 = torch.empty((B, Ho, Wo, Cout), dtype=F32, device=dev) if f32 else None
+        o16 = torch.empty((B, 1, Ho, Wo, Cout), dtype=F16, device=dev) if f16 else None
+        a16 = x.need_f16()
+        strides = (Ho * Wo * Cout, 2 * Wo * Cout, 2 * Cout)
+        for p in range(4):
+            off = ((p >> 1) * Wo + (p & 1)) * Cout
+            ops.conv_igemm(a16, B, H, W, a16.shape[-1], 0, Cin, self._sub_w[p], Cout, 2, 2, 2 + p, self.bias, None,
+                           o32.reshape(-1)[off:] if f32 else None, o16.reshape(-1)[off:] if f16 else None, strides,
+                           out_stats=st)
+        return Act(o32, o16, st)
+
     def _pack_cat(self, c0, scale):
         """Packed weight whose input-channel columns >= c0 (of every tap) carry the skip-connection scale."""
         key = (self.weight.data_ptr(), self.weight._version, c0, float(scale))
@@ -430,6 +466,9 @@ class Conv2d(nn.Conv2d):
         else:
             Ho, Wo = H, W
         kw = dict(residual=residual, f32=f32, f16=f16, stats=stats)
+        if upsample and SUBPIXEL_UPSAMPLE and not isinstance(x, Cat) and residual is None and self.kernel_size == (3, 3) \
+                and get_ops().igemm_supported(H, W, C, self.out_channels):
+            return self._run_subpixel(x, B, H, W, f32=f32, f16=f16, stats=stats)
         if self.tc_ok(Ho, Wo):
             if not upsample and geom == 'same':
                 if isinstance(x, Cat):

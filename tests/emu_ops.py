@@ -70,6 +70,11 @@ class EmuOps:
         w = wp.float().reshape(c_out, kh, kw, c_in).permute(0, 3, 1, 2)           # OIHW
         if mode == 0:
             y = F.conv2d(a[:, 0].permute(0, 3, 1, 2), w, None, stride=1, padding=(kh // 2, kw // 2))
+        elif mode >= 2:
+            # sub-pixel phase (pa, pb): taps (r, s) read low-res pixel (y + pa-1+r, x + pb-1+s)
+            pa, pb = (mode - 2) >> 1, (mode - 2) & 1
+            x = F.pad(a[:, 0].permute(0, 3, 1, 2), (1, 1, 1, 1))
+            y = F.conv2d(x[:, :, pa:pa + H + 1, pb:pb + W + 1], w, None)
         else:
             # un-split the 4 phases back to the (2H, 2W) input: phase p = (h&1)*2 + (w&1)
             full = torch.zeros((B, 2 * H, 2 * W, c_in))

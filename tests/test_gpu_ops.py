@@ -297,6 +297,61 @@ def test_conv_igemm_two_sources(native):
         assert rel_l2(o_n, o_e) < 2e-5
 
 
+@pytest.mark.parametrize("B,H,W,C0,C1,Cout", [(2, 32, 32, 128, 0, 128),     # swapped halo kernel, 32 x 8 tiles
+                                               (1, 64, 16, 64, 0, 256),      # 16-wide images: three shifted tile copies
+                                               (2, 32, 32, 64, 64, 128),     # two TMA sources, 32 x 8 tiles
+                                               (3, 16, 16, 128, 64, 128)])   # two TMA sources, 16 x 16 tiles
+def test_conv3x3_swapped_halo_paths(native, B, H, W, C0, C1, Cout):
+    """3x3 convs with C_out % 128 == 0 run on the swapped-operand halo kernels (channels in TMEM lanes): bias, residual,
+    both output copies and the epilogue GroupNorm statistics, single and two-source inputs"""
+    Cin = C0 + C1
+    a0 = _rand(B, 1, H, W, C0, seed=90).to(F16)
+    a1 = _rand(B, 1, H, W, C1, seed=91).to(F16) if C1 else None
+    w = _rand(Cout, Cin, 3, 3, seed=92, scale=(9 * Cin) ** -0.5)
+    b, r = _rand(Cout, seed=93), _rand(B, H, W, Cout, seed=94)
+    wp = EMU.pack_conv_weight(w)
+    strides = (H * W * Cout, W * Cout, Cout)
+    kw = dict(act2=a1, lda2=C1, c_in1=C0) if C1 else {}
+    o_e, o16_e = torch.zeros(B, H, W, Cout), torch.zeros(B, H, W, Cout, dtype=F16)
+    st_e = torch.zeros(B, Cout // 16, 2, dtype=F64)
+    EMU.conv_igemm(a0, B, H, W, C0, 0, Cin, wp, Cout, 3, 3, 0, b, r, o_e, o16_e, strides, out_stats=st_e, **kw)
+    o_n = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    o16_n = torch.zeros(B, H, W, Cout, dtype=F16, device="cuda")
+    st_n = torch.zeros(B, Cout // 16, 2, dtype=F64, device="cuda")
+    kwn = dict(act2=a1.cuda(), lda2=C1, c_in1=C0) if C1 else {}
+    native.conv_igemm(a0.cuda(), B, H, W, C0, 0, Cin, wp.cuda(), Cout, 3, 3, 0, b.cuda(), r.cuda(), o_n, o16_n, strides,
+                      out_stats=st_n, **kwn)
+    torch.cuda.synchronize()
+    assert rel_l2(o_n, o_e) < 2e-5
+    assert rel_l2(o16_n, o_e) < 1e-3
+    assert rel_l2(st_n, st_e) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 256), (2, 8, 8, 64, 64)])
+def test_conv_igemm_subpixel_upsample_phases(native, B, H, W, Cin, Cout):
+    """modes 2..5: the four 2x2 sub-pixel phases of 'nearest x2 upsample + 3x3 conv' on the low-res tensor, written
+    interleaved into the 2H x 2W output; vs the emulation and vs the literal upsample + conv"""
+    act = _rand(B, 1, H, W, Cin, seed=95).to(F16)
+    k2 = [_rand(Cout, Cin, 2, 2, seed=96 + p, scale=(4 * Cin) ** -0.5) for p in range(4)]
+    bias = _rand(Cout, seed=99)
+    Ho, Wo = 2 * H, 2 * W
+    strides = (Ho * Wo * Cout, 2 * Wo * Cout, 2 * Cout)
+    o_e = torch.zeros(B, Ho, Wo, Cout)
+    o_n = torch.full((B, Ho, Wo, Cout), float("nan"), device="cuda")
+    st_e = torch.zeros(B, Cout // 16, 2, dtype=F64)
+    st_n = torch.zeros(B, Cout // 16, 2, dtype=F64, device="cuda")
+    for p in range(4):
+        off = ((p >> 1) * Wo + (p & 1)) * Cout
+        wp = EMU.pack_conv_weight(k2[p])
+        EMU.conv_igemm(act, B, H, W, Cin, 0, Cin, wp, Cout, 2, 2, 2 + p, bias, None, o_e.reshape(-1)[off:], None, strides,
+                       out_stats=st_e)
+        native.conv_igemm(act.cuda(), B, H, W, Cin, 0, Cin, wp.cuda(), Cout, 2, 2, 2 + p, bias.cuda(), None,
+                          o_n.reshape(-1)[off:], None, strides, out_stats=st_n)
+    torch.cuda.synchronize()
+    assert rel_l2(o_n, o_e) < 2e-5
+    assert rel_l2(st_n, st_e) < 1e-5
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("f16", [True, False])
 @pytest.mark.parametrize("in16", [False, True])

@@ -159,3 +159,30 @@ def test_signatures_match_reference():
     ref_defaults = {k: v.default for k, v in inspect.signature(RU.Unet.__init__).parameters.items()}
     my_defaults = {k: v.default for k, v in inspect.signature(MU.Unet.__init__).parameters.items()}
     assert ref_defaults == my_defaults
+
+
+def test_subpixel_upsample_conv_equals_upsample_then_conv(emu):
+    """Upsample (layers.py:502-515: nearest x2 + 3x3 conv) lowered to four 2x2 sub-pixel convs on the low-res tensor:
+    same function as the literal composition (fp16 operands either way; the folded weights are rounded once)"""
+    from minimagen_b200 import layers
+    torch.manual_seed(3)
+    conv = layers.Conv2d(64, 128, 3, padding=1)
+    x = torch.randn(2, 8, 8, 64)
+    ref = torch.nn.functional.conv2d(
+        torch.nn.functional.interpolate(x.half().float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest"),
+        conv.weight, conv.bias, padding=1).permute(0, 2, 3, 1)
+    outs = {}
+    for flag in (True, False):
+        layers.SUBPIXEL_UPSAMPLE = flag
+        try:
+            with torch.no_grad():
+                act = conv.run(x, upsample=True, f32=True, f16=True, stats=True)
+        finally:
+            layers.SUBPIXEL_UPSAMPLE = True
+        outs[flag] = act
+        assert rel_l2(act.f32, ref) < 1e-3
+        blk = act.f32.double().reshape(2, 256, 8, 16)
+        assert rel_l2(act.stats[:, :, 0], blk.sum(dim=(1, 3))) < 1e-6
+        assert rel_l2(act.stats[:, :, 1], (blk * blk).sum(dim=(1, 3))) < 1e-6
+    assert "conv_igemm" in emu.calls
+    assert rel_l2(outs[True].f32, outs[False].f32) < 1e-3
