@@ -52,6 +52,8 @@ int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, in
  *   (H, W)    OUTPUT pixel grid.  mode 0: stride 1, "same" zero padding, kh x kw odd taps, phases = 1.
  *             mode 1: the reference's Downsample (4x4, stride 2, pad 1); act is the 4-phase split of the
  *             (2H x 2W) input produced by mi_cast_act(mode=2).
+ *             mode 6: the same Downsample conv reading the UN-split fp16 input [B][2H][2W][lda] in place (TMA element
+ *             stride 2 picks every second pixel of each tap's box) -- no phase-split copy.
  *             mode 2+p (p = 2a+b in 0..3), kh = kw = 2: sub-pixel phase (a, b) of the reference's Upsample
  *             (nn.Upsample(scale_factor=2, 'nearest') followed by Conv2d 3x3 pad 1, layers.py:513-514): the outputs
  *             (2y+a, 2x+b) depend only on the LOW-RES pixels (y+a-1+r, x+b-1+s), r,s in {0,1}, through the 3x3 weights

@@ -90,6 +90,16 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
                 p.dh[t] = (int8_t)(rr < 0 ? -1 : (rr >> 1)); p.dw[t] = (int8_t)(ss < 0 ? -1 : (ss >> 1));
                 p.ph[t] = (int8_t)((rr & 1) * 2 + (ss & 1));
             }
+    } else if (mode == 6) {
+        // Downsample read in place: tap (r, s) of output pixel (ho, wo) is input pixel (2*ho + r - 1, 2*wo + s - 1)
+        if (kh != 4 || kw != 4) return fail(-4, "mi_conv2d_igemm_f16: mode 6 is the 4x4 stride-2 pad-1 conv");
+        if (act2) return fail(-4, "mi_conv2d_igemm_f16: mode 6 takes one activation tensor");
+        p.phases = 1; p.num_taps = 16; p.in_stride = 2;
+        for (int r = 0; r < 4; ++r)
+            for (int s = 0; s < 4; ++s) {
+                const int t = r * 4 + s;
+                p.dh[t] = (int8_t)(r - 1); p.dw[t] = (int8_t)(s - 1); p.ph[t] = 0;
+            }
     } else if (mode >= 2 && mode <= 5) {
         // sub-pixel phase (a, b) = ((mode-2) >> 1, (mode-2) & 1) of "nearest x2 upsample, then 3x3 conv": output pixel
         // (2y+a, 2x+b) only sees the low-res pixels (y + a-1 + r, x + b-1 + s), r,s in {0,1}, with 3x3 weights pre-summed

@@ -125,11 +125,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         } else {
                             ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
                             if (j < args.a_split)
-                                ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 + dw,
-                                                 h0 + dh, ph, b0);
+                                ptx::tma_load_5d(&tmA, &full_bar[stage], sa, args.a_chan_off + j * kConvBlockK, w0 * args.in_stride + dw,
+                                                 h0 * args.in_stride + dh, ph, b0);
                             else   // second half of a virtual channel concat (skip connection)
                                 ptx::tma_load_5d(&tmA2, &full_bar[stage], sa,
-                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 + dw, h0 + dh, ph,
+                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, w0 * args.in_stride + dw,
+                                                 h0 * args.in_stride + dh, ph,
                                                  b0);
                             ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * kConvBlockK, n0);
                         }
@@ -342,10 +343,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         const int jj = j + kc;
                         if (jj < args.a_split)
                             ptx::tma_load_5d_2sm(&tmA, &full_bar[stage], sa + kc * kABytes,
-                                                 args.a_chan_off + jj * kConvBlockK, w0 + dw, h0 + dh, ph, b0);
+                                                 args.a_chan_off + jj * kConvBlockK, w0 * args.in_stride + dw,
+                                                 h0 * args.in_stride + dh, ph, b0);
                         else
                             ptx::tma_load_5d_2sm(&tmA2, &full_bar[stage], sa + kc * kABytes,
-                                                 args.a_chan_off2 + (jj - args.a_split) * kConvBlockK, w0 + dw, h0 + dh,
+                                                 args.a_chan_off2 + (jj - args.a_split) * kConvBlockK, w0 * args.in_stride + dw,
+                                                 h0 * args.in_stride + dh,
                                                  ph, b0);
                         ptx::tma_load_2d_2sm(&tmB, &full_bar[stage], sb + kc * C::kBBytes, (kb + kc) * kConvBlockK, n0);
                     }
@@ -1180,6 +1183,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     a.tiles_b = (p.B + BB - 1) / BB;
     a.B = p.B; a.H = p.H; a.W = p.W;
     a.a_chan_off = p.a_chan_off;
+    a.in_stride = p.in_stride == 2 ? 2 : 1;
     a.out_sb = p.out_sb; a.out_sh = p.out_sh; a.out_sw = p.out_sw;
     a.out_sc = p.out_sc > 0 ? p.out_sc : 1;
     a.n_valid = p.n_valid > 0 ? p.n_valid : p.Cout;
@@ -1232,7 +1236,8 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     a.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK;
     a.a_chan_off2 = p.a_chan_off2;
     if (p.act2) {
-        if (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) || (reinterpret_cast<uintptr_t>(p.act2) & 15))
+        if (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) || (reinterpret_cast<uintptr_t>(p.act2) & 15) ||
+            a.in_stride != 1)
             return -8;
         cuuint64_t gdim[5] = {(cuuint64_t)p.lda2, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.phases, (cuuint64_t)p.B};
         cuuint64_t gstr[4] = {(cuuint64_t)p.lda2 * 2, (cuuint64_t)p.W * p.lda2 * 2, (cuuint64_t)p.H * p.W * p.lda2 * 2,
@@ -1245,12 +1250,16 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
             return -6;
     }
     {
-        cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.phases,
+        // in_stride == 2 (Downsample read in place): the tensor is the (2H x 2W) input, the box spans 2*BW x 2*BH pixels
+        // and the element strides make TMA keep every second pixel -> the same 128-pixel tile lands in shared memory
+        const cuuint64_t IS = a.in_stride;
+        cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W * IS, (cuuint64_t)p.H * IS, (cuuint64_t)p.phases,
                               (cuuint64_t)p.B};
-        cuuint64_t gstr[4] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.W * p.lda * 2, (cuuint64_t)p.H * p.W * p.lda * 2,
-                              (cuuint64_t)p.phases * p.H * p.W * p.lda * 2};
-        cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)BW, (cuuint32_t)BH, 1, (cuuint32_t)BB};
-        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        cuuint64_t gstr[4] = {(cuuint64_t)p.lda * 2, (cuuint64_t)p.W * IS * p.lda * 2,
+                              (cuuint64_t)p.H * IS * p.W * IS * p.lda * 2,
+                              (cuuint64_t)p.phases * p.H * IS * p.W * IS * p.lda * 2};
+        cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)(BW * IS), (cuuint32_t)(BH * IS), 1, (cuuint32_t)BB};
+        cuuint32_t estr[5] = {1, (cuuint32_t)IS, (cuuint32_t)IS, 1, 1};
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(p.act), gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -17,6 +17,7 @@ struct ConvTcArgs {
     int tiles_w, tiles_h, tiles_b, tiles_n;
     int B, H, W;                          // output pixel grid (== TMA pixel grid of every phase)
     int a_chan_off;                       // first input channel inside the activation buffer
+    int in_stride;                        // 1, or 2: taps address the (2H x 2W) input directly (TMA element stride 2)
     int a_split, a_chan_off2;             // k-chunks >= a_split come from the second activation tensor (virtual concat)
     long long out_sb, out_sh, out_sw;     // output (and residual) strides in elements
     long long out_sc;                     // channel stride (1 = NHWC-style contiguous channels; H*W for NCHW output)
@@ -40,6 +41,7 @@ struct ConvTcProblem {
     const void* act;        // fp16 activations, layout [B][phases][H][W][lda]
     int B, H, W;            // pixel grid of each phase == output pixel grid
     int phases;             // 1, or 4 for the phase-split input of a stride-2 conv
+    int in_stride;          // 0/1, or 2: act is the un-split [B][2H][2W][lda] input of a stride-2 conv; dh/dw are full-res offsets
     int lda;                // elements per pixel in the activation buffer (>= a_chan_off + Cin)
     int a_channels;         // channel extent visible to TMA (usually lda)
     int a_chan_off;         // first channel used

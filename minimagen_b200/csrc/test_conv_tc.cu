@@ -64,7 +64,8 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
 
     // device input layout: stride 1 -> [B][1][H][W][C]; stride 2 -> phase split [B][4][Ho][Wo][C], phase = (h&1)*2 + (w&1)
     std::vector<__half> h_dev_in(n_in);
-    if (c.stride == 1) {
+    const bool direct_s2 = (c.stride == 2 && c.pair == 9);   // stride-2 conv read in place (TMA element strides)
+    if (c.stride == 1 || direct_s2) {
         h_dev_in = h_in;
     } else {
         for (int b = 0; b < c.B; ++b)
@@ -91,13 +92,13 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
     if (c.f16out) { CK(cudaMalloc(&d_o16, n_out * 2)); CK(cudaMemset(d_o16, 0xFF, n_out * 2)); }
 
     ConvTcProblem p{};
-    p.act = d_in; p.B = c.B; p.H = Ho; p.W = Wo; p.phases = c.stride == 2 ? 4 : 1;
+    p.act = d_in; p.B = c.B; p.H = Ho; p.W = Wo; p.phases = (c.stride == 2 && c.pair != 9) ? 4 : 1; p.in_stride = (c.stride == 2 && c.pair == 9) ? 2 : 1;
     p.lda = c.Cin; p.a_channels = c.Cin; p.a_chan_off = 0; p.Cin = c.Cin;
     p.wpacked = d_w; p.Cout = c.Cout; p.num_taps = taps;
     for (int r = 0; r < c.k; ++r)
         for (int s = 0; s < c.k; ++s) {
             const int t = r * c.k + s;
-            if (c.stride == 1) { p.dh[t] = r - pad; p.dw[t] = s - pad; p.ph[t] = 0; }
+            if (c.stride == 1 || direct_s2) { p.dh[t] = r - pad; p.dw[t] = s - pad; p.ph[t] = 0; }
             else {
                 // input row = 2*ho + r - 1  ->  phase row (r-1)&1, block shift floor((r-1)/2)
                 const int rr = r - 1, ss = s - 1;
@@ -112,6 +113,7 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
     if (c.pair == 5) { p.cta_pair = 2; p.stream_k = 2; }
     if (c.pair == 6) { p.cta_pair = 2; p.stream_k = 1; }
     if (c.pair == 7) { p.cta_pair = 2; p.stream_k = 2; p.dbg = 4; }
+    if (c.pair == 9) p.cta_pair = 0;
 
     *g_err = 0;
     int rc = conv_tc_launch(p, 0);
@@ -227,6 +229,11 @@ int main(int argc, char** argv) {
             {"h_c3_n16", 2, 32, 32, 128, 16, 3, 1, true, false, false, 0, 3},
             {"h_c3_n16_k256", 3, 32, 64, 256, 16, 3, 1, true, false, false, 0, 3},
             {"h_c3_n16_persist", 4, 128, 128, 64, 16, 3, 1, false, false, false, 0, 3},
+            // ---- 4x4 stride-2 conv read in place through TMA element strides (pair == 9; kernel chosen automatically)
+            {"s2_direct_small", 2, 32, 32, 64, 128, 4, 2, true, false, true, 0, 9},
+            {"s2_direct_w256", 1, 8, 256, 64, 64, 4, 2, false, false, false, 0, 9},
+            {"s2_direct_pair", 8, 64, 64, 64, 256, 4, 2, true, false, false, 0, 9},
+            {"s2_direct_8x8", 3, 16, 16, 128, 128, 4, 2, true, false, false, 0, 9},
             // ---- 3x3 halo kernel with swapped operands (pair == 8)
             {"t_c3_32x32", 1, 32, 32, 128, 128, 3, 1, true, false, false, 0, 8},
             {"t_c3_32x8_k64", 3, 32, 8, 64, 128, 3, 1, false, false, true, 0, 8},
@@ -283,6 +290,10 @@ int main(int argc, char** argv) {
             {"D1(noTMA) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 11},
             {"D2(noEpi) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 12},
             {"D3(neither) sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 13},
+            {"S2 direct 256->128 128ch", 32, 256, 256, 128, 128, 4, 2, true, false, false, 0, 9},
+            {"S2 split  256->128 128ch", 32, 256, 256, 128, 128, 4, 2, true, false, false, 0, 0},
+            {"S2 direct 64->32 256->512", 32, 64, 64, 256, 512, 4, 2, true, false, false, 0, 9},
+            {"S2 split  64->32 256->512", 32, 64, 64, 256, 512, 4, 2, true, false, false, 0, 0},
             {"T sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 8},
             {"T sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128, 8},
             {"T sr_128_256to128", 32, 128, 128, 256, 128, 3, 1, true, true, false, 128, 8},

@@ -36,6 +36,9 @@ FUSE_GN_CONV = False         # False: never; True: only where C_out is not a mul
 # nearest-x2 upsample + 3x3 conv as four 2x2 sub-pixel convs on the low-res tensor (4/9 of the FLOPs, no upsampled copy)
 SUBPIXEL_UPSAMPLE = True
 
+# Downsample (4x4 stride 2) reads the producer's fp16 copy in place (TMA element strides) instead of a phase-split copy
+INPLACE_DOWNSAMPLE = True
+
 
 class ZeroArena:
     """One zero-filled fp64 buffer per forward pass from which the (many, tiny) GroupNorm statistics accumulators are
@@ -351,7 +354,8 @@ class Conv2d(nn.Conv2d):
         kh, kw = self.kernel_size
         return kh * kw <= 16 and get_ops().igemm_supported(H, W, self.in_channels, self.out_channels)
 
-    def run_prepared(self, a, B, H, W, residual=None, f32=True, f16=False, stats=False, a2=None, c_in1=0, wp=None):
+    def run_prepared(self, a, B, H, W, residual=None, f32=True, f16=False, stats=False, a2=None, c_in1=0, wp=None,
+                     in_place_s2=False):
         """Conv over an already prepared operand `a`:
            tensor-core path: fp16 [B, P, H, W, C] (P = 4 phases for the stride-2 geometry), (H, W) = output grid;
                              optional second source `a2` (virtual concat: channels [c_in1, C_in) come from it);
@@ -364,7 +368,8 @@ class Conv2d(nn.Conv2d):
         strides = (H * W * Cout, W * Cout, Cout)
         dev = a.device
         if a.dtype == F16:
-            mode = 1 if self._geom == 'down' else 0
+            # Downsample: 4-phase split operand (mode 1) or the fp16 activation read in place with TMA element strides (6)
+            mode = (6 if in_place_s2 else 1) if self._geom == 'down' else 0
             st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0) else None
             if not f32 and not f16:
                 f32 = True
@@ -478,6 +483,8 @@ class Conv2d(nn.Conv2d):
                                                  wp=self._pack_cat(c0, x.scale), **kw)
                 else:
                     return self.run_prepared(x.need_f16(), B, H, W, **kw)
+            if geom == 'down' and INPLACE_DOWNSAMPLE and not isinstance(x, Cat) and x.f16 is not None:
+                return self.run_prepared(x.f16, B, Ho, Wo, in_place_s2=True, **kw)
             s0, C0, s1, C1, sc = _srcs(x, True)
             mode = 1 if upsample else (2 if geom == 'down' else 0)
             a = torch.empty((B, 4 if mode == 2 else 1, Ho, Wo, C), dtype=F16, device=x.device)

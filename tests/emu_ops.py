@@ -62,6 +62,12 @@ class EmuOps:
         self._log("conv_igemm")
         assert act.dtype == F16 and wp.dtype == F16
         P = 4 if mode == 1 else 1
+        if mode == 6:
+            a = act.reshape(B, 2 * H, 2 * W, lda)[..., c_off:c_off + c_in].float()
+            w = wp.float().reshape(c_out, kh, kw, c_in).permute(0, 3, 1, 2)
+            y = F.conv2d(a.permute(0, 3, 1, 2), w, None, stride=2, padding=1).permute(0, 2, 3, 1)
+            return self._conv_finish(y, B, H, W, c_out, bias, residual, out_f32, out_f16, out_strides, out_sc, n_valid,
+                                     out_stats)
         if act2 is None:
             a = act.reshape(B, P, H, W, lda)[..., c_off:c_off + c_in].float()
         else:
@@ -82,6 +88,9 @@ class EmuOps:
                 full[:, (p >> 1)::2, (p & 1)::2] = a[:, p]
             y = F.conv2d(full.permute(0, 3, 1, 2), w, None, stride=2, padding=1)
         y = y.permute(0, 2, 3, 1)                                                 # B,H,W,Cout
+        self._conv_finish(y, B, H, W, c_out, bias, residual, out_f32, out_f16, out_strides, out_sc, n_valid, out_stats)
+
+    def _conv_finish(self, y, B, H, W, c_out, bias, residual, out_f32, out_f16, out_strides, out_sc, n_valid, out_stats):
         if bias is not None:
             y = y + bias
         sb, sh, sw = out_strides
