@@ -180,10 +180,16 @@ int mi_silu_f32(const float* in, long long n, float* out, void* stream);
  * Fused softmax attention, dim_head 64: CrossAttention.forward (layers.py:220-251) with kv_head_stride = 64, and the
  * multi-query Attention.forward (layers.py:52-104) with kv_head_stride = 0.  q must already carry the dim_head**-0.5
  * scale.  Key 0 is the learned null_kv [2][64] fp32 (layers.py:65-67,232-235); key_mask: uint8 [B][m] or NULL
- * (masked_fill(~mask, -FLT_MAX), layers.py:92-95,242-245).  q/out: [B][n][ld] with head h at column h*64. */
+ * (masked_fill(~mask, -FLT_MAX), layers.py:92-95,242-245).  q/out: [B][n][ld] with head h at column h*64.
+ * workspace (optional, 128-byte aligned, size from mi_attention_workspace_bytes): lends the tcgen05 kernel room for the
+ * null-prepended padded K and the transposed V; it is used when key_mask is NULL, n % 128 == 0 and q is batch-contiguous
+ * (q_bs == n*ldq) -- S = QK^T and O = PV then run as tcgen05.mma with TMEM accumulators, the softmax in between reads S from
+ * TMEM and hands P to the second GEMM through shared memory.  Otherwise (or with workspace NULL) a mma.sync kernel runs. */
+long long mi_attention_workspace_bytes(int B, int heads, int kv_head_stride, int m);
 int mi_attention_fwd(const void* q_f16, long long q_bs, int ldq, const void* k_f16, const void* v_f16, long long kv_bs,
                      int ldkv, int kv_head_stride, const float* null_kv, const uint8_t* key_mask, int B, int heads,
-                     int n, int m, void* out_f16, long long o_bs, int ldo, void* stream);
+                     int n, int m, void* out_f16, long long o_bs, int ldo, void* workspace, long long workspace_bytes,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------- DDPM step
  * Imagen._p_mean_variance / _p_sample after the U-Net (Imagen.py:307-326, :361-370).  Images are NCHW fp32 [B][n].

@@ -41,14 +41,16 @@ SIGNATURES = {
     "mi_nchw_to_nhwc": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
     "mi_stem_unroll_f16": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
     "mi_silu_f32": [_P, _L, _P, _P],
-    "mi_attention_fwd": [_P, _L, _I, _P, _P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _L, _I, _P],
+    "mi_attention_workspace_bytes": [_I, _I, _I, _I],
+    "mi_attention_fwd": [_P, _L, _I, _P, _P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _L, _I, _P, _L, _P],
     "mi_step_x0": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _P, _P],
     "mi_step_quantile": [_P, _I, _I, _I, _I, _F, _F, _P, _P],
     "mi_step_posterior": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
     "mi_step_finalize": [_P, _L, _I, _P, _P],
     "mi_q_sample": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
 }
-_RESTYPES = {"mi_last_error": c_char_p, "mi_conv2d_igemm_workspace_bytes": c_longlong}
+_RESTYPES = {"mi_last_error": c_char_p, "mi_conv2d_igemm_workspace_bytes": c_longlong,
+             "mi_attention_workspace_bytes": c_longlong}
 
 _lib = None
 launch_count = 0   # number of kernel launches issued through this binding (bench.py reports it)

@@ -1,0 +1,416 @@
+// Attention core on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), head dim 64, no mask.
+//
+// Replaces the softmax(q k^T) v core of Attention.forward (layers.py:56-104; one shared k/v head = multi-query) and
+// CrossAttention.forward (layers.py:226-251; per-head k/v over the text tokens), both with the learned null key/value
+// prepended (layers.py:67-70, :240-242).  q arrives pre-scaled (dim_head**-0.5 folded into to_q).
+//
+// One CTA = 128 queries of one (batch, head).  Keys are processed in blocks of 128:
+//   S = Q K_j^T        tcgen05.mma  M = 128 queries, N = 128 keys, K = 64   -> TMEM (fp32, double-buffered)
+//   P = exp(S - max)   8 softmax warps: one query row x 64 keys per thread (tcgen05.ld), fp16 P written to smem in the
+//                      128B-swizzled K-major layout the next MMA reads
+//   O += P V_j         tcgen05.mma  M = 128 queries, N = 64, K = 128 keys    -> TMEM
+// The exact row maximum is found in a first sweep over the keys (S only), so the second sweep never rescales O: two QK^T
+// sweeps (cheap, N = 128) instead of an online-softmax correction path.  K comes from a padded copy with the null key
+// prepended, V from a TRANSPOSED padded copy (keys contiguous = the K-major B operand of the second GEMM); both are
+// written by attn_prep_kernel into a caller-provided workspace.  Warp roles: 0-7 softmax / epilogue (two warps per TMEM
+// lane quarter, each owning one 64-key half of every block and one 32-dim half of the output), 8 TMA producer, 9 MMA
+// issuer + TMEM allocator.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+#include "launch.cuh"
+#include "ptx.cuh"
+
+namespace mi {
+
+namespace {
+
+constexpr int kD = 64, kBQ = 128, kBK = 128;
+constexpr int kSoftmaxWarps = 8;                     // two per TMEM lane quarter: keys [0,64) and [64,128) of every block
+constexpr int kThreads = 32 * (kSoftmaxWarps + 2);    // + TMA producer (warp 8) + MMA issuer / TMEM allocator (warp 9)
+constexpr uint32_t kQBytes = kBQ * kD * 2;            // 16 KB
+constexpr uint32_t kKBytes = kBK * kD * 2;            // 16 KB
+constexpr uint32_t kVBytes = kD * kBK * 2;            // 16 KB: two [64 dims][64 keys] chunks
+constexpr uint32_t kPBytes = kBQ * kBK * 2;           // 32 KB: two [128 q][64 keys] chunks
+constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 1024;
+constexpr uint32_t kTmemCols = 512;                   // S0 [0,128) S1 [128,256) O [256,320)
+
+// ------------------------------------------------------------------------------------------------ operand preparation
+// Kp[bh][key][64]: key 0 = null key, keys 1..m = k, keys > m = 0.   Vt[bh][dim][key]: the same, transposed.
+__global__ void __launch_bounds__(256)
+attn_prep_kernel(const __half* __restrict__ k, const __half* __restrict__ v, long long kv_bs, int ldkv, int kv_hs,
+                 const float* __restrict__ null_kv, int hkv, int m, int Mp, __half* __restrict__ Kp,
+                 __half* __restrict__ Vt) {
+    pdl_wait();
+    pdl_trigger();
+    __shared__ __half tile[64][kD + 2];               // 64 keys x 64 dims of V (padded: conflict-free transpose)
+    const int bh = blockIdx.y, b = bh / hkv, h = bh % hkv;
+    const int key0 = blockIdx.x * 64;
+    const __half* kb = k + (long long)b * kv_bs + (long long)h * kv_hs;
+    const __half* vb = v + (long long)b * kv_bs + (long long)h * kv_hs;
+    for (int i = threadIdx.x; i < 64 * kD; i += blockDim.x) {
+        const int r = i / kD, d = i % kD;
+        const int key = key0 + r;                      // padded index: 0 = null, 1..m = real
+        __half kk = __float2half_rn(0.f), vv = kk;
+        if (key == 0) { kk = __float2half_rn(null_kv[d]); vv = __float2half_rn(null_kv[kD + d]); }
+        else if (key <= m) { kk = kb[(long long)(key - 1) * ldkv + d]; vv = vb[(long long)(key - 1) * ldkv + d]; }
+        Kp[((long long)bh * Mp + key) * kD + d] = kk;
+        tile[r][d] = vv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * kD; i += blockDim.x) {
+        const int d = i / 64, r = i % 64;
+        Vt[((long long)bh * kD + d) * Mp + key0 + r] = tile[r][d];
+    }
+}
+
+struct AttnArgs {
+    int n, heads, hkv, Mp, nblk, kv_len;       // kv_len = m + 1 valid (padded) keys
+    __half* out; long long o_bs; int ldo;
+    int* err;
+};
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnArgs a) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + kQBytes;                 // [2]
+    uint8_t* sV = sK + 2 * kKBytes;             // [2]
+    uint8_t* sP = sV + 2 * kVBytes;             // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+    uint64_t* q_full = bars;
+    uint64_t* k_full = bars + 1;                // [2]
+    uint64_t* k_empty = bars + 3;
+    uint64_t* v_full = bars + 5;
+    uint64_t* v_empty = bars + 7;
+    uint64_t* s_full = bars + 9;
+    uint64_t* s_empty = bars + 11;
+    uint64_t* p_full = bars + 13;
+    uint64_t* p_empty = bars + 15;
+    uint64_t* o_full = bars + 17;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
+    float* s_xchg = reinterpret_cast<float*>(bars + 20);     // [2][128]: row max / row sum exchange between the column halves
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
+    const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
+    int* err = a.err;
+
+    if (warp == 8 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmK);
+        ptx::prefetch_tensormap(&tmV);
+    }
+    if (warp == 9 && lane == 0) {
+        ptx::mbar_init(q_full, 1);
+        ptx::mbar_init(o_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1);
+            ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
+            ptx::mbar_init(&s_full[i], 1); ptx::mbar_init(&s_empty[i], 32 * kSoftmaxWarps);
+            ptx::mbar_init(&p_full[i], 32 * kSoftmaxWarps); ptx::mbar_init(&p_empty[i], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 9) {
+        ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
+
+    const int nblk = a.nblk;
+
+    if (warp == 8) {
+        // ===================== TMA producer =====================
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(q_full, kQBytes);
+            ptx::tma_load_2d(&tmQ, q_full, sQ, h * kD, b * a.n + q0);
+        }
+        int ik = 0, iv = 0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int j = 0; j < nblk; ++j) {
+                {
+                    const int s = ik & 1;
+                    ptx::mbar_wait(&k_empty[s], ((ik >> 1) & 1) ^ 1, err, 4100 + s);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&k_full[s], kKBytes);
+                        ptx::tma_load_2d(&tmK, &k_full[s], sK + s * kKBytes, 0, bh * a.Mp + j * kBK);
+                    }
+                    ++ik;
+                }
+                if (pass == 1) {
+                    const int s = iv & 1;
+                    ptx::mbar_wait(&v_empty[s], ((iv >> 1) & 1) ^ 1, err, 4200 + s);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&v_full[s], kVBytes);
+                        ptx::tma_load_2d(&tmV, &v_full[s], sV + s * kVBytes, j * kBK, bh * kD);
+                        ptx::tma_load_2d(&tmV, &v_full[s], sV + s * kVBytes + kVBytes / 2, j * kBK + 64, bh * kD);
+                    }
+                    ++iv;
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = ptx::make_idesc_f16(kBQ, kBK, 0);
+        constexpr uint32_t idesc_o = ptx::make_idesc_f16(kBQ, kD, 0);
+        const uint32_t tmem_o = tmem_base + 256;
+        ptx::mbar_wait(q_full, 0, err, 4300);
+        int ik = 0, is = 0, ip = 0, iv = 0;
+        auto issue_qk = [&]() {
+            const int ks = ik & 1, ss = is & 1;
+            ptx::mbar_wait(&k_full[ks], (ik >> 1) & 1, err, 4310 + ks);
+            ptx::mbar_wait(&s_empty[ss], ((is >> 1) & 1) ^ 1, err, 4320 + ss);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sQ));
+                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sK + ks * kKBytes));
+#pragma unroll
+                for (int k = 0; k < kD / 16; ++k)
+                    ptx::umma_f16(tmem_base + ss * kBK, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+                ptx::umma_commit(&k_empty[ks]);
+                ptx::umma_commit(&s_full[ss]);
+            }
+            ++ik; ++is;
+        };
+        // sweep 1: S only (row maxima)
+        for (int j = 0; j < nblk; ++j) issue_qk();
+        // sweep 2: S of block j+1 is issued before P V of block j so the softmax warps always have work
+        issue_qk();
+        for (int j = 0; j < nblk; ++j) {
+            if (j + 1 < nblk) issue_qk();
+            const int ps = ip & 1, vs = iv & 1;
+            ptx::mbar_wait(&p_full[ps], (ip >> 1) & 1, err, 4330 + ps);
+            ptx::mbar_wait(&v_full[vs], (iv >> 1) & 1, err, 4340 + vs);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP + ps * kPBytes + c * (kPBytes / 2)));
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV + vs * kVBytes + c * (kVBytes / 2)));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (j | c | k) != 0);
+                }
+                ptx::umma_commit(&p_empty[ps]);
+                ptx::umma_commit(&v_empty[vs]);
+                if (j + 1 == nblk) ptx::umma_commit(o_full);
+            }
+            ++ip; ++iv;
+        }
+    } else {
+        // ===================== softmax / epilogue: one query row x one 64-key half per thread =====================
+        const int q4 = warp & 3, half = warp >> 2;
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+        const int c_lo = half * 64;                    // this thread's key columns inside every block
+        constexpr float kLog2e = 1.4426950408889634f;
+        int is = 0, ip = 0;
+        // ---- sweep 1: exact row maximum (four independent running maxima: no 128-long dependent chain)
+        float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        for (int j = 0; j < nblk; ++j, ++is) {
+            const int ss = is & 1;
+            ptx::mbar_wait(&s_full[ss], (is >> 1) & 1, err, 4400 + ss);
+            ptx::tc_fence_after();
+            const bool tail = (j + 1) * kBK > a.kv_len;       // only the last block can hold padded keys
+#pragma unroll
+            for (int c = c_lo; c < c_lo + 64; c += 32) {
+                uint32_t v0[16], v1[16];
+                ptx::tmem_ld_x16(lane_addr + ss * kBK + c, v0);
+                ptx::tmem_ld_x16(lane_addr + ss * kBK + c + 16, v1);
+                ptx::tmem_ld_wait();
+                if (!tail) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
+                        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
+                    }
+                } else {
+                    const int key = j * kBK + c;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (key + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
+                        if (key + 16 + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&s_empty[ss]);
+        }
+        float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+        s_xchg[half * 128 + row] = mx;
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
+        mx = fmaxf(mx, s_xchg[(half ^ 1) * 128 + row]);         // key 0 (null) is always valid -> finite
+        const float mneg = -mx * kLog2e;
+        // ---- sweep 2: P = exp(S - max) -> shared memory (fp16, swizzled), row sums in four partial accumulators
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < nblk; ++j, ++is, ++ip) {
+            const int ss = is & 1, ps = ip & 1;
+            ptx::mbar_wait(&s_full[ss], (is >> 1) & 1, err, 4410 + ss);
+            ptx::mbar_wait(&p_empty[ps], ((ip >> 1) & 1) ^ 1, err, 4420 + ps);
+            ptx::tc_fence_after();
+            // this thread's 64 keys are exactly chunk `half` of the P tile: row r, 16-byte groups XOR-swizzled with r % 8
+            uint8_t* chunk = sP + ps * kPBytes + half * (kPBytes / 2) + row * 128;
+            const bool tail = (j + 1) * kBK > a.kv_len;
+#pragma unroll
+            for (int c = 0; c < 64; c += 32) {
+                uint32_t v0[16], v1[16];
+                ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + c, v0);
+                ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + c + 16, v1);
+                ptx::tmem_ld_wait();
+                float p[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    p[i] = ptx::ex2_approx(fmaf(__uint_as_float(v0[i]), kLog2e, mneg));
+                    p[16 + i] = ptx::ex2_approx(fmaf(__uint_as_float(v1[i]), kLog2e, mneg));
+                }
+                if (tail) {
+                    const int key = j * kBK + c_lo + c;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (key + i >= a.kv_len) p[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
+                const int g0 = c >> 3;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    uint4 w;
+                    w.x = pack_h2(p[8 * g + 0], p[8 * g + 1]); w.y = pack_h2(p[8 * g + 2], p[8 * g + 3]);
+                    w.z = pack_h2(p[8 * g + 4], p[8 * g + 5]); w.w = pack_h2(p[8 * g + 6], p[8 * g + 7]);
+                    *reinterpret_cast<uint4*>(chunk + (((g0 + g) ^ (row & 7)) << 4)) = w;
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::fence_proxy_async_smem();          // generic-proxy stores of P -> visible to the tensor core (async proxy)
+            ptx::mbar_arrive(&s_empty[ss]);
+            ptx::mbar_arrive(&p_full[ps]);
+        }
+        float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has read the maxima
+        s_xchg[half * 128 + row] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l += s_xchg[(half ^ 1) * 128 + row];
+        // ---- epilogue: O / l -> fp16 [b][q0 + row][h*64 + 32*half ..]
+        ptx::mbar_wait(o_full, 0, err, 4500);
+        ptx::tc_fence_after();
+        const float inv = 1.f / l;
+        __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + row) * a.ldo + h * kD + half * 32;
+        {
+            uint32_t v0[16], v1[16];
+            ptx::tmem_ld_x16(lane_addr + 256 + half * 32, v0);
+            ptx::tmem_ld_x16(lane_addr + 256 + half * 32 + 16, v1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint4 w0, w1;
+                w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
+                w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
+                w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
+                w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
+                w1.x = pack_h2(__uint_as_float(v1[8 * g + 0]) * inv, __uint_as_float(v1[8 * g + 1]) * inv);
+                w1.y = pack_h2(__uint_as_float(v1[8 * g + 2]) * inv, __uint_as_float(v1[8 * g + 3]) * inv);
+                w1.z = pack_h2(__uint_as_float(v1[8 * g + 4]) * inv, __uint_as_float(v1[8 * g + 5]) * inv);
+                w1.w = pack_h2(__uint_as_float(v1[8 * g + 6]) * inv, __uint_as_float(v1[8 * g + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + 8 * g) = w0;
+                *reinterpret_cast<uint4*>(orow + 16 + 8 * g) = w1;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace
+
+long long attention_tc_workspace_bytes(int B, int heads, int kv_hs, int m) {
+    const int hkv = kv_hs == 0 ? 1 : heads;
+    const long long Mp = ((long long)(m + 1) + kBK - 1) / kBK * kBK;
+    return 2 * (long long)B * hkv * Mp * kD * (long long)sizeof(__half);
+}
+
+bool attention_tc_supported(int n, int ldq, int ldo, long long q_bs, const void* mask) {
+    return mask == nullptr && n > 0 && (n % kBQ) == 0 && (ldq % 8) == 0 && (ldo % 8) == 0 && q_bs == (long long)n * ldq;
+}
+
+int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
+                     int kv_hs, const float* null_kv, int B, int heads, int n, int m, __half* out, long long o_bs, int ldo,
+                     void* workspace, long long workspace_bytes, int* err_flag, cudaStream_t st) {
+    if (!attention_tc_supported(n, ldq, ldo, q_bs, nullptr) || (o_bs % 8) || (reinterpret_cast<uintptr_t>(q) & 15) ||
+        (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 127))
+        return -1;
+    if (workspace_bytes < attention_tc_workspace_bytes(B, heads, kv_hs, m)) return -1;
+    PFN_tmaEncodeTiled enc = get_tma_encode();
+    if (!enc) return -5;
+    const int hkv = kv_hs == 0 ? 1 : heads;
+    const int Mp = (m + 1 + kBK - 1) / kBK * kBK;
+    __half* Kp = reinterpret_cast<__half*>(workspace);
+    __half* Vt = Kp + (long long)B * hkv * Mp * kD;
+    {
+        dim3 grid(Mp / 64, B * hkv);
+        launch_k(attn_prep_kernel, grid, 256, 0, st, k, v, kv_bs, ldkv, kv_hs, null_kv, hkv, m, Mp, Kp, Vt);
+        if (cudaGetLastError() != cudaSuccess) return -2;
+    }
+    CUtensorMap tmQ, tmK, tmV;
+    cuuint32_t estr[2] = {1, 1};
+    {
+        cuuint64_t dim[2] = {(cuuint64_t)ldq, (cuuint64_t)B * n};
+        cuuint64_t str[1] = {(cuuint64_t)ldq * 2};
+        cuuint32_t box[2] = {kD, kBQ};
+        if (enc(&tmQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(q), dim, str, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return -6;
+    }
+    {
+        cuuint64_t dim[2] = {kD, (cuuint64_t)B * hkv * Mp};
+        cuuint64_t str[1] = {kD * 2};
+        cuuint32_t box[2] = {kD, kBK};
+        if (enc(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Kp, dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+            CUDA_SUCCESS)
+            return -6;
+    }
+    {
+        cuuint64_t dim[2] = {(cuuint64_t)Mp, (cuuint64_t)B * hkv * kD};
+        cuuint64_t str[1] = {(cuuint64_t)Mp * 2};
+        cuuint32_t box[2] = {64, kD};
+        if (enc(&tmV, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Vt, dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
+            CUDA_SUCCESS)
+            return -6;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+            return -10;
+        attr_set = true;
+    }
+    AttnArgs a{};
+    a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / kBK; a.kv_len = m + 1;
+    a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
+    dim3 grid(n / kBQ, heads, B);
+    launch_k(attn_tc_kernel, grid, kThreads, kSmemBytes, st, tmQ, tmK, tmV, a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+}  // namespace mi

@@ -25,6 +25,7 @@
 #include <stdio.h>
 
 #include "conv_epilogue.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 #include "launch.cuh"
 
@@ -1019,6 +1020,8 @@ int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
 }
 
 }  // namespace
+
+PFN_tmaEncodeTiled get_tma_encode() { return get_encode(); }
 
 const char* conv_tc_strerror(int code) {
     switch (code) {

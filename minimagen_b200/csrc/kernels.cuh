@@ -2,6 +2,7 @@
 // The public boundary is the C ABI in include/minimagen_b200.h (capi.cu).
 #pragma once
 #include <cuda_fp16.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -41,6 +42,19 @@ int conv_direct_f32(const float* in, int B, int Hin, int Win, int Cin, int ldi, 
 int attention_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
                   int kv_hs, const float* null_kv, const uint8_t* mask, int B, int heads, int n, int m, __half* out,
                   long long o_bs, int ldo, cudaStream_t st);
+
+// attention_tc.cu: tcgen05 / TMEM path (no mask, n % 128 == 0, contiguous q); workspace = padded K and transposed V
+bool attention_tc_supported(int n, int ldq, int ldo, long long q_bs, const void* mask);
+long long attention_tc_workspace_bytes(int B, int heads, int kv_hs, int m);
+int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
+                     int kv_hs, const float* null_kv, int B, int heads, int n, int m, __half* out, long long o_bs, int ldo,
+                     void* workspace, long long workspace_bytes, int* err_flag, cudaStream_t st);
+
+// conv_tc.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+typedef CUresult (*PFN_tmaEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_tmaEncodeTiled get_tma_encode();
 
 // step.cu
 int step_x0(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,

@@ -64,6 +64,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {     // one MUFU.EX2, no range fix-up code
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

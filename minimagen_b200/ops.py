@@ -32,6 +32,7 @@ class NativeOps:
     # empty wave of whole tiles costs nothing (idle SMs free power for the busy ones) while the partial-tile exchange costs
     # ~10 % on the affected layers (profiles/r01_streamk_study.md)
     stream_k = False
+    attention_tc = True      # tcgen05 attention core where the shape allows (mi_attention_fwd workspace)
 
     def __init__(self):
         self._ws = {}        # (device index, stream handle) -> uint8 workspace
@@ -175,8 +176,15 @@ class NativeOps:
         if q.dtype != F16 or k.dtype != F16 or v.dtype != F16 or out.dtype != F16:
             raise TypeError("attention operands must be fp16")
         _chk(null_kv, F32, "null_kv"); _chk(mask, U8, "mask")
+        ws = None
+        if self.attention_tc and mask is None and n % 128 == 0:
+            # operand workspace of the tcgen05 kernel (null-prepended padded K, transposed V); per call, so it is safe under
+            # CUDA-graph capture and concurrent streams
+            nbytes = int(N.load().mi_attention_workspace_bytes(B, heads, kv_hs, m))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
         N.call("mi_attention_fwd", N.ptr(q), q_bs, ldq, N.ptr(k), N.ptr(v), kv_bs, ldkv, kv_hs, N.ptr(null_kv),
-               N.ptr(mask), B, heads, n, m, N.ptr(out), o_bs, ldo, N.stream())
+               N.ptr(mask), B, heads, n, m, N.ptr(out), o_bs, ldo, N.ptr(ws), ws.numel() if ws is not None else 0,
+               N.stream())
 
     # ---------------------------------------------------------------- DDPM step
     def step_x0(self, x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, B, n, x0):

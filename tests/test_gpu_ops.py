@@ -441,7 +441,10 @@ def test_posemb_and_text_tokens(native):
 # ---------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,heads,n,m,shared,use_mask", [(2, 8, 256, 260, False, False), (2, 8, 64, 258, False, True),
                                                          (1, 8, 1024, 1024, True, False), (2, 8, 256, 256, True, True),
-                                                         (1, 2, 100, 37, False, True)])
+                                                         (1, 2, 100, 37, False, True),
+                                                         (3, 8, 128, 59, False, False),      # one padded key block
+                                                         (2, 4, 384, 127, True, False),      # m + 1 == 128 exactly
+                                                         (2, 8, 4096, 4096, True, False)])   # base U-Net 64x64 tokens
 def test_attention(native, B, heads, n, m, shared, use_mask):
     inner = heads * 64
     q = (_rand(B * n, inner, seed=34) * 0.125).to(F16)

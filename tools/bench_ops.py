@@ -101,24 +101,28 @@ def bench_quantile(ops):
 
 
 def bench_attn(ops):
-    B, heads, n, d = 32, 8, 256, 64
-    q = torch.randn(B, n, heads * d, device=dev, dtype=F16)
-    out = torch.empty(B, n, heads * d, device=dev, dtype=F16)
-    null_kv = torch.randn(2, d, device=dev)
+    heads, d = 8, 64
     inner = heads * d
-    # self-attention (layers.py:14-104): one shared k/v head (multi-query), m = n
-    kv = torch.randn(B, n, 2 * d, device=dev, dtype=F16)
-    f = lambda: ops.attention(q, n * inner, inner, kv, kv[..., d:], n * 2 * d, 2 * d, 0, null_kv, None, B, heads, n, n, out,
-                              n * inner, inner)
-    ms = timeit([f])
-    print(f"attention self n={n} m={n} multi-query            {ms * 1e3:8.1f} us  ({4.0 * B * heads * n * (n + 1) * d / ms / 1e9:.1f} TFLOP/s)", flush=True)
-    # cross-attention (layers.py:180-251): per-head k/v over m text tokens
-    m = 59
-    kv = torch.randn(B, m, 2 * inner, device=dev, dtype=F16)
-    f = lambda: ops.attention(q, n * inner, inner, kv, kv[..., inner:], m * 2 * inner, 2 * inner, d, null_kv, None, B, heads, n,
-                              m, out, n * inner, inner)
-    ms = timeit([f])
-    print(f"attention cross n={n} m={m} per-head kv            {ms * 1e3:8.1f} us  ({4.0 * B * heads * n * (m + 1) * d / ms / 1e9:.1f} TFLOP/s)", flush=True)
+    for (B, n, m, shared) in [(32, 256, 256, True), (32, 256, 59, False), (64, 1024, 1024, True), (64, 4096, 4096, True),
+                              (64, 1024, 258, False), (64, 4096, 258, False)]:
+        q = torch.randn(B, n, inner, device=dev, dtype=F16) * 0.125
+        out = torch.empty(B, n, inner, device=dev, dtype=F16)
+        null_kv = torch.randn(2, d, device=dev)
+        if shared:      # self-attention (layers.py:14-104): one shared k/v head (multi-query)
+            kv = torch.randn(B, m, 2 * d, device=dev, dtype=F16)
+            args = (kv, kv[..., d:], m * 2 * d, 2 * d, 0)
+        else:           # cross-attention (layers.py:180-251): per-head k/v over m text tokens
+            kv = torch.randn(B, m, 2 * inner, device=dev, dtype=F16)
+            args = (kv, kv[..., inner:], m * 2 * inner, 2 * inner, d)
+        fl = 4.0 * B * heads * n * (m + 1) * d
+        res = []
+        for tc in (True, False):
+            ops.attention_tc = tc
+            f = lambda: ops.attention(q, n * inner, inner, *args, null_kv, None, B, heads, n, m, out, n * inner, inner)
+            ms = timeit([f], reps=5)
+            res.append(f"{'tcgen05' if tc else 'mma.sync'} {ms * 1e3:9.1f} us ({fl / ms / 1e9:6.1f} TFLOP/s)")
+        ops.attention_tc = True
+        print(f"attention B={B} n={n} m={m} {'multi-query' if shared else 'per-head kv'}:  " + "   ".join(res), flush=True)
 
 
 def bench_cast(ops):
