@@ -6,15 +6,15 @@
 //
 // One CTA = 128 queries of one (batch, head).  Keys are processed in blocks of 128:
 //   S = Q K_j^T        tcgen05.mma  M = 128 queries, N = 128 keys, K = 64   -> TMEM (fp32, double-buffered)
-//   P = exp(S - max)   8 softmax warps: one query row x 64 keys per thread (tcgen05.ld), fp16 P written to smem in the
+//   P = exp(S - max)   16 softmax warps: one query row x 32 keys per thread (tcgen05.ld), fp16 P written to smem in the
 //                      128B-swizzled K-major layout the next MMA reads
 //   O += P V_j         tcgen05.mma  M = 128 queries, N = 64, K = 128 keys    -> TMEM
 // The exact row maximum is found in a first sweep over the keys (S only), so the second sweep never rescales O: two QK^T
 // sweeps (cheap, N = 128) instead of an online-softmax correction path.  K comes from a padded copy with the null key
 // prepended, V from a TRANSPOSED padded copy (keys contiguous = the K-major B operand of the second GEMM); both are
-// written by attn_prep_kernel into a caller-provided workspace.  Warp roles: 0-7 softmax / epilogue (two warps per TMEM
-// lane quarter, each owning one 64-key half of every block and one 32-dim half of the output), 8 TMA producer, 9 MMA
-// issuer + TMEM allocator.
+// written by attn_prep_kernel into a caller-provided workspace.  Warp roles: 0-15 softmax / epilogue (four warps per
+// TMEM lane quarter, each owning 32 keys of every block and 16 dims of the output), 16 TMA producer, 17 MMA issuer + TMEM
+// allocator.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -29,13 +29,13 @@ namespace mi {
 namespace {
 
 constexpr int kD = 64, kBQ = 128, kBK = 128;
-constexpr int kSoftmaxWarps = 8;                     // two per TMEM lane quarter: keys [0,64) and [64,128) of every block
+constexpr int kSoftmaxWarps = 16;                    // four per TMEM lane quarter, each owning 32 keys of every 128-key block
 constexpr int kThreads = 32 * (kSoftmaxWarps + 2);    // + TMA producer (warp 8) + MMA issuer / TMEM allocator (warp 9)
 constexpr uint32_t kQBytes = kBQ * kD * 2;            // 16 KB
 constexpr uint32_t kKBytes = kBK * kD * 2;            // 16 KB
 constexpr uint32_t kVBytes = kD * kBK * 2;            // 16 KB: two [64 dims][64 keys] chunks
 constexpr uint32_t kPBytes = kBQ * kBK * 2;           // 32 KB: two [128 q][64 keys] chunks
-constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 1024;
+constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 2048;
 constexpr uint32_t kTmemCols = 512;                   // S0 [0,128) S1 [128,256) O [256,320)
 
 // ------------------------------------------------------------------------------------------------ operand preparation
@@ -100,19 +100,19 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* p_empty = bars + 15;
     uint64_t* o_full = bars + 17;
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
-    float* s_xchg = reinterpret_cast<float*>(bars + 20);     // [2][128]: row max / row sum exchange between the column halves
+    float* s_xchg = reinterpret_cast<float*>(bars + 20);     // [4][128]: row max / row sum exchange between the column parts
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * kBQ, h = blockIdx.y, b = blockIdx.z;
     const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
     int* err = a.err;
 
-    if (warp == 8 && lane == 0) {
+    if (warp == kSoftmaxWarps && lane == 0) {
         ptx::prefetch_tensormap(&tmQ);
         ptx::prefetch_tensormap(&tmK);
         ptx::prefetch_tensormap(&tmV);
     }
-    if (warp == 9 && lane == 0) {
+    if (warp == kSoftmaxWarps + 1 && lane == 0) {
         ptx::mbar_init(q_full, 1);
         ptx::mbar_init(o_full, 1);
         for (int i = 0; i < 2; ++i) {
@@ -123,7 +123,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 9) {
+    if (warp == kSoftmaxWarps + 1) {
         ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
         ptx::tmem_relinquish();
     }
@@ -135,7 +135,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
     const int nblk = a.nblk;
 
-    if (warp == 8) {
+    if (warp == kSoftmaxWarps) {
         // ===================== TMA producer =====================
         if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(q_full, kQBytes);
@@ -165,7 +165,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kSoftmaxWarps + 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_s = ptx::make_idesc_f16(kBQ, kBK, 0);
         constexpr uint32_t idesc_o = ptx::make_idesc_f16(kBQ, kD, 0);
@@ -214,127 +214,113 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ++ip; ++iv;
         }
     } else {
-        // ===================== softmax / epilogue: one query row x one 64-key half per thread =====================
-        const int q4 = warp & 3, half = warp >> 2;
+        // ===================== softmax / epilogue: one query row x 32 keys of every block per thread =====================
+        const int q4 = warp & 3, part = warp >> 2;     // TMEM lane quarter, key columns [32*part, 32*part + 32)
         const int row = q4 * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-        const int c_lo = half * 64;                    // this thread's key columns inside every block
+        const int c_lo = part * 32;
         constexpr float kLog2e = 1.4426950408889634f;
         int is = 0, ip = 0;
-        // ---- sweep 1: exact row maximum (four independent running maxima: no 128-long dependent chain)
+        // ---- sweep 1: exact row maximum (four independent running maxima: no long dependent chain)
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int j = 0; j < nblk; ++j, ++is) {
             const int ss = is & 1;
             ptx::mbar_wait(&s_full[ss], (is >> 1) & 1, err, 4400 + ss);
             ptx::tc_fence_after();
-            const bool tail = (j + 1) * kBK > a.kv_len;       // only the last block can hold padded keys
+            uint32_t v0[16], v1[16];
+            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo, v0);
+            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + 16, v1);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&s_empty[ss]);                     // S is in registers: release the buffer early
+            if ((j + 1) * kBK <= a.kv_len) {                    // only the last block can hold padded keys
 #pragma unroll
-            for (int c = c_lo; c < c_lo + 64; c += 32) {
-                uint32_t v0[16], v1[16];
-                ptx::tmem_ld_x16(lane_addr + ss * kBK + c, v0);
-                ptx::tmem_ld_x16(lane_addr + ss * kBK + c + 16, v1);
-                ptx::tmem_ld_wait();
-                if (!tail) {
+                for (int i = 0; i < 16; ++i) {
+                    mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
+                    mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
+                }
+            } else {
+                const int key = j * kBK + c_lo;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
-                        mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
-                    }
-                } else {
-                    const int key = j * kBK + c;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        if (key + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
-                        if (key + 16 + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    if (key + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
+                    if (key + 16 + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
                 }
             }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&s_empty[ss]);
         }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        s_xchg[half * 128 + row] = mx;
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight softmax warps only
-        mx = fmaxf(mx, s_xchg[(half ^ 1) * 128 + row]);         // key 0 (null) is always valid -> finite
+        s_xchg[part * 128 + row] = mx;
+        asm volatile("bar.sync 1, 512;" ::: "memory");          // the sixteen softmax warps only
+        mx = fmaxf(fmaxf(s_xchg[row], s_xchg[128 + row]), fmaxf(s_xchg[256 + row], s_xchg[384 + row]));   // key 0 (null) is valid
         const float mneg = -mx * kLog2e;
         // ---- sweep 2: P = exp(S - max) -> shared memory (fp16, swizzled), row sums in four partial accumulators
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nblk; ++j, ++is, ++ip) {
             const int ss = is & 1, ps = ip & 1;
             ptx::mbar_wait(&s_full[ss], (is >> 1) & 1, err, 4410 + ss);
-            ptx::mbar_wait(&p_empty[ps], ((ip >> 1) & 1) ^ 1, err, 4420 + ps);
             ptx::tc_fence_after();
-            // this thread's 64 keys are exactly chunk `half` of the P tile: row r, 16-byte groups XOR-swizzled with r % 8
-            uint8_t* chunk = sP + ps * kPBytes + half * (kPBytes / 2) + row * 128;
-            const bool tail = (j + 1) * kBK > a.kv_len;
-#pragma unroll
-            for (int c = 0; c < 64; c += 32) {
-                uint32_t v0[16], v1[16];
-                ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + c, v0);
-                ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + c + 16, v1);
-                ptx::tmem_ld_wait();
-                float p[32];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    p[i] = ptx::ex2_approx(fmaf(__uint_as_float(v0[i]), kLog2e, mneg));
-                    p[16 + i] = ptx::ex2_approx(fmaf(__uint_as_float(v1[i]), kLog2e, mneg));
-                }
-                if (tail) {
-                    const int key = j * kBK + c_lo + c;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (key + i >= a.kv_len) p[i] = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
-                const int g0 = c >> 3;
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    uint4 w;
-                    w.x = pack_h2(p[8 * g + 0], p[8 * g + 1]); w.y = pack_h2(p[8 * g + 2], p[8 * g + 3]);
-                    w.z = pack_h2(p[8 * g + 4], p[8 * g + 5]); w.w = pack_h2(p[8 * g + 6], p[8 * g + 7]);
-                    *reinterpret_cast<uint4*>(chunk + (((g0 + g) ^ (row & 7)) << 4)) = w;
-                }
-            }
+            uint32_t v0[16], v1[16];
+            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo, v0);
+            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + 16, v1);
+            ptx::tmem_ld_wait();
             ptx::tc_fence_before();
-            ptx::fence_proxy_async_smem();          // generic-proxy stores of P -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(&s_empty[ss]);
+            float p[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                p[i] = ptx::ex2_approx(fmaf(__uint_as_float(v0[i]), kLog2e, mneg));
+                p[16 + i] = ptx::ex2_approx(fmaf(__uint_as_float(v1[i]), kLog2e, mneg));
+            }
+            if ((j + 1) * kBK > a.kv_len) {
+                const int key = j * kBK + c_lo;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (key + i >= a.kv_len) p[i] = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
+            // keys [32*part, +32) of row r: chunk part/2, 16-byte groups 4*(part%2) .. +3, XOR-swizzled with r % 8
+            ptx::mbar_wait(&p_empty[ps], ((ip >> 1) & 1) ^ 1, err, 4420 + ps);
+            uint8_t* chunk = sP + ps * kPBytes + (part >> 1) * (kPBytes / 2) + row * 128;
+            const int g0 = (part & 1) * 4;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 w;
+                w.x = pack_h2(p[8 * g + 0], p[8 * g + 1]); w.y = pack_h2(p[8 * g + 2], p[8 * g + 3]);
+                w.z = pack_h2(p[8 * g + 4], p[8 * g + 5]); w.w = pack_h2(p[8 * g + 6], p[8 * g + 7]);
+                *reinterpret_cast<uint4*>(chunk + (((g0 + g) ^ (row & 7)) << 4)) = w;
+            }
+            ptx::fence_proxy_async_smem();          // generic-proxy stores of P -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(&p_full[ps]);
         }
         float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        asm volatile("bar.sync 1, 256;" ::: "memory");          // everyone has read the maxima
-        s_xchg[half * 128 + row] = l;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        l += s_xchg[(half ^ 1) * 128 + row];
-        // ---- epilogue: O / l -> fp16 [b][q0 + row][h*64 + 32*half ..]
+        asm volatile("bar.sync 1, 512;" ::: "memory");          // everyone has read the maxima
+        s_xchg[part * 128 + row] = l;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        l = (s_xchg[row] + s_xchg[128 + row]) + (s_xchg[256 + row] + s_xchg[384 + row]);
+        // ---- epilogue: O / l -> fp16 [b][q0 + row][h*64 + 16*part ..]
         ptx::mbar_wait(o_full, 0, err, 4500);
         ptx::tc_fence_after();
         const float inv = 1.f / l;
-        __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + row) * a.ldo + h * kD + half * 32;
+        __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + row) * a.ldo + h * kD + part * 16;
         {
-            uint32_t v0[16], v1[16];
-            ptx::tmem_ld_x16(lane_addr + 256 + half * 32, v0);
-            ptx::tmem_ld_x16(lane_addr + 256 + half * 32 + 16, v1);
+            uint32_t v0[16];
+            ptx::tmem_ld_x16(lane_addr + 256 + part * 16, v0);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < 2; ++g) {
-                uint4 w0, w1;
+                uint4 w0;
                 w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
                 w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
                 w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
                 w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
-                w1.x = pack_h2(__uint_as_float(v1[8 * g + 0]) * inv, __uint_as_float(v1[8 * g + 1]) * inv);
-                w1.y = pack_h2(__uint_as_float(v1[8 * g + 2]) * inv, __uint_as_float(v1[8 * g + 3]) * inv);
-                w1.z = pack_h2(__uint_as_float(v1[8 * g + 4]) * inv, __uint_as_float(v1[8 * g + 5]) * inv);
-                w1.w = pack_h2(__uint_as_float(v1[8 * g + 6]) * inv, __uint_as_float(v1[8 * g + 7]) * inv);
                 *reinterpret_cast<uint4*>(orow + 8 * g) = w0;
-                *reinterpret_cast<uint4*>(orow + 16 + 8 * g) = w1;
             }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 9) {
+    if (warp == kSoftmaxWarps + 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
