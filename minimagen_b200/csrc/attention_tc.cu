@@ -28,15 +28,24 @@ namespace mi {
 
 namespace {
 
-constexpr int kD = 64, kBQ = 128, kBK = 128;
-constexpr int kSoftmaxWarps = 16;                    // four per TMEM lane quarter, each owning 32 keys of every 128-key block
-constexpr int kThreads = 32 * (kSoftmaxWarps + 2);    // + TMA producer (warp 8) + MMA issuer / TMEM allocator (warp 9)
+constexpr int kD = 64, kBQ = 128;
+constexpr int kSoftmaxWarps = 16;                    // four per TMEM lane quarter, each owning a quarter of every key block
+constexpr int kThreads = 32 * (kSoftmaxWarps + 2);    // + TMA producer (warp 16) + MMA issuer / TMEM allocator (warp 17)
 constexpr uint32_t kQBytes = kBQ * kD * 2;            // 16 KB
-constexpr uint32_t kKBytes = kBK * kD * 2;            // 16 KB
-constexpr uint32_t kVBytes = kD * kBK * 2;            // 16 KB: two [64 dims][64 keys] chunks
-constexpr uint32_t kPBytes = kBQ * kBK * 2;           // 32 KB: two [128 q][64 keys] chunks
-constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + 2 * kPBytes + 1024 + 256 + 2048;
-constexpr uint32_t kTmemCols = 512;                   // S0 [0,128) S1 [128,256) O [256,320)
+constexpr uint32_t kTmemCols = 512;                   // S tiles in [0,256), O in [256,320)
+
+// BK = keys per block = N of the S = Q K^T instruction.  128: S and P double-buffered (short key sequences pad less);
+// 256: one S tile, one P tile, but N = 256 instructions (long self-attention sequences, +10 % at 4096 tokens).
+template <int BK>
+struct AC {
+    static constexpr int kSBuf = BK == 128 ? 2 : 1;            // S tiles in TMEM (512 columns: kSBuf * BK for S + 64 for O)
+    static constexpr int kPBuf = BK == 128 ? 2 : 1;            // P tiles in shared memory
+    static constexpr int kChunks = BK / 64;                    // 64-key (128-byte) swizzle chunks per block
+    static constexpr uint32_t kKBytes = BK * kD * 2;
+    static constexpr uint32_t kVBytes = kD * BK * 2;           // kChunks x [64 dims][64 keys]
+    static constexpr uint32_t kPBytes = kBQ * BK * 2;          // kChunks x [128 q][64 keys]
+    static constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBuf * kPBytes + 1024 + 256 + 2048;
+};
 
 // ------------------------------------------------------------------------------------------------ operand preparation
 // Kp[bh][key][64]: key 0 = null key, keys 1..m = k, keys > m = 0.   Vt[bh][dim][key]: the same, transposed.
@@ -78,17 +87,21 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
+template <int kBK>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnArgs a) {
     pdl_trigger();
+    using C = AC<kBK>;
+    constexpr int kSBuf = C::kSBuf, kPBuf = C::kPBuf, kChunks = C::kChunks;
+    constexpr uint32_t kKBytes = C::kKBytes, kVBytes = C::kVBytes, kPBytes = C::kPBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kQBytes;                 // [2]
     uint8_t* sV = sK + 2 * kKBytes;             // [2]
-    uint8_t* sP = sV + 2 * kVBytes;             // [2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+    uint8_t* sP = sV + 2 * kVBytes;             // [kPBuf]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBuf * kPBytes);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                // [2]
     uint64_t* k_empty = bars + 3;
@@ -158,8 +171,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     ptx::mbar_wait(&v_empty[s], ((iv >> 1) & 1) ^ 1, err, 4200 + s);
                     if (ptx::elect_one()) {
                         ptx::mbar_arrive_expect_tx(&v_full[s], kVBytes);
-                        ptx::tma_load_2d(&tmV, &v_full[s], sV + s * kVBytes, j * kBK, bh * kD);
-                        ptx::tma_load_2d(&tmV, &v_full[s], sV + s * kVBytes + kVBytes / 2, j * kBK + 64, bh * kD);
+#pragma unroll
+                        for (int c = 0; c < kChunks; ++c)
+                            ptx::tma_load_2d(&tmV, &v_full[s], sV + s * kVBytes + c * (kVBytes / kChunks), j * kBK + c * 64,
+                                             bh * kD);
                     }
                     ++iv;
                 }
@@ -173,9 +188,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         ptx::mbar_wait(q_full, 0, err, 4300);
         int ik = 0, is = 0, ip = 0, iv = 0;
         auto issue_qk = [&]() {
-            const int ks = ik & 1, ss = is & 1;
+            const int ks = ik & 1, ss = is % kSBuf;
             ptx::mbar_wait(&k_full[ks], (ik >> 1) & 1, err, 4310 + ks);
-            ptx::mbar_wait(&s_empty[ss], ((is >> 1) & 1) ^ 1, err, 4320 + ss);
+            ptx::mbar_wait(&s_empty[ss], ((is / kSBuf) & 1) ^ 1, err, 4320 + ss);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
                 const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sQ));
@@ -194,15 +209,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         issue_qk();
         for (int j = 0; j < nblk; ++j) {
             if (j + 1 < nblk) issue_qk();
-            const int ps = ip & 1, vs = iv & 1;
-            ptx::mbar_wait(&p_full[ps], (ip >> 1) & 1, err, 4330 + ps);
+            const int ps = ip % kPBuf, vs = iv & 1;
+            ptx::mbar_wait(&p_full[ps], (ip / kPBuf) & 1, err, 4330 + ps);
             ptx::mbar_wait(&v_full[vs], (iv >> 1) & 1, err, 4340 + vs);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP + ps * kPBytes + c * (kPBytes / 2)));
-                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV + vs * kVBytes + c * (kVBytes / 2)));
+                for (int c = 0; c < kChunks; ++c) {
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP + ps * kPBytes + c * (kPBytes / kChunks)));
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV + vs * kVBytes + c * (kVBytes / kChunks)));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         ptx::umma_f16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (j | c | k) != 0);
@@ -214,38 +229,34 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ++ip; ++iv;
         }
     } else {
-        // ===================== softmax / epilogue: one query row x 32 keys of every block per thread =====================
-        const int q4 = warp & 3, part = warp >> 2;     // TMEM lane quarter, key columns [32*part, 32*part + 32)
+        // ===================== softmax / epilogue: one query row x kPer keys of every block per thread ================
+        constexpr int kPer = kBK / 4;                  // 32 or 64 keys per thread and block
+        const int q4 = warp & 3, part = warp >> 2;     // TMEM lane quarter, key columns [kPer*part, kPer*part + kPer)
         const int row = q4 * 32 + lane;
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
-        const int c_lo = part * 32;
+        const int c_lo = part * kPer;
         constexpr float kLog2e = 1.4426950408889634f;
         int is = 0, ip = 0;
         // ---- sweep 1: exact row maximum (four independent running maxima: no long dependent chain)
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         for (int j = 0; j < nblk; ++j, ++is) {
-            const int ss = is & 1;
-            ptx::mbar_wait(&s_full[ss], (is >> 1) & 1, err, 4400 + ss);
+            const int ss = is % kSBuf;
+            ptx::mbar_wait(&s_full[ss], (is / kSBuf) & 1, err, 4400 + ss);
             ptx::tc_fence_after();
-            uint32_t v0[16], v1[16];
-            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo, v0);
-            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + 16, v1);
+            uint32_t v[kPer];
+#pragma unroll
+            for (int c = 0; c < kPer; c += 16) ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&s_empty[ss]);                     // S is in registers: release the buffer early
             if ((j + 1) * kBK <= a.kv_len) {                    // only the last block can hold padded keys
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
-                    mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
-                }
+                for (int i = 0; i < kPer; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
             } else {
                 const int key = j * kBK + c_lo;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (key + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v0[i]));
-                    if (key + 16 + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v1[i]));
-                }
+                for (int i = 0; i < kPer; ++i)
+                    if (key + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
             }
         }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
@@ -256,40 +267,38 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // ---- sweep 2: P = exp(S - max) -> shared memory (fp16, swizzled), row sums in four partial accumulators
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nblk; ++j, ++is, ++ip) {
-            const int ss = is & 1, ps = ip & 1;
-            ptx::mbar_wait(&s_full[ss], (is >> 1) & 1, err, 4410 + ss);
+            const int ss = is % kSBuf, ps = ip % kPBuf;
+            ptx::mbar_wait(&s_full[ss], (is / kSBuf) & 1, err, 4410 + ss);
             ptx::tc_fence_after();
-            uint32_t v0[16], v1[16];
-            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo, v0);
-            ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + 16, v1);
+            uint32_t v[kPer];
+#pragma unroll
+            for (int c = 0; c < kPer; c += 16) ptx::tmem_ld_x16(lane_addr + ss * kBK + c_lo + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&s_empty[ss]);
-            float p[32];
+            const bool tail = (j + 1) * kBK > a.kv_len;
+            const int key = j * kBK + c_lo;
+            uint32_t pk[kPer / 2];                              // fp16 pairs
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                p[i] = ptx::ex2_approx(fmaf(__uint_as_float(v0[i]), kLog2e, mneg));
-                p[16 + i] = ptx::ex2_approx(fmaf(__uint_as_float(v1[i]), kLog2e, mneg));
+            for (int i = 0; i < kPer; i += 2) {
+                float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
+                if (tail) {
+                    if (key + i >= a.kv_len) p0 = 0.f;
+                    if (key + i + 1 >= a.kv_len) p1 = 0.f;
+                }
+                l4[i & 3] += p0;
+                l4[(i + 1) & 3] += p1;
+                pk[i >> 1] = pack_h2(p0, p1);
             }
-            if ((j + 1) * kBK > a.kv_len) {
-                const int key = j * kBK + c_lo;
+            // keys [c_lo, c_lo + kPer) of row r: chunk c_lo/64, 16-byte groups (c_lo%64)/8 .., XOR-swizzled with r % 8
+            ptx::mbar_wait(&p_empty[ps], ((ip / kPBuf) & 1) ^ 1, err, 4420 + ps);
+            uint8_t* chunk = sP + ps * kPBytes + (c_lo >> 6) * (kPBytes / kChunks) + row * 128;
+            const int g0 = (c_lo & 63) >> 3;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (key + i >= a.kv_len) p[i] = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 32; ++i) l4[i & 3] += p[i];
-            // keys [32*part, +32) of row r: chunk part/2, 16-byte groups 4*(part%2) .. +3, XOR-swizzled with r % 8
-            ptx::mbar_wait(&p_empty[ps], ((ip >> 1) & 1) ^ 1, err, 4420 + ps);
-            uint8_t* chunk = sP + ps * kPBytes + (part >> 1) * (kPBytes / 2) + row * 128;
-            const int g0 = (part & 1) * 4;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint4 w;
-                w.x = pack_h2(p[8 * g + 0], p[8 * g + 1]); w.y = pack_h2(p[8 * g + 2], p[8 * g + 3]);
-                w.z = pack_h2(p[8 * g + 4], p[8 * g + 5]); w.w = pack_h2(p[8 * g + 6], p[8 * g + 7]);
-                *reinterpret_cast<uint4*>(chunk + (((g0 + g) ^ (row & 7)) << 4)) = w;
-            }
+            for (int g = 0; g < kPer / 8; ++g)
+                *reinterpret_cast<uint4*>(chunk + (((g0 + g) ^ (row & 7)) << 4)) =
+                    make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
             ptx::fence_proxy_async_smem();          // generic-proxy stores of P -> visible to the tensor core (async proxy)
             ptx::mbar_arrive(&p_full[ps]);
         }
@@ -328,14 +337,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 
 }  // namespace
 
+// key-block size: 256-key blocks pay off on long sequences, 128-key blocks pad short ones less
+static inline int attn_block_keys(int m) { return m >= 1024 ? 256 : 128; }
+
 long long attention_tc_workspace_bytes(int B, int heads, int kv_hs, int m) {
     const int hkv = kv_hs == 0 ? 1 : heads;
-    const long long Mp = ((long long)(m + 1) + kBK - 1) / kBK * kBK;
+    const int bk = attn_block_keys(m);
+    const long long Mp = ((long long)(m + 1) + bk - 1) / bk * bk;
     return 2 * (long long)B * hkv * Mp * kD * (long long)sizeof(__half);
 }
 
 bool attention_tc_supported(int n, int ldq, int ldo, long long q_bs, const void* mask) {
     return mask == nullptr && n > 0 && (n % kBQ) == 0 && (ldq % 8) == 0 && (ldo % 8) == 0 && q_bs == (long long)n * ldq;
+}
+
+template <int BK>
+static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnArgs& a, dim3 grid,
+                       cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(attn_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<BK>::kSmemBytes) !=
+            cudaSuccess)
+            return -10;
+        attr_set = true;
+    }
+    launch_k(attn_tc_kernel<BK>, grid, kThreads, AC<BK>::kSmemBytes, st, tmQ, tmK, tmV, a);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
 int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
@@ -348,7 +375,8 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     PFN_tmaEncodeTiled enc = get_tma_encode();
     if (!enc) return -5;
     const int hkv = kv_hs == 0 ? 1 : heads;
-    const int Mp = (m + 1 + kBK - 1) / kBK * kBK;
+    const int bk = attn_block_keys(m);
+    const int Mp = (m + 1 + bk - 1) / bk * bk;
     __half* Kp = reinterpret_cast<__half*>(workspace);
     __half* Vt = Kp + (long long)B * hkv * Mp * kD;
     {
@@ -370,7 +398,7 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     {
         cuuint64_t dim[2] = {kD, (cuuint64_t)B * hkv * Mp};
         cuuint64_t str[1] = {kD * 2};
-        cuuint32_t box[2] = {kD, kBK};
+        cuuint32_t box[2] = {kD, (cuuint32_t)bk};
         if (enc(&tmK, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, Kp, dim, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) !=
             CUDA_SUCCESS)
@@ -385,18 +413,11 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
             CUDA_SUCCESS)
             return -6;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
-            return -10;
-        attr_set = true;
-    }
     AttnArgs a{};
-    a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / kBK; a.kv_len = m + 1;
+    a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / bk; a.kv_len = m + 1;
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
     dim3 grid(n / kBQ, heads, B);
-    launch_k(attn_tc_kernel, grid, kThreads, kSmemBytes, st, tmQ, tmK, tmV, a);
-    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    return bk == 256 ? launch_attn<256>(tmQ, tmK, tmV, a, grid, st) : launch_attn<128>(tmQ, tmK, tmV, a, grid, st);
 }
 
 }  // namespace mi
