@@ -120,7 +120,7 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     // kernel selection (measured on B200, profiles/r01_conv_tc_selftest_v9.log): 3x3 layers run fastest on the swapped-operand
     // halo kernel (needs C_out % 128 == 0, H % 32 == 0), C_out = 128 / 16 layers it cannot take on the pixel-major halo
     // kernel, everything else on the CTA-pair kernel (all chosen inside conv_tc_launch)
-    p.halo = (mode == 0 && kh == 3 && kw == 3) ? 1 : 0;
+    p.halo = (mode == 0 && kh == 3 && kw == 3) ? 1 : ((mode == 0 && kh == 15 && kw == 1) ? 3 : 0);   // 3: 15-tap vertical (stem)
     const int rc = mi::conv_tc_launch(p, S(stream));
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;

@@ -693,15 +693,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 // zero-fills the out-of-image column) -- and tap (dh, dw) reads rows dh.. of the dw copy: 32 segments at the standard
 // 1024-byte stride.  2.5x the activation bytes into shared memory, still less L2 traffic than pixel-major tiles.
 constexpr int kHtPix = 256;                                                   // UMMA N
-template <bool kW16>
+// Geometry V15 (the stem, CrossEmbedLayer as a 15-tap vertical conv over the 128-wide unrolled operand): 32 x 8 output
+// pixels from a (32+14) x 8 tile; tap dh is the window that starts dh rows in (segments at the standard 1024-byte stride).
+enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2 };
+template <int G>
 struct CfgT {
+    static constexpr bool kW16 = G == kG16x16;
+    static constexpr int kTaps = G == kGV15 ? 15 : 9;
     static constexpr int kTH = kW16 ? 16 : 32, kTW = kW16 ? 16 : 8;           // output tile
-    static constexpr int kBoxH = kTH + 2, kBoxW = kW16 ? 16 : 10;             // TMA box (pixels)
-    static constexpr uint32_t kHaloBytes = kBoxH * kBoxW * 128;               // 36864 / 43520
-    static constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;     // 36864 / 44032
+    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : kTH + 2;
+    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : 8);          // TMA box (pixels)
+    static constexpr uint32_t kHaloBytes = kBoxH * kBoxW * 128;               // 43520 / 36864 / 47104
+    static constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;
     static constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                // one (tap, chunk) weight tile
     static constexpr int kHStages = kW16 ? 3 : 2;
-    static constexpr int kWStages = (kRingBudget - kHStages * kHaloStride) / kWBytes;   // 5 / 6
+    static constexpr int kWStages = (kRingBudget - kHStages * kHaloStride) / kWBytes;   // 6 / 5 / 6
     static constexpr uint32_t kTmemCols = 2 * kHtPix;                         // 512: two accumulator stages
     static constexpr uint32_t kSmemBytes = kHStages * kHaloStride + kWStages * kWBytes + 1024 + 256;
 };
@@ -715,15 +721,16 @@ __device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t smem_addr, uint32_
     return d;
 }
 
-template <bool kW16>
+template <int G>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
     pdl_trigger();
-    using C = CfgT<kW16>;
+    using C = CfgT<G>;
+    constexpr bool kW16 = C::kW16;
     constexpr int NH = C::kHStages, NW = C::kWStages;
     constexpr int kLoads = kW16 ? 3 : 1;           // activation tile loads per 64-channel chunk
-    constexpr int kTapsPerLoad = 9 / kLoads;
+    constexpr int kTapsPerLoad = C::kTaps / kLoads;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_w = smem + NH * C::kHaloStride;
@@ -781,14 +788,15 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int l = 0; l < kLoads; ++l) {
                     ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 3100 + sh);
                     if (ptx::elect_one()) {
-                        const int wc = kW16 ? w0 + l - 1 : w0 - 1;      // G16x16: copy l is shifted by dw = l - 1
+                        const int wc = kW16 ? w0 + l - 1 : (G == kGV15 ? w0 : w0 - 1);   // G16x16: copy l is shifted by dw = l - 1
+                        const int hc = G == kGV15 ? h0 - 7 : h0 - 1;
                         ptx::mbar_arrive_expect_tx(&fullH[sh], C::kHaloBytes);
                         if (j < args.a_split)
                             ptx::tma_load_5d(&tmA, &fullH[sh], smem + sh * C::kHaloStride,
-                                             args.a_chan_off + j * kConvBlockK, wc, h0 - 1, 0, b0);
+                                             args.a_chan_off + j * kConvBlockK, wc, hc, 0, b0);
                         else
                             ptx::tma_load_5d(&tmA2, &fullH[sh], smem + sh * C::kHaloStride,
-                                             args.a_chan_off2 + (j - args.a_split) * kConvBlockK, wc, h0 - 1, 0, b0);
+                                             args.a_chan_off2 + (j - args.a_split) * kConvBlockK, wc, hc, 0, b0);
                     }
                     if (++sh == NH) { sh = 0; ph ^= 1; }
                     for (int u = 0; u < kTapsPerLoad; ++u) {
@@ -826,9 +834,10 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_w + sw * C::kWBytes));
                             // G32x8: tap u = dh*3 + dw starts (dh*10 + dw) pixels into the halo tile, segments one halo
                             // row apart; G16x16: tap (dh = u) of copy dw = l starts dh rows in, segments 1024 B apart
+                            // V15: tap u = dh starts dh rows (8 pixels each) in, segments 1024 B apart
                             const uint64_t db = kW16 ? make_halo_t_desc(h_base + u * 16 * 128, 1024)
-                                                     : make_halo_t_desc(h_base + ((u / 3) * C::kBoxW + (u % 3)) * 128,
-                                                                        C::kBoxW * 128);
+                                : (G == kGV15 ? make_halo_t_desc(h_base + u * 8 * 128, 1024)
+                                              : make_halo_t_desc(h_base + ((u / 3) * C::kBoxW + (u % 3)) * 128, C::kBoxW * 128));
 #pragma unroll
                             for (int k = 0; k < kConvBlockK / 16; ++k)
                                 ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (j | l | u | k) != 0);
@@ -1003,19 +1012,19 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
-template <bool kW16>
+template <int G>
 int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
                   int total_tiles, int num_sms, cudaStream_t stream) {
-    using C = CfgT<kW16>;
+    using C = CfgT<G>;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv3x3_halo_t_kernel<kW16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (cudaFuncSetAttribute(conv3x3_halo_t_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  C::kSmemBytes) != cudaSuccess)
             return -10;
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    launch_k(conv3x3_halo_t_kernel<kW16>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, args);
+    launch_k(conv3x3_halo_t_kernel<G>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -1070,16 +1079,18 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     // ---- 3x3 halo kernel with swapped operands (channels in TMEM lanes): 128-wide channel tiles, H % 32 == 0, W % 8 == 0
     const bool t16 = p.W == 16 && p.H % 16 == 0;                       // G16x16: one 16 x 16 tile per image (row block)
     const bool t32 = !t16 && p.H % 32 == 0 && p.W % 8 == 0;            // G32x8
-    if (p.halo && p.halo != 2 && p.num_taps == 9 && p.phases == 1 && (t16 || t32) &&
+    const bool v15 = p.halo == 3 && p.num_taps == 15 && t32 && !p.act2;   // 15-tap vertical conv (stem)
+    if (p.halo && p.halo != 2 && (v15 || (p.halo != 3 && p.num_taps == 9)) && p.phases == 1 && (t16 || t32) &&
         p.Cout % 128 == 0 && p.out_sc <= 1 && (p.n_valid == 0 || p.n_valid == p.Cout) && p.dbg == 0) {
         bool canon = true;
-        for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
+        if (v15) for (int t = 0; t < 15; ++t) canon = canon && p.dh[t] == t - 7 && p.dw[t] == 0 && p.ph[t] == 0;
+        else for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
         if (p.act2 && (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) ||
                        (reinterpret_cast<uintptr_t>(p.act2) & 15)))
             return -8;
         if (canon) {
             ConvTcArgs h{};
-            h.num_taps = 9; h.chunks_per_tap = p.Cin / kConvBlockK;
+            h.num_taps = p.num_taps; h.chunks_per_tap = p.Cin / kConvBlockK;
             h.tiles_w = t16 ? 1 : p.W / 8; h.tiles_h = t16 ? p.H / 16 : p.H / 32; h.tiles_b = p.B; h.tiles_n = p.Cout / 128;
             h.B = p.B; h.H = p.H; h.W = p.W; h.a_chan_off = p.a_chan_off;
             h.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK; h.a_chan_off2 = p.a_chan_off2;
@@ -1090,7 +1101,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             CUtensorMap tmA, tmA2, tmB;
-            cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)(t16 ? 16 : 10), (cuuint32_t)(t16 ? 18 : 34), 1, 1};
+            cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)(t16 ? 16 : (v15 ? 8 : 10)), (cuuint32_t)(t16 ? 18 : (v15 ? 46 : 34)), 1, 1};
             cuuint32_t estr[5] = {1, 1, 1, 1, 1};
             {
                 cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
@@ -1111,7 +1122,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                     return -6;
             }
-            const cuuint64_t K = (cuuint64_t)9 * p.Cin;
+            const cuuint64_t K = (cuuint64_t)p.num_taps * p.Cin;
             cuuint64_t wdim[2] = {K, (cuuint64_t)p.Cout};
             cuuint64_t wstr[1] = {K * 2};
             cuuint32_t wbox[2] = {kConvBlockK, 128};
@@ -1121,8 +1132,9 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return -7;
             const int total = h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n;
-            return t16 ? launch_halo_t<true>(tmA, tmA2, tmB, h, total, num_sms, stream)
-                       : launch_halo_t<false>(tmA, tmA2, tmB, h, total, num_sms, stream);
+            if (v15) return launch_halo_t<kGV15>(tmA, tmA2, tmB, h, total, num_sms, stream);
+            return t16 ? launch_halo_t<kG16x16>(tmA, tmA2, tmB, h, total, num_sms, stream)
+                       : launch_halo_t<kG32x8>(tmA, tmA2, tmB, h, total, num_sms, stream);
         }
     }
 

@@ -59,7 +59,7 @@ struct ConvTcProblem {
     int block_n_hint;       // 0 = auto; > 0 preferred tile width; < 0: |value| with the 1-CTA kernel forced
     int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
     int halo;               // 1 = use a 3x3 halo-tile kernel when the geometry allows (swapped-operand form preferred),
-                            // 2 = only the pixel-major halo kernel
+                            // 2 = only the pixel-major halo kernel, 3 = 15 x 1 vertical taps (stem) on the swapped kernel
     int kmerge;             // 0 = auto (two k-chunks per stage when possible), 1 = one k-chunk per stage
     int dbg;                // profiling experiments only
     double* stats;          // optional GroupNorm block statistics of the output (pre-zeroed), see ConvTcArgs

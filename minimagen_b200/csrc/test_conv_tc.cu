@@ -47,8 +47,10 @@ static long long g_ws_bytes = 0;
 // returns max abs error (or -1 on failure)
 static double run_case(const Case& c, bool check, int reps, double* ms_out) {
     const int Ho = c.H / c.stride, Wo = c.W / c.stride;
-    const int pad = (c.k == 3) ? 1 : (c.k == 4 ? 1 : 0);
-    const int taps = c.k * c.k;
+    const bool vert = c.k == 15;                         // 15 x 1 vertical conv (the stem geometry), pad 7
+    const int pad = (c.k == 3) ? 1 : (c.k == 4 ? 1 : (vert ? 7 : 0));
+    const int taps = vert ? 15 : c.k * c.k;
+    const int kw_ = vert ? 1 : c.k;
     const size_t n_in = (size_t)c.B * c.H * c.W * c.Cin;
     const size_t n_w = (size_t)c.Cout * taps * c.Cin;
     const size_t n_out = (size_t)c.B * Ho * Wo * c.Cout;
@@ -96,9 +98,10 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
     p.lda = c.Cin; p.a_channels = c.Cin; p.a_chan_off = 0; p.Cin = c.Cin;
     p.wpacked = d_w; p.Cout = c.Cout; p.num_taps = taps;
     for (int r = 0; r < c.k; ++r)
-        for (int s = 0; s < c.k; ++s) {
-            const int t = r * c.k + s;
-            if (c.stride == 1 || direct_s2) { p.dh[t] = r - pad; p.dw[t] = s - pad; p.ph[t] = 0; }
+        for (int s = 0; s < kw_; ++s) {
+            const int t = r * kw_ + s;
+            if (vert) { p.dh[t] = r - pad; p.dw[t] = 0; p.ph[t] = 0; }
+            else if (c.stride == 1 || direct_s2) { p.dh[t] = r - pad; p.dw[t] = s - pad; p.ph[t] = 0; }
             else {
                 // input row = 2*ho + r - 1  ->  phase row (r-1)&1, block shift floor((r-1)/2)
                 const int rr = r - 1, ss = s - 1;
@@ -108,7 +111,7 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
         }
     p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
     p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
-    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3) ? 2 : (c.pair == 8 ? 1 : 0); if (c.pair == 8) p.cta_pair = 1; p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair == 7) p.cta_pair = 2; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
+    p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3) ? 2 : (c.pair == 8 ? (c.k == 15 ? 3 : 1) : 0); if (c.pair == 8) p.cta_pair = 1; p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair == 7) p.cta_pair = 2; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
     p.splitk_ws = g_ws; p.splitk_ws_bytes = g_ws_bytes;
     if (c.pair == 5) { p.cta_pair = 2; p.stream_k = 2; }
     if (c.pair == 6) { p.cta_pair = 2; p.stream_k = 1; }
@@ -152,11 +155,11 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
                         for (int r = 0; r < c.k; ++r) {
                             const int hi = ho * c.stride + r - pad;
                             if (hi < 0 || hi >= c.H) continue;
-                            for (int s = 0; s < c.k; ++s) {
-                                const int wi = wo * c.stride + s - pad;
+                            for (int s = 0; s < kw_; ++s) {
+                                const int wi = wo * c.stride + s - (vert ? 0 : pad);
                                 if (wi < 0 || wi >= c.W) continue;
                                 const float* a = &f_in[(((size_t)b * c.H + hi) * c.W + wi) * c.Cin];
-                                const float* wv = &f_w[((size_t)n * taps + r * c.k + s) * c.Cin];
+                                const float* wv = &f_w[((size_t)n * taps + r * kw_ + s) * c.Cin];
                                 double d = 0;
                                 for (int ci = 0; ci < c.Cin; ++ci) d += (double)a[ci] * wv[ci];
                                 acc += d;
@@ -241,6 +244,8 @@ int main(int argc, char** argv) {
             {"t_c3_n256", 2, 32, 32, 128, 256, 3, 1, true, true, false, 0, 8},
             {"t_c3_w256", 1, 32, 256, 64, 128, 3, 1, false, false, false, 0, 8},
             {"t16_c3", 3, 16, 16, 128, 128, 3, 1, true, true, true, 0, 8},
+            {"v15_stem_t", 2, 64, 32, 128, 128, 15, 1, true, false, true, 0, 8},
+            {"v15_stem_pair", 2, 64, 32, 128, 128, 15, 1, true, false, true, 0, 2},
             {"t16_c3_h32_n256", 2, 32, 16, 64, 256, 3, 1, true, false, false, 0, 8},
             {"t16_c3_persist", 160, 16, 16, 64, 128, 3, 1, false, true, false, 0, 8},
             // ---- CTA-pair (cta_group::2) kernel
@@ -294,6 +299,8 @@ int main(int argc, char** argv) {
             {"S2 split  256->128 128ch", 32, 256, 256, 128, 128, 4, 2, true, false, false, 0, 0},
             {"S2 direct 64->32 256->512", 32, 64, 64, 256, 512, 4, 2, true, false, false, 0, 9},
             {"S2 split  64->32 256->512", 32, 64, 64, 256, 512, 4, 2, true, false, false, 0, 0},
+            {"T stem_256 15x1", 32, 256, 256, 128, 128, 15, 1, true, false, true, 128, 8},
+            {"P stem_256 15x1", 32, 256, 256, 128, 128, 15, 1, true, false, true, 128, 2},
             {"T sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 8},
             {"T sr_128_128_f16", 32, 128, 128, 128, 128, 3, 1, true, false, true, 128, 8},
             {"T sr_128_256to128", 32, 128, 128, 256, 128, 3, 1, true, true, false, 128, 8},
@@ -353,7 +360,7 @@ int main(int argc, char** argv) {
         for (const Case& c : cases) {
             double ms = 0;
             run_case(c, false, 10, &ms);
-            const double flops = 2.0 * c.B * (c.H / c.stride) * (c.W / c.stride) * (double)c.Cout * c.k * c.k * c.Cin;
+            const double flops = 2.0 * c.B * (c.H / c.stride) * (c.W / c.stride) * (double)c.Cout * (c.k == 15 ? 15 : c.k * c.k) * c.Cin;
             printf("[perf %s hint=%d pair=%d] B=%d %dx%d %d->%d k=%d : %.3f ms  %.1f TFLOP/s\n", c.name, c.hint, c.pair, c.B, c.H, c.W,
                    c.Cin, c.Cout, c.k, ms, flops / ms * 1e-9);
             fflush(stdout);
