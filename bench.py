@@ -154,7 +154,7 @@ def cpu_baseline(wl, sd, steps=3, warmup=1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3")
@@ -374,8 +374,11 @@ def main():
         "e2e": {"value": world * args.steps / (e2e_ms / 1000.0), "unit": "steps/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + noise_host.numel() * 4 + t_host.numel() * 8),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
-        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit GEMM)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (conv3x3_halo_t_kernel + conv_tc*_kernel; "
+                                                          "all launches of one step)", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                     "traffic_note": "per-launch DRAM bytes of the four layer classes: profiles/r01_halo_t_ncu_v12.md (at or "
+                                     "below the algorithmic bytes)",
                      "launches_timed": conv_calls, "kernel_ms_per_step": conv_ms,
                      "kernel_share_of_step": conv_ms / (ms / args.steps) if ms else None, "peak_source": peak_src,
                      "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peak_tf},
