@@ -176,6 +176,15 @@ int mi_stem_unroll_f16(const float* a, int ca, const float* b, int cb, int B, in
  * step to the shared time embedding instead of once per block */
 int mi_silu_f32(const float* in, long long n, float* out, void* stream);
 
+/* Inter-stage image resize of the cascade: helpers.resize_image_to (helpers.py:138-164 -> resize_right.resize, called at
+ * Imagen.py:482 between U-Nets).  Separable resampling of `planes` fp32 images [h_in][w_in] -> [h_out][w_out] with
+ * per-output-coordinate tap tables: iy/wy [h_out][taps_y], ix/wx [w_out][taps_x] (source index after boundary handling,
+ * normalised weight); rows are reduced first, then columns, then the optional clamp(lo, hi) (helpers.py:161-162).  The
+ * tables encode the interpolation method (minimagen_b200/helpers.py builds resize_right's cubic / antialiased ones). */
+int mi_resize_separable(const float* in, long long planes, int h_in, int w_in, float* out, int h_out, int w_out,
+                        const int* iy, const float* wy, int taps_y, const int* ix, const float* wx, int taps_x,
+                        int has_clamp, float lo, float hi, void* stream);
+
 /* ------------------------------------------------------------------------------------------------- attention
  * Fused softmax attention, dim_head 64: CrossAttention.forward (layers.py:220-251) with kv_head_stride = 64, and the
  * multi-query Attention.forward (layers.py:52-104) with kv_head_stride = 0.  q must already carry the dim_head**-0.5

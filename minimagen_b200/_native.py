@@ -40,6 +40,7 @@ SIGNATURES = {
     "mi_select_rows": [_P, _P, _P, _P, _I, _I, _P, _P],
     "mi_nchw_to_nhwc": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
     "mi_stem_unroll_f16": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "mi_resize_separable": [_P, _L, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _I, _I, _F, _F, _P],
     "mi_silu_f32": [_P, _L, _P, _P],
     "mi_attention_workspace_bytes": [_I, _I, _I, _I],
     "mi_attention_fwd": [_P, _L, _I, _P, _P, _L, _I, _I, _P, _P, _I, _I, _I, _I, _P, _L, _I, _P, _L, _P],

@@ -208,6 +208,13 @@ int mi_nchw_to_nhwc(const float* a, int ca, const float* b, int cb, int B, int h
 int mi_stem_unroll_f16(const float* a, int ca, const float* b, int cb, int B, int H, int W, void* out, void* stream) {
     return check(mi::stem_unroll(a, ca, b, cb, B, H, W, (__half*)out, S(stream)), "mi_stem_unroll_f16");
 }
+int mi_resize_separable(const float* in, long long planes, int h_in, int w_in, float* out, int h_out, int w_out,
+                        const int* iy, const float* wy, int taps_y, const int* ix, const float* wx, int taps_x,
+                        int has_clamp, float lo, float hi, void* stream) {
+    return check(mi::resize_sep(in, planes, h_in, w_in, out, h_out, w_out, iy, wy, taps_y, ix, wx, taps_x, has_clamp, lo, hi,
+                                S(stream)),
+                 "mi_resize_separable");
+}
 int mi_silu_f32(const float* in, long long n, float* out, void* stream) {
     return check(mi::silu_f32(in, n, out, S(stream)), "mi_silu_f32");
 }

@@ -599,6 +599,33 @@ stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict_
     }
 }
 
+// Inter-stage resize of the cascade (helpers.py:138-164 -> resize_right.resize): separable resampling
+// with per-output-coordinate tap tables (indices already reflected / clamped, weights already normalised -- built by the
+// host, minimagen_b200/helpers.py).  Rows first, then columns, like the two-pass reference:
+//   out[b][c][y][x] = clamp( sum_j wx[x][j] * ( sum_i wy[y][i] * in[b][c][iy[y][i]][ix[x][j]] ) )
+__global__ void __launch_bounds__(256)
+resize_sep_kernel(const float* __restrict__ in, int Hin, int Win, float* __restrict__ out, int Hout, int Wout,
+                  const int* __restrict__ iy, const float* __restrict__ wy, int ty, const int* __restrict__ ix,
+                  const float* __restrict__ wx, int tx, int has_clamp, float lo, float hi, long long total) {
+    pdl_wait();
+    pdl_trigger();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % Wout);
+    const int y = (int)((idx / Wout) % Hout);
+    const long long plane = idx / ((long long)Wout * Hout);
+    const float* src = in + plane * (long long)Hin * Win;
+    float acc = 0.f;
+    for (int j = 0; j < tx; ++j) {
+        const int xi = ix[x * tx + j];
+        float col = 0.f;
+        for (int i = 0; i < ty; ++i) col = __fadd_rn(col, __fmul_rn(wy[y * ty + i], src[(long long)iy[y * ty + i] * Win + xi]));
+        acc = __fadd_rn(acc, __fmul_rn(wx[x * tx + j], col));
+    }
+    if (has_clamp) acc = fminf(fmaxf(acc, lo), hi);
+    out[idx] = acc;
+}
+
 __global__ void silu_kernel(const float* __restrict__ in, long long n, float* __restrict__ out) {
     pdl_wait();
     pdl_trigger();
@@ -711,6 +738,16 @@ int stem_unroll(const float* a, int Ca, const float* b, int Cb, int B, int H, in
     if (Ca + Cb > 8 || Ca < 1) return -1;
     dim3 grid((W + kStemCols - 1) / kStemCols, (H + kStemRows - 1) / kStemRows, B);
     launch_k(stem_unroll_kernel, grid, 256, 0, st, a, Ca, b, Cb, B, H, W, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int resize_sep(const float* in, long long planes, int Hin, int Win, float* out, int Hout, int Wout, const int* iy,
+               const float* wy, int ty, const int* ix, const float* wx, int tx, int has_clamp, float lo, float hi,
+               cudaStream_t st) {
+    if (ty < 1 || tx < 1 || planes < 1) return -1;
+    const long long total = planes * Hout * Wout;
+    launch_k(resize_sep_kernel, grid1d(total, 256), 256, 0, st, in, Hin, Win, out, Hout, Wout, iy, wy, ty, ix, wx, tx,
+             has_clamp, lo, hi, total);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

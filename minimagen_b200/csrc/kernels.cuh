@@ -31,6 +31,9 @@ int select_rows(const float* a, const float* nullv, const uint8_t* keep, const f
 int nchw_to_nhwc(const float* a, int Ca, const float* b, int Cb, int B, int HW, int Cp, float* out, cudaStream_t st);
 int stem_unroll(const float* a, int Ca, const float* b, int Cb, int B, int H, int W, __half* out, cudaStream_t st);
 int silu_f32(const float* in, long long n, float* out, cudaStream_t st);
+int resize_sep(const float* in, long long planes, int Hin, int Win, float* out, int Hout, int Wout, const int* iy,
+               const float* wy, int ty, const int* ix, const float* wx, int tx, int has_clamp, float lo, float hi,
+               cudaStream_t st);
 int pack_conv_weight(const float* w, int O, int I, int KH, int KW, float scale, __half* out, cudaStream_t st);
 
 // conv_direct.cu

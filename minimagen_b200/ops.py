@@ -166,6 +166,14 @@ class NativeOps:
         _chk(a, F32, "a"); _chk(b, F32, "b"); _chk(out, F16, "out")
         N.call("mi_stem_unroll_f16", N.ptr(a), ca, N.ptr(b), cb, B, H, W, N.ptr(out), N.stream())
 
+    def resize_separable(self, inp, planes, hin, win, out, hout, wout, iy, wy, ix, wx, clamp=None):
+        """iy / ix: int32 [n_out, taps] source indices; wy / wx: fp32 [n_out, taps] weights (see helpers.resize_tables)."""
+        _chk(inp, F32, "inp"); _chk(out, F32, "out"); _chk(wy, F32, "wy"); _chk(wx, F32, "wx")
+        _chk(iy, torch.int32, "iy"); _chk(ix, torch.int32, "ix")
+        N.call("mi_resize_separable", N.ptr(inp), planes, hin, win, N.ptr(out), hout, wout, N.ptr(iy), N.ptr(wy),
+               iy.shape[1], N.ptr(ix), N.ptr(wx), ix.shape[1], int(clamp is not None),
+               float(clamp[0]) if clamp is not None else 0.0, float(clamp[1]) if clamp is not None else 0.0, N.stream())
+
     def silu(self, inp, out):
         _chk(inp, F32, "inp"); _chk(out, F32, "out")
         N.call("mi_silu_f32", N.ptr(inp), inp.numel(), N.ptr(out), N.stream())

@@ -111,6 +111,47 @@ def sample_case():
     print("sample_loop x std", [t.std().item() for t in traj])
 
 
+def cascade_case():
+    """The unmodified reference's Imagen.sample over a tiny 2-stage cascade (base 16x16 -> SR 32x32, T=25, CFG w=2): every
+    normal draw is recorded in call order so that the implementation under test can replay it (inter-stage resize runs on
+    the resize_right stand-in, see oracle/shims)."""
+    import minimagen.Imagen as MI
+    from minimagen.Imagen import Imagen
+    from minimagen.Unet import Unet, BaseTest, SuperTest
+    torch.manual_seed(5)
+    u0, u1 = Unet(**BaseTest.defaults), Unet(**SuperTest.defaults)
+    im = Imagen(unets=(u0, u1), text_encoder_name='t5_small', image_sizes=(16, 32), timesteps=25, cond_drop_prob=0.1).eval()
+    g = torch.Generator().manual_seed(21)
+    te = torch.randn(2, 7, 512, generator=g)
+    tm = torch.ones(2, 7, dtype=torch.bool)
+    tm[1, 5:] = False
+    te = te * tm[..., None]
+    draws = []
+    real_randn, real_like = MI.torch.randn, MI.torch.randn_like
+
+    def rec_randn(*a, **k):
+        out = real_randn(*a, **{kk: v for kk, v in k.items() if kk != 'device'})
+        draws.append(out.clone())
+        return out
+
+    def rec_like(z):
+        out = real_like(z)
+        draws.append(out.clone())
+        return out
+    MI.torch.randn, MI.torch.randn_like = rec_randn, rec_like
+    try:
+        torch.manual_seed(77)
+        with torch.no_grad():
+            out = im.sample(text_embeds=te, text_masks=tm, cond_scale=2., lowres_sample_noise_level=0.2)
+    finally:
+        MI.torch.randn, MI.torch.randn_like = real_randn, real_like
+    torch.save(dict(cfgs=(dict(BaseTest.defaults), dict(SuperTest.defaults)),
+                    state_dicts=(im.unets[0].state_dict(), im.unets[1].state_dict()), text_embeds=te, text_mask=tm,
+                    draws=draws, out=out, image_sizes=(16, 32), timesteps=25, cond_scale=2., lowres_noise_level=0.2),
+               os.path.join(OUT, "cascade_tiny.pt"))
+    print("cascade_tiny: draws", [tuple(d.shape) for d in draws], "out", tuple(out.shape), float(out.mean()))
+
+
 if __name__ == "__main__":
     reference.load()
     os.makedirs(OUT, exist_ok=True)
@@ -119,3 +160,4 @@ if __name__ == "__main__":
     unet_case("unet_tiny_sr", dict(SuperTest.defaults, lowres_cond=True), 64, True)
     step_case()
     sample_case()
+    cascade_case()

@@ -271,6 +271,15 @@ class EmuOps:
             o[:, :, :, j, :C] = xp[:, :, :, j:j + W].permute(0, 2, 3, 1)
         out.reshape(B, H, W, 128).copy_(o.reshape(B, H, W, 128).to(F16))
 
+    def resize_separable(self, inp, planes, hin, win, out, hout, wout, iy, wy, ix, wx, clamp=None):
+        self._log("resize_separable")
+        x = inp.reshape(planes, hin, win)
+        rows = (x[:, iy.long(), :] * wy[None, :, :, None]).sum(2)            # planes, hout, win
+        res = (rows[:, :, ix.long()] * wx[None, None, :, :]).sum(3)          # planes, hout, wout
+        if clamp is not None:
+            res = res.clamp(*clamp)
+        out.reshape(planes, hout, wout).copy_(res)
+
     def silu(self, inp, out):
         self._log("silu")
         out.copy_(F.silu(inp))

@@ -438,6 +438,21 @@ def test_posemb_and_text_tokens(native):
     assert torch.equal(n_n.cpu(), n_e)
 
 
+# ---------------------------------------------------------------------------------------------- cascade resize
+@pytest.mark.parametrize("n_in,n_out,pad,clamp", [(64, 256, "reflect", None), (128, 64, "reflect", (-1., 1.)),
+                                                  (24, 36, "constant", (0., 1.))])
+def test_resize_separable(native, n_in, n_out, pad, clamp):
+    from minimagen_b200.helpers import resize_tables
+    x = _rand(2, 3, n_in, n_in, seed=120)
+    scale = n_out / n_in
+    ho, iy, wy = resize_tables(n_in, scale, pad, torch.device("cpu"))
+    o_e = torch.zeros(2, 3, ho, ho)
+    EMU.resize_separable(x, 6, n_in, n_in, o_e, ho, ho, iy, wy, iy, wy, clamp=clamp)
+    o_n = torch.zeros(2, 3, ho, ho, device="cuda")
+    native.resize_separable(x.cuda(), 6, n_in, n_in, o_n, ho, ho, iy.cuda(), wy.cuda(), iy.cuda(), wy.cuda(), clamp=clamp)
+    assert (o_n.cpu() - o_e).abs().max().item() < 2e-6
+
+
 # ---------------------------------------------------------------------------------------------- attention
 @pytest.mark.parametrize("B,heads,n,m,shared,use_mask", [(2, 8, 256, 260, False, False), (2, 8, 64, 258, False, True),
                                                          (1, 8, 1024, 1024, True, False), (2, 8, 256, 256, True, True),

@@ -203,3 +203,19 @@ def test_cfg3_full_size_vs_oracle_and_properties(native):
         assert e_alone < 1e-3 and e_alone_ref < 1e-3
         cfg1 = u.forward_with_cond_scale(x.cuda(), t.cuda(), cond_scale=1.0, **cu)
         assert rel_l2(cfg1, out) < 1e-5
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_full_cascade_sample_vs_reference_golden(native, graph):
+    """The whole cascade on the GPU (base 16x16 -> resize -> noise augmentation -> SR 32x32, T=25, CFG w=2) against the
+    unmodified reference's `Imagen.sample` output, replaying its normal draws (tests/golden/cascade_tiny.pt)."""
+    from test_host_logic import _cascade_from_golden
+    g = load_golden("cascade_tiny.pt")
+    im, it = _cascade_from_golden(g, "cuda")
+    im.use_cuda_graph = graph
+    out = im.sample(text_embeds=g["text_embeds"].cuda(), text_masks=g["text_mask"].cuda(), cond_scale=g["cond_scale"],
+                    lowres_sample_noise_level=g["lowres_noise_level"])
+    assert next(it, None) is None
+    err = rel_l2(out, g["out"])
+    print(f"cascade (graph={graph}): rel-L2 vs reference = {err:.3e}")
+    assert err < 1e-3

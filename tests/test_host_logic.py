@@ -186,3 +186,54 @@ def test_subpixel_upsample_conv_equals_upsample_then_conv(emu):
         assert rel_l2(act.stats[:, :, 1], (blk * blk).sum(dim=(1, 3))) < 1e-6
     assert "conv_igemm" in emu.calls
     assert rel_l2(outs[True].f32, outs[False].f32) < 1e-3
+
+
+@pytest.mark.parametrize("n_in,n_out,pad,clamp", [(64, 256, "reflect", None), (16, 64, "reflect", (0., 1.)),
+                                                  (128, 64, "reflect", (-1., 1.)), (24, 36, "constant", None),
+                                                  (32, 128, "edge", None)])
+def test_resize_image_to_vs_reference_helper(emu, n_in, n_out, pad, clamp):
+    """helpers.resize_image_to (inter-stage resize) vs the reference's helper running on the
+    resize_right stand-in (published algorithm; the third-party source is not in the container: parity-unpinned)."""
+    if not reference.available():
+        pytest.skip("reference not present")
+    ref = reference.load()
+    from minimagen_b200 import helpers
+    x = torch.rand(2, 3, n_in, n_in, generator=torch.Generator().manual_seed(n_in)) * 2 - 0.5
+    want = ref.helpers.resize_image_to(x, n_out, clamp_range=clamp, pad_mode=pad)
+    got = helpers.resize_image_to(x, n_out, clamp_range=clamp, pad_mode=pad)
+    assert got.shape == want.shape == (2, 3, n_out, n_out)
+    assert (got - want).abs().max().item() < 2e-6
+    assert "resize_separable" in emu.calls
+    assert helpers.resize_image_to(x, n_in) is x
+
+
+def _cascade_from_golden(g, device):
+    from minimagen_b200.Imagen import Imagen
+    from minimagen_b200.Unet import Unet
+    unets = [Unet(**c) for c in g["cfgs"]]
+    im = Imagen(unets=unets, text_encoder_name="t5_small", image_sizes=g["image_sizes"], timesteps=g["timesteps"],
+                cond_drop_prob=0.1).eval().to(device)
+    for u, sd in zip(im.unets, g["state_dicts"]):
+        u.load_state_dict(sd)
+    it = iter(g["draws"])
+
+    def noise_fn(kind, shape, step):
+        d = next(it)
+        assert tuple(d.shape) == tuple(shape), (kind, step, d.shape, shape)
+        return d
+    im.noise_fn = noise_fn
+    return im, it
+
+
+def test_full_cascade_sample_vs_reference_golden(emu):
+    """Imagen.sample over a 2-stage cascade (base 16x16 -> SR 32x32, T=25, CFG w=2, lowres noise augmentation and the
+    inter-stage resize included) against the unmodified reference's output, replaying the reference's normal draws in
+    call order (tests/golden/cascade_tiny.pt, made by oracle/make_golden.py::cascade_case)."""
+    g = load_golden("cascade_tiny.pt")
+    im, it = _cascade_from_golden(g, "cpu")
+    out = im.sample(text_embeds=g["text_embeds"], text_masks=g["text_mask"], cond_scale=g["cond_scale"],
+                    lowres_sample_noise_level=g["lowres_noise_level"])
+    assert next(it, None) is None                      # every recorded draw was consumed, in the reference's order
+    assert out.shape == g["out"].shape
+    assert rel_l2(out, g["out"]) < 1e-3
+    assert "resize_separable" in emu.calls
