@@ -36,6 +36,10 @@ CFGS = [
     ("unet_default_d128", dict(text_embed_dim=768), 64, False, 1),                        # cfg 2a structure at b=1
     ("sr_d64", dict(dim=64, dim_mults=(1, 2, 4), num_resnet_blocks=(1, 2, 2), layer_attns=(False, False, True),
                     layer_cross_attns=(False, True, True), lowres_cond=True, memory_efficient=True), 64, True, 2),
+    # ragged geometry: 40x40 images (40/20/10 are neither powers of two nor multiples of the conv tiles -> the fp32
+    # direct-conv path; 100-token attention rows are not a multiple of the 128-query tile -> mma.sync attention), batch 3
+    ("ragged_40x40_d64", dict(dim=64, dim_mults=(1, 2, 4), layer_attns=(False, True, True),
+                              layer_cross_attns=(False, True, True), text_embed_dim=768), 40, False, 3),
 ]
 
 
@@ -53,7 +57,7 @@ def test_tensor_core_configs_vs_restatement(native, name, cfg, s, lowres, b):
     kw = dict(text_embeds=te, text_mask=tm)
     if lowres:
         kw.update(lowres_cond_img=torch.randn(b, 3, s, s, generator=g), lowres_noise_times=torch.full((b,), 200))
-    t = torch.tensor([999, 0][:b])
+    t = torch.tensor([999, 0, 500][:b])
     with torch.no_grad():
         ref_out = R.unet_forward(sd, cfg, x, t, **kw)
         u = u.cuda()
