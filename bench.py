@@ -266,7 +266,8 @@ def main():
         print(f"[bench] launches/step={launches_per_step}", file=sys.stderr, flush=True)
         # per-kernel timing of the dominant kernel (tcgen05 implicit GEMM): CUDA events around every launch of one
         # eager step, on the launching stream
-        conv_ms, conv_flops, conv_calls = measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev)
+        conv = measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev)
+        conv_ms, conv_flops, conv_calls = conv["all"][0], conv["all"][1], conv["all"][2]
 
         # steady-state step function: CUDA graph replay (device-resident inputs)
         use_graph = not args.no_graph
@@ -365,6 +366,32 @@ def main():
     value = world * args.steps / (ms / 1000.0)
     achieved = conv_flops / (conv_ms / 1000.0) / 1e12 if conv_ms > 0 else 0.0
     step_tflops = (value * B * GFLOP_PER_IMG.get(args.workload, 0.0)) / 1000.0 / world    # per GPU
+    # dominant kernel = conv3x3_halo_t_kernel: algorithmic FLOPs per launch / CUDA-event time per launch, live; DRAM traffic
+    # per launch from the committed ncu capture of the same step (profiles/r01_halo_t_dram_v16.json)
+    t_ms, t_fl, t_n, t_bytes = conv["halo_t"]
+    dom = t_n > 0
+    d_ms, d_fl, d_n, d_bytes = (t_ms, t_fl, t_n, t_bytes) if dom else tuple(conv["all"])
+    d_achieved = d_fl / (d_ms / 1000.0) / 1e12 if d_ms > 0 else 0.0
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r01_halo_t_dram_v16.json")))
+        if dom and args.workload == "cfg3" and B == 32 and prof.get("launches") == d_n:
+            traffic = prof["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "tensor",
+                "kernel": "conv3x3_halo_t_kernel (tcgen05 swapped-operand 3x3 / 15x1 halo conv)" if dom else
+                          "tcgen05 implicit-GEMM convolutions (all launches)",
+                "achieved": d_achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": d_achieved / peak_tf,
+                "frac_of_burst_peak": d_achieved / peaks["bf16_tflops_burst"] if peaks.get("bf16_tflops_burst") else None,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_halo_t_dram_v16.json)",
+                "algorithmic_bytes_per_launch": d_bytes / d_n if d_n else None,
+                "algorithmic_flops_per_launch": d_fl / d_n if d_n else None,
+                "launches_timed": d_n, "kernel_ms_per_launch": d_ms / d_n if d_n else None,
+                "kernel_ms_per_step": d_ms, "kernel_share_of_step": d_ms / (ms / args.steps) if ms else None,
+                "all_conv_launches": {"achieved": achieved, "frac": achieved / peak_tf, "launches": conv_calls,
+                                      "ms_per_step": conv_ms, "share_of_step": conv_ms / (ms / args.steps) if ms else None},
+                "peak_source": peak_src, "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peak_tf}
     result = {
         "metric": METRIC if args.workload == "cfg3" else f"denoising steps/sec ({args.workload})",
         "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -374,14 +401,7 @@ def main():
         "e2e": {"value": world * args.steps / (e2e_ms / 1000.0), "unit": "steps/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + noise_host.numel() * 4 + t_host.numel() * 8),
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolutions (conv3x3_halo_t_kernel + conv_tc*_kernel; "
-                                                          "all launches of one step)", "achieved": achieved,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
-                     "traffic_note": "per-launch DRAM bytes of the four layer classes: profiles/r01_halo_t_ncu_v12.md (at or "
-                                     "below the algorithmic bytes)",
-                     "launches_timed": conv_calls, "kernel_ms_per_step": conv_ms,
-                     "kernel_share_of_step": conv_ms / (ms / args.steps) if ms else None, "peak_source": peak_src,
-                     "whole_step_tflops_per_gpu": step_tflops, "whole_step_frac": step_tflops / peak_tf},
+        "roofline": roofline,
         "clocks": clocks, "cuda_graph": use_graph, "launches_per_step": launches_per_step,
         "batch_streams": unet.batch_streams, "gn_input": "f32" if layers.GN_INPUT_F32 else "f16",
     }
@@ -415,19 +435,28 @@ def kernel_table(fn, steps, path):
 
 
 def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):
-    """Run one eager step with CUDA events around every tcgen05 conv launch; return (total ms, algorithmic FLOPs, n)."""
+    """Run one eager step with CUDA events around every tcgen05 conv launch.  Returns a dict with the totals over all
+    conv launches and, separately, over the launches that run on the dominant kernel (conv3x3_halo_t_kernel: 3x3 / 15x1
+    stride-1 convs with C_out % 128 == 0 on a 32x8- or 16x16-tileable grid -- the selection rule of csrc/capi.cu)."""
     from minimagen_b200 import ops as ops_mod
     real = ops_mod.get_ops()
-    events, flops = [], [0.0]
+    events = []
 
     class Timed(type(real)):
-        def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw_, mode, *a, **k):
+        def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw_, mode, bias, residual, out_f32, out_f16,
+                       *a, **k):
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            super().conv_igemm(act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw_, mode, *a, **k)
+            super().conv_igemm(act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw_, mode, bias, residual, out_f32, out_f16,
+                               *a, **k)
             e.record()
-            events.append((s, e))
-            flops[0] += 2.0 * B * H * W * c_out * kh * kw_ * c_in
+            halo_t = (mode == 0 and (kh, kw_) in ((3, 3), (15, 1)) and c_out % 128 == 0 and
+                      ((W == 16 and H % 16 == 0 and kh == 3) or (H % 32 == 0 and W % 8 == 0 and W != 16)))
+            mn = B * H * W * c_out
+            nbytes = (B * H * W * c_in * 2 * (4 if mode == 6 else 1) + c_out * kh * kw_ * c_in * 2 +
+                      (4 * mn if residual is not None else 0) + (4 * mn if out_f32 is not None else 0) +
+                      (2 * mn if out_f16 is not None else 0))
+            events.append((s, e, 2.0 * mn * kh * kw_ * c_in, nbytes, halo_t))
 
     ops_mod.set_ops(Timed())
     streams = unet.batch_streams
@@ -438,8 +467,13 @@ def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):
     finally:
         ops_mod.set_ops(real)
         unet.batch_streams = streams
-    total = sum(s.elapsed_time(e) for s, e in events)
-    return total, flops[0], len(events)
+    res = {"all": [0.0, 0.0, 0, 0.0], "halo_t": [0.0, 0.0, 0, 0.0]}       # ms, flops, launches, algorithmic bytes
+    for s, e, fl, nb, ht in events:
+        ms = s.elapsed_time(e)
+        for key in (("all", "halo_t") if ht else ("all",)):
+            r = res[key]
+            r[0] += ms; r[1] += fl; r[2] += 1; r[3] += nb
+    return res
 
 
 if __name__ == "__main__":
