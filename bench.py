@@ -383,7 +383,7 @@ def main():
                 "kernel": "conv3x3_halo_t_kernel (tcgen05 swapped-operand 3x3 / 15x1 halo conv)" if dom else
                           "tcgen05 implicit-GEMM convolutions (all launches)",
                 "achieved": d_achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": d_achieved / peak_tf,
-                "frac_of_burst_peak": d_achieved / peaks["bf16_tflops_burst"] if peaks.get("bf16_tflops_burst") else None,
+                "frac_of_burst_peak": d_achieved / peaks["bf16_tflops"] if peaks.get("bf16_tflops") else None,
                 "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_halo_t_dram_v16.json)",
                 "algorithmic_bytes_per_launch": d_bytes / d_n if d_n else None,
                 "algorithmic_flops_per_launch": d_fl / d_n if d_n else None,
