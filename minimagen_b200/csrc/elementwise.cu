@@ -670,7 +670,7 @@ int gn_apply_silu(const void* src0, int C0, const void* src1, int C1, float scal
         if (C0 % sb0 || Cg % sb0 || (C1 && (sb1 <= 0 || C1 % sb1 || Cg % sb1 || !stats1))) return -1;
         if (C1 && (C0 % sb1)) return -1;
     }
-    int pix = 16384 / C;               // ~16K elements per CTA
+    int pix = 16384 / C;               // ~16K elements per CTA (8K / 32K / 64K measured slower, tools/bench_ops.py gn)
     if (pix < 1) pix = 1;
     if (pix > HW) pix = HW;
     const size_t smem = 2 * (size_t)C * sizeof(float);
