@@ -121,6 +121,10 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     // halo kernel (needs C_out % 128 == 0, H % 32 == 0), C_out = 128 / 16 layers it cannot take on the pixel-major halo
     // kernel, everything else on the CTA-pair kernel (all chosen inside conv_tc_launch)
     p.halo = (mode == 0 && kh == 3 && kw == 3) ? 1 : ((mode == 0 && kh == 15 && kw == 1) ? 3 : 0);   // 3: 15-tap vertical (stem)
+    // 1x1 convs stay on the pixel-major 1-CTA kernel: the swapped-operand row-tile form (conv3x3_halo_t_kernel<kGLin>,
+    // parity-tested in test_conv_tc) measured 0.037 / 0.047 / 0.066 / 0.119 ms against 0.033 / 0.043 / 0.056 / 0.095 ms on the
+    // four res_conv shapes of cfg 3 -- short-K layers are output-bound and the smem-transposing epilogue wins there
+    p.lin1x1 = 0;
     const int rc = mi::conv_tc_launch(p, S(stream));
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;

@@ -695,18 +695,20 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 constexpr int kHtPix = 256;                                                   // UMMA N
 // Geometry V15 (the stem, CrossEmbedLayer as a 15-tap vertical conv over the 128-wide unrolled operand): 32 x 8 output
 // pixels from a (32+14) x 8 tile; tap dh is the window that starts dh rows in (segments at the standard 1024-byte stride).
-enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2 };
+// Geometry Lin (1x1 convs / linears): the pixels of an NHWC tensor are just rows, so a tile is 256 consecutive rows (one 2-D
+// TMA box, zero-filled past the end), one tap, no halo.
+enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2, kGLin = 3 };
 template <int G>
 struct CfgT {
     static constexpr bool kW16 = G == kG16x16;
-    static constexpr int kTaps = G == kGV15 ? 15 : 9;
-    static constexpr int kTH = kW16 ? 16 : 32, kTW = kW16 ? 16 : 8;           // output tile
-    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : kTH + 2;
-    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : 8);          // TMA box (pixels)
+    static constexpr int kTaps = G == kGV15 ? 15 : (G == kGLin ? 1 : 9);
+    static constexpr int kTH = G == kGLin ? 256 : (kW16 ? 16 : 32), kTW = G == kGLin ? 1 : (kW16 ? 16 : 8);   // output tile
+    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : (G == kGLin ? 256 : kTH + 2);
+    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : (G == kGLin ? 1 : 8));          // TMA box (pixels)
     static constexpr uint32_t kHaloBytes = kBoxH * kBoxW * 128;               // 43520 / 36864 / 47104
     static constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;
     static constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                // one (tap, chunk) weight tile
-    static constexpr int kHStages = kW16 ? 3 : 2;
+    static constexpr int kHStages = kW16 ? 3 : (G == kGLin ? 4 : 2);          // Lin: 4 MMAs per activation stage -> deeper ring
     static constexpr int kWStages = (kRingBudget - kHStages * kHaloStride) / kWBytes;   // 6 / 5 / 6
     static constexpr uint32_t kTmemCols = 2 * kHtPix;                         // 512: two accumulator stages
     static constexpr uint32_t kSmemBytes = kHStages * kHaloStride + kWStages * kWBytes + 1024 + 256;
@@ -791,7 +793,14 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const int wc = kW16 ? w0 + l - 1 : (G == kGV15 ? w0 : w0 - 1);   // G16x16: copy l is shifted by dw = l - 1
                         const int hc = G == kGV15 ? h0 - 7 : h0 - 1;
                         ptx::mbar_arrive_expect_tx(&fullH[sh], C::kHaloBytes);
-                        if (j < args.a_split)
+                        if constexpr (G == kGLin) {      // rows [h0, h0 + 256) of the (channels, pixels) matrix
+                            if (j < args.a_split)
+                                ptx::tma_load_2d(&tmA, &fullH[sh], smem + sh * C::kHaloStride,
+                                                 args.a_chan_off + j * kConvBlockK, h0);
+                            else
+                                ptx::tma_load_2d(&tmA2, &fullH[sh], smem + sh * C::kHaloStride,
+                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, h0);
+                        } else if (j < args.a_split)
                             ptx::tma_load_5d(&tmA, &fullH[sh], smem + sh * C::kHaloStride,
                                              args.a_chan_off + j * kConvBlockK, wc, hc, 0, b0);
                         else
@@ -836,7 +845,8 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             // row apart; G16x16: tap (dh = u) of copy dw = l starts dh rows in, segments 1024 B apart
                             // V15: tap u = dh starts dh rows (8 pixels each) in, segments 1024 B apart
                             const uint64_t db = kW16 ? make_halo_t_desc(h_base + u * 16 * 128, 1024)
-                                : (G == kGV15 ? make_halo_t_desc(h_base + u * 8 * 128, 1024)
+                                : (G == kGLin ? make_halo_t_desc(h_base, 1024)
+                                : G == kGV15 ? make_halo_t_desc(h_base + u * 8 * 128, 1024)
                                               : make_halo_t_desc(h_base + ((u / 3) * C::kBoxW + (u % 3)) * 128, C::kBoxW * 128));
 #pragma unroll
                             for (int k = 0; k < kConvBlockK / 16; ++k)
@@ -853,7 +863,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
     } else if (warp >= 4) {
         // ===================== epilogue: lane = channel, columns = pixels =====================
-        constexpr int kTwLog2 = kW16 ? 4 : 3;
+        constexpr int kTwLog2 = kW16 ? 4 : (G == kGLin ? 0 : 3);
         const int q = warp & 3;                       // TMEM lane quarter -> channels [32q, 32q + 32) of the tile
         const int half = warp >= 8 ? 1 : 0;           // pixel columns [128*half, 128*half + 128)
         int iter = 0;
@@ -862,11 +872,14 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int mt = tile / args.tiles_n;
             const int w0 = (mt % args.tiles_w) * C::kTW;
             const int h0 = ((mt / args.tiles_w) % args.tiles_h) * C::kTH;
-            const int b = mt / (args.tiles_w * args.tiles_h);
+            // Lin: "rows" are pixels of the whole tensor (args.H = pixels per image, args.B = pixels in total, out_sh = pixel
+            // stride, out_sb = out_sw = 0); the other geometries tile one image
+            const int b = G == kGLin ? h0 / args.H : mt / (args.tiles_w * args.tiles_h);
             const int n = nt * 128 + q * 32 + lane;   // this thread's output channel
             const float bias_v = args.bias ? __ldg(args.bias + n) : 0.f;
-            const long long base = (long long)b * args.out_sb + (long long)(h0 + half * (C::kTH / 2)) * args.out_sh +
-                                   (long long)w0 * args.out_sw + n;
+            const long long base = (G == kGLin ? 0 : (long long)b * args.out_sb) +
+                                   (long long)(h0 + half * (C::kTH / 2)) * args.out_sh + (long long)w0 * args.out_sw + n;
+            const int lin_left = G == kGLin ? args.B - (h0 + half * 128) : 0;     // valid pixels of this thread's half tile
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 3600 + as);
@@ -883,12 +896,15 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (args.residual) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        r[i] = args.residual[rowb + (long long)(i >> kTwLog2) * args.out_sh +
-                                             (long long)(i & (C::kTW - 1)) * args.out_sw];
+                        r[i] = (G != kGLin || c + i < lin_left)
+                                   ? args.residual[rowb + (long long)(i >> kTwLog2) * args.out_sh +
+                                                   (long long)(i & (C::kTW - 1)) * args.out_sw]
+                                   : 0.f;
                 }
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
+                    if (G == kGLin && c + i >= lin_left) continue;            // rows past the end of the tensor
                     float f = __uint_as_float(i < 16 ? v0[i] : v1[i - 16]) + bias_v;
                     if (args.residual) f += r[i];
                     st_s += f;
@@ -1075,6 +1091,61 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         return -8;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -5;
+
+    // ---- 1x1 convs / linears on the swapped-operand kernel: 256 consecutive pixels (rows) x 128 channels per tile
+    {
+        const long long M = (long long)p.B * p.H * p.W;
+        const bool dense_out = p.out_sc <= 1 && (p.H == 1 || p.out_sh == (long long)p.W * p.out_sw) &&
+                               (p.B == 1 || p.out_sb == (long long)p.H * p.W * p.out_sw);   // pixel-linear output
+        const bool dense_in = true;     // [B][1][H][W][lda]: pixel p of the tensor is row p
+        if (p.lin1x1 && p.num_taps == 1 && p.phases == 1 && p.in_stride <= 1 && p.Cout % 128 == 0 && dense_out && dense_in &&
+            (p.n_valid == 0 || p.n_valid == p.Cout) && p.dbg == 0 && M >= 256 && M < (1LL << 31) &&
+            (!p.stats || ((long long)p.H * p.W) % 256 == 0) && p.dh[0] == 0 && p.dw[0] == 0) {
+            if (p.act2 && (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) ||
+                           (reinterpret_cast<uintptr_t>(p.act2) & 15)))
+                return -8;
+            ConvTcArgs h{};
+            h.num_taps = 1; h.chunks_per_tap = p.Cin / kConvBlockK;
+            h.tiles_w = 1; h.tiles_h = (int)((M + 255) / 256); h.tiles_b = 1; h.tiles_n = p.Cout / 128;
+            h.B = (int)M; h.H = p.H * p.W; h.W = 1; h.a_chan_off = p.a_chan_off;
+            h.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK; h.a_chan_off2 = p.a_chan_off2;
+            h.out_sb = 0; h.out_sh = p.out_sw; h.out_sw = 0; h.out_sc = 1; h.n_valid = p.Cout;
+            h.out_f32 = p.out_f32; h.out_f16 = p.out_f16; h.bias = p.bias; h.residual = p.residual; h.err_flag = p.err_flag;
+            h.stats = p.stats; h.stats_blocks = p.Cout / 16;
+            int dev = 0, num_sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            CUtensorMap tmA, tmA2, tmB;
+            cuuint32_t estr[2] = {1, 1};
+            cuuint32_t box[2] = {kConvBlockK, 256};
+            {
+                cuuint64_t gdim[2] = {(cuuint64_t)p.a_channels, (cuuint64_t)M};
+                cuuint64_t gstr[1] = {(cuuint64_t)p.lda * 2};
+                if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.act), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return -6;
+            }
+            tmA2 = tmA;
+            if (p.act2) {
+                cuuint64_t gdim[2] = {(cuuint64_t)p.lda2, (cuuint64_t)M};
+                cuuint64_t gstr[1] = {(cuuint64_t)p.lda2 * 2};
+                if (enc(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.act2), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                    return -6;
+            }
+            const cuuint64_t K = (cuuint64_t)p.Cin;
+            cuuint64_t wdim[2] = {K, (cuuint64_t)p.Cout};
+            cuuint64_t wstr[1] = {K * 2};
+            cuuint32_t wbox[2] = {kConvBlockK, 128};
+            if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.wpacked), wdim, wstr, wbox, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                return -7;
+            return launch_halo_t<kGLin>(tmA, tmA2, tmB, h, h.tiles_h * h.tiles_n, num_sms, stream);
+        }
+    }
 
     // ---- 3x3 halo kernel with swapped operands (channels in TMEM lanes): 128-wide channel tiles, H % 32 == 0, W % 8 == 0
     const bool t16 = p.W == 16 && p.H % 16 == 0;                       // G16x16: one 16 x 16 tile per image (row block)

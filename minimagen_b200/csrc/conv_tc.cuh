@@ -60,6 +60,7 @@ struct ConvTcProblem {
     int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
     int halo;               // 1 = use a 3x3 halo-tile kernel when the geometry allows (swapped-operand form preferred),
                             // 2 = only the pixel-major halo kernel, 3 = 15 x 1 vertical taps (stem) on the swapped kernel
+    int lin1x1;             // 1 = 1x1 convs / linears may use the swapped-operand kernel (256-pixel row tiles)
     int kmerge;             // 0 = auto (two k-chunks per stage when possible), 1 = one k-chunk per stage
     int dbg;                // profiling experiments only
     double* stats;          // optional GroupNorm block statistics of the output (pre-zeroed), see ConvTcArgs

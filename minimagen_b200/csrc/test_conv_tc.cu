@@ -117,6 +117,7 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
     if (c.pair == 6) { p.cta_pair = 2; p.stream_k = 1; }
     if (c.pair == 7) { p.cta_pair = 2; p.stream_k = 2; p.dbg = 4; }
     if (c.pair == 9) p.cta_pair = 0;
+    if (c.pair == 8 && c.k == 1) p.lin1x1 = 1;
 
     *g_err = 0;
     int rc = conv_tc_launch(p, 0);
@@ -244,6 +245,9 @@ int main(int argc, char** argv) {
             {"t_c3_n256", 2, 32, 32, 128, 256, 3, 1, true, true, false, 0, 8},
             {"t_c3_w256", 1, 32, 256, 64, 128, 3, 1, false, false, false, 0, 8},
             {"t16_c3", 3, 16, 16, 128, 128, 3, 1, true, true, true, 0, 8},
+            {"lin_1x1", 2, 16, 16, 256, 256, 1, 1, true, true, true, 0, 8},
+            {"lin_1x1_ragged", 5, 8, 8, 128, 128, 1, 1, true, false, true, 0, 8},
+            {"lin_1x1_persist", 40, 32, 32, 64, 256, 1, 1, false, true, false, 0, 8},
             {"v15_stem_t", 2, 64, 32, 128, 128, 15, 1, true, false, true, 0, 8},
             {"v15_stem_pair", 2, 64, 32, 128, 128, 15, 1, true, false, true, 0, 2},
             {"t16_c3_h32_n256", 2, 32, 16, 64, 256, 3, 1, true, false, false, 0, 8},
@@ -299,6 +303,13 @@ int main(int argc, char** argv) {
             {"S2 split  256->128 128ch", 32, 256, 256, 128, 128, 4, 2, true, false, false, 0, 0},
             {"S2 direct 64->32 256->512", 32, 64, 64, 256, 512, 4, 2, true, false, false, 0, 9},
             {"S2 split  64->32 256->512", 32, 64, 64, 256, 512, 4, 2, true, false, false, 0, 0},
+            {"T pw_16_2048", 32, 16, 16, 2048, 1024, 1, 1, true, false, false, 256, 8},
+            {"T pw_32_1024", 32, 32, 32, 1024, 512, 1, 1, true, false, false, 256, 8},
+            {"T pw_64_512", 32, 64, 64, 512, 256, 1, 1, true, false, false, 256, 8},
+            {"T pw_128_256", 32, 128, 128, 256, 128, 1, 1, true, false, false, 128, 8},
+            {"pw_32_1024", 32, 32, 32, 1024, 512, 1, 1, true, false, false, 256, 1},
+            {"pw_64_512", 32, 64, 64, 512, 256, 1, 1, true, false, false, 256, 1},
+            {"pw_128_256", 32, 128, 128, 256, 128, 1, 1, true, false, false, 128, 1},
             {"T stem_256 15x1", 32, 256, 256, 128, 128, 15, 1, true, false, true, 128, 8},
             {"P stem_256 15x1", 32, 256, 256, 128, 128, 15, 1, true, false, true, 128, 2},
             {"T sr_128_128", 32, 128, 128, 128, 128, 3, 1, true, true, false, 128, 8},
