@@ -112,6 +112,7 @@ class Imagen(nn.Module):
         # B200 additions (not part of the reference surface)
         self.use_cuda_graph = True       # replay each denoising step from a captured CUDA graph
         self.noise_fn: Callable = None   # see module docstring
+        self.cfg_batched = False         # classifier-free guidance as ONE 2B-sample forward (not yet measured on B200)
         self._graphs = {}
 
     # -------------------------------------------------------------------------------------------- bookkeeping
@@ -208,9 +209,17 @@ class Imagen(nn.Module):
         if exists(model_output):
             eps = model_output.to(F32).contiguous()
         else:
-            eps = unet.forward(x, t, **kw)
-            if cond_scale != 1:
-                eps_null = unet.forward(x, t, cond_drop_prob=1., **kw)
+            if cond_scale != 1 and self.cfg_batched:
+                # conditional and unconditional pass as ONE batch of 2B (per-sample keep mask instead of two forwards)
+                two = lambda v: torch.cat((v, v), dim=0) if exists(v) else None
+                keep = torch.cat((torch.ones(B, dtype=torch.uint8, device=x.device),
+                                  torch.zeros(B, dtype=torch.uint8, device=x.device)))
+                both = unet.forward(two(x), two(t), cond_keep=keep, **{k: two(v) for k, v in kw.items()})
+                eps, eps_null = both[:B], both[B:]
+            else:
+                eps = unet.forward(x, t, **kw)
+                if cond_scale != 1:
+                    eps_null = unet.forward(x, t, cond_drop_prob=1., **kw)
         x = x.contiguous()
         x0 = torch.empty_like(x)
         ops.step_x0(x, eps, eps_null, cond_scale, t, sch.sqrt_recip_alphas_cumprod, sch.sqrt_recipm1_alphas_cumprod, B, n,

@@ -165,9 +165,11 @@ class Unet(nn.Module):
         return self.__class__(**{**self._locals, **updated})
 
     def forward(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None,
-                cond_drop_prob: float = 0.):
+                cond_drop_prob: float = 0., cond_keep=None):
         """x: (b, c, s, s) fp32 NCHW noised images; time: (b,) int64.  Returns the predicted noise, (b, c_out, s, s).
-        Orchestration follows the reference's Unet.forward (Unet.py:355-472) block for block."""
+        Orchestration follows the reference's Unet.forward (Unet.py:355-472) block for block.
+        `cond_keep` (extension, uint8/bool [b]): explicit per-sample keep mask instead of the Bernoulli(1 - cond_drop_prob)
+        draw of Unet.py:587 -- lets the conditional and the unconditional pass of classifier-free guidance share one batch."""
         assert not (self.lowres_cond and not exists(lowres_cond_img)), \
             'low resolution conditioning image must be present'
         assert not (self.lowres_cond and not exists(lowres_noise_times)), \
@@ -180,7 +182,7 @@ class Unet(nn.Module):
 
         # conditioning for the whole batch (cheap, weight-streaming bound) on the caller's stream
         t, time_tokens = self._generate_t_tokens(time, lowres_noise_times)
-        t, c = self._text_condition(text_embeds, B, cond_drop_prob, device, text_mask, t, time_tokens)
+        t, c = self._text_condition(text_embeds, B, cond_drop_prob, device, text_mask, t, time_tokens, cond_keep)
         # every ResnetBlock's time_mlp (SiLU -> Linear, layers.py:396-399) in ONE GEMM over the shared time embedding
         ss = self._all_scale_shifts(t)
 
@@ -339,7 +341,7 @@ class Unet(nn.Module):
             tokens = torch.cat((tokens, lowres_tokens), dim=-2)
         return t, tokens
 
-    def _text_condition(self, text_embeds, batch_size, cond_drop_prob, device, text_mask, t, time_tokens):
+    def _text_condition(self, text_embeds, batch_size, cond_drop_prob, device, text_mask, t, time_tokens, cond_keep=None):
         """-> (t, c): t gains the pooled-text hidden (or the learned null hidden), c = LayerNorm(cat(time tokens,
         256 text tokens with masked / dropped rows replaced by null_text_embed))   (reference Unet.py:538-634)"""
         ops = get_ops()
@@ -354,7 +356,8 @@ class Unet(nn.Module):
             proj = torch.empty((B * L, D), dtype=F32, device=device)
             ops.linear_f32(text_embeds.to(F32).contiguous().reshape(B * L, E), B * L, E, self.text_to_cond.weight,
                            self.text_to_cond.bias, D, 0, 0, None, proj, None)
-            keep = prob_mask_like((B,), 1 - cond_drop_prob, device=device).to(torch.uint8)
+            keep = (cond_keep.to(device=device, dtype=torch.uint8).contiguous() if exists(cond_keep)
+                    else prob_mask_like((B,), 1 - cond_drop_prob, device=device).to(torch.uint8))
             mask_u8 = text_mask.to(torch.uint8).contiguous() if exists(text_mask) else None
             pooled = torch.empty((B, D), dtype=F32, device=device)
             ops.text_tokens(proj, B, L, D, mask_u8, keep, self.null_text_embed.detach().reshape(self.max_text_len, D),

@@ -259,3 +259,18 @@ def test_bench_reference_arm_contract():
     assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_cfg_as_one_batch_matches_two_forwards(emu):
+    """Imagen.cfg_batched: the conditional and unconditional passes of classifier-free guidance as one 2B-sample forward
+    (explicit per-sample keep mask, Unet.forward(cond_keep=...)) give the same step as the reference's two forwards
+    (Unet.py:474-506, Imagen.py:295-301)."""
+    g = load_golden("cascade_tiny.pt")
+    outs = []
+    for batched in (False, True):
+        im, it = _cascade_from_golden(g, "cpu")
+        im.cfg_batched = batched
+        outs.append(im.sample(text_embeds=g["text_embeds"], text_masks=g["text_mask"], cond_scale=g["cond_scale"],
+                              lowres_sample_noise_level=g["lowres_noise_level"]))
+    assert rel_l2(outs[1], outs[0]) < 1e-5
+    assert rel_l2(outs[1], g["out"]) < 1e-3
