@@ -214,7 +214,7 @@ class Imagen(nn.Module):
                 two = lambda v: torch.cat((v, v), dim=0) if exists(v) else None
                 keep = torch.cat((torch.ones(B, dtype=torch.uint8, device=x.device),
                                   torch.zeros(B, dtype=torch.uint8, device=x.device)))
-                both = unet.forward(two(x), two(t), cond_keep=keep, **{k: two(v) for k, v in kw.items()})
+                both = unet._forward_impl(two(x), two(t), cond_keep=keep, **{k: two(v) for k, v in kw.items()})
                 eps, eps_null = both[:B], both[B:]
             else:
                 eps = unet.forward(x, t, **kw)

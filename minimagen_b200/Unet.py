@@ -165,10 +165,17 @@ class Unet(nn.Module):
         return self.__class__(**{**self._locals, **updated})
 
     def forward(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None,
-                cond_drop_prob: float = 0., cond_keep=None):
+                cond_drop_prob: float = 0.):
+        """x: (b, c, s, s) fp32 NCHW noised images; time: (b,) int64.  Returns the predicted noise, (b, c_out, s, s)
+        (reference signature, Unet.py:355-363)."""
+        return self._forward_impl(x, time, lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
+                                  text_embeds=text_embeds, text_mask=text_mask, cond_drop_prob=cond_drop_prob)
+
+    def _forward_impl(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None,
+                      cond_drop_prob: float = 0., cond_keep=None):
         """x: (b, c, s, s) fp32 NCHW noised images; time: (b,) int64.  Returns the predicted noise, (b, c_out, s, s).
         Orchestration follows the reference's Unet.forward (Unet.py:355-472) block for block.
-        `cond_keep` (extension, uint8/bool [b]): explicit per-sample keep mask instead of the Bernoulli(1 - cond_drop_prob)
+        `cond_keep` (internal, uint8/bool [b]): explicit per-sample keep mask instead of the Bernoulli(1 - cond_drop_prob)
         draw of Unet.py:587 -- lets the conditional and the unconditional pass of classifier-free guidance share one batch."""
         assert not (self.lowres_cond and not exists(lowres_cond_img)), \
             'low resolution conditioning image must be present'

@@ -263,7 +263,7 @@ def test_bench_reference_arm_contract():
 
 def test_cfg_as_one_batch_matches_two_forwards(emu):
     """Imagen.cfg_batched: the conditional and unconditional passes of classifier-free guidance as one 2B-sample forward
-    (explicit per-sample keep mask, Unet.forward(cond_keep=...)) give the same step as the reference's two forwards
+    (explicit per-sample keep mask, Unet._forward_impl(cond_keep=...)) give the same step as the reference's two forwards
     (Unet.py:474-506, Imagen.py:295-301)."""
     g = load_golden("cascade_tiny.pt")
     outs = []
