@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MI_ABI_VERSION 1
+#define MI_ABI_VERSION 2
 
 int mi_abi_version(void);
 const char* mi_last_error(void);
@@ -212,6 +212,21 @@ int mi_step_quantile(const float* x0, int B, int n, int rank_lo, int rank_hi, fl
 int mi_step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
                       const float* posterior_mean_coef1, const float* posterior_mean_coef2, const float* sigma, int B,
                       int n, float* out, void* stream);
+/* The three calls above as ONE kernel -- everything Imagen._p_sample does after the U-Net (Imagen.py:307-326, :361-370;
+ * Unet.py:506 for the guidance combine): an 8-CTA cluster per image computes x0 into registers, selects the dynamic-
+ * threshold order statistics there, and writes x_{t-1}; the x0 tensor never exists in memory.  `out` may be `x_t` (in-place
+ * update of the sampling state).  s_out: optional [B] (the thresholds).  Images with more than 196 608 values (3 x 1024 x
+ * 1024) exceed the register-resident select: they take the three-kernel form through the caller's scratch
+ * x0_workspace (mi_step_epilogue_workspace_floats(B, n) floats; 0 = not needed) and then s_out is required. */
+long long mi_step_epilogue_workspace_floats(int B, int n);
+int mi_step_epilogue(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+                     const float* sqrt_recip_alphas_cumprod, const float* sqrt_recipm1_alphas_cumprod,
+                     const float* posterior_mean_coef1, const float* posterior_mean_coef2, const float* sigma,
+                     const float* noise, int B, int n, int rank_lo, int rank_hi, float weight, float min_s, float* out,
+                     float* s_out, float* x0_workspace, void* stream);
+/* t[b] <- max(t[b] - 1, 0): the next iteration's timestep of Imagen._p_sample_loop (Imagen.py:398-415 walks the list of
+ * diffusion_model.py:81-87), advanced on the device so that a captured step can be replayed back to back */
+int mi_step_advance_t(long long* t, int B, void* stream);
 /* clamp_(-1,1) and (x+1)*0.5 (Imagen.py:418-419) */
 int mi_step_finalize(const float* x, long long n, int unnormalize, float* out, void* stream);
 /* GaussianDiffusion.q_sample (diffusion_model.py:127-147) followed by v*post_scale + post_shift */

@@ -24,6 +24,7 @@ from .Unet import Unet
 from .diffusion_model import GaussianDiffusion
 from .helpers import (cast_tuple, default, eval_decorator, exists, identity, maybe, module_device,
                       normalize_neg_one_to_one, null_context, resize_image_to, unnormalize_zero_to_one)
+from . import _native as N
 from .ops import get_ops
 from .t5 import get_encoded_dim, t5_encode_text
 
@@ -40,12 +41,27 @@ def quantile_rank(n: int, q: float):
 
 
 class _StepGraph:
-    """One captured denoising step (U-Net pass(es) + step epilogue) with static input/output buffers."""
+    """One captured denoising step (U-Net pass(es) + step epilogue) over STATIC buffers:
+         x      [B, C, s, s]  the image, updated IN PLACE by every replay (x_t -> x_{t-1});
+         t      [B] int64     the timestep, decremented (floor 0) at the end of every replay;
+         noise  [B, C, s, s]  the step's Gaussian draw: drawn INSIDE the graph (graph-safe Philox) unless the caller
+                              injects noise, in which case it is copied here before each replay;
+         cond   static copies of text_embeds / text_mask / lowres_cond_img / lowres_noise_times (`set_cond` refreshes them).
+    A whole sampling loop is then `set x, t; replay() * T` -- no per-step host-side tensor ops."""
 
     def __init__(self):
         self.graph = None
-        self.key = None
-        self.x = self.t = self.noise = self.out = None
+        self.x = self.t = self.noise = None
+        self.cond = {}
+        self.inject_noise = False
+
+    def set_cond(self, **tensors):
+        for k, v in tensors.items():
+            if v is not None:
+                self.cond[k].copy_(v)
+
+    def replay(self):
+        self.graph.replay()
 
 
 class Imagen(nn.Module):
@@ -114,6 +130,7 @@ class Imagen(nn.Module):
         self.noise_fn: Callable = None   # see module docstring
         self.cfg_batched = False         # classifier-free guidance as ONE 2B-sample forward (not yet measured on B200)
         self._graphs = {}
+        self.max_cached_graphs = 4
 
     # -------------------------------------------------------------------------------------------- bookkeeping
     @property
@@ -194,8 +211,17 @@ class Imagen(nn.Module):
                 noise_scheduler.posterior_log_variance_clipped.gather(-1, t).reshape(shp))
 
     def _step(self, unet, x, t, noise, *, noise_scheduler, text_embeds, text_mask, lowres_cond_img, lowres_noise_times,
-              cond_scale, model_output=None):
-        """x_{t-1} = posterior_mean(x_t, clamp-thresholded x0(x_t, eps)) + [t != 0] * sigma_t * noise."""
+              cond_scale, model_output=None, out=None):
+        """x_{t-1} = posterior_mean(x_t, clamp-thresholded x0(x_t, eps)) + [t != 0] * sigma_t * noise.
+        `out` may be `x` itself (the captured step updates the image in place)."""
+        with N.device_of(x):
+            return self._step_impl(unet, x, t, noise, noise_scheduler=noise_scheduler, text_embeds=text_embeds,
+                                   text_mask=text_mask, lowres_cond_img=lowres_cond_img,
+                                   lowres_noise_times=lowres_noise_times, cond_scale=cond_scale,
+                                   model_output=model_output, out=out)
+
+    def _step_impl(self, unet, x, t, noise, *, noise_scheduler, text_embeds, text_mask, lowres_cond_img,
+                   lowres_noise_times, cond_scale, model_output=None, out=None):
         assert not (cond_scale != 1. and not self.can_classifier_guidance), \
             'imagen was not trained with conditional dropout, and thus one cannot use classifier free guidance ' \
             '(cond_scale anything other than 1)'
@@ -221,14 +247,13 @@ class Imagen(nn.Module):
                 if cond_scale != 1:
                     eps_null = unet.forward(x, t, cond_drop_prob=1., **kw)
         x = x.contiguous()
-        x0 = torch.empty_like(x)
-        ops.step_x0(x, eps, eps_null, cond_scale, t, sch.sqrt_recip_alphas_cumprod, sch.sqrt_recipm1_alphas_cumprod, B, n,
-                    x0)
         lo, hi, w = quantile_rank(n, self.dynamic_thresholding_percentile)
-        s = torch.empty((B,), dtype=F32, device=x.device)
-        ops.step_quantile(x0, B, n, lo, hi, w, 1.0, s)
-        out = torch.empty_like(x)
-        ops.step_posterior(x0, x, noise, s, t, sch.posterior_mean_coef1, sch.posterior_mean_coef2, sch.sigma, B, n, out)
+        if out is None:
+            out = torch.empty_like(x)
+        # ONE kernel: CFG combine + x0 + exact dynamic-threshold quantile + clamp/divide + posterior mean + noise
+        # (mi_step_epilogue; images too large for its register-resident select take the three-kernel form inside the ABI)
+        ops.step_epilogue(x, eps, eps_null, cond_scale, t, sch.sqrt_recip_alphas_cumprod, sch.sqrt_recipm1_alphas_cumprod,
+                          sch.posterior_mean_coef1, sch.posterior_mean_coef2, sch.sigma, noise, B, n, lo, hi, w, 1.0, out)
         return out
 
     @torch.no_grad()
@@ -242,66 +267,102 @@ class Imagen(nn.Module):
                           cond_scale=cond_scale)
 
     # -------------------------------------------------------------------------------------------- sampling loop
-    def _graph_step_fn(self, unet, shape, noise_scheduler, text_embeds, text_mask, lowres_cond_img,
-                       lowres_noise_times, cond_scale):
-        """Capture `_step` once for this (unet, shape, conditioning) and return a replay closure (x, t, noise) -> x'."""
+    def _graph_key(self, unet, shape, noise_scheduler, text_embeds, text_mask, lowres_cond_img, lowres_noise_times,
+                   cond_scale):
+        sig = lambda v: None if v is None else (tuple(v.shape), str(v.dtype))
+        p0 = next(unet.parameters())
+        return (id(unet), tuple(shape), float(cond_scale), bool(self.cfg_batched), exists(self.noise_fn),
+                noise_scheduler.num_timesteps, sig(text_embeds), sig(text_mask), sig(lowres_cond_img),
+                sig(lowres_noise_times), p0.data_ptr(), sum(p._version for p in unet.parameters()),
+                self.dynamic_thresholding_percentile)
+
+    def clear_graphs(self):
+        """Drop the captured step graphs (and the activation memory their pools hold)."""
+        self._graphs = {}
+        self.max_cached_graphs = 4
+
+    def _step_graph(self, unet, shape, *, noise_scheduler, text_embeds, text_mask, lowres_cond_img,
+                    lowres_noise_times, cond_scale):
+        """The captured step for this (unet, shape, conditioning signature, weights version): captured once, then reused by
+        every later sampling loop of the same signature; the conditioning tensors are refreshed in its static buffers."""
         device = self.device
+        key = self._graph_key(unet, shape, noise_scheduler, text_embeds, text_mask, lowres_cond_img,
+                              lowres_noise_times, cond_scale)
+        cond = dict(text_embeds=text_embeds, text_mask=text_mask, lowres_cond_img=lowres_cond_img,
+                    lowres_noise_times=lowres_noise_times)
+        g = self._graphs.get(key)
+        if g is not None:
+            g.set_cond(**cond)
+            return g
+        if len(self._graphs) >= self.max_cached_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
         g = _StepGraph()
+        g.inject_noise = exists(self.noise_fn)
         g.x = torch.zeros(shape, dtype=F32, device=device)
         g.noise = torch.zeros(shape, dtype=F32, device=device)
         g.t = torch.zeros((shape[0],), dtype=torch.long, device=device)
-        kw = dict(noise_scheduler=noise_scheduler, text_embeds=text_embeds, text_mask=text_mask,
-                  lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times, cond_scale=cond_scale)
+        g.cond = {k: v.clone() for k, v in cond.items() if v is not None}
+        kw = dict(noise_scheduler=noise_scheduler, cond_scale=cond_scale,
+                  **{k: g.cond.get(k) for k in cond})
+        ops = get_ops()
+
+        def body():
+            if not g.inject_noise:
+                g.noise.normal_()                       # the reference's randn_like(x) (Imagen.py:361), graph-safe Philox
+            self._step(unet, g.x, g.t, g.noise, out=g.x, **kw)
+            ops.step_advance_t(g.t, shape[0])           # t <- max(t - 1, 0): the next loop iteration's timestep
+
         # warm-up on a side stream (packs weights, sizes the caching allocator), then capture
         side = torch.cuda.Stream(device=device)
         side.wait_stream(torch.cuda.current_stream(device))
         with torch.cuda.stream(side):
-            self._step(unet, g.x, g.t, g.noise, **kw)
+            body()
         torch.cuda.current_stream(device).wait_stream(side)
         torch.cuda.synchronize(device)
         g.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g.graph):
-            g.out = self._step(unet, g.x, g.t, g.noise, **kw)
-
-        def run(x, t, noise):
-            g.x.copy_(x)
-            g.t.copy_(t)
-            g.noise.copy_(noise)
-            g.graph.replay()
-            return g.out.clone()
-        return run
+            body()
+        self._graphs[key] = g
+        return g
 
     @torch.no_grad()
     def _p_sample_loop(self, unet, shape, *, noise_scheduler, text_embeds=None, text_mask=None, lowres_cond_img=None,
-                       lowres_noise_times=None, cond_scale=1., max_steps=None):
+                       lowres_noise_times=None, cond_scale=1., max_steps=None, out=None):
         """Reverse diffusion from x_T ~ N(0, I) to x_0 (reference Imagen.py:372-420).  `max_steps` (not in the
-        reference) stops after that many iterations -- used by the benchmark / parity harness."""
+        reference) stops after that many iterations -- used by the benchmark / parity harness; `out` (not in the
+        reference) receives the finished images (e.g. this rank's slot of the all-gather buffer)."""
         device = self.device
-        ops = get_ops()
-        lowres_cond_img = maybe(self.normalize_img)(lowres_cond_img)
-        if exists(lowres_cond_img):
-            lowres_cond_img = lowres_cond_img.to(F32).contiguous()
-        batch = shape[0]
-        timesteps = noise_scheduler._get_sampling_timesteps(batch, device=device)
-        if exists(max_steps):
-            timesteps = timesteps[:max_steps]
-        img = self._noise('init', shape, -1, device)
+        with N.device_of(self._temp):
+            ops = get_ops()
+            lowres_cond_img = maybe(self.normalize_img)(lowres_cond_img)
+            if exists(lowres_cond_img):
+                lowres_cond_img = lowres_cond_img.to(F32).contiguous()
+            batch = shape[0]
+            timesteps = noise_scheduler._get_sampling_timesteps(batch, device=device)
+            if exists(max_steps):
+                timesteps = timesteps[:max_steps]
+            img = self._noise('init', shape, -1, device)
 
-        kw = dict(noise_scheduler=noise_scheduler, text_embeds=text_embeds, text_mask=text_mask,
-                  lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times, cond_scale=cond_scale)
-        step_fn = None
-        if self.use_cuda_graph and img.is_cuda and len(timesteps) > 2:
-            step_fn = self._graph_step_fn(unet, tuple(shape), **kw)
-        for i, times in enumerate(timesteps):
-            noise = self._noise('step', shape, noise_scheduler.num_timesteps - 1 - i, device)
-            if exists(step_fn):
-                img = step_fn(img, times, noise)
+            kw = dict(noise_scheduler=noise_scheduler, text_embeds=text_embeds, text_mask=text_mask,
+                      lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times, cond_scale=cond_scale)
+            if self.use_cuda_graph and img.is_cuda and len(timesteps) > 2:
+                g = self._step_graph(unet, tuple(shape), **kw)
+                g.x.copy_(img)
+                g.t.copy_(timesteps[0])
+                for i in range(len(timesteps)):
+                    if g.inject_noise:
+                        g.noise.copy_(self._noise('step', shape, noise_scheduler.num_timesteps - 1 - i, device))
+                    g.replay()                              # x <- x_{t-1} in place, t <- t - 1
+                img = g.x
             else:
-                img = self._step(unet, img, times, noise, **kw)
+                for i, times in enumerate(timesteps):
+                    noise = self._noise('step', shape, noise_scheduler.num_timesteps - 1 - i, device)
+                    img = self._step(unet, img, times, noise, **kw)
 
-        out = torch.empty_like(img)
-        ops.step_finalize(img.contiguous(), img.numel(), int(self.auto_normalize_img), out)   # clamp_(-1,1); (x+1)/2
-        return out
+            if out is None:
+                out = torch.empty(tuple(shape), dtype=F32, device=device)
+            ops.step_finalize(img.contiguous(), img.numel(), int(self.auto_normalize_img), out)   # clamp_(-1,1); (x+1)/2
+            return out
 
     @torch.no_grad()
     @eval_decorator
@@ -309,11 +370,19 @@ class Imagen(nn.Module):
                lowres_sample_noise_level: float = None, return_pil_images: bool = False, device=None,
                distributed: bool = False):
         """Generate images (reference Imagen.py:422-510).  With `distributed=True` inside an initialised
-        torch.distributed (NCCL) job, rank r samples rows [r*b/G, (r+1)*b/G) of the conditioning and a single
+        torch.distributed (NCCL) job, rank r samples rows [r*b/G, (r+1)*b/G) of the conditioning; the last stage's
+        finalize kernel writes its images straight into this rank's slot of the gather buffer and ONE in-place
         all-gather returns the full batch on every rank."""
-        device = default(device, self.device)
+        device = torch.device(default(device, self.device))
         self._reset_unets_all_one_device(device=device)
+        if self._temp.device != device:
+            self.to(device)
+        with N.device_of(self._temp):
+            return self._sample_impl(texts, text_masks, text_embeds, cond_scale, lowres_sample_noise_level,
+                                     return_pil_images, device, distributed)
 
+    def _sample_impl(self, texts, text_masks, text_embeds, cond_scale, lowres_sample_noise_level, return_pil_images,
+                     device, distributed):
         if exists(texts) and not exists(text_embeds):
             text_embeds, text_masks = t5_encode_text(texts, name=self.text_encoder_name)
             text_embeds, text_masks = map(lambda t: t.to(device), (text_embeds, text_masks))
@@ -340,8 +409,10 @@ class Imagen(nn.Module):
         ops = get_ops()
 
         img = None
+        gathered = None
+        n_stages = len(self.unets)
         for unet_number, unet, channel, image_size, noise_scheduler in zip(
-                range(1, len(self.unets) + 1), self.unets, self.sample_channels, self.image_sizes,
+                range(1, n_stages + 1), self.unets, self.sample_channels, self.image_sizes,
                 self.noise_schedulers):
             with self._one_unet_in_gpu(unet=unet):
                 lowres_cond_img = lowres_noise_times = None
@@ -357,15 +428,20 @@ class Imagen(nn.Module):
                                  noised)
                     lowres_cond_img = noised
                 shape = (batch_size, self.channels, image_size, image_size)
+                slot = None
+                if distributed and world > 1 and unet_number == n_stages:
+                    # the last stage finalises straight into this rank's slot of the all-gather buffer (no staging copy)
+                    gathered = torch.empty((world * batch_size, *shape[1:]), dtype=F32, device=device)
+                    slot = gathered[rank * batch_size:(rank + 1) * batch_size]
                 img = self._p_sample_loop(unet, shape, text_embeds=text_embeds, text_mask=text_masks,
                                           cond_scale=cond_scale, lowres_cond_img=lowres_cond_img,
-                                          lowres_noise_times=lowres_noise_times, noise_scheduler=noise_scheduler)
+                                          lowres_noise_times=lowres_noise_times, noise_scheduler=noise_scheduler,
+                                          out=slot)
 
         outputs = img
-        if distributed and world > 1:
+        if gathered is not None:
             import torch.distributed as dist
-            gathered = torch.empty((world * batch_size, *outputs.shape[1:]), dtype=outputs.dtype, device=device)
-            dist.all_gather_into_tensor(gathered, outputs.contiguous())
+            dist.all_gather_into_tensor(gathered, img)      # in place: `img` IS gathered[rank slot]
             outputs = gathered
 
         if not return_pil_images:

@@ -15,6 +15,7 @@ from torch import nn
 from .helpers import cast_tuple, default, exists, prob_mask_like
 from .layers import (Attention, Cat, Context, Conv2d, CrossEmbedLayer, Downsample, Identity, Parallel, ResnetBlock,
                      SinusoidalPosEmb, TokenView, TransformerBlock, Upsample, _no_grad_check, _ResidualAttention)
+from . import _native
 from .ops import get_ops
 from .t5 import get_encoded_dim
 
@@ -171,7 +172,12 @@ class Unet(nn.Module):
         return self._forward_impl(x, time, lowres_cond_img=lowres_cond_img, lowres_noise_times=lowres_noise_times,
                                   text_embeds=text_embeds, text_mask=text_mask, cond_drop_prob=cond_drop_prob)
 
-    def _forward_impl(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None,
+    def _forward_impl(self, x, *args, **kwargs):
+        # kernels are enqueued on the current device's stream: make the input's device current for the duration
+        with _native.device_of(x):
+            return self._forward_dev(x, *args, **kwargs)
+
+    def _forward_dev(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None,
                       cond_drop_prob: float = 0., cond_keep=None):
         """x: (b, c, s, s) fp32 NCHW noised images; time: (b,) int64.  Returns the predicted noise, (b, c_out, s, s).
         Orchestration follows the reference's Unet.forward (Unet.py:355-472) block for block.

@@ -47,11 +47,14 @@ SIGNATURES = {
     "mi_step_x0": [_P, _P, _P, _F, _P, _P, _P, _I, _I, _P, _P],
     "mi_step_quantile": [_P, _I, _I, _I, _I, _F, _F, _P, _P],
     "mi_step_posterior": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P],
+    "mi_step_epilogue_workspace_floats": [_I, _I],
+    "mi_step_epilogue": [_P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P],
+    "mi_step_advance_t": [_P, _I, _P],
     "mi_step_finalize": [_P, _L, _I, _P, _P],
     "mi_q_sample": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
 }
 _RESTYPES = {"mi_last_error": c_char_p, "mi_conv2d_igemm_workspace_bytes": c_longlong,
-             "mi_attention_workspace_bytes": c_longlong}
+             "mi_attention_workspace_bytes": c_longlong, "mi_step_epilogue_workspace_floats": c_longlong}
 
 _lib = None
 launch_count = 0   # number of kernel launches issued through this binding (bench.py reports it)
@@ -71,7 +74,7 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, c_int)
-    if lib.mi_abi_version() != 1:
+    if lib.mi_abi_version() != 2:
         raise RuntimeError("minimagen_b200: ABI version mismatch between _native.py and the shared library")
     _lib = lib
     return lib
@@ -97,8 +100,23 @@ def ptr(t):
         return None
     if not t.is_cuda:
         raise RuntimeError("minimagen_b200: tensor is not on a CUDA device; the kernels have no CPU fallback")
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's current stream (and size grids / build tensor maps for it)
+        raise RuntimeError(
+            f"minimagen_b200: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            f"enter `torch.cuda.device(tensor.device)` (Unet.forward / Imagen.sample do this for their inputs)")
     return t.data_ptr()
 
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def device_of(*tensors):
+    """`torch.cuda.device` context of the first CUDA tensor among `tensors` (a no-op context if there is none):
+    the public entry points wrap their work in it so that a model on cuda:1 runs there whatever the current device is."""
+    for t in tensors:
+        if t is not None and getattr(t, "is_cuda", False):
+            return torch.cuda.device(t.device)
+    import contextlib
+    return contextlib.nullcontext()

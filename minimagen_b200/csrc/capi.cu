@@ -69,6 +69,8 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     p.wpacked = w; p.Cout = c_out;
     p.act2 = act2; p.lda2 = lda2; p.a_chan_off2 = c_off2; p.Cin1 = c_in1; p.stats = out_stats;
     if (out_stats && (out_sc > 1 || (c_out % 32) != 0)) return fail(-8, "mi_conv2d_igemm_f16: out_stats needs channel-contiguous output and c_out % 32 == 0");
+    if (out_stats && ((long long)H * W) % 32 != 0)
+        return fail(-8, "mi_conv2d_igemm_f16: out_stats needs H*W % 32 == 0 (a warp's 32 output rows must belong to one image)");
     p.out_f32 = out_f32; p.out_f16 = (__half*)out_f16; p.bias = bias; p.residual = residual;
     p.out_sb = out_sb; p.out_sh = out_sh; p.out_sw = out_sw; p.out_sc = out_sc; p.n_valid = n_valid;
     p.block_n_hint = block_n; p.err_flag = err_flag;
@@ -251,6 +253,20 @@ int mi_step_quantile(const float* x0, int B, int n, int rank_lo, int rank_hi, fl
 int mi_step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
                       const float* c1, const float* c2, const float* sigma, int B, int n, float* out, void* stream) {
     return check(mi::step_posterior(x0, x_t, noise, s, t, c1, c2, sigma, B, n, out, S(stream)), "mi_step_posterior");
+}
+long long mi_step_epilogue_workspace_floats(int B, int n) {
+    return mi::step_epilogue_fused_ok(n) ? 0 : (long long)B * n;
+}
+int mi_step_epilogue(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+                     const float* tab_a, const float* tab_b, const float* c1, const float* c2, const float* sigma,
+                     const float* noise, int B, int n, int rank_lo, int rank_hi, float weight, float min_s, float* out,
+                     float* s_out, float* x0_workspace, void* stream) {
+    return check(mi::step_epilogue(x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, c1, c2, sigma, noise, B, n, rank_lo,
+                                   rank_hi, weight, min_s, out, s_out, x0_workspace, S(stream)),
+                 "mi_step_epilogue");
+}
+int mi_step_advance_t(long long* t, int B, void* stream) {
+    return check(mi::step_advance_t(t, B, S(stream)), "mi_step_advance_t");
 }
 int mi_step_finalize(const float* x, long long n, int unnormalize, float* out, void* stream) {
     return check(mi::step_finalize(x, n, unnormalize, out, S(stream)), "mi_step_finalize");

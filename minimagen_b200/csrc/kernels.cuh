@@ -67,6 +67,12 @@ int step_quantile(const float* x0, int B, int n_per_img, int rank_lo, int rank_h
 int step_posterior(const float* x0, const float* x_t, const float* noise, const float* s, const long long* t,
                    const float* tab_c1, const float* tab_c2, const float* tab_sigma, int B, int n_per_img, float* out,
                    cudaStream_t st);
+bool step_epilogue_fused_ok(int n_per_img);
+int step_epilogue(const float* x_t, const float* eps_cond, const float* eps_null, float cond_scale, const long long* t,
+                  const float* tab_recip, const float* tab_recipm1, const float* tab_c1, const float* tab_c2,
+                  const float* tab_sigma, const float* noise, int B, int n_per_img, int rank_lo, int rank_hi,
+                  float weight, float min_s, float* out, float* s_out, float* x0_ws, cudaStream_t st);
+int step_advance_t(long long* t, int B, cudaStream_t st);
 int step_finalize(const float* x, long long n, int unnormalize, float* out, cudaStream_t st);
 int q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_b, int B,
              int n_per_img, float post_scale, float post_shift, float* out, cudaStream_t st);

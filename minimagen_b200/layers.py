@@ -370,7 +370,8 @@ class Conv2d(nn.Conv2d):
         if a.dtype == F16:
             # Downsample: 4-phase split operand (mode 1) or the fp16 activation read in place with TMA element strides (6)
             mode = (6 if in_place_s2 else 1) if self._geom == 'down' else 0
-            st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0) else None
+            # epilogue statistics credit a warp's 32 pixel rows to ONE image: needs whole images per 32-row slab
+            st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0 and (H * W) % 32 == 0) else None
             if not f32 and not f16:
                 f32 = True
             o32 = torch.empty((B, H, W, Cout), dtype=F32, device=dev) if f32 else None
@@ -407,7 +408,7 @@ class Conv2d(nn.Conv2d):
         Ho, Wo = 2 * H, 2 * W
         if not f32 and not f16:
             f32 = True
-        st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0) else None
+        st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0 and (H * W) % 32 == 0) else None
         o32 = torch.empty((B, Ho, Wo, Cout), dtype=F32, device=dev) if f32 else None
         o16 = torch.empty((B, 1, Ho, Wo, Cout), dtype=F16, device=dev) if f16 else None
         a16 = x.need_f16()
@@ -580,7 +581,7 @@ class CrossEmbedLayer(nn.Module):
             C = self.dim_out
             out = torch.empty((B, H, W, C), dtype=F32, device=x.device)
             out16 = torch.empty((B, 1, H, W, C), dtype=F16, device=x.device)
-            st = stats_zeros((B, C // STATS_BLOCK, 2), x.device) if C % 32 == 0 else None
+            st = stats_zeros((B, C // STATS_BLOCK, 2), x.device) if (C % 32 == 0 and (H * W) % 32 == 0) else None
             ops.conv_igemm(a, B, H, W, 128, 0, 128, wp, C, 15, 1, 0, bias, None, out, out16, (H * W * C, W * C, C),
                            out_stats=st)
             return Act(out, out16, st)

@@ -216,6 +216,27 @@ class NativeOps:
         N.call("mi_step_posterior", N.ptr(x0), N.ptr(x_t), N.ptr(noise), N.ptr(s), N.ptr(t), N.ptr(c1), N.ptr(c2),
                N.ptr(sigma), B, n, N.ptr(out), N.stream())
 
+    def step_epilogue(self, x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, c1, c2, sigma, noise, B, n, rank_lo,
+                      rank_hi, weight, min_s, out, s_out=None):
+        """CFG combine + x0 + exact dynamic-threshold quantile + clamp/divide + posterior mean + noise; `out` may be `x_t`."""
+        for nm, tt in (("x_t", x_t), ("eps_cond", eps_cond), ("eps_null", eps_null), ("tab_a", tab_a), ("tab_b", tab_b),
+                       ("c1", c1), ("c2", c2), ("sigma", sigma), ("noise", noise), ("out", out), ("s_out", s_out)):
+            _chk(tt, F32, nm)
+        _chk(t, I64, "t")
+        ws = None
+        nws = int(N.load().mi_step_epilogue_workspace_floats(B, n))
+        if nws:
+            ws = torch.empty(nws, dtype=F32, device=x_t.device)
+            if s_out is None:
+                s_out = torch.empty(B, dtype=F32, device=x_t.device)
+        N.call("mi_step_epilogue", N.ptr(x_t), N.ptr(eps_cond), N.ptr(eps_null), float(cond_scale), N.ptr(t), N.ptr(tab_a),
+               N.ptr(tab_b), N.ptr(c1), N.ptr(c2), N.ptr(sigma), N.ptr(noise), B, n, int(rank_lo), int(rank_hi),
+               float(weight), float(min_s), N.ptr(out), N.ptr(s_out), N.ptr(ws), N.stream())
+
+    def step_advance_t(self, t, B):
+        _chk(t, I64, "t")
+        N.call("mi_step_advance_t", N.ptr(t), B, N.stream())
+
     def step_finalize(self, x, n, unnormalize, out):
         _chk(x, F32, "x"); _chk(out, F32, "out")
         N.call("mi_step_finalize", N.ptr(x), n, int(unnormalize), N.ptr(out), N.stream())

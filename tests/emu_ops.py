@@ -326,6 +326,24 @@ class EmuOps:
         sig = torch.where(t == 0, torch.zeros_like(sigma[t]), sigma[t])[:, None]
         out.reshape(B, n).copy_(mean + sig * noise.reshape(B, n))
 
+    def step_epilogue(self, x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, c1, c2, sigma, noise, B, n, rank_lo,
+                      rank_hi, weight, min_s, out, s_out=None):
+        """contract of mi_step_epilogue == x0 -> quantile -> posterior (out may alias x_t)"""
+        self._log("step_epilogue")
+        x0 = torch.empty_like(x_t)
+        s = torch.empty(B, dtype=F32, device=x_t.device)
+        self.step_x0(x_t, eps_cond, eps_null, cond_scale, t, tab_a, tab_b, B, n, x0)
+        self.step_quantile(x0, B, n, rank_lo, rank_hi, weight, min_s, s)
+        res = torch.empty_like(x_t)
+        self.step_posterior(x0, x_t, noise, s, t, c1, c2, sigma, B, n, res)
+        out.copy_(res)
+        if s_out is not None:
+            s_out.copy_(s)
+
+    def step_advance_t(self, t, B):
+        self._log("step_advance_t")
+        t.copy_((t - 1).clamp(min=0))
+
     def step_finalize(self, x, n, unnormalize, out):
         self._log("step_finalize")
         v = x.clamp(-1., 1.)

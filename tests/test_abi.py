@@ -25,7 +25,7 @@ def test_library_exports_all_declared_symbols():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     lib.mi_abi_version.restype = ctypes.c_int
-    assert lib.mi_abi_version() == 1
+    assert lib.mi_abi_version() == 2
 
 
 def test_binding_covers_header():
