@@ -5,6 +5,7 @@
 
 #include "conv_tc.cuh"
 #include "ptx.cuh"
+#include "sat_half.cuh"
 
 namespace mi {
 namespace {
@@ -40,7 +41,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
                         const long long o = pix + (long long)(n + i) * args.out_sc;
                         if (args.residual && args.out_sc == 1) f += args.residual[o];
                         if (args.out_f32) args.out_f32[o] = f;
-                        if (args.out_f16) args.out_f16[o] = __float2half_rn(f);
+                        if (args.out_f16) args.out_f16[o] = sat_half(f);
                     }
                 }
             }
@@ -106,7 +107,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
                 st_q += (f.x * f.x + f.y * f.y) + (f.z * f.z + f.w * f.w);
                 if (args.out_f32) *reinterpret_cast<float4*>(args.out_f32 + p + n + cv) = f;
                 if (args.out_f16) {
-                    __half2 lo = __floats2half2_rn(f.x, f.y), hi = __floats2half2_rn(f.z, f.w);
+                    __half2 lo = sat_half2(f.x, f.y), hi = sat_half2(f.z, f.w);
                     uint2 pk;
                     pk.x = *reinterpret_cast<uint32_t*>(&lo);
                     pk.y = *reinterpret_cast<uint32_t*>(&hi);

@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "launch.cuh"
+#include "sat_half.cuh"
 
 namespace mi {
 
@@ -912,7 +913,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     const long long o = rowb + (long long)(i >> kTwLog2) * args.out_sh +
                                         (long long)(i & (C::kTW - 1)) * args.out_sw;
                     if (args.out_f32) args.out_f32[o] = f;
-                    if (args.out_f16) args.out_f16[o] = __float2half_rn(f);
+                    if (args.out_f16) args.out_f16[o] = sat_half(f);
                 }
             }
             if (args.stats) {

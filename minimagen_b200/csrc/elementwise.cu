@@ -8,6 +8,7 @@
 
 #include "kernels.cuh"
 #include "launch.cuh"
+#include "sat_half.cuh"
 
 namespace mi {
 
@@ -50,7 +51,7 @@ __device__ __forceinline__ void load_cat8(const T* __restrict__ src0, int C0, co
 }
 
 __device__ __forceinline__ uint2 pack_half4(float a, float b, float c, float d) {
-    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    __half2 lo = sat_half2(a, b), hi = sat_half2(c, d);
     uint2 r;
     r.x = *reinterpret_cast<uint32_t*>(&lo);
     r.y = *reinterpret_cast<uint32_t*>(&hi);
@@ -369,7 +370,7 @@ linear_f32_kernel(const float* __restrict__ in, int M, int K, const float* __res
             if (out_act == 1) y = silu_f(y);
             y *= out_scale;
             if (out_f32) out_f32[oi] = y;
-            if (out_f16) out_f16[oi] = __float2half_rn(y);
+            if (out_f16) out_f16[oi] = sat_half(y);
         }
     }
 }
@@ -448,7 +449,7 @@ linear_tiled_kernel(const float* __restrict__ in, int M, int K, const float* __r
             if (out_act == 1) y = silu_f(y);
             y *= out_scale;
             if (out_f32) out_f32[oi] = y;
-            if (out_f16) out_f16[oi] = __float2half_rn(y);
+            if (out_f16) out_f16[oi] = sat_half(y);
         }
     }
 }
@@ -583,7 +584,7 @@ stem_unroll_kernel(const float* __restrict__ a, int Ca, const float* __restrict_
                 if (c < Ca) f = a[((b * Ca + c) * H + h) * W + ws];
                 else if (c < Ca + Cb) f = b2[((b * Cb + (c - Ca)) * H + h) * W + ws];
             }
-            v[c] = __float2half_rn(f);
+            v[c] = sat_half(f);
         }
         s_px[r][t] = *reinterpret_cast<const uint4*>(v);
     }

@@ -10,8 +10,11 @@ namespace mi {
 bool pdl_enabled();          // capi.cu (mi_set_launch_mode)
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the NEXT kernel of the stream be scheduled (on SMs this grid no longer occupies) as soon as every CTA of this grid
+// has passed this point; the dependent still blocks in pdl_wait() until this grid has completed and flushed its memory, so
+// only its private prologue overlaps.  A no-op unless the dependent was launched with the programmatic-serialization attribute.
 __device__ __forceinline__ void pdl_trigger() {
-#ifdef MI_PDL_EARLY_TRIGGER
+#ifndef MI_PDL_NO_EARLY_TRIGGER
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }

@@ -543,3 +543,77 @@ def test_step_kernels_vs_golden(native, T):
     sa = g["tables"]["sqrt_alphas_cumprod"][g["t"]].reshape(3, 1, 1, 1)
     sb = g["tables"]["sqrt_one_minus_alphas_cumprod"][g["t"]].reshape(3, 1, 1, 1)
     assert torch.equal(q.cpu(), sa * g["x"] + sb * g["noise"])
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+@pytest.mark.parametrize("case", [(2, 32, 32, 64, 128), (1, 64, 64, 128, 256), (3, 16, 16, 256, 512)])
+def test_conv_igemm_mode6_inplace_downsample(native, case):
+    """ABI mode 6: the 4x4 stride-2 pad-1 Downsample conv reading the un-split fp16 input in place (TMA element strides)."""
+    B, H, W, Cin, Cout = case                         # (H, W) = OUTPUT grid, input is 2H x 2W
+    act = _rand(B, 1, 2 * H, 2 * W, Cin, seed=21).to(F16)
+    w = _rand(Cout, Cin, 4, 4, seed=22, scale=(16 * Cin) ** -0.5)
+    b = _rand(Cout, seed=23)
+    wp = EMU.pack_conv_weight(w)
+    strides = (H * W * Cout, W * Cout, Cout)
+    o_e = torch.zeros(B, H, W, Cout)
+    EMU.conv_igemm(act, B, H, W, Cin, 0, Cin, wp, Cout, 4, 4, 6, b, None, o_e, None, strides)
+    o_n = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    st = torch.zeros(B, Cout // 16, 2, dtype=F64, device="cuda")
+    native.conv_igemm(act.cuda(), B, H, W, Cin, 0, Cin, wp.cuda(), Cout, 4, 4, 6, b.cuda(), None, o_n, None, strides,
+                      out_stats=st)
+    assert rel_l2(o_n, o_e) < 2e-5
+    ref_st = o_e.double().reshape(B, H * W, Cout // 16, 16)
+    assert rel_l2(st[:, :, 0], ref_st.sum(dim=(1, 3))) < 1e-4 and rel_l2(st[:, :, 1], (ref_st ** 2).sum(dim=(1, 3))) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 128, 64, 128, 1), (1, 32, 32, 64, 192, 256, 1), (2, 32, 32, 128, 128, 128, 3)])
+def test_conv_igemm_two_source_virtual_concat(native, case):
+    """1x1 (res_conv of the up path) and 3x3 convs over the VIRTUAL concat of two activation tensors (act / act2)."""
+    B, H, W, C0, C1, Cout, k = case
+    a0 = _rand(B, 1, H, W, C0, seed=31).to(F16)
+    a1 = _rand(B, 1, H, W, C1, seed=32).to(F16)
+    w = _rand(Cout, C0 + C1, k, k, seed=33, scale=(k * k * (C0 + C1)) ** -0.5)
+    wp = EMU.pack_conv_weight(w)
+    strides = (H * W * Cout, W * Cout, Cout)
+    o_e = torch.zeros(B, H, W, Cout)
+    EMU.conv_igemm(a0, B, H, W, C0, 0, C0 + C1, wp, Cout, k, k, 0, None, None, o_e, None, strides, act2=a1, lda2=C1,
+                   c_in1=C0)
+    o_n = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    native.conv_igemm(a0.cuda(), B, H, W, C0, 0, C0 + C1, wp.cuda(), Cout, k, k, 0, None, None, o_n, None, strides,
+                      act2=a1.cuda(), lda2=C1, c_in1=C0)
+    assert rel_l2(o_n, o_e) < 2e-5
+
+
+@pytest.mark.parametrize("B,n,cfg", [(3, 3 * 64 * 64, True), (2, 3 * 256 * 256, False), (1, 3 * 272 * 272, True)])
+def test_step_epilogue_fused_is_bit_exact(native, B, n, cfg):
+    """mi_step_epilogue (one cluster kernel; or, beyond 196 608 values per image, its three-kernel form) == the x0 ->
+    quantile -> posterior chain bit for bit, also when it updates x_t in place; mi_step_advance_t."""
+    from minimagen_b200.Imagen import quantile_rank
+    from oracle import restatement as R
+    tabs = {k: v.cuda() for k, v in R.ddpm_tables(1000).items()}
+    sigma = torch.exp(0.5 * tabs["posterior_log_variance_clipped"])
+    g = torch.Generator().manual_seed(B * 7 + n)
+    x = (torch.randn(B, n, generator=g) * 1.3).cuda()
+    eps = torch.randn(B, n, generator=g).cuda()
+    eps0 = torch.randn(B, n, generator=g).cuda() if cfg else None
+    noise = torch.randn(B, n, generator=g).cuda()
+    t = torch.tensor([999, 0, 417][:B]).cuda()
+    lo, hi, w = quantile_rank(n, 0.9)
+    x0 = torch.empty_like(x)
+    s = torch.empty(B, device="cuda")
+    ref = torch.empty_like(x)
+    a, b_ = tabs["sqrt_recip_alphas_cumprod"], tabs["sqrt_recipm1_alphas_cumprod"]
+    c1, c2 = tabs["posterior_mean_coef1"], tabs["posterior_mean_coef2"]
+    native.step_x0(x, eps, eps0, 7.0, t, a, b_, B, n, x0)
+    native.step_quantile(x0, B, n, lo, hi, w, 1.0, s)
+    native.step_posterior(x0, x, noise, s, t, c1, c2, sigma, B, n, ref)
+    out = torch.empty_like(x)
+    s2 = torch.empty(B, device="cuda")
+    native.step_epilogue(x, eps, eps0, 7.0, t, a, b_, c1, c2, sigma, noise, B, n, lo, hi, w, 1.0, out, s_out=s2)
+    assert torch.equal(out, ref) and torch.equal(s2, s)
+    xin = x.clone()
+    native.step_epilogue(xin, eps, eps0, 7.0, t, a, b_, c1, c2, sigma, noise, B, n, lo, hi, w, 1.0, xin)   # in place
+    assert torch.equal(xin, ref)
+    tt = t.clone()
+    native.step_advance_t(tt, B)
+    assert torch.equal(tt, (t - 1).clamp(min=0))
