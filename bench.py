@@ -548,12 +548,13 @@ def main():
         torch.cuda.empty_cache()
         common = dict(world=world, rank=rank, dev=dev, peak_tf=peak_tf)
 
-        def guarded(key, fn):
+        def guarded(key, fn, model=None):
             try:
                 secondary[key] = fn()
             except Exception as ex:              # a secondary row must never take the headline down
                 secondary[key] = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
-            imagen.clear_graphs()
+            if model is not None:
+                model.clear_graphs()
             torch.cuda.empty_cache()
             print(f"[bench] secondary {key}: {json.dumps(secondary[key])[:300]}", file=sys.stderr, flush=True)
 
@@ -561,7 +562,7 @@ def main():
             w2 = workload("cfg2a")
             guarded("cfg2a", lambda: dict(measure_config(
                 imagen, imagen.unets[0], w2, "cfg2a", per_gpu=64, micro=64, cond_scale=1.0, cfg_batched=False, steps=10,
-                warmup=3, global_batch=64 * world, scaling="weak", **common), workload=w2["desc"]))
+                warmup=3, global_batch=64 * world, scaling="weak", **common), workload=w2["desc"]), imagen)
         if "cfg4" in sec_list and 128 % world == 0:
             per = 128 // world
             w2, w3 = workload("cfg2a"), workload("cfg3")
@@ -591,7 +592,7 @@ def main():
                 r["note"] = ("both stages run T=1000 steps: cascade throughput = 1 / (base ms/step + SR ms/step); per-GPU batch "
                              f"{per} as micro-batches of <= 64 (base) / 32 (SR)")
                 return r
-            guarded("cfg4", cascade)
+            guarded("cfg4", cascade, imagen)
         # the remaining rows need their own models: release the headline model first
         del imagen, unet
         if use_graph:

@@ -91,11 +91,13 @@ int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c
 long long mi_conv2d_igemm_workspace_bytes(void);
 
 /* Fused Block.forward (layers.py:131-145): GroupNorm -> (scale + 1, shift) -> SiLU -> Conv2d 3x3 in ONE kernel; the
- * normalised tensor never exists in HBM.  The raw fp32 NHWC input (optionally the virtual concat cat(src0, src1*scale1),
- * Unet.py:445) is fetched as halo tiles by TMA, transformed to the fp16 tensor-core operand in shared memory
- * (GroupNorm mean/rstd from the producers' 16-channel block statistics stats0/stats1 = out_stats of the convs that wrote
- * src0/src1), and convolved on tcgen05.  Epilogue as mi_conv2d_igemm_f16 (bias, fp32 residual, fp32/fp16 outputs
- * [B][H][W][c_out] contiguous, out_stats).  Requirements: mi_conv3x3_gn_supported (H % 16 == 0, W % 8 == 0,
+ * normalised tensor never exists in HBM.  The swapped-operand 3x3 halo convolution (weights = M, 256 pixels = N) with the TMA
+ * load of its activation halo replaced by a prologue: eight warps read the raw fp32 NHWC input (optionally the virtual
+ * concat cat(src0, src1*scale1), Unet.py:445) straight from global memory, apply y = SiLU(x*A[b,c] + B[b,c]) (GroupNorm
+ * mean/rstd from the producers' 16-channel block statistics stats0/stats1 = out_stats of the convs that wrote src0/src1,
+ * affine, FiLM and skip scale folded into A, B) and write the fp16 operand directly in the 128B-swizzled layout tcgen05.mma
+ * reads; zero padding is applied to the ACTIVATED tensor.  Epilogue as mi_conv2d_igemm_f16 (bias, fp32 residual, fp32/fp16
+ * outputs [B][H][W][c_out] contiguous, out_stats).  Requirements: mi_conv3x3_gn_supported (H % 32 == 0, W % 8 == 0,
  * c0 % 64 == 0, c1 % 64 == 0, c_out % 128 == 0, (c0+c1)/groups % 16 == 0). */
 int mi_conv3x3_gn_supported(int H, int W, int c0, int c1, int c_out, int groups);
 int mi_conv3x3_gn_silu_f16(const float* src0, int c0, const float* src1, int c1, float scale1, int B, int H, int W,

@@ -76,6 +76,8 @@ long long conv_tc_splitk_bytes();
 
 // GroupNorm / FiLM / SiLU prologue of the fused Block kernel (conv_gn.cu)
 struct GnPrologueArgs {
+    const float* src0;            // fp32 NHWC [B][H][W][C0]
+    const float* src1;            // fp32 NHWC [B][H][W][C1] or null
     int C0, C1, groups;           // channels of source 0 / source 1 (virtual concat), GroupNorm groups
     float scale1, eps;            // source-1 scale (skip connection 2^-1/2), GroupNorm eps
     const double* stats0;         // [B][C0/16][2] block statistics of source 0

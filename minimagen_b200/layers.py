@@ -9,6 +9,7 @@ NHWC fp32 activations `[B, H, W, C]` and makes C-ABI calls via `minimagen_b200.o
 simply wraps `run`.  Inference only: there is no autograd through the kernels (training is SURVEY.md 8f-2, "next").
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -28,10 +29,9 @@ STATS_BLOCK = 16   # channels per GroupNorm block-statistics entry written by th
 # element written and re-read; ~5 % faster steps) at 1.05e-3 rel-L2.
 GN_INPUT_F32 = True
 
-# Block.forward as ONE kernel (GroupNorm/FiLM/SiLU in the conv's shared-memory prologue) where the geometry allows
-FUSE_GN_CONV = False         # False: never; True: only where C_out is not a multiple of 256 (N=128 tiles); 'all': everywhere.
-#                          Measured on cfg 3 (B200, ms/step): off 32.9, N=128 layers 34.4, all 38.4 -- the 4 transform warps
-#                          and the single-CTA halo main loop do not yet beat the CTA-pair conv + stand-alone apply kernel.
+# Block.forward as ONE kernel (GroupNorm/FiLM/SiLU as the conv's prologue: mi_conv3x3_gn_silu_f16) where the geometry allows
+# (3x3, H % 32 == 0, W % 8 == 0, channels % 64, C_out % 128, fp32 sources with epilogue block statistics)
+FUSE_GN_CONV = os.environ.get("MI_FUSE_GN_CONV", "0") == "1"
 
 # nearest-x2 upsample + 3x3 conv as four 2x2 sub-pixel convs on the low-res tensor (4/9 of the FLOPs, no upsampled copy)
 SUBPIXEL_UPSAMPLE = True
@@ -633,8 +633,7 @@ class Block(nn.Module):
         tc = self.project.tc_ok(H, W)
         parts = [x.a, x.b] if isinstance(x, Cat) else [x]
         block_mode = tc and Cg % STATS_BLOCK == 0 and all(p.shape[3] % STATS_BLOCK == 0 for p in parts)
-        if (block_mode and FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or self.project.out_channels % 256 != 0)
-                and all(p.f32 is not None for p in parts)
+        if (block_mode and FUSE_GN_CONV and all(p.f32 is not None for p in parts)
                 and ops.conv_gn_supported(H, W, parts[0].shape[3], parts[1].shape[3] if len(parts) > 1 else 0,
                                           self.project.out_channels, G)):
             # one kernel: GroupNorm/FiLM/SiLU as the conv's shared-memory prologue (mi_conv3x3_gn_silu_f16)

@@ -110,7 +110,7 @@ class EmuOps:
 
     def conv_gn_supported(self, H, W, c0, c1, c_out, groups):
         C = c0 + c1
-        return (H % 16 == 0 and W % 8 == 0 and c0 % 64 == 0 and c1 % 64 == 0 and C > 0 and c_out % 128 == 0
+        return (H % 32 == 0 and W % 8 == 0 and c0 > 0 and c0 % 64 == 0 and c1 % 64 == 0 and C > 0 and c_out % 128 == 0
                 and 1 <= groups <= 32 and C % groups == 0 and (C // groups) % 16 == 0)
 
     def conv_gn(self, src0, c0, src1, c1, scale1, B, H, W, groups, stats0, stats1, gamma, beta, scale_shift, ss_ld, eps,

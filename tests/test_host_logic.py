@@ -274,3 +274,32 @@ def test_cfg_as_one_batch_matches_two_forwards(emu):
                               lowres_sample_noise_level=g["lowres_noise_level"]))
     assert rel_l2(outs[1], outs[0]) < 1e-5
     assert rel_l2(outs[1], g["out"]) < 1e-3
+
+
+def test_fused_groupnorm_conv_orchestration(emu):
+    """layers.FUSE_GN_CONV routes Block.forward through conv_gn (one call instead of gn_apply_silu + conv_igemm) wherever
+    the geometry allows, with the same result as the un-fused lowering."""
+    from minimagen_b200 import layers
+    from minimagen_b200.Unet import Unet
+    cfg = dict(dim=128, dim_mults=(1, 2), num_resnet_blocks=(1, 1), layer_attns=False, layer_cross_attns=(False, True),
+               lowres_cond=True, memory_efficient=True, text_embed_dim=512)
+    torch.manual_seed(0)
+    u = Unet(**cfg).eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 3, 64, 64, generator=g)
+    kw = dict(text_embeds=torch.randn(1, 9, 512, generator=g), text_mask=torch.ones(1, 9, dtype=torch.bool),
+              lowres_cond_img=torch.randn(1, 3, 64, 64, generator=g), lowres_noise_times=torch.tensor([200]))
+    t = torch.tensor([321])
+    prev = layers.FUSE_GN_CONV
+    try:
+        with torch.no_grad():
+            layers.FUSE_GN_CONV = False
+            a = u(x, t, **kw)
+            n_apply = emu.calls.count("gn_apply_silu")
+            emu.calls.clear()
+            layers.FUSE_GN_CONV = True
+            b = u(x, t, **kw)
+    finally:
+        layers.FUSE_GN_CONV = prev
+    assert emu.calls.count("conv_gn") > 0 and emu.calls.count("gn_apply_silu") < n_apply
+    assert rel_l2(b, a) < 1e-5
