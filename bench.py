@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--no-torch-gpu", action="store_true")
     ap.add_argument("--secondary", default="cfg1,cfg2a,cfg2b,cfg4,cfg5", help="comma list of secondary configurations")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--fuse", default=None, choices=["off", "on"], help="fused GroupNorm+conv kernel usage")
+    ap.add_argument("--fuse", default=None, choices=["off", "on", "all"], help="fused GroupNorm+conv kernel usage")
     ap.add_argument("--kernel-table", default=None, help="write a CUPTI per-kernel time table of 3 steps to this path")
     ap.add_argument("--pdl", type=int, default=None, help="programmatic dependent launch on (1) / off (0)")
     ap.add_argument("--gn-f16", action="store_true", help="GroupNorm inputs in fp16 (faster, 1.05e-3 instead of 9e-4 rel-L2)")
@@ -392,7 +392,7 @@ def main():
     if args.gn_f16:
         layers.GN_INPUT_F32 = False
     if args.fuse is not None:
-        layers.FUSE_GN_CONV = args.fuse == "on"
+        layers.FUSE_GN_CONV = {"off": False, "on": True, "all": "all"}[args.fuse]
     ops = __import__("minimagen_b200.ops", fromlist=["get_ops"]).get_ops()
 
     peaks = {}
@@ -684,7 +684,7 @@ def main():
                 "d2h_bytes_per_step": int(out_host.numel() * 4)},
         "roofline": roofline,
         "clocks": clocks, "cuda_graph": use_graph, "launches_per_step": launches_per_step,
-        "fused_gn_conv": bool(layers.FUSE_GN_CONV), "gn_input": "f32" if layers.GN_INPUT_F32 else "f16",
+        "fused_gn_conv": layers.FUSE_GN_CONV, "gn_input": "f32" if layers.GN_INPUT_F32 else "f16",
         "peak_mem_gb": peak_mem,
         "weight_ingestion": {"first_step_s": first_step_s, "eager_step_s": eager_step_s,
                              "note": "first step = lazy fp16 weight pack of all layers (checkpoint fp32 (C_out,C_in,kh,kw) -> "

@@ -236,6 +236,45 @@ int mi_q_sample(const float* x0, const float* noise, const long long* t, const f
                 const float* sqrt_one_minus_alphas_cumprod, int B, int n, float post_scale, float post_shift,
                 float* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------- training (backward)
+ * The training side of the same path: Imagen.forward / _p_losses (Imagen.py:512-650) back-propagate through Unet.forward
+ * (train.py:103 -> training.py:368).  minimagen_b200/autograd.py wraps every forward entry point above in a
+ * torch.autograd.Function whose backward calls the entry points below (or, for the data gradient of tensor-core-shaped
+ * convolutions, mi_conv2d_igemm_f16 itself on flipped / transposed packed weights).  All fp32, NHWC. */
+
+/* C[z] (+)= alpha * A[z] x B[z] with explicit element strides: A(m,k) at A + z1*a_b1 + z2*a_b2 + m*a_sm + k*a_sk,
+ * B(k,n) at B + ... + k*b_sk + n*b_sn, C(m,n) at C + ... + m*c_sm + n*c_sn; batch z = z1*Z2 + z2.
+ * nn.Linear backward (dX = dY W, dW = dY^T X) and the fp32 attention of the training path (S = q k^T, dP = dO v^T,
+ * dq = dS k, dk = dS^T q, dv = P^T dO; layers.py:79-99, :239-248). */
+int mi_gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, long long a_sm, long long a_sk,
+                long long b_sk, long long b_sn, long long c_sm, long long c_sn, int Z1, int Z2, long long a_b1,
+                long long a_b2, long long b_b1, long long b_b2, long long c_b1, long long c_b2, float alpha,
+                int accumulate, void* stream);
+/* out[n] (+)= sum_m x[m][n]  (bias gradients) */
+int mi_colsum_f32(const float* x, long long M, int N, float* out, int accumulate, void* stream);
+/* dL/dx of nn.Conv2d(c_in, c_out, (kh, kw), stride, pad): dy [B][Hout][Wout][c_out], w OIHW, dx [B][Hin][Win][c_in] */
+int mi_conv2d_dgrad_f32(const float* dy, int B, int Hout, int Wout, int c_out, const float* w_oihw, int c_in, int kh, int kw,
+                        int stride, int pad, float* dx, int Hin, int Win, void* stream);
+/* dL/dW of the same conv: x [B][Hin][Win][c_in], dy [B][Hout][Wout][c_out] -> dw OIHW (overwritten) */
+int mi_conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hin, int Win, int c_in, int Hout, int Wout, int c_out,
+                        int kh, int kw, int stride, int pad, float* dw, void* stream);
+/* Backward of mi_gn_apply_silu over ONE fp32 source x [B][hw][C] (sums = mi_gn_stats group sums [B][groups][2]):
+ * dx; dgamma / dbeta ACCUMULATED into (caller zeroes or carries .grad); d_scale_shift [B][.. ld ..] = [d scale(C) | d shift(C)]
+ * or NULL; workspace: (2*B*C + 2*B*groups) floats. */
+int mi_gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int hw, int C, int groups,
+                   const float* gamma, const float* beta, const float* scale_shift, int scale_shift_ld, float eps,
+                   float* dx, float* dgamma, float* dbeta, float* d_scale_shift, int d_scale_shift_ld, float* workspace,
+                   void* stream);
+/* Backward of mi_ln_rows (without its residual, which passes the gradient through): dx [R][C]; dgamma / dbeta accumulated
+ * (either may be NULL). */
+int mi_ln_rows_bwd(const float* in, const float* dy, long long rows, int C, const float* gamma, float eps, int pre_gelu,
+                   float* dx, float* dgamma, float* dbeta, void* stream);
+/* in-place row softmax of s [R][L], and its backward dS = P * (dP - sum_j P dP) written over dP */
+int mi_softmax_rows(float* s, long long R, int L, void* stream);
+int mi_softmax_rows_bwd(const float* P, float* dP, long long R, int L, void* stream);
+/* backward of nn.Upsample(scale_factor=2, 'nearest'): dy [B][2H][2W][C] -> dx [B][H][W][C] */
+int mi_upsample2x_bwd(const float* dy, int B, int H, int W, int C, float* dx, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

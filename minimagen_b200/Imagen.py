@@ -449,14 +449,77 @@ class Imagen(nn.Module):
         import torchvision.transforms as T
         return list(map(T.ToPILImage(), outputs.unbind(dim=0)))
 
-    # -------------------------------------------------------------------------------------------- training (next row)
-    def _p_losses(self, *args, **kwargs):
-        raise NotImplementedError(
-            "Imagen._p_losses / forward (the training loss, reference Imagen.py:512-650) need backward kernels for the "
-            "U-Net; that is SURVEY.md 8f-2, the next row after the sampling hot path. Not built yet.")
+    # -------------------------------------------------------------------------------------------- training
+    def _p_losses(self, unet, x_start, times, *, noise_scheduler, lowres_cond_img=None, lowres_aug_times=None,
+                  text_embeds=None, text_mask=None, noise=None):
+        """Forward-diffuse the training images, predict the noise with `unet` and return the loss (reference
+        Imagen.py:512-573).  The U-Net call runs under autograd (minimagen_b200/train_path.py): `loss.backward()` reaches every
+        parameter through the library's backward kernels."""
+        ops = get_ops()
+        with N.device_of(x_start):
+            x_start = x_start.to(F32)
+            noise = default(noise, lambda: self._noise('train_noise', x_start.shape, -1, x_start.device))
+            x_start = self.normalize_img(x_start).contiguous()
+            lowres_cond_img = maybe(self.normalize_img)(lowres_cond_img)
+            B, n = x_start.shape[0], x_start[0].numel()
+            x_noisy = torch.empty_like(x_start)
+            ops.q_sample(x_start, noise.to(F32).contiguous(), times, noise_scheduler.sqrt_alphas_cumprod,
+                         noise_scheduler.sqrt_one_minus_alphas_cumprod, B, n, 1.0, 0.0, x_noisy)
+            lowres_noisy = None
+            if exists(lowres_cond_img):
+                lowres_aug_times = default(lowres_aug_times, times)
+                sch = self.lowres_noise_schedule
+                lowres_cond_img = lowres_cond_img.to(F32).contiguous()
+                aug = self._noise('train_lowres_noise', lowres_cond_img.shape, -1, lowres_cond_img.device)
+                lowres_noisy = torch.empty_like(lowres_cond_img)
+                ops.q_sample(lowres_cond_img, aug, lowres_aug_times, sch.sqrt_alphas_cumprod,
+                             sch.sqrt_one_minus_alphas_cumprod, B, lowres_cond_img[0].numel(), 1.0, 0.0, lowres_noisy)
+            pred = unet.forward(x_noisy, times, text_embeds=text_embeds, text_mask=text_mask,
+                                lowres_noise_times=lowres_aug_times, lowres_cond_img=lowres_noisy,
+                                cond_drop_prob=self.cond_drop_prob)
+            return self.loss_fn(pred, noise)
 
     def forward(self, images, texts: List[str] = None, text_embeds=None, text_masks=None, unet_number: int = None):
+        """Training step: noise the images and return the U-Net's noise-prediction loss (reference Imagen.py:575-650)."""
         assert not (len(self.unets) > 1 and not exists(unet_number)), \
             f'you must specify which unet you want trained, from a range of 1 to {len(self.unets)}, ' \
             f'if you are training cascading DDPM (multiple unets)'
-        return self._p_losses()
+        unet_number = default(unet_number, 1)
+        assert not exists(self.only_train_unet_number) or self.only_train_unet_number == unet_number, \
+            f'you can only train on unet #{self.only_train_unet_number}'
+
+        unet_index = unet_number - 1
+        unet = self._get_unet(unet_number)
+        noise_scheduler = self.noise_schedulers[unet_index]
+        target_image_size = self.image_sizes[unet_index]
+        prev_image_size = self.image_sizes[unet_index - 1] if unet_index > 0 else None
+        b, c, h, w = images.shape
+        device = images.device
+        assert images.dim() == 4 and c == self.channels, f'images must be (b, {self.channels}, h, w)'
+        assert h >= target_image_size and w >= target_image_size
+
+        times = noise_scheduler._sample_random_times(b, device=device)
+
+        if exists(texts) and not exists(text_embeds):
+            assert len(texts) == len(images), 'number of text captions does not match up with the number of images given'
+            text_embeds, text_masks = t5_encode_text(texts, name=self.text_encoder_name)
+            text_embeds, text_masks = map(lambda t: t.to(images.device), (text_embeds, text_masks))
+
+        assert exists(text_embeds), 'text or text encodings must be passed into decoder'
+        assert not (exists(text_embeds) and text_embeds.shape[-1] != self.text_embed_dim), \
+            f'invalid text embedding dimension being passed in (should be {self.text_embed_dim})'
+
+        lowres_cond_img = lowres_aug_times = None
+        with N.device_of(images):
+            if exists(prev_image_size):
+                lowres_cond_img = resize_image_to(images, prev_image_size, clamp_range=self.input_image_range,
+                                                  pad_mode='reflect')
+                lowres_cond_img = resize_image_to(lowres_cond_img, target_image_size, clamp_range=self.input_image_range,
+                                                  pad_mode='reflect')
+                lowres_aug_time = self.lowres_noise_schedule._sample_random_times(1, device=device)
+                lowres_aug_times = lowres_aug_time.repeat(b)
+            images = resize_image_to(images, target_image_size)
+
+        return self._p_losses(unet, images, times, text_embeds=text_embeds, text_mask=text_masks,
+                              noise_scheduler=noise_scheduler, lowres_cond_img=lowres_cond_img,
+                              lowres_aug_times=lowres_aug_times)

@@ -175,6 +175,10 @@ class Unet(nn.Module):
     def _forward_impl(self, x, *args, **kwargs):
         # kernels are enqueued on the current device's stream: make the input's device current for the duration
         with _native.device_of(x):
+            if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+                # training side of the path: the same network through the autograd Functions
+                from .train_path import unet_forward_train
+                return unet_forward_train(self, x, *args, **kwargs)
             return self._forward_dev(x, *args, **kwargs)
 
     def _forward_dev(self, x, time, *, lowres_cond_img=None, lowres_noise_times=None, text_embeds=None, text_mask=None,
@@ -187,7 +191,6 @@ class Unet(nn.Module):
             'low resolution conditioning image must be present'
         assert not (self.lowres_cond and not exists(lowres_noise_times)), \
             'low resolution conditioning noise time must be present'
-        _no_grad_check(x, self.null_text_embed)
         B, Cx, H, W = x.shape
         device = x.device
         x = x.to(F32).contiguous()

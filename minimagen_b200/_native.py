@@ -52,6 +52,16 @@ SIGNATURES = {
     "mi_step_advance_t": [_P, _I, _P],
     "mi_step_finalize": [_P, _L, _I, _P, _P],
     "mi_q_sample": [_P, _P, _P, _P, _P, _I, _I, _F, _F, _P, _P],
+    # training side (backward)
+    "mi_gemm_f32": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _I, _L, _L, _L, _L, _L, _L, _F, _I, _P],
+    "mi_colsum_f32": [_P, _L, _I, _P, _I, _P],
+    "mi_conv2d_dgrad_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
+    "mi_conv2d_wgrad_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mi_gn_silu_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _P, _P],
+    "mi_ln_rows_bwd": [_P, _P, _L, _I, _P, _F, _I, _P, _P, _P, _P],
+    "mi_softmax_rows": [_P, _L, _I, _P],
+    "mi_softmax_rows_bwd": [_P, _P, _L, _I, _P],
+    "mi_upsample2x_bwd": [_P, _I, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {"mi_last_error": c_char_p, "mi_conv2d_igemm_workspace_bytes": c_longlong,
              "mi_attention_workspace_bytes": c_longlong, "mi_step_epilogue_workspace_floats": c_longlong}

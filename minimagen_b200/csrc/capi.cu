@@ -276,4 +276,47 @@ int mi_q_sample(const float* x0, const float* noise, const long long* t, const f
     return check(mi::q_sample(x0, noise, t, tab_a, tab_b, B, n, post_scale, post_shift, out, S(stream)), "mi_q_sample");
 }
 
+int mi_gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, long long a_sm, long long a_sk,
+                long long b_sk, long long b_sn, long long c_sm, long long c_sn, int Z1, int Z2, long long a_b1,
+                long long a_b2, long long b_b1, long long b_b2, long long c_b1, long long c_b2, float alpha,
+                int accumulate, void* stream) {
+    return check(mi::gemm_f32(A, B, C, M, N, K, a_sm, a_sk, b_sk, b_sn, c_sm, c_sn, Z1, Z2, a_b1, a_b2, b_b1, b_b2, c_b1, c_b2,
+                              alpha, accumulate, S(stream)),
+                 "mi_gemm_f32");
+}
+int mi_colsum_f32(const float* x, long long M, int N, float* out, int accumulate, void* stream) {
+    return check(mi::colsum_f32(x, M, N, out, accumulate, S(stream)), "mi_colsum_f32");
+}
+int mi_conv2d_dgrad_f32(const float* dy, int B, int Hout, int Wout, int c_out, const float* w, int c_in, int kh, int kw,
+                        int stride, int pad, float* dx, int Hin, int Win, void* stream) {
+    return check(mi::conv2d_dgrad_f32(dy, B, Hout, Wout, c_out, w, c_in, kh, kw, stride, pad, dx, Hin, Win, S(stream)),
+                 "mi_conv2d_dgrad_f32");
+}
+int mi_conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hin, int Win, int c_in, int Hout, int Wout, int c_out,
+                        int kh, int kw, int stride, int pad, float* dw, void* stream) {
+    return check(mi::conv2d_wgrad_f32(dy, x, B, Hin, Win, c_in, Hout, Wout, c_out, kh, kw, stride, pad, dw, S(stream)),
+                 "mi_conv2d_wgrad_f32");
+}
+int mi_gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int hw, int C, int groups,
+                   const float* gamma, const float* beta, const float* scale_shift, int scale_shift_ld, float eps,
+                   float* dx, float* dgamma, float* dbeta, float* d_scale_shift, int d_scale_shift_ld, float* workspace,
+                   void* stream) {
+    return check(mi::gn_silu_bwd(x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, scale_shift_ld, eps, dx, dgamma,
+                                 dbeta, d_scale_shift, d_scale_shift_ld, workspace, S(stream)),
+                 "mi_gn_silu_bwd");
+}
+int mi_ln_rows_bwd(const float* in, const float* dy, long long rows, int C, const float* gamma, float eps, int pre_gelu,
+                   float* dx, float* dgamma, float* dbeta, void* stream) {
+    return check(mi::ln_rows_bwd(in, dy, rows, C, gamma, eps, pre_gelu, dx, dgamma, dbeta, S(stream)), "mi_ln_rows_bwd");
+}
+int mi_softmax_rows(float* s, long long R, int L, void* stream) {
+    return check(mi::softmax_rows(s, R, L, S(stream)), "mi_softmax_rows");
+}
+int mi_softmax_rows_bwd(const float* P, float* dP, long long R, int L, void* stream) {
+    return check(mi::softmax_rows_bwd(P, dP, R, L, S(stream)), "mi_softmax_rows_bwd");
+}
+int mi_upsample2x_bwd(const float* dy, int B, int H, int W, int C, float* dx, void* stream) {
+    return check(mi::upsample2x_bwd(dy, B, H, W, C, dx, S(stream)), "mi_upsample2x_bwd");
+}
+
 }  // extern "C"

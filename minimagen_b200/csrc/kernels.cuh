@@ -77,4 +77,22 @@ int step_finalize(const float* x, long long n, int unnormalize, float* out, cuda
 int q_sample(const float* x0, const float* noise, const long long* t, const float* tab_a, const float* tab_b, int B,
              int n_per_img, float post_scale, float post_shift, float* out, cudaStream_t st);
 
+// backward.cu: fp32 backward kernels of the training side
+int gemm_f32(const float* A, const float* B, float* C, int M, int N, int K, long long a_sm, long long a_sk, long long b_sk,
+             long long b_sn, long long c_sm, long long c_sn, int Z1, int Z2, long long a_b1, long long a_b2, long long b_b1,
+             long long b_b2, long long c_b1, long long c_b2, float alpha, int accumulate, cudaStream_t st);
+int colsum_f32(const float* x, long long M, int N, float* out, int accumulate, cudaStream_t st);
+int conv2d_dgrad_f32(const float* dy, int B, int Ho, int Wo, int Cout, const float* w, int Cin, int KH, int KW, int stride,
+                     int pad, float* dx, int Hi, int Wi, cudaStream_t st);
+int conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hi, int Wi, int Cin, int Ho, int Wo, int Cout, int KH,
+                     int KW, int stride, int pad, float* dw, cudaStream_t st);
+int gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int HW, int C, int groups, const float* gamma,
+                const float* beta, const float* ss, int ss_ld, float eps, float* dx, float* dgamma, float* dbeta,
+                float* dss, int dss_ld, float* workspace, cudaStream_t st);
+int ln_rows_bwd(const float* in, const float* dy, long long R, int C, const float* gamma, float eps, int pre_gelu, float* dx,
+                float* dgamma, float* dbeta, cudaStream_t st);
+int softmax_rows(float* s, long long R, int L, cudaStream_t st);
+int softmax_rows_bwd(const float* P, float* dP, long long R, int L, cudaStream_t st);
+int upsample2x_bwd(const float* dy, int B, int H, int W, int C, float* dx, cudaStream_t st);
+
 }  // namespace mi

@@ -31,7 +31,11 @@ GN_INPUT_F32 = True
 
 # Block.forward as ONE kernel (GroupNorm/FiLM/SiLU as the conv's prologue: mi_conv3x3_gn_silu_f16) where the geometry allows
 # (3x3, H % 32 == 0, W % 8 == 0, channels % 64, C_out % 128, fp32 sources with epilogue block statistics)
-FUSE_GN_CONV = os.environ.get("MI_FUSE_GN_CONV", "0") == "1"
+# True: where it pays -- C_out == 128 (one channel tile per pixel tile: every activation element is transformed once; these are
+# the full-resolution, output-bound layers that also carry most of the GroupNorm-apply traffic).  'all': wherever supported (with
+# C_out = 256..1024 every one of the 2..8 channel tiles re-does the transform and the prologue warps, not the tensor pipe, set
+# the pace: measured 18.2 ms vs 10.4 + 4.0 ms for the 70 G32x8 layers of cfg 3).  False: never.
+FUSE_GN_CONV = {"0": False, "1": True, "all": "all"}.get(os.environ.get("MI_FUSE_GN_CONV", "0"), False)
 
 # nearest-x2 upsample + 3x3 conv as four 2x2 sub-pixel convs on the low-res tensor (4/9 of the FLOPs, no upsampled copy)
 SUBPIXEL_UPSAMPLE = True
@@ -633,7 +637,8 @@ class Block(nn.Module):
         tc = self.project.tc_ok(H, W)
         parts = [x.a, x.b] if isinstance(x, Cat) else [x]
         block_mode = tc and Cg % STATS_BLOCK == 0 and all(p.shape[3] % STATS_BLOCK == 0 for p in parts)
-        if (block_mode and FUSE_GN_CONV and all(p.f32 is not None for p in parts)
+        if (block_mode and FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or self.project.out_channels == 128)
+                and all(p.f32 is not None for p in parts)
                 and ops.conv_gn_supported(H, W, parts[0].shape[3], parts[1].shape[3] if len(parts) > 1 else 0,
                                           self.project.out_channels, G)):
             # one kernel: GroupNorm/FiLM/SiLU as the conv's shared-memory prologue (mi_conv3x3_gn_silu_f16)

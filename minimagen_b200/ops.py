@@ -247,6 +247,61 @@ class NativeOps:
                float(post_shift), N.ptr(out), N.stream())
 
 
+    # ---------------------------------------------------------------- training side (backward kernels, fp32)
+    def gemm_f32(self, A, B, C, M, N, K, a_str, b_str, c_str, Z1=1, Z2=1, a_b=(0, 0), b_b=(0, 0), c_b=(0, 0), alpha=1.0,
+                 accumulate=False):
+        """C[z](m,n) (+)= alpha * sum_k A[z](m,k) B[z](k,n); a_str = (a_sm, a_sk), b_str = (b_sk, b_sn), c_str = (c_sm, c_sn)
+        element strides, *_b = (stride of z1, stride of z2), z = z1*Z2 + z2.  Tensors only provide base pointers."""
+        for nm, t in (("A", A), ("B", B), ("C", C)):
+            if t.dtype != F32:
+                raise TypeError(f"{nm}: expected float32")
+        from . import _native as nat       # (the GEMM's own `N` shadows the module alias used elsewhere in this class)
+        nat.call("mi_gemm_f32", nat.ptr(A), nat.ptr(B), nat.ptr(C), M, N, K, a_str[0], a_str[1], b_str[0], b_str[1], c_str[0],
+                 c_str[1], Z1, Z2, a_b[0], a_b[1], b_b[0], b_b[1], c_b[0], c_b[1], float(alpha), int(accumulate), nat.stream())
+
+    def colsum(self, x, M, Nc, out, accumulate=False):
+        _chk(x, F32, "x"); _chk(out, F32, "out")
+        N.call("mi_colsum_f32", N.ptr(x), M, Nc, N.ptr(out), int(accumulate), N.stream())
+
+    def conv_dgrad(self, dy, B, Ho, Wo, c_out, w, c_in, kh, kw, stride, pad, dx, Hi, Wi):
+        _chk(dy, F32, "dy"); _chk(w, F32, "w"); _chk(dx, F32, "dx")
+        N.call("mi_conv2d_dgrad_f32", N.ptr(dy), B, Ho, Wo, c_out, N.ptr(w), c_in, kh, kw, stride, pad, N.ptr(dx), Hi, Wi,
+               N.stream())
+
+    def conv_wgrad(self, dy, x, B, Hi, Wi, c_in, Ho, Wo, c_out, kh, kw, stride, pad, dw):
+        _chk(dy, F32, "dy"); _chk(x, F32, "x"); _chk(dw, F32, "dw")
+        N.call("mi_conv2d_wgrad_f32", N.ptr(dy), N.ptr(x), B, Hi, Wi, c_in, Ho, Wo, c_out, kh, kw, stride, pad, N.ptr(dw),
+               N.stream())
+
+    def gn_silu_bwd(self, x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, ss_ld, eps, dx, dgamma, dbeta, dss, dss_ld):
+        """dgamma / dbeta are ACCUMULATED into (zero them first); dss [B, dss_ld] = [d scale | d shift] or None."""
+        _chk(x, F32, "x"); _chk(dy, F32, "dy"); _chk(sums, F64, "sums"); _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta")
+        _chk_out(scale_shift, F32, "scale_shift"); _chk(dx, F32, "dx"); _chk(dgamma, F32, "dgamma"); _chk(dbeta, F32, "dbeta")
+        _chk(dss, F32, "dss")
+        ws = torch.empty(2 * B * C + 2 * B * groups, dtype=F32, device=x.device)
+        N.call("mi_gn_silu_bwd", N.ptr(x), N.ptr(dy), N.ptr(sums), B, hw, C, groups, N.ptr(gamma), N.ptr(beta),
+               N.ptr(scale_shift), int(ss_ld), float(eps), N.ptr(dx), N.ptr(dgamma), N.ptr(dbeta), N.ptr(dss), int(dss_ld),
+               N.ptr(ws), N.stream())
+
+    def ln_rows_bwd(self, inp, dy, R, C, gamma, eps, pre_gelu, dx, dgamma, dbeta):
+        _chk(inp, F32, "inp"); _chk(dy, F32, "dy"); _chk(gamma, F32, "gamma"); _chk(dx, F32, "dx")
+        _chk(dgamma, F32, "dgamma"); _chk(dbeta, F32, "dbeta")
+        N.call("mi_ln_rows_bwd", N.ptr(inp), N.ptr(dy), R, C, N.ptr(gamma), float(eps), int(pre_gelu), N.ptr(dx),
+               N.ptr(dgamma), N.ptr(dbeta), N.stream())
+
+    def softmax_rows(self, s, R, L):
+        _chk(s, F32, "s")
+        N.call("mi_softmax_rows", N.ptr(s), R, L, N.stream())
+
+    def softmax_rows_bwd(self, P, dP, R, L):
+        _chk(P, F32, "P"); _chk(dP, F32, "dP")
+        N.call("mi_softmax_rows_bwd", N.ptr(P), N.ptr(dP), R, L, N.stream())
+
+    def upsample2x_bwd(self, dy, B, H, W, C, dx):
+        _chk(dy, F32, "dy"); _chk(dx, F32, "dx")
+        N.call("mi_upsample2x_bwd", N.ptr(dy), B, H, W, C, N.ptr(dx), N.stream())
+
+
 _OPS = None
 
 

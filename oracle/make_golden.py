@@ -152,12 +152,72 @@ def cascade_case():
     print("cascade_tiny: draws", [tuple(d.shape) for d in draws], "out", tuple(out.shape), float(out.mean()))
 
 
+def train_case():
+    """Training side: the reference's own `Imagen._p_losses` (Imagen.py:512-573) + `loss.backward()` on the tiny
+    base and super-resolution U-Nets, with every random draw pinned: `times` / `noise` are passed in, the conditional-dropout
+    keep mask (Unet.py:587 `prob_mask_like`) and the low-res augmentation noise (`torch.randn_like`, Imagen.py:556) are recorded."""
+    import minimagen.Imagen as MI
+    import minimagen.Unet as MU
+    from minimagen.Imagen import Imagen
+    from minimagen.Unet import Unet, BaseTest, SuperTest
+    torch.manual_seed(0)
+    im = Imagen(unets=(Unet(**BaseTest.defaults), Unet(**SuperTest.defaults)), text_encoder_name='t5_small',
+                image_sizes=(16, 32), timesteps=25, cond_drop_prob=0.15)
+    g = torch.Generator().manual_seed(11)
+    b = 3
+    te = torch.randn(b, 9, 512, generator=g)
+    tm = torch.ones(b, 9, dtype=torch.bool)
+    tm[1, 5:] = False
+    te[1, 5:] = 0.
+    keep = torch.tensor([True, False, True])
+    cases = []
+    real_mask, real_like = MU.prob_mask_like, MI.torch.randn_like
+    MU.prob_mask_like = lambda shape, prob, device: keep.to(device)
+    try:
+        for idx, size in ((0, 16), (1, 32)):
+            unet = im.unets[idx]
+            for p in im.parameters():
+                p.grad = None
+            x0 = torch.rand(b, 3, size, size, generator=g)                  # training images in [0, 1]
+            noise = torch.randn(b, 3, size, size, generator=g)
+            times = torch.tensor([3, 24, 11])
+            kw = dict(noise_scheduler=im.noise_schedulers[idx], text_embeds=te, text_mask=tm, noise=noise)
+            rec = {}
+            if idx == 1:
+                kw.update(lowres_cond_img=torch.rand(b, 3, size, size, generator=g), lowres_aug_times=torch.tensor([7, 7, 7]))
+
+                def rec_like(t, **k2):
+                    rec['lowres_noise'] = real_like(t, **k2)
+                    return rec['lowres_noise']
+                MI.torch.randn_like = rec_like
+            torch.manual_seed(5)
+            loss = im._p_losses(unet, x0, times, **kw)
+            MI.torch.randn_like = real_like
+            loss.backward()
+            grads = {k: p.grad.clone() for k, p in unet.named_parameters() if p.grad is not None}
+            cases.append(dict(cfg=dict(BaseTest.defaults if idx == 0 else SuperTest.defaults), unet_index=idx, size=size,
+                              state_dict={k: v.clone() for k, v in unet.state_dict().items()}, x0=x0, noise=noise,
+                              times=times, lowres_cond_img=kw.get('lowres_cond_img'),
+                              lowres_aug_times=kw.get('lowres_aug_times'), lowres_noise=rec.get('lowres_noise'),
+                              loss=loss.detach().clone(), grads=grads))
+            print("train case", idx, "loss", float(loss), "grad tensors", len(grads),
+                  "missing grads", [k for k, p in unet.named_parameters() if p.grad is None])
+    finally:
+        MU.prob_mask_like, MI.torch.randn_like = real_mask, real_like
+    torch.save(dict(cases=cases, text_embeds=te, text_mask=tm, keep=keep, image_sizes=(16, 32), timesteps=25,
+                    cond_drop_prob=0.15), os.path.join(OUT, "train_tiny.pt"))
+
+
 if __name__ == "__main__":
     reference.load()
     os.makedirs(OUT, exist_ok=True)
     from minimagen.Unet import BaseTest, SuperTest
+    if len(sys.argv) > 1 and sys.argv[1] == "train":
+        train_case()
+        sys.exit(0)
     unet_case("unet_tiny_base", dict(BaseTest.defaults), 64, False)
     unet_case("unet_tiny_sr", dict(SuperTest.defaults, lowres_cond=True), 64, True)
     step_case()
     sample_case()
     cascade_case()
+    train_case()

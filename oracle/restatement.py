@@ -94,7 +94,7 @@ def _posemb(t, dim):
     """layers.SinusoidalPosEmb (layers.py:455-465)"""
     half = dim // 2
     step = math.log(10000) / (half - 1)
-    freqs = torch.exp(torch.arange(half) * -step)
+    freqs = torch.exp(torch.arange(half, device=t.device) * -step)
     arg = t[:, None] * freqs[None, :]
     return torch.cat((arg.sin(), arg.cos()), dim=-1)
 
@@ -219,7 +219,7 @@ def unet_forward(sd, cfg, x, time, lowres_cond_img=None, lowres_noise_times=None
         rem = max_len - tok.shape[1]
         if rem > 0:
             tok = F.pad(tok, (0, 0, 0, rem))
-        keep = torch.full((bsz,), cond_drop_prob == 0, dtype=torch.bool)
+        keep = torch.full((bsz,), cond_drop_prob == 0, dtype=torch.bool, device=x.device)
         keep_embed = keep[:, None, None]
         if text_mask is not None:
             tm = F.pad(text_mask, (0, rem), value=False) if rem > 0 else text_mask

@@ -353,3 +353,80 @@ class EmuOps:
         self._log("q_sample")
         v = tab_a[t][:, None] * x0.reshape(B, n) + tab_b[t][:, None] * noise.reshape(B, n)
         out.reshape(B, n).copy_(v * post_scale + post_shift)
+
+
+    # ---------------------------------------------------------------- training side (contracts of the backward entry points)
+    def gemm_f32(self, A, B, C, M, N, K, a_str, b_str, c_str, Z1=1, Z2=1, a_b=(0, 0), b_b=(0, 0), c_b=(0, 0), alpha=1.0,
+                 accumulate=False):
+        self._log("gemm_f32")
+        Av = A.as_strided((Z1, Z2, M, K), (a_b[0], a_b[1], a_str[0], a_str[1]), A.storage_offset())
+        Bv = B.as_strided((Z1, Z2, K, N), (b_b[0], b_b[1], b_str[0], b_str[1]), B.storage_offset())
+        Cv = C.as_strided((Z1, Z2, M, N), (c_b[0], c_b[1], c_str[0], c_str[1]), C.storage_offset())
+        R = alpha * torch.matmul(Av, Bv)
+        Cv.copy_(Cv + R if accumulate else R)
+
+    def colsum(self, x, M, Nc, out, accumulate=False):
+        self._log("colsum")
+        r = x.reshape(M, Nc).sum(dim=0)
+        out.copy_(out + r if accumulate else r)
+
+    def conv_dgrad(self, dy, B, Ho, Wo, c_out, w, c_in, kh, kw, stride, pad, dx, Hi, Wi):
+        self._log("conv_dgrad")
+        g = torch.nn.grad.conv2d_input((B, c_in, Hi, Wi), w.detach().reshape(c_out, c_in, kh, kw),
+                                       dy.reshape(B, Ho, Wo, c_out).permute(0, 3, 1, 2), stride=stride, padding=pad)
+        dx.reshape(B, Hi, Wi, c_in).copy_(g.permute(0, 2, 3, 1))
+
+    def conv_wgrad(self, dy, x, B, Hi, Wi, c_in, Ho, Wo, c_out, kh, kw, stride, pad, dw):
+        self._log("conv_wgrad")
+        g = torch.nn.grad.conv2d_weight(x.reshape(B, Hi, Wi, c_in).permute(0, 3, 1, 2), (c_out, c_in, kh, kw),
+                                        dy.reshape(B, Ho, Wo, c_out).permute(0, 3, 1, 2), stride=stride, padding=pad)
+        dw.reshape(c_out, c_in, kh, kw).copy_(g)
+
+    def gn_silu_bwd(self, x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, ss_ld, eps, dx, dgamma, dbeta, dss, dss_ld):
+        self._log("gn_silu_bwd")
+        with torch.enable_grad():
+            x_ = x.detach().reshape(B, hw, C).clone().requires_grad_(True)
+            g_ = gamma.detach().clone().requires_grad_(True)
+            b_ = beta.detach().clone().requires_grad_(True)
+            y = F.group_norm(x_.transpose(1, 2), groups, g_, b_, eps).transpose(1, 2)
+            leaves = [x_, g_, b_]
+            if scale_shift is not None:
+                ss_ = torch.as_strided(scale_shift, (B, 2 * C), (ss_ld, 1), scale_shift.storage_offset()).detach().clone()
+                ss_.requires_grad_(True)
+                y = y * (ss_[:, None, :C] + 1) + ss_[:, None, C:]
+                leaves.append(ss_)
+            y = F.silu(y)
+            grads = torch.autograd.grad(y, leaves, dy.reshape(B, hw, C))
+        dx.reshape(B, hw, C).copy_(grads[0])
+        dgamma.add_(grads[1])
+        dbeta.add_(grads[2])
+        if dss is not None:
+            torch.as_strided(dss, (B, 2 * C), (dss_ld, 1), dss.storage_offset()).copy_(grads[3])
+
+    def ln_rows_bwd(self, inp, dy, R, C, gamma, eps, pre_gelu, dx, dgamma, dbeta):
+        self._log("ln_rows_bwd")
+        with torch.enable_grad():
+            x_ = inp.detach().reshape(R, C).clone().requires_grad_(True)
+            g_ = gamma.detach().reshape(C).clone().requires_grad_(True)
+            v = F.gelu(x_) if pre_gelu else x_
+            y = F.layer_norm(v, (C,), None, None, eps) * g_
+            gx, gg = torch.autograd.grad(y, [x_, g_], dy.reshape(R, C))
+        dx.reshape(R, C).copy_(gx)
+        if dgamma is not None:
+            dgamma.reshape(C).add_(gg)
+        if dbeta is not None:
+            dbeta.reshape(C).add_(dy.reshape(R, C).sum(dim=0))
+
+    def softmax_rows(self, s, R, L):
+        self._log("softmax_rows")
+        v = s.reshape(R, L)
+        v.copy_(torch.softmax(v, dim=-1))
+
+    def softmax_rows_bwd(self, P, dP, R, L):
+        self._log("softmax_rows_bwd")
+        p, d = P.reshape(R, L), dP.reshape(R, L)
+        d.copy_(p * (d - (p * d).sum(dim=-1, keepdim=True)))
+
+    def upsample2x_bwd(self, dy, B, H, W, C, dx):
+        self._log("upsample2x_bwd")
+        dx.reshape(B, H, W, C).copy_(dy.reshape(B, H, 2, W, 2, C).sum(dim=(2, 4)))

@@ -236,7 +236,7 @@ def test_groupnorm_block_statistics_from_conv_epilogue(native):
     (1, 64, 64, 128, 0, 256, False, True),
     (2, 32, 16, 128, 256, 128, True, True),          # GroupNorm groups (48 channels) straddle the two sources
     (1, 32, 32, 512, 512, 512, True, True),          # deep K (16 chunks), 4 channel tiles
-    (5, 64, 32, 64, 0, 128, True, False),            # single chunk, more tiles than a wave's worth per image
+    (5, 64, 32, 128, 0, 128, True, False),           # two chunks, many tiles per image
 ])
 def test_fused_groupnorm_conv(native, B, H, W, C0, C1, Cout, res, ss):
     """mi_conv3x3_gn_silu_f16 == mi_gn_apply_silu (block statistics) followed by mi_conv2d_igemm_f16"""

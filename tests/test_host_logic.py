@@ -297,7 +297,7 @@ def test_fused_groupnorm_conv_orchestration(emu):
             a = u(x, t, **kw)
             n_apply = emu.calls.count("gn_apply_silu")
             emu.calls.clear()
-            layers.FUSE_GN_CONV = True
+            layers.FUSE_GN_CONV = 'all'
             b = u(x, t, **kw)
     finally:
         layers.FUSE_GN_CONV = prev
