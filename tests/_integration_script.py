@@ -80,6 +80,30 @@ for m in (src, loaded):
     m = m.to(dev)
     m.noise_fn = noise_fn
     outs.append(m.sample(text_embeds=te.to(dev), text_masks=tm.to(dev), cond_scale=2.).cpu())
+# ---- 3. the reference's own training loop (training.MinimagenTrain, the body of train.py) driving the B200 classes:
+#         imagen(images, text_embeds=, text_masks=, unet_number=) -> loss.backward() -> optimizer.step(), its checkpointing,
+#         its validation pass; then the reference's load_minimagen reads what it wrote
+torch.manual_seed(0)
+trn = Imagen(unets=[Unet(**p) for p in unets_params], **imagen_params).to(dev)
+w_before = [p.detach().clone() for p in trn.parameters()]
+gb = torch.Generator().manual_seed(7)
+mk = lambda: dict(image=torch.rand(2, 3, 32, 32, generator=gb).to(dev), encoding=torch.randn(2, 7, 512, generator=gb).to(dev),
+                  mask=torch.ones(2, 7, dtype=torch.bool).to(dev))
+train_dl, valid_dl = [mk(), mk(), mk()], [mk()]
+with tempfile.TemporaryDirectory() as tmp2:
+    tdir2 = os.path.join(tmp2, "training_run")
+    cm2 = training.create_directory(tdir2)
+    targs = Namespace(RESTART_DIRECTORY=None, ACCUM_ITER=1, CHCKPT_NUM=2, EPOCHS=1)
+    training.save_training_info(targs, ts, unets_params, imagen_params, training.get_model_size(trn), cm2)
+    opt = torch.optim.Adam(trn.parameters(), lr=1e-3)
+    training.MinimagenTrain(ts, targs, list(trn.unets), trn, train_dl, valid_dl, cm2, opt, timeout=300)
+    res["train_files"] = sorted(os.listdir(os.path.join(tdir2, "state_dicts")))
+    res["train_progress_lines"] = len(open(os.path.join(tdir2, "training_progess.txt")).read().splitlines())
+    trained = load_minimagen(tdir2)
+trn._reset_unets_all_one_device()
+res["train_weights_changed"] = any(not torch.equal(a, b.detach()) for a, b in zip(w_before, trn.parameters()))
+res["trained_loaded_type"] = type(trained).__module__
+
 res["sample_shape"] = list(outs[1].shape)
 res["sample_equal"] = bool(torch.allclose(outs[0], outs[1], atol=1e-6))
 res["sample_finite"] = bool(torch.isfinite(outs[1]).all())

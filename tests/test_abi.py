@@ -51,9 +51,13 @@ def test_missing_library_fails_loudly(monkeypatch):
         _native.load()
 
 
-def test_training_path_is_explicitly_not_built(emu):
+def test_grad_mode_routes_to_the_training_path(emu):
+    """Unet.forward under grad mode runs the autograd path (train_path.py), under no_grad the sampling path."""
     from minimagen_b200.Unet import Unet, BaseTest
     u = Unet(**BaseTest.defaults)
     x = torch.randn(1, 3, 32, 32)
-    with pytest.raises(NotImplementedError, match="inference"):
-        u(x, torch.zeros(1, dtype=torch.long), text_embeds=torch.randn(1, 4, 512))   # grad mode on
+    out = u(x, torch.zeros(1, dtype=torch.long), text_embeds=torch.randn(1, 4, 512))   # grad mode on
+    assert out.requires_grad and out.grad_fn is not None
+    with torch.no_grad():
+        out2 = u(x, torch.zeros(1, dtype=torch.long), text_embeds=torch.randn(1, 4, 512))
+    assert not out2.requires_grad

@@ -131,8 +131,12 @@ def test_imagen_surface_and_asserts(emu):
                  lowres_cond_img=None, lowres_noise_times=None, cond_scale=3.)
     with pytest.raises(AssertionError, match="at least 20"):
         Imagen(unets=u0, text_encoder_name="t5_small", image_sizes=(32,), timesteps=10)
-    with pytest.raises(NotImplementedError, match="8f-2"):
-        im(torch.zeros(1, 3, 64, 64), text_embeds=torch.zeros(1, 4, 512), unet_number=1)
+    with pytest.raises(AssertionError, match="you must specify which unet"):
+        im(torch.zeros(1, 3, 64, 64), text_embeds=torch.zeros(1, 4, 512))
+    with pytest.raises(AssertionError, match="invalid text embedding dimension"):
+        im(torch.zeros(1, 3, 64, 64), text_embeds=torch.zeros(1, 4, 7), unet_number=1)
+    loss = im(torch.rand(1, 3, 64, 64), text_embeds=torch.zeros(1, 4, 512), unet_number=1)      # training.py:368
+    assert loss.dim() == 0 and loss.requires_grad
 
 
 @pytest.mark.skipif(not reference.available(), reason="reference tree only exists in the build container")

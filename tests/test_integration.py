@@ -33,6 +33,9 @@ def test_reference_generate_loads_b200_classes_from_training_directory():
     assert res["unet_types"] == ["minimagen_b200.Unet"]
     assert res["weights_equal"] and res["sample_equal"] and res["sample_finite"]
     assert res["sample_shape"] == [2, 3, 32, 32]
+    # the reference's training loop (training.MinimagenTrain) trained the B200 classes and wrote loadable checkpoints
+    assert res["train_weights_changed"] and res["trained_loaded_type"] == "minimagen_b200.Imagen"
+    assert res["train_files"] == ["unet_0_state_20260101_000000.pth", "unet_1_state_20260101_000000.pth"]
 
 
 def test_install_as_minimagen_without_reference_is_alias_only():
