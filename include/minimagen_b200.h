@@ -84,6 +84,19 @@ int mi_conv2d_igemm_f16(const void* act_f16, int B, int H, int W, int lda, int c
                         const float* bias, const float* residual, float* out_f32, void* out_f16, double* out_stats,
                         long long out_sb, long long out_sh, long long out_sw, long long out_sc, int n_valid,
                         int block_n, int* err_flag, void* workspace, long long workspace_bytes, void* stream);
+/* ResnetBlock.forward's tail (layers.py:437-439)  block2.project(h) + res_conv(x)  as ONE launch of the swapped-operand 3x3
+ * kernel: after the nine taps of the 3x3 conv over `act` (the GroupNorm/SiLU operand of block2), the 1x1 res_conv rides in the
+ * same accumulator as x_cin/64 extra K chunks read at the centre tap of x's halo tile -- no separate 1x1 launch, no fp32
+ * round trip of the residual branch through HBM.  w_f16 = [c_out][9*c_in + x_cin]: each row is the packed 3x3 weight followed
+ * by the 1x1 weight; bias = the sum of both convs' biases.  Both operands may be virtual concats (act2 / x_act2 hold channels
+ * >= c_in1 / x_cin1, the skip scale folded into the weight columns).  Outputs [B][H][W][c_out] contiguous; residual, out_stats
+ * as mi_conv2d_igemm_f16.  Requirements: mi_conv3x3_res1x1_supported (H % 32 == 0 and W % 8 == 0, or W == 16 and H % 16 == 0;
+ * c_in % 64 == 0, x_cin % 64 == 0, c_out % 128 == 0). */
+int mi_conv3x3_res1x1_supported(int H, int W, int c_in, int c_out, int x_cin);
+int mi_conv3x3_res1x1_f16(const void* act_f16, int B, int H, int W, int lda, int c_in, const void* act2_f16, int lda2,
+                          int c_in1, const void* x_f16, int ldx, int x_cin, const void* x2_f16, int ldx2, int x_cin1,
+                          const void* w_f16, int c_out, const float* bias, const float* residual, float* out_f32,
+                          void* out_f16, double* out_stats, int* err_flag, void* stream);
 /* Optional scratch for mi_conv2d_igemm_f16 (NULL = none): lets layers whose tile count is not a multiple of the SM-pair
  * count split their LAST wave along K ("stream-K": every CTA pair gets the same number of k-steps; partial fp32 tiles
  * meet in this buffer).  Size from this call; the first 4096 bytes must be zero before the first use (the kernels leave

@@ -24,6 +24,8 @@ SIGNATURES = {
     "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
     "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _L, _L,
                             _I, _I, _P, _P, _L, _P],
+    "mi_conv3x3_res1x1_supported": [_I, _I, _I, _I, _I],
+    "mi_conv3x3_res1x1_f16": [_P, _I, _I, _I, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _I, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "mi_conv2d_igemm_workspace_bytes": [],
     "mi_conv3x3_gn_supported": [_I, _I, _I, _I, _I, _I],
     "mi_conv3x3_gn_silu_f16": [_P, _I, _P, _I, _F, _I, _I, _I, _I, _P, _P, _P, _P, _P, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P,

@@ -57,12 +57,16 @@ int mi_pack_conv_weight_f16(const float* w, int c_out, int c_in, int kh, int kw,
 
 int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out) { return mi::conv_tc_supported(H, W, c_in, c_out) ? 1 : 0; }
 
-int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* act2, int lda2,
+static int igemm_common(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* act2, int lda2,
                         int c_off2, int c_in1, const void* w, int c_out, int kh, int kw, int mode, const float* bias,
                         const float* residual, float* out_f32, void* out_f16, double* out_stats, long long out_sb,
                         long long out_sh, long long out_sw, long long out_sc, int n_valid, int block_n, int* err_flag,
-                        void* workspace, long long workspace_bytes, void* stream) {
+                        void* workspace, long long workspace_bytes, const void* x_act, int ldx, int x_off, int x_cin,
+                        const void* x_act2, int ldx2, int x_off2, int x_cin1, void* stream) {
     mi::ConvTcProblem p{};
+    p.x_act = x_act; p.x_lda = ldx; p.x_chan_off = x_off; p.Cx = x_cin;
+    p.x_act2 = x_act2; p.x_lda2 = ldx2; p.x_chan_off2 = x_off2; p.Cx1 = x_cin1;
+    if (x_act && !(mode == 0 && kh == 3 && kw == 3)) return fail(-9, "mi_conv3x3_res1x1_f16: the folded 1x1 operand needs a 3x3 stride-1 conv");
     p.splitk_ws = workspace; p.splitk_ws_bytes = workspace ? workspace_bytes : 0;
     if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15)) return fail(-8, "mi_conv2d_igemm_f16: workspace must be 16-byte aligned");
     p.act = act; p.B = B; p.H = H; p.W = W; p.lda = lda; p.a_channels = lda; p.a_chan_off = c_off; p.Cin = c_in;
@@ -130,6 +134,32 @@ int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off
     const int rc = mi::conv_tc_launch(p, S(stream));
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;
+}
+
+int mi_conv2d_igemm_f16(const void* act, int B, int H, int W, int lda, int c_off, int c_in, const void* act2, int lda2,
+                        int c_off2, int c_in1, const void* w, int c_out, int kh, int kw, int mode, const float* bias,
+                        const float* residual, float* out_f32, void* out_f16, double* out_stats, long long out_sb,
+                        long long out_sh, long long out_sw, long long out_sc, int n_valid, int block_n, int* err_flag,
+                        void* workspace, long long workspace_bytes, void* stream) {
+    return igemm_common(act, B, H, W, lda, c_off, c_in, act2, lda2, c_off2, c_in1, w, c_out, kh, kw, mode, bias, residual,
+                        out_f32, out_f16, out_stats, out_sb, out_sh, out_sw, out_sc, n_valid, block_n, err_flag, workspace,
+                        workspace_bytes, nullptr, 0, 0, 0, nullptr, 0, 0, 0, stream);
+}
+
+int mi_conv3x3_res1x1_supported(int H, int W, int c_in, int c_out, int x_cin) {
+    const bool t16 = W == 16 && H % 16 == 0, t32 = !t16 && H % 32 == 0 && W % 8 == 0;
+    return (t16 || t32) && c_in > 0 && c_in % 64 == 0 && x_cin > 0 && x_cin % 64 == 0 && c_out % 128 == 0;
+}
+
+int mi_conv3x3_res1x1_f16(const void* act, int B, int H, int W, int lda, int c_in, const void* act2, int lda2, int c_in1,
+                          const void* x_act, int ldx, int x_cin, const void* x_act2, int ldx2, int x_cin1, const void* w,
+                          int c_out, const float* bias, const float* residual, float* out_f32, void* out_f16,
+                          double* out_stats, int* err_flag, void* stream) {
+    if (!mi_conv3x3_res1x1_supported(H, W, c_in, c_out, x_cin))
+        return fail(-9, "mi_conv3x3_res1x1_f16: unsupported geometry (see mi_conv3x3_res1x1_supported)");
+    return igemm_common(act, B, H, W, lda, 0, c_in, act2, lda2, 0, c_in1, w, c_out, 3, 3, 0, bias, residual, out_f32, out_f16,
+                        out_stats, (long long)H * W * c_out, (long long)W * c_out, c_out, 1, 0, 0, err_flag, nullptr, 0, x_act,
+                        ldx, 0, x_cin, x_act2, ldx2, 0, x_cin1, stream);
 }
 
 long long mi_conv2d_igemm_workspace_bytes(void) { return mi::conv_tc_splitk_bytes(); }

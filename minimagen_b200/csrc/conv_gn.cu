@@ -3,7 +3,7 @@
 //
 // This is conv3x3_halo_t_kernel<G32x8> (conv_tc.cu: swapped operands, D^T[128 channels][256 pixels] = W_tile x window^T, the
 // nine taps as descriptor windows into one (32+2) x (8+2)-pixel halo tile per 64-channel chunk) with the TMA load of the
-// activation halo replaced by a PROLOGUE executed by eight dedicated warps:
+// activation halo replaced by a PROLOGUE executed by twelve dedicated warps:
 //
 //   raw input    the fp32 NHWC residual-stream tensor(s) (optionally the virtual concat cat(x, skip * s), Unet.py:445), read
 //                straight from global memory / L2 into registers with coalesced 128-bit loads (one pixel's 64 channels =
@@ -18,7 +18,7 @@
 //   main loop / epilogue   as conv3x3_halo_t_kernel: weights [C_out][9*C_in] by TMA, accumulators double-buffered in TMEM,
 //                lane = channel epilogue with bias / fp32 residual / fp32 + fp16 stores / GroupNorm block statistics.
 //
-// Warp roles (640 threads): 0 TMA (weights), 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue, 12-19 transform.
+// Warp roles (768 threads): 0 TMA (weights), 1 MMA issuer, 2 TMEM allocator, 4-11 epilogue, 12-23 transform.
 #include "conv_tc.cuh"
 
 #include <cuda_runtime.h>
@@ -32,8 +32,9 @@ namespace mi {
 
 namespace {
 
-constexpr int kGnThreads = 640;
-constexpr int kXformWarp0 = 12, kXformThreads = 256, kGnEpiWarps = 8;
+constexpr int kGnThreads = 768;
+constexpr int kXformWarp0 = 12, kXformThreads = 384, kGnEpiWarps = 8;
+constexpr int kXformRows = kXformThreads / 8;                            // halo pixels covered per iteration (48: a multiple of 8)
 constexpr int kTH = 32, kTW = 8, kBoxW = kTW + 2, kBoxH = kTH + 2, kHaloPix = kBoxH * kBoxW;   // 340 halo pixels
 constexpr uint32_t kHaloBytes = kHaloPix * 128;                          // fp16 operand tile: 43520 B
 constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;           // 44032
@@ -41,10 +42,11 @@ constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                      // one 
 constexpr int kHStages = 2, kWStages = 6;
 constexpr int kPix = 256;                                                // UMMA N
 constexpr uint32_t kTmemCols = 2 * kPix;
-constexpr uint32_t kAuxBytes = 512 + 1024;                               // barriers + group mean/rstd, chunk coefficients
-constexpr uint32_t kSmemBytes = kHStages * kHaloStride + kWStages * kWBytes + 1024 + kAuxBytes;
+constexpr uint32_t kAuxBytes = 512;                                      // barriers + group mean / rstd
+constexpr uint32_t kSmemBase = kHStages * kHaloStride + kWStages * kWBytes + 1024 + kAuxBytes;   // + 8 * C_in (coefficient table)
+constexpr uint32_t kSmemMax = 227 * 1024;
 constexpr int kItems = kHaloPix * 8;                                     // 16-byte operand chunks per halo tile
-constexpr int kIters = (kItems + kXformThreads - 1) / kXformThreads;     // 11
+constexpr int kIters = (kItems + kXformThreads - 1) / kXformThreads;     // 8
 constexpr int kBatch = 4;                                                // loads in flight per thread: kBatch x 32 B
 
 __device__ __forceinline__ uint64_t make_win_desc(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -56,8 +58,8 @@ __device__ __forceinline__ uint64_t make_win_desc(uint32_t smem_addr, uint32_t s
     return d;
 }
 
-__device__ __forceinline__ void xform_bar_sync() {           // the eight transform warps only
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+__device__ __forceinline__ void xform_bar_sync() {           // the twelve transform warps only
+    asm volatile("bar.sync 1, 384;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(kGnThreads, 1)
@@ -79,7 +81,7 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
     static_assert((2 * NH + 2 * NW + 4) * 8 + 8 <= 256, "barrier block too large");
     float* s_mean = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);     // [32]
     float* s_rstd = s_mean + 32;                                                          // [32]
-    float* s_coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);     // [2 buffers][A 64 | B 64]
+    float* s_coef = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);     // A[C_in] then Bc[C_in] of the current image
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -160,24 +162,26 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
         }
     } else if (warp >= kXformWarp0) {
         // ===================== transform: fp32 global -> GroupNorm/FiLM/SiLU -> fp16 swizzled halo operand =====================
-        const int tt = threadIdx.x - kXformWarp0 * 32;      // 0..255
+        const int tt = threadIdx.x - kXformWarp0 * 32;      // 0..383
         const int lq = tt & 7;                              // logical 16-byte chunk: channels [8*lq, 8*lq + 8) of the k-chunk
-        const int prow = tt >> 3;                           // halo pixel of iteration it: p = it*32 + prow; p & 7 == prow & 7
+        const int prow = tt >> 3;                           // halo pixel of iteration it: p = it*48 + prow; p & 7 == prow & 7
         const int qo = lq ^ (prow & 7);                     // physical (swizzled) chunk position inside the 128-byte row
         const int C0 = gn.C0, C1 = gn.C1, Ctot = C0 + C1, Cg = Ctot / gn.groups;
         const int H = args.H, W = args.W;
+        float* sA = s_coef;
+        float* sB = s_coef + Ctot;
         int sh = 0;
         uint32_t ph = 0;
         int cur_b = -1;
-        int jj = 0;                                          // running chunk counter -> coefficient buffer parity
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const int mt = tile / args.tiles_n;
             const int w0 = (mt % args.tiles_w) * kTW;
             const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kTH;
             const int b = mt / (args.tiles_w * args.tiles_h);
             if (b != cur_b) {
-                // per-image group statistics from the producers' 16-channel block statistics (same arithmetic as
-                // gn_apply_silu_kernel).  Every reader of s_mean / s_rstd is behind the previous chunk's bar.sync.
+                // Coefficient table of image b for ALL input channels: y = SiLU(x * A[c] + Bc[c]) (same arithmetic as
+                // gn_apply_silu_kernel).  Rebuilt only when the image changes; no per-chunk barrier or global load afterwards.
+                xform_bar_sync();                            // every thread has finished reading the previous table
                 if (tt < gn.groups) {
                     const int g = tt;
                     double su = 0.0, sq = 0.0;
@@ -199,16 +203,8 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     s_mean[g] = (float)mean;
                     s_rstd[g] = (float)(1.0 / sqrt(var + (double)gn.eps));
                 }
-                cur_b = b;
                 xform_bar_sync();
-            }
-            const long long img = (long long)b * H * W;
-            for (int j = 0; j < chunks; ++j, ++jj) {
-                // --- coefficients of this 64-channel chunk (threads 0..63), double-buffered by chunk parity
-                float* cA = s_coef + (jj & 1) * 128;
-                float* cB = cA + 64;
-                if (tt < 64) {
-                    const int cc = j * kConvBlockK + tt;                  // channel of the virtual concat
+                for (int cc = tt; cc < Ctot; cc += kXformThreads) {
                     const int g = cc / Cg;
                     float a = s_rstd[g] * gn.gamma[cc];
                     float bb = gn.beta[cc] - s_mean[g] * a;
@@ -219,12 +215,18 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                         bb = bb * sc + shv;
                     }
                     if (cc >= C0) a *= gn.scale1;                        // skip * 2^-1/2 folded into the multiplier
-                    cA[tt] = a;
-                    cB[tt] = bb;
+                    sA[cc] = a;
+                    sB[cc] = bb;
                 }
+                cur_b = b;
                 xform_bar_sync();
-                const float4 a0 = *reinterpret_cast<const float4*>(cA + lq * 8), a1 = *reinterpret_cast<const float4*>(cA + lq * 8 + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(cB + lq * 8), b1 = *reinterpret_cast<const float4*>(cB + lq * 8 + 4);
+            }
+            const long long img = (long long)b * H * W;
+            for (int j = 0; j < chunks; ++j) {
+                const float* cA = sA + j * kConvBlockK + lq * 8;
+                const float* cB = sB + j * kConvBlockK + lq * 8;
+                const float4 a0 = *reinterpret_cast<const float4*>(cA), a1 = *reinterpret_cast<const float4*>(cA + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(cB), b1 = *reinterpret_cast<const float4*>(cB + 4);
 
                 const bool first = j < args.a_split;
                 const int Cs = first ? C0 : C1;
@@ -239,7 +241,7 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     bool ok[kBatch];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int p = (it0 + u) * 32 + prow;
+                        const int p = (it0 + u) * kXformRows + prow;
                         const int hr = p / kBoxW, hc = p - hr * kBoxW;
                         const int gh = h0 - 1 + hr, gw = w0 - 1 + hc;
                         ok[u] = (p < kHaloPix) && gh >= 0 && gh < H && gw >= 0 && gw < W;
@@ -251,7 +253,7 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     }
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int p = (it0 + u) * 32 + prow;
+                        const int p = (it0 + u) * kXformRows + prow;
                         if (p >= kHaloPix) continue;
                         uint4 o = make_uint4(0u, 0u, 0u, 0u);
                         if (ok[u]) {
@@ -348,6 +350,7 @@ bool conv_gn_supported(int H, int W, int C0, int C1, int Cout, int groups) {
     const int C = C0 + C1;
     if (H <= 0 || W <= 0 || H % kTH || W % kTW || C0 <= 0 || C0 % 64 || C1 < 0 || C1 % 64 || Cout <= 0 || Cout % 128) return false;
     if (groups < 1 || groups > 32 || C % groups) return false;
+    if (kSmemBase + 8u * (uint32_t)C > kSmemMax) return false;          // coefficient table A[C], Bc[C] in shared memory
     return (C / groups) % 16 == 0;
 }
 
@@ -395,13 +398,13 @@ int conv_gn_launch(const ConvGnProblem& p, cudaStream_t stream) {
         return -7;
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(conv3x3_gn_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess)
+        if (cudaFuncSetAttribute(conv3x3_gn_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax) != cudaSuccess)
             return -10;
         attr_set = true;
     }
     const int total = a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
     const int grid = total < num_sms ? total : num_sms;
-    launch_k(conv3x3_gn_t_kernel, grid, kGnThreads, kSmemBytes, stream, tmB, a, g);
+    launch_k(conv3x3_gn_t_kernel, grid, kGnThreads, kSmemBase + 8u * (uint32_t)C, stream, tmB, a, g);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 

@@ -727,7 +727,8 @@ __device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t smem_addr, uint32_
 template <int G>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
+                      const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX,
+                      const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ ConvTcArgs args) {
     pdl_trigger();
     using C = CfgT<G>;
     constexpr bool kW16 = C::kW16;
@@ -820,6 +821,28 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     }
                 }
             }
+            if constexpr (G == kG32x8 || G == kG16x16) {
+                // folded 1x1 conv (res_conv): one halo tile (the dw = 0 copy for 16-wide images) + one weight tile per chunk of x
+                for (int jx = 0; jx < args.x_chunks; ++jx) {
+                    ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 3150 + sh);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&fullH[sh], C::kHaloBytes);
+                        if (jx < args.x_split)
+                            ptx::tma_load_5d(&tmX, &fullH[sh], smem + sh * C::kHaloStride, args.x_chan_off + jx * kConvBlockK,
+                                             kW16 ? w0 : w0 - 1, h0 - 1, 0, b0);
+                        else
+                            ptx::tma_load_5d(&tmX2, &fullH[sh], smem + sh * C::kHaloStride,
+                                             args.x_chan_off2 + (jx - args.x_split) * kConvBlockK, kW16 ? w0 : w0 - 1, h0 - 1, 0, b0);
+                    }
+                    if (++sh == NH) { sh = 0; ph ^= 1; }
+                    ptx::mbar_wait(&emptyW[sw], pw ^ 1, err, 3250 + sw);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_arrive_expect_tx(&fullW[sw], C::kWBytes);
+                        ptx::tma_load_2d(&tmB, &fullW[sw], smem_w + sw * C::kWBytes, C::kTaps * Cin + jx * kConvBlockK, n0);
+                    }
+                    if (++sw == NW) { sw = 0; pw ^= 1; }
+                }
+            }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: D^T[128 ch][256 px] += W_tile[128][64] x window^T =====================
@@ -857,6 +880,25 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         if (++sw == NW) { sw = 0; pw ^= 1; }
                     }
                     if (ptx::elect_one()) ptx::umma_commit(&emptyH[sh]);
+                    if (++sh == NH) { sh = 0; ph ^= 1; }
+                }
+            }
+            if constexpr (G == kG32x8 || G == kG16x16) {
+                for (int jx = 0; jx < args.x_chunks; ++jx) {          // folded 1x1 conv: the centre-tap window of x's halo tile
+                    ptx::mbar_wait(&fullH[sh], ph, err, 3450 + sh);
+                    const uint32_t h_base = ptx::smem_u32(smem + sh * C::kHaloStride);
+                    ptx::mbar_wait(&fullW[sw], pw, err, 3550 + sw);
+                    ptx::tc_fence_after();
+                    if (ptx::elect_one()) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem_w + sw * C::kWBytes));
+                        const uint64_t db = kW16 ? make_halo_t_desc(h_base + 16 * 128, 1024)
+                                                 : make_halo_t_desc(h_base + (C::kBoxW + 1) * 128, C::kBoxW * 128);
+#pragma unroll
+                        for (int k = 0; k < kConvBlockK / 16; ++k) ptx::umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1);
+                        ptx::umma_commit(&emptyW[sw]);
+                        ptx::umma_commit(&emptyH[sh]);
+                    }
+                    if (++sw == NW) { sw = 0; pw ^= 1; }
                     if (++sh == NH) { sh = 0; ph ^= 1; }
                 }
             }
@@ -1030,8 +1072,8 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs
 }
 
 template <int G>
-int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
-                  int total_tiles, int num_sms, cudaStream_t stream) {
+int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const CUtensorMap& tmX,
+                  const CUtensorMap& tmX2, const ConvTcArgs& args, int total_tiles, int num_sms, cudaStream_t stream) {
     using C = CfgT<G>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1041,7 +1083,7 @@ int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
         attr_set = true;
     }
     const int grid = total_tiles < num_sms ? total_tiles : num_sms;
-    launch_k(conv3x3_halo_t_kernel<G>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, args);
+    launch_k(conv3x3_halo_t_kernel<G>, grid, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, tmX, tmX2, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -1060,6 +1102,7 @@ const char* conv_tc_strerror(int code) {
         case -6: return "conv_tc: tensor map encode failed (activations)";
         case -7: return "conv_tc: tensor map encode failed (weights)";
         case -8: return "conv_tc: pointer/stride alignment (16 B) violated";
+        case -9: return "conv_tc: folded 1x1 operand needs the swapped-operand 3x3 kernel (C_out % 128, H % 32 / W % 8 or 16x16 tiles)";
         case -10: return "conv_tc: cudaFuncSetAttribute(max dynamic smem) failed";
         case -11: return "conv_tc: kernel launch failed";
         default: return "conv_tc: unknown error";
@@ -1144,7 +1187,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return -7;
-            return launch_halo_t<kGLin>(tmA, tmA2, tmB, h, h.tiles_h * h.tiles_n, num_sms, stream);
+            return launch_halo_t<kGLin>(tmA, tmA2, tmB, tmA, tmA, h, h.tiles_h * h.tiles_n, num_sms, stream);
         }
     }
 
@@ -1194,7 +1237,30 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                     return -6;
             }
-            const cuuint64_t K = (cuuint64_t)p.num_taps * p.Cin;
+            // folded 1x1 conv over a second operand x (res_conv): same halo geometry, its own tensor map(s)
+            CUtensorMap tmX = tmA, tmX2 = tmA;
+            if (p.x_act) {
+                if (v15 || p.Cx <= 0 || p.Cx % kConvBlockK || (p.x_lda % 8) || (reinterpret_cast<uintptr_t>(p.x_act) & 15)) return -8;
+                if (p.x_act2 && (p.Cx1 <= 0 || p.Cx1 % kConvBlockK || p.Cx1 >= p.Cx || (p.x_lda2 % 8) ||
+                                 (reinterpret_cast<uintptr_t>(p.x_act2) & 15)))
+                    return -8;
+                h.x_chunks = p.Cx / kConvBlockK;
+                h.x_split = (p.x_act2 ? p.Cx1 : p.Cx) / kConvBlockK;
+                h.x_chan_off = p.x_chan_off; h.x_chan_off2 = p.x_chan_off2;
+                for (int which = 0; which < (p.x_act2 ? 2 : 1); ++which) {
+                    const void* ptr = which ? p.x_act2 : p.x_act;
+                    const cuuint64_t ld = which ? p.x_lda2 : p.x_lda;
+                    cuuint64_t gdim[5] = {ld, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
+                    cuuint64_t gstr[4] = {ld * 2, (cuuint64_t)p.W * ld * 2, (cuuint64_t)p.H * p.W * ld * 2,
+                                          (cuuint64_t)p.H * p.W * ld * 2};
+                    if (enc(which ? &tmX2 : &tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+                        return -6;
+                }
+                if (!p.x_act2) tmX2 = tmX;
+            }
+            const cuuint64_t K = (cuuint64_t)p.num_taps * p.Cin + (p.x_act ? (cuuint64_t)p.Cx : 0);
             cuuint64_t wdim[2] = {K, (cuuint64_t)p.Cout};
             cuuint64_t wstr[1] = {K * 2};
             cuuint32_t wbox[2] = {kConvBlockK, 128};
@@ -1204,11 +1270,13 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
                 return -7;
             const int total = h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n;
-            if (v15) return launch_halo_t<kGV15>(tmA, tmA2, tmB, h, total, num_sms, stream);
-            return t16 ? launch_halo_t<kG16x16>(tmA, tmA2, tmB, h, total, num_sms, stream)
-                       : launch_halo_t<kG32x8>(tmA, tmA2, tmB, h, total, num_sms, stream);
+            if (v15) return launch_halo_t<kGV15>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream);
+            return t16 ? launch_halo_t<kG16x16>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream)
+                       : launch_halo_t<kG32x8>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream);
         }
     }
+
+    if (p.x_act) return -9;      // the folded 1x1 operand exists only in the swapped-operand 3x3 kernel above
 
     // ---- 3x3 halo kernel (opt-in via p.halo): needs the canonical 3x3 tap order, H % 16 == 0, W % 8 == 0
     if (p.halo && !p.act2 && p.num_taps == 9 && p.phases == 1 && p.H % kHaloTH == 0 && p.W % kHaloTW == 0 &&

@@ -19,6 +19,8 @@ struct ConvTcArgs {
     int a_chan_off;                       // first input channel inside the activation buffer
     int in_stride;                        // 1, or 2: taps address the (2H x 2W) input directly (TMA element stride 2)
     int a_split, a_chan_off2;             // k-chunks >= a_split come from the second activation tensor (virtual concat)
+    int x_chunks, x_split;                // folded 1x1 conv (ResnetBlock.res_conv): extra k-chunks of a second operand x,
+    int x_chan_off, x_chan_off2;          //   read at the centre tap; chunks >= x_split come from its second tensor (concat)
     long long out_sb, out_sh, out_sw;     // output (and residual) strides in elements
     long long out_sc;                     // channel stride (1 = NHWC-style contiguous channels; H*W for NCHW output)
     int n_valid;                          // channels >= n_valid are computed (zero-padded weights) but not stored
@@ -48,8 +50,12 @@ struct ConvTcProblem {
     int Cin;                // channels per tap
     const void* act2;       // optional second activation tensor: channels [Cin1, Cin) of every tap come from it
     int lda2, a_chan_off2, Cin1;
-    const void* wpacked;    // fp16 [Cout][num_taps*Cin]
+    const void* wpacked;    // fp16 [Cout][num_taps*Cin (+ Cx)]
     int Cout;
+    // optional folded 1x1 conv over a second operand x (swapped-operand 3x3 kernel only): out += W1x1 x, with the 1x1 weights
+    // appended to every row of wpacked as Cx extra K columns; x may itself be a virtual concat (x_act2 holds channels >= Cx1)
+    const void* x_act; int x_lda, x_chan_off, Cx;
+    const void* x_act2; int x_lda2, x_chan_off2, Cx1;
     int num_taps;
     int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
     float* out_f32; __half* out_f16; const float* bias; const float* residual;

@@ -37,6 +37,10 @@ GN_INPUT_F32 = True
 # the pace: measured 18.2 ms vs 10.4 + 4.0 ms for the 70 G32x8 layers of cfg 3).  False: never.
 FUSE_GN_CONV = {"0": False, "1": True, "all": "all"}.get(os.environ.get("MI_FUSE_GN_CONV", "0"), False)
 
+# ResnetBlock tail  block2.project(h) + res_conv(x)  as ONE launch (mi_conv3x3_res1x1_f16: the 1x1 conv rides the 3x3 conv's
+# accumulator as extra K chunks) where block2's conv runs on the swapped-operand 3x3 kernel
+FOLD_RES_CONV = os.environ.get("MI_FOLD_RES_CONV", "1") == "1"
+
 # nearest-x2 upsample + 3x3 conv as four 2x2 sub-pixel convs on the low-res tensor (4/9 of the FLOPs, no upsampled copy)
 SUBPIXEL_UPSAMPLE = True
 
@@ -358,6 +362,46 @@ class Conv2d(nn.Conv2d):
         kh, kw = self.kernel_size
         return kh * kw <= 16 and get_ops().igemm_supported(H, W, self.in_channels, self.out_channels)
 
+    def _pack_fold(self, rc, c0, scale):
+        """[C_out][9*C_in + C_x] fp16: this 3x3 conv's packed weight followed by the 1x1 conv `rc`'s (input channels >= c0 of
+        rc carry the skip-connection scale), and the summed bias -- the operands of mi_conv3x3_res1x1_f16."""
+        key = (self.weight.data_ptr(), self.weight._version, rc.weight.data_ptr(), rc.weight._version, c0, float(scale),
+               self.bias._version if exists(self.bias) else -1, rc.bias._version if exists(rc.bias) else -1)
+        if getattr(self, "_fold_key", None) != key:
+            ops = get_ops()
+            w1 = rc.weight.detach().clone()
+            if c0 is not None:
+                w1[:, c0:] *= scale
+            self._fold_w = torch.cat((ops.pack_conv_weight(self.weight), ops.pack_conv_weight(w1)), dim=1).contiguous()
+            b = torch.zeros((self.out_channels,), dtype=F32, device=self.weight.device)
+            if exists(self.bias):
+                b = b + self.bias.detach()
+            if exists(rc.bias):
+                b = b + rc.bias.detach()
+            self._fold_b = b.contiguous()
+            self._fold_key = key
+        return self._fold_w, self._fold_b
+
+    def run_folded(self, a, B, H, W, xsrc, rc, residual=None, f32=True, f16=False, stats=False):
+        """conv3x3(a) + rc(xsrc) in one launch (see FOLD_RES_CONV); a: fp16 [B,1,H,W,C_in]; xsrc: Act / Cat; rc: 1x1 Conv2d."""
+        ops = get_ops()
+        Cin, Cout = self.in_channels, self.out_channels
+        dev = a.device
+        cat = isinstance(xsrc, Cat)
+        parts = [xsrc.a, xsrc.b] if cat else [xsrc]
+        x0 = parts[0].need_f16()
+        x1 = parts[1].need_f16() if cat else None
+        c0 = parts[0].shape[3] if cat else None
+        wp, bias = self._pack_fold(rc, c0, xsrc.scale if cat else 1.0)
+        st = stats_zeros((B, Cout // STATS_BLOCK, 2), dev) if (stats and Cout % 32 == 0 and (H * W) % 32 == 0) else None
+        if not f32 and not f16:
+            f32 = True
+        o32 = torch.empty((B, H, W, Cout), dtype=F32, device=dev) if f32 else None
+        o16 = torch.empty((B, 1, H, W, Cout), dtype=F16, device=dev) if f16 else None
+        ops.conv_res1x1(a, B, H, W, a.shape[-1], Cin, None, 0, 0, x0, x0.shape[-1], rc.in_channels, x1,
+                        x1.shape[-1] if cat else 0, c0 if cat else 0, wp, Cout, bias, residual, o32, o16, st)
+        return Act(o32, o16, st)
+
     def run_prepared(self, a, B, H, W, residual=None, f32=True, f16=False, stats=False, a2=None, c_in1=0, wp=None,
                      in_place_s2=False):
         """Conv over an already prepared operand `a`:
@@ -624,8 +668,9 @@ class Block(nn.Module):
         self.activation = nn.SiLU()
         self.project = Conv2d(dim, dim_out, 3, padding=1)
 
-    def run(self, x, scale_shift=None, residual=None, f32=True, f16=False, stats=False):
-        """x: Act / Cat.  GroupNorm statistics come from the producers' epilogue block statistics when every source has
+    def run(self, x, scale_shift=None, residual=None, f32=True, f16=False, stats=False, fold=None):
+        """x: Act / Cat.  `fold` = (xsrc, res_conv): add res_conv(xsrc) inside the conv launch (ResnetBlock tail), or None.
+        GroupNorm statistics come from the producers' epilogue block statistics when every source has
         (or can cheaply get) them and the groups are unions of 16-channel blocks; otherwise from one mi_gn_stats pass."""
         ops = get_ops()
         x = as_act(x)
@@ -637,7 +682,7 @@ class Block(nn.Module):
         tc = self.project.tc_ok(H, W)
         parts = [x.a, x.b] if isinstance(x, Cat) else [x]
         block_mode = tc and Cg % STATS_BLOCK == 0 and all(p.shape[3] % STATS_BLOCK == 0 for p in parts)
-        if (block_mode and FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or self.project.out_channels == 128)
+        if (fold is None and block_mode and FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or self.project.out_channels == 128)
                 and all(p.f32 is not None for p in parts)
                 and ops.conv_gn_supported(H, W, parts[0].shape[3], parts[1].shape[3] if len(parts) > 1 else 0,
                                           self.project.out_channels, G)):
@@ -668,6 +713,8 @@ class Block(nn.Module):
         ss_ld = scale_shift.stride(0) if exists(scale_shift) else 0
         ops.gn_apply_silu(s0, C0, s1, C1, sc, B, H * W, G, st0, sb0, st1, sb1, gn.weight, gn.bias, scale_shift, ss_ld,
                           gn.eps, a)
+        if fold is not None:
+            return self.project.run_folded(a, B, H, W, fold[0], fold[1], residual, f32=f32, f16=f16, stats=stats)
         return self.project.run_prepared(a, B, H, W, residual, f32=f32, f16=f16, stats=stats)
 
     def forward(self, x, scale_shift=None):
@@ -720,6 +767,17 @@ class ResnetBlock(nn.Module):
             assert not isinstance(x, Cat)
             res = x.need_f32()
         else:
+            _, H, W, _ = x.shape
+            c2 = self.block2.project
+            xparts = [x.a, x.b] if isinstance(x, Cat) else [x]
+            fused_gn = FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or c2.out_channels == 128) and ops.conv_gn_supported(
+                H, W, c2.in_channels, 0, c2.out_channels, self.block2.groupnorm.num_groups)
+            if (FOLD_RES_CONV and tc and not fused_gn and self.res_conv.kernel_size == (1, 1)
+                    and all(p.shape[3] % 64 == 0 for p in xparts)
+                    and ops.conv_res1x1_supported(H, W, c2.in_channels, c2.out_channels, self.res_conv.in_channels)):
+                # res_conv(x) rides block2's conv launch: no separate 1x1 kernel, no fp32 round trip of the residual branch
+                return self.block2.run(h, scale_shift, residual=None, f32=out_f32 or not tc, f16=tc, stats=tc,
+                                       fold=(x, self.res_conv))
             res = self.res_conv.run(x, f32=True).f32
         return self.block2.run(h, scale_shift, residual=res, f32=out_f32 or not tc, f16=tc, stats=tc)
 

@@ -80,6 +80,20 @@ class NativeOps:
                N.ptr(out_stats), sb, sh, sw, out_sc, n_valid, block_n, None, N.ptr(ws), ws.numel() if ws is not None else 0,
                N.stream())
 
+    def conv_res1x1_supported(self, H, W, c_in, c_out, x_cin):
+        return bool(N.load().mi_conv3x3_res1x1_supported(int(H), int(W), int(c_in), int(c_out), int(x_cin)))
+
+    def conv_res1x1(self, act, B, H, W, lda, c_in, act2, lda2, c_in1, x, ldx, x_cin, x2, ldx2, x_cin1, wp, c_out, bias,
+                    residual, out_f32, out_f16, out_stats):
+        """3x3 conv over act (+act2) plus a folded 1x1 conv over x (+x2) in one launch; wp = [c_out][9*c_in + x_cin]."""
+        for nm, t in (("act", act), ("act2", act2), ("x", x), ("x2", x2), ("wp", wp)):
+            _chk(t, F16, nm)
+        _chk(bias, F32, "bias"); _chk(residual, F32, "residual"); _chk(out_f32, F32, "out_f32"); _chk(out_f16, F16, "out_f16")
+        _chk(out_stats, F64, "out_stats")
+        N.call("mi_conv3x3_res1x1_f16", N.ptr(act), B, H, W, lda, c_in, N.ptr(act2), lda2, c_in1, N.ptr(x), ldx, x_cin,
+               N.ptr(x2), ldx2, x_cin1, N.ptr(wp), c_out, N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16),
+               N.ptr(out_stats), None, N.stream())
+
     def conv_gn_supported(self, H, W, c0, c1, c_out, groups):
         return bool(N.load().mi_conv3x3_gn_supported(int(H), int(W), int(c0), int(c1), int(c_out), int(groups)))
 

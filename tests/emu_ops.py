@@ -108,6 +108,26 @@ class EmuOps:
         if out_f16 is not None:
             _strided(out_f16, (B, H, W, nv), (sb, sh, sw, out_sc)).copy_(y.to(F16))
 
+    def conv_res1x1_supported(self, H, W, c_in, c_out, x_cin):
+        t16 = W == 16 and H % 16 == 0
+        t32 = (not t16) and H % 32 == 0 and W % 8 == 0
+        return (t16 or t32) and c_in > 0 and c_in % 64 == 0 and x_cin > 0 and x_cin % 64 == 0 and c_out % 128 == 0
+
+    def conv_res1x1(self, act, B, H, W, lda, c_in, act2, lda2, c_in1, x, ldx, x_cin, x2, ldx2, x_cin1, wp, c_out, bias,
+                    residual, out_f32, out_f16, out_stats):
+        self._log("conv_res1x1")
+        K3 = 9 * c_in
+        y = torch.zeros((B, H, W, c_out))
+        st = (H * W * c_out, W * c_out, c_out)
+        self.conv_igemm(act, B, H, W, lda, 0, c_in, wp[:, :K3].contiguous(), c_out, 3, 3, 0, None, None, y, None, st,
+                        act2=act2, lda2=lda2, c_in1=c_in1)
+        self.calls.pop()
+        y1 = torch.zeros((B, H, W, c_out))
+        self.conv_igemm(x, B, H, W, ldx, 0, x_cin, wp[:, K3:].contiguous(), c_out, 1, 1, 0, None, None, y1, None, st,
+                        act2=x2, lda2=ldx2, c_in1=x_cin1)
+        self.calls.pop()
+        self._conv_finish(y + y1, B, H, W, c_out, bias, residual, out_f32, out_f16, st, 1, 0, out_stats)
+
     def conv_gn_supported(self, H, W, c0, c1, c_out, groups):
         C = c0 + c1
         return (H % 32 == 0 and W % 8 == 0 and c0 > 0 and c0 % 64 == 0 and c1 % 64 == 0 and C > 0 and c_out % 128 == 0

@@ -622,3 +622,38 @@ def test_step_epilogue_fused_is_bit_exact(native, B, n, cfg):
     tt = t.clone()
     native.step_advance_t(tt, B)
     assert torch.equal(tt, (t - 1).clamp(min=0))
+
+
+@pytest.mark.parametrize("case", [
+    # B, H, W, Cin, Cout, Cx0, Cx1, residual, stats
+    (2, 32, 16, 128, 128, 256, 0, False, True),        # G32x8, single-tensor x
+    (2, 16, 16, 256, 256, 256, 256, True, True),       # G16x16, x = virtual concat (up-path ResnetBlock)
+    (1, 64, 32, 128, 128, 128, 128, False, False),     # G32x8, concat x
+    (3, 32, 32, 512, 512, 512, 512, False, True),      # deep K
+])
+def test_conv_res1x1_folded(native, case):
+    """mi_conv3x3_res1x1_f16 == conv3x3(act) + conv1x1(cat(x0, x1)) (+bias sum, +residual, block statistics)."""
+    B, H, W, Cin, Cout, Cx0, Cx1, res, stats = case
+    Cx = Cx0 + Cx1
+    assert native.conv_res1x1_supported(H, W, Cin, Cout, Cx)
+    a = _rand(B, 1, H, W, Cin, seed=41).to(F16)
+    x0 = _rand(B, 1, H, W, Cx0, seed=42).to(F16)
+    x1 = _rand(B, 1, H, W, Cx1, seed=43).to(F16) if Cx1 else None
+    w3 = _rand(Cout, Cin, 3, 3, seed=44, scale=(9 * Cin) ** -0.5)
+    w1 = _rand(Cout, Cx, 1, 1, seed=45, scale=Cx ** -0.5)
+    bias = _rand(Cout, seed=46)
+    r = _rand(B, H, W, Cout, seed=47) if res else None
+    wp = torch.cat((EMU.pack_conv_weight(w3), EMU.pack_conv_weight(w1)), dim=1).contiguous()
+    o_e = torch.zeros(B, H, W, Cout)
+    st_e = torch.zeros(B, Cout // 16, 2, dtype=F64) if stats else None
+    EMU.conv_res1x1(a, B, H, W, Cin, Cin, None, 0, 0, x0, Cx0, Cx, x1, Cx1, Cx0 if Cx1 else 0, wp, Cout, bias, r, o_e, None, st_e)
+    o_n = torch.full((B, H, W, Cout), float("nan"), device="cuda")
+    o16_n = torch.zeros(B, 1, H, W, Cout, dtype=F16, device="cuda")
+    st_n = torch.zeros(B, Cout // 16, 2, dtype=F64, device="cuda") if stats else None
+    native.conv_res1x1(a.cuda(), B, H, W, Cin, Cin, None, 0, 0, x0.cuda(), Cx0, Cx, _cu(x1), Cx1, Cx0 if Cx1 else 0, wp.cuda(),
+                       Cout, bias.cuda(), _cu(r), o_n, o16_n, st_n)
+    torch.cuda.synchronize()
+    assert rel_l2(o_n, o_e) < 2e-5
+    assert rel_l2(o16_n.reshape(B, H, W, Cout), o_e) < 1e-3
+    if stats:
+        assert rel_l2(st_n, st_e) < 1e-4
