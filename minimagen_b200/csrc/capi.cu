@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -127,6 +128,7 @@ static int igemm_common(const void* act, int B, int H, int W, int lda, int c_off
     // halo kernel (needs C_out % 128 == 0, H % 32 == 0), C_out = 128 / 16 layers it cannot take on the pixel-major halo
     // kernel, everything else on the CTA-pair kernel (all chosen inside conv_tc_launch)
     p.halo = (mode == 0 && kh == 3 && kw == 3) ? 1 : ((mode == 0 && kh == 15 && kw == 1) ? 3 : 0);   // 3: 15-tap vertical (stem)
+    if (mode >= 2 && mode <= 5 && !getenv("MI_SUBPIX_PAIR")) p.halo = 4;   // sub-pixel phase on the swapped-operand kernel (32 x 8 tiles)
     // 1x1 convs stay on the pixel-major 1-CTA kernel: the swapped-operand row-tile form (conv3x3_halo_t_kernel<kGLin>,
     // parity-tested in test_conv_tc) measured 0.037 / 0.047 / 0.066 / 0.119 ms against 0.033 / 0.043 / 0.056 / 0.095 ms on the
     // four res_conv shapes of cfg 3 -- short-K layers are output-bound and the smem-transposing epilogue wins there

@@ -698,14 +698,17 @@ constexpr int kHtPix = 256;                                                   //
 // pixels from a (32+14) x 8 tile; tap dh is the window that starts dh rows in (segments at the standard 1024-byte stride).
 // Geometry Lin (1x1 convs / linears): the pixels of an NHWC tensor are just rows, so a tile is 256 consecutive rows (one 2-D
 // TMA box, zero-filled past the end), one tap, no halo.
-enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2, kGLin = 3 };
+// Geometry Sub (one sub-pixel phase of "nearest x2 up-sampling + 3x3 conv", ABI modes 2..5): 2 x 2 taps on the LOW-RES tensor; a
+// 32 x 8 tile reads a (32+1) x (8+1) halo tile whose origin is the phase's first tap; tap (r, s) starts (r*9 + s) pixels in,
+// segments one 9-pixel halo row apart; the epilogue writes every second pixel / row of the 2H x 2W output (caller's strides).
+enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2, kGLin = 3, kGSub = 4 };
 template <int G>
 struct CfgT {
     static constexpr bool kW16 = G == kG16x16;
-    static constexpr int kTaps = G == kGV15 ? 15 : (G == kGLin ? 1 : 9);
+    static constexpr int kTaps = G == kGV15 ? 15 : (G == kGLin ? 1 : (G == kGSub ? 4 : 9));
     static constexpr int kTH = G == kGLin ? 256 : (kW16 ? 16 : 32), kTW = G == kGLin ? 1 : (kW16 ? 16 : 8);   // output tile
-    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : (G == kGLin ? 256 : kTH + 2);
-    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : (G == kGLin ? 1 : 8));          // TMA box (pixels)
+    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : (G == kGLin ? 256 : (G == kGSub ? kTH + 1 : kTH + 2));
+    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : (G == kGLin ? 1 : (G == kGSub ? 9 : 8)));   // TMA box (pixels)
     static constexpr uint32_t kHaloBytes = kBoxH * kBoxW * 128;               // 43520 / 36864 / 47104
     static constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;
     static constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                // one (tap, chunk) weight tile
@@ -792,8 +795,8 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 for (int l = 0; l < kLoads; ++l) {
                     ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 3100 + sh);
                     if (ptx::elect_one()) {
-                        const int wc = kW16 ? w0 + l - 1 : (G == kGV15 ? w0 : w0 - 1);   // G16x16: copy l is shifted by dw = l - 1
-                        const int hc = G == kGV15 ? h0 - 7 : h0 - 1;
+                        const int wc = kW16 ? w0 + l - 1 : (G == kGV15 ? w0 : (G == kGSub ? w0 + args.dw[0] : w0 - 1));   // G16x16: copy l is shifted by dw = l - 1
+                        const int hc = G == kGV15 ? h0 - 7 : (G == kGSub ? h0 + args.dh[0] : h0 - 1);          // Sub: origin = the phase's first tap
                         ptx::mbar_arrive_expect_tx(&fullH[sh], C::kHaloBytes);
                         if constexpr (G == kGLin) {      // rows [h0, h0 + 256) of the (channels, pixels) matrix
                             if (j < args.a_split)
@@ -871,6 +874,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             const uint64_t db = kW16 ? make_halo_t_desc(h_base + u * 16 * 128, 1024)
                                 : (G == kGLin ? make_halo_t_desc(h_base, 1024)
                                 : G == kGV15 ? make_halo_t_desc(h_base + u * 8 * 128, 1024)
+                                : G == kGSub ? make_halo_t_desc(h_base + ((u >> 1) * C::kBoxW + (u & 1)) * 128, C::kBoxW * 128)
                                               : make_halo_t_desc(h_base + ((u / 3) * C::kBoxW + (u % 3)) * 128, C::kBoxW * 128));
 #pragma unroll
                             for (int k = 0; k < kConvBlockK / 16; ++k)
@@ -1195,10 +1199,12 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
     const bool t16 = p.W == 16 && p.H % 16 == 0;                       // G16x16: one 16 x 16 tile per image (row block)
     const bool t32 = !t16 && p.H % 32 == 0 && p.W % 8 == 0;            // G32x8
     const bool v15 = p.halo == 3 && p.num_taps == 15 && t32 && !p.act2;   // 15-tap vertical conv (stem)
-    if (p.halo && p.halo != 2 && (v15 || (p.halo != 3 && p.num_taps == 9)) && p.phases == 1 && (t16 || t32) &&
+    const bool sub = p.halo == 4 && p.num_taps == 4 && t32 && !p.act2 && !p.x_act;   // one sub-pixel phase of the up-sampling conv
+    if (p.halo && p.halo != 2 && (v15 || sub || (p.halo != 3 && p.halo != 4 && p.num_taps == 9)) && p.phases == 1 && (t16 || t32) &&
         p.Cout % 128 == 0 && p.out_sc <= 1 && (p.n_valid == 0 || p.n_valid == p.Cout) && p.dbg == 0) {
         bool canon = true;
         if (v15) for (int t = 0; t < 15; ++t) canon = canon && p.dh[t] == t - 7 && p.dw[t] == 0 && p.ph[t] == 0;
+        else if (sub) for (int t = 0; t < 4; ++t) canon = canon && p.dh[t] == p.dh[0] + (t >> 1) && p.dw[t] == p.dw[0] + (t & 1) && p.ph[t] == 0;
         else for (int t = 0; t < 9; ++t) canon = canon && p.dh[t] == t / 3 - 1 && p.dw[t] == t % 3 - 1 && p.ph[t] == 0;
         if (p.act2 && (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) ||
                        (reinterpret_cast<uintptr_t>(p.act2) & 15)))
@@ -1212,11 +1218,13 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
             h.out_sb = p.out_sb; h.out_sh = p.out_sh; h.out_sw = p.out_sw; h.out_sc = 1; h.n_valid = p.Cout;
             h.out_f32 = p.out_f32; h.out_f16 = p.out_f16; h.bias = p.bias; h.residual = p.residual; h.err_flag = p.err_flag;
             h.stats = p.stats; h.stats_blocks = p.Cout / 16;
+            h.dh[0] = p.dh[0]; h.dw[0] = p.dw[0];        // Sub: halo origin relative to the tile (the phase's first tap)
             int dev = 0, num_sms = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
             CUtensorMap tmA, tmA2, tmB;
-            cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)(t16 ? 16 : (v15 ? 8 : 10)), (cuuint32_t)(t16 ? 18 : (v15 ? 46 : 34)), 1, 1};
+            cuuint32_t box[5] = {kConvBlockK, (cuuint32_t)(t16 ? 16 : (v15 ? 8 : (sub ? 9 : 10))),
+                                 (cuuint32_t)(t16 ? 18 : (v15 ? 46 : (sub ? 33 : 34))), 1, 1};
             cuuint32_t estr[5] = {1, 1, 1, 1, 1};
             {
                 cuuint64_t gdim[5] = {(cuuint64_t)p.a_channels, (cuuint64_t)p.W, (cuuint64_t)p.H, 1, (cuuint64_t)p.B};
@@ -1271,6 +1279,7 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
                 return -7;
             const int total = h.tiles_w * h.tiles_h * h.tiles_b * h.tiles_n;
             if (v15) return launch_halo_t<kGV15>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream);
+            if (sub) return launch_halo_t<kGSub>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream);
             return t16 ? launch_halo_t<kG16x16>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream)
                        : launch_halo_t<kG32x8>(tmA, tmA2, tmB, tmX, tmX2, h, total, num_sms, stream);
         }

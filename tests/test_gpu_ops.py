@@ -332,7 +332,8 @@ def test_conv3x3_swapped_halo_paths(native, B, H, W, C0, C1, Cout):
     assert rel_l2(st_n, st_e) < 1e-5
 
 
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 256), (2, 8, 8, 64, 64)])
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 256), (2, 8, 8, 64, 64),
+                                           (3, 64, 16, 128, 128), (2, 32, 8, 64, 128), (1, 64, 64, 256, 128)])   # last three: swapped-operand Sub geometry
 def test_conv_igemm_subpixel_upsample_phases(native, B, H, W, Cin, Cout):
     """modes 2..5: the four 2x2 sub-pixel phases of 'nearest x2 upsample + 3x3 conv' on the low-res tensor, written
     interleaved into the 2H x 2W output; vs the emulation and vs the literal upsample + conv"""
