@@ -739,6 +739,8 @@ def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):
     stem_alg_per_pixel = sum(2.0 * c.kernel_size[0] ** 2 * c.in_channels * c.out_channels for c in stem.convs)
 
     def is_halo_t(H, W, c_out, kh, kw_, mode):
+        if 2 <= mode <= 5:          # sub-pixel phase on the swapped-operand kernel's Sub geometry
+            return c_out % 128 == 0 and H % 32 == 0 and W % 8 == 0 and W != 16 and not os.environ.get("MI_SUBPIX_PAIR")
         return (mode == 0 and (kh, kw_) in ((3, 3), (15, 1)) and c_out % 128 == 0 and
                 ((W == 16 and H % 16 == 0 and kh == 3) or (H % 32 == 0 and W % 8 == 0 and W != 16)))
 
@@ -764,6 +766,20 @@ def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):
                       (4 * mn if residual is not None else 0) + (4 * mn if out_f32 is not None else 0) +
                       (2 * mn if out_f16 is not None else 0))
             events.append((s, e, alg, exe, nbytes, is_halo_t(H, W, c_out, kh, kw_, mode)))
+
+        def conv_res1x1(self, act, B, H, W, lda, c_in, act2, lda2, c_in1, x, ldx, x_cin, x2, ldx2, x_cin1, wp, c_out, bias,
+                        residual, out_f32, out_f16, out_stats):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            super().conv_res1x1(act, B, H, W, lda, c_in, act2, lda2, c_in1, x, ldx, x_cin, x2, ldx2, x_cin1, wp, c_out, bias,
+                                residual, out_f32, out_f16, out_stats)
+            e.record()
+            px = B * H * W
+            fl = 2.0 * px * c_out * (9 * c_in + x_cin)               # the 3x3 conv plus the folded 1x1 res_conv
+            mn = px * c_out
+            nbytes = (px * (c_in + x_cin) * 2 + c_out * (9 * c_in + x_cin) * 2 + (4 * mn if residual is not None else 0) +
+                      (4 * mn if out_f32 is not None else 0) + (2 * mn if out_f16 is not None else 0))
+            events.append((s, e, fl, fl, nbytes, True))
 
         def conv_gn(self, src0, c0, src1, c1, scale1, B, H, W, groups, stats0, stats1, gamma, beta, scale_shift, ss_ld,
                     eps, wp, c_out, bias, residual, out_f32, out_f16, out_stats, *a, **k):
@@ -795,8 +811,8 @@ def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):
         for key in (("all", "dominant") if dom else ("all",)):
             r = res[key]
             r["ms"] += ms; r["alg_flops"] += alg; r["exe_flops"] += exe; r["n"] += 1; r["bytes"] += nb
-    res["dominant_name"] = ("conv3x3_halo_t_kernel family (tcgen05 swapped-operand 3x3 / 15x1 halo conv, incl. its fused "
-                            "GroupNorm-prologue form)")
+    res["dominant_name"] = ("conv3x3_halo_t_kernel family (tcgen05 swapped-operand halo conv: 3x3, 3x3 + folded 1x1 res_conv, 15x1 "
+                            "stem, 2x2 sub-pixel phases; incl. the fused GroupNorm-prologue form when enabled)")
     if res["dominant"]["n"] == 0:
         res["dominant"] = res["all"]
         res["dominant_name"] = "tcgen05 implicit-GEMM convolutions (all launches)"

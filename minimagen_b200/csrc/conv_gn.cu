@@ -65,7 +65,6 @@ __device__ __forceinline__ void xform_bar_sync() {           // the twelve trans
 __global__ void __launch_bounds__(kGnThreads, 1)
 conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args,
                     const __grid_constant__ GnPrologueArgs gn) {
-    pdl_trigger();
     constexpr int NH = kHStages, NW = kWStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -126,6 +125,7 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                 }
             }
         }
+        pdl_trigger();      // last weight loads issued: the next kernel may be scheduled behind this one's final tile(s)
     } else if (warp == 1) {
         // ===================== MMA issuer: D^T[128 ch][256 px] += W_tile[128][64] x window^T =====================
         constexpr uint32_t idesc = ptx::make_idesc_f16(128, kPix, 0);

@@ -52,7 +52,6 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
-    pdl_trigger();
     using C = Cfg<BLOCK_N>;
     constexpr int STAGES = C::kStages;
 
@@ -141,6 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         }
+        pdl_trigger();      // last loads issued: the next kernel may be scheduled behind this one's final tile(s)
     } else if (warp == 1) {
         // ===================== MMA issuer (warp stays converged, one elected lane issues) =====================
         constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0 /*fp16*/);
@@ -264,7 +264,6 @@ template <int BLOCK_N, int KC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kNumThreads, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvTcArgs args) {
-    pdl_trigger();
     using C = Cfg2<BLOCK_N, KC>;
     constexpr int STAGES = C::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -361,6 +360,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (j >= args.chunks_per_tap) { j = 0; ++t; }
             }
         }
+        pdl_trigger();      // last loads issued: the next kernel may be scheduled behind this one's final tile(s)
     } else if (warp == 1) {
         if (leader) {
             // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
@@ -516,7 +516,6 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ ConvTcArgs args) {
-    pdl_trigger();
     using C = CfgH<BLOCK_N>;
     constexpr int NA = C::kAStages, NB = C::kBStages;
     extern __shared__ uint8_t smem_raw[];
@@ -603,6 +602,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
+        pdl_trigger();      // last loads issued: the next kernel may be scheduled behind this one's final tile(s)
     } else if (warp == 1) {
         // ===================== MMA issuer (converged warp, one elected lane issues) =====================
         constexpr uint32_t idesc = ptx::make_idesc_f16(kConvBlockM, BLOCK_N, 0);
@@ -732,7 +732,6 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                       const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmX,
                       const __grid_constant__ CUtensorMap tmX2, const __grid_constant__ ConvTcArgs args) {
-    pdl_trigger();
     using C = CfgT<G>;
     constexpr bool kW16 = C::kW16;
     constexpr int NH = C::kHStages, NW = C::kWStages;
@@ -847,6 +846,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 }
             }
         }
+        pdl_trigger();      // last loads issued: the next kernel may be scheduled behind this one's final tile(s)
     } else if (warp == 1) {
         // ===================== MMA issuer: D^T[128 ch][256 px] += W_tile[128][64] x window^T =====================
         constexpr uint32_t idesc = ptx::make_idesc_f16(128, kHtPix, 0);
