@@ -144,7 +144,7 @@ def physical_cores():
     return max(1, len(sets)), len(cpus)
 
 
-def cpu_baseline(wl, sd, batches=(1, 2, 4), steps=2, warmup=1, budget_s=45.0):
+def cpu_baseline(wl, sd, batches=(1, 2, 4), steps=2, warmup=1, budget_s=70.0):
     """The reference's algorithm (CPU oracle port) on the host cores: U-Net forward + DDPM step at batch 1, 2 and 4 (each:
     `warmup` + `steps` timed), the per-image time of the LARGEST batch scaled linearly to the workload batch (SURVEY.md 8d;
     the full batch would take ~1 minute per step).  Stops adding batch sizes once `budget_s` of CPU time is spent."""
@@ -324,6 +324,8 @@ def main():
     ap.add_argument("--fuse", default=None, choices=["off", "on", "all"], help="fused GroupNorm+conv kernel usage")
     ap.add_argument("--kernel-table", default=None, help="write a CUPTI per-kernel time table of 3 steps to this path")
     ap.add_argument("--pdl", type=int, default=None, help="programmatic dependent launch on (1) / off (0)")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (for `ncu --profile-from-start off`: launch lists of exactly K steps)")
     ap.add_argument("--gn-f16", action="store_true", help="GroupNorm inputs in fp16 (faster, 1.05e-3 instead of 9e-4 rel-L2)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -482,9 +484,14 @@ def main():
         sampler = ClockSampler(local_rank) if rank == 0 else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        if args.profiler_range:
+            torch.cuda.profiler.start()
         e0.record()
         for _ in range(args.steps):
             replay()
+        if args.profiler_range:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         if world > 1:
             ops.step_finalize(state().contiguous(), state().numel(), 1, slot)     # straight into this rank's gather slot
             dist.all_gather_into_tensor(gathered, slot)                            # the path's single collective, in place
@@ -708,23 +715,43 @@ def main():
 
 
 def kernel_table(fn, steps, path):
-    """Diagnostics only (never a bench value): CUPTI kernel records of `steps` un-serialised steps, summed per kernel."""
+    """Diagnostics only (never a bench value): CUPTI kernel records of `steps` un-serialised steps, summed per kernel, plus
+    the idle gaps between consecutive kernels (start of the next minus end of the previous) attributed to the PRECEDING kernel."""
     import collections
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         fn()
         torch.cuda.synchronize()
     agg = collections.defaultdict(lambda: [0, 0.0])
+    recs = []
     for ev in prof.events():
         if ev.device_type is not None and str(ev.device_type).endswith("CUDA"):
             a = agg[ev.name[:110]]
             a[0] += 1
-            a[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            dur = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            a[1] += dur
+            try:
+                recs.append((ev.time_range.start, ev.time_range.start + dur, ev.name[:70]))
+            except Exception:
+                pass
     tot = sum(t for _, t in agg.values())
     with open(path, "w") as f:
         f.write(f"# per-step kernel time (CUPTI, {steps} steps averaged), total {tot / steps / 1e3:.3f} ms/step\n")
         for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"{t / steps / 1e3:9.3f} ms {c / steps:7.1f} launches  {name}\n")
+        if len(recs) > 2:
+            recs.sort()
+            gaps = collections.defaultdict(lambda: [0, 0.0])
+            span = recs[-1][1] - recs[0][0]
+            for (s0, e0, n0), (s1, e1, n1) in zip(recs, recs[1:]):
+                g = max(0.0, s1 - e0)
+                gaps[n0][0] += 1
+                gaps[n0][1] += g
+            gtot = sum(v[1] for v in gaps.values())
+            f.write(f"# idle gaps between consecutive kernels: {gtot / steps / 1e3:.3f} ms/step of a {span / steps / 1e3:.3f} ms/step "
+                    f"span; by preceding kernel (total ms/step, mean us per boundary):\n")
+            for name, (c, t) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:12]:
+                f.write(f"#   {t / steps / 1e3:7.3f} ms  {t / max(c, 1):6.2f} us x {c / steps:6.1f}  after {name}\n")
 
 
 def measure_conv_kernels(imagen, unet, x, t_dev, shape, kw, dev):

@@ -133,6 +133,8 @@ gn_stats_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ sr
 // (scale, shift) into ONE per-channel multiply-add   y = x * A[c] + Bc[c]   kept in shared memory (cost C, amortised
 // over kGnApplyPix * C elements), so the streaming loop is 2 x LDG.128 + 4 x LDS.128 + 8 FMA + 8 SiLU + 1 x STG.128.
 // grid = (ceil(HW / pix_per_cta), B)
+constexpr int kGnSlab = 256;      // channels per CTA of gn_apply_silu_kernel (a multiple of 8)
+
 template <typename InT, typename OutT, bool kFast>
 __global__ void __launch_bounds__(256)
 gn_apply_silu_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict__ src1, int C1, float scale1,
@@ -176,9 +178,15 @@ gn_apply_silu_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict
         s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
     }
     __syncthreads();
+    // this CTA's channel slab [c_lo, c_lo + slab): only its coefficients are built (at C = 1024..4096 a CTA that covered all
+    // channels of a few pixels spent as long on the table as on the data)
+    const int slab = min(C, kGnSlab);
+    const int c_lo = blockIdx.z * slab;
+    const int c_n = min(slab, C - c_lo);
     float* sA = s_ab;
-    float* sB = s_ab + C;
-    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float* sB = s_ab + slab;
+    for (int cl = threadIdx.x; cl < c_n; cl += blockDim.x) {
+        const int ch = c_lo + cl;
         const int g = ch / Cg;
         float a = s_rstd[g] * gamma[ch];
         float bb = beta[ch] - s_mean[g] * a;
@@ -188,29 +196,29 @@ gn_apply_silu_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict
             a *= sc;
             bb = bb * sc + sh;
         }
-        sA[ch] = a;
-        sB[ch] = bb;
+        sA[cl] = a;
+        sB[cl] = bb;
     }
     __syncthreads();
-    const int V8 = C >> 3;
+    const int V8 = c_n >> 3;
     const int p0 = blockIdx.x * pix_per_cta;
     const int npix = min(pix_per_cta, HW - p0);
     const int total = npix * V8;
     const long long pix_base = (long long)b * HW + p0;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int c = (idx % V8) << 3;
+    auto one = [&](int idx, const float (&v_in)[8]) {
+        const int cl = (idx % V8) << 3;
         const long long pix = pix_base + idx / V8;
         float v[8];
-        load_cat8<InT>(src0, C0, src1, C1, scale1, pix, c, v);
-        const float4 a0 = *reinterpret_cast<const float4*>(sA + c), a1 = *reinterpret_cast<const float4*>(sA + c + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(sB + c), b1 = *reinterpret_cast<const float4*>(sB + c + 4);
-        v[0] = fmaf(v[0], a0.x, b0.x); v[1] = fmaf(v[1], a0.y, b0.y); v[2] = fmaf(v[2], a0.z, b0.z); v[3] = fmaf(v[3], a0.w, b0.w);
-        v[4] = fmaf(v[4], a1.x, b1.x); v[5] = fmaf(v[5], a1.y, b1.y); v[6] = fmaf(v[6], a1.z, b1.z); v[7] = fmaf(v[7], a1.w, b1.w);
+        const float4 a0 = *reinterpret_cast<const float4*>(sA + cl), a1 = *reinterpret_cast<const float4*>(sA + cl + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(sB + cl), b1 = *reinterpret_cast<const float4*>(sB + cl + 4);
+        v[0] = fmaf(v_in[0], a0.x, b0.x); v[1] = fmaf(v_in[1], a0.y, b0.y); v[2] = fmaf(v_in[2], a0.z, b0.z); v[3] = fmaf(v_in[3], a0.w, b0.w);
+        v[4] = fmaf(v_in[4], a1.x, b1.x); v[5] = fmaf(v_in[5], a1.y, b1.y); v[6] = fmaf(v_in[6], a1.z, b1.z); v[7] = fmaf(v_in[7], a1.w, b1.w);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             if constexpr (kFast) v[e] = __fdividef(v[e], 1.0f + __expf(-v[e]));
             else v[e] = silu_f(v[e]);
         }
+        const int c = c_lo + cl;
         if constexpr (sizeof(OutT) == 2) {
             const uint2 lo = pack_half4(v[0], v[1], v[2], v[3]), hi = pack_half4(v[4], v[5], v[6], v[7]);
             *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(out) + pix * C + c) = make_uint4(lo.x, lo.y, hi.x, hi.y);
@@ -219,6 +227,21 @@ gn_apply_silu_kernel(const InT* __restrict__ src0, int C0, const InT* __restrict
             *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
         }
+    };
+    // two independent items per iteration: both loads are in flight before either is consumed
+    int idx = threadIdx.x;
+    for (; idx + (int)blockDim.x < total; idx += 2 * blockDim.x) {
+        const int i1 = idx + blockDim.x;
+        float x0[8], x1[8];
+        load_cat8<InT>(src0, C0, src1, C1, scale1, pix_base + idx / V8, c_lo + ((idx % V8) << 3), x0);
+        load_cat8<InT>(src0, C0, src1, C1, scale1, pix_base + i1 / V8, c_lo + ((i1 % V8) << 3), x1);
+        one(idx, x0);
+        one(i1, x1);
+    }
+    if (idx < total) {
+        float x0[8];
+        load_cat8<InT>(src0, C0, src1, C1, scale1, pix_base + idx / V8, c_lo + ((idx % V8) << 3), x0);
+        one(idx, x0);
     }
 }
 
@@ -671,12 +694,12 @@ int gn_apply_silu(const void* src0, int C0, const void* src1, int C1, float scal
         if (C0 % sb0 || Cg % sb0 || (C1 && (sb1 <= 0 || C1 % sb1 || Cg % sb1 || !stats1))) return -1;
         if (C1 && (C0 % sb1)) return -1;
     }
-    int pix = 16384 / C;               // ~16K elements per CTA (8K / 32K / 64K measured slower, tools/bench_ops.py gn)
+    const int slab = C < kGnSlab ? C : kGnSlab;              // channels per CTA (grid.z walks the slabs)
+    int pix = 16384 / slab;            // ~16K elements per CTA (8K / 32K / 64K measured slower, tools/bench_ops.py gn)
     if (pix < 1) pix = 1;
     if (pix > HW) pix = HW;
-    const size_t smem = 2 * (size_t)C * sizeof(float);
-    if (smem > 48 * 1024) return -1;
-    dim3 grid((HW + pix - 1) / pix, B);
+    const size_t smem = 2 * (size_t)slab * sizeof(float);
+    dim3 grid((HW + pix - 1) / pix, B, (C + slab - 1) / slab);
 #define MI_GN_LAUNCH(IN, OUT, FAST)                                                                                 \
     launch_k(gn_apply_silu_kernel<IN, OUT, FAST>, grid, 256, smem, st, (const IN*)src0, C0, (const IN*)src1, C1, scale1, HW, \
                                                                  groups, stats0, sb0, stats1, sb1, gamma, beta,      \
