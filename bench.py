@@ -321,7 +321,7 @@ def main():
     ap.add_argument("--no-torch-gpu", action="store_true")
     ap.add_argument("--secondary", default="cfg1,cfg2a,cfg2b,cfg4,cfg5", help="comma list of secondary configurations")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--fuse", default=None, choices=["off", "on", "all"], help="fused GroupNorm+conv kernel usage")
+    ap.add_argument("--fuse", default=None, choices=["off", "pair", "on", "all"], help="fused GroupNorm+conv kernel usage")
     ap.add_argument("--kernel-table", default=None, help="write a CUPTI per-kernel time table of 3 steps to this path")
     ap.add_argument("--pdl", type=int, default=None, help="programmatic dependent launch on (1) / off (0)")
     ap.add_argument("--profiler-range", action="store_true",
@@ -394,7 +394,7 @@ def main():
     if args.gn_f16:
         layers.GN_INPUT_F32 = False
     if args.fuse is not None:
-        layers.FUSE_GN_CONV = {"off": False, "on": True, "all": "all"}[args.fuse]
+        layers.FUSE_GN_CONV = {"off": False, "pair": "pair", "on": True, "all": "all"}[args.fuse]
     ops = __import__("minimagen_b200.ops", fromlist=["get_ops"]).get_ops()
 
     peaks = {}

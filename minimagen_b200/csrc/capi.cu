@@ -181,7 +181,9 @@ int mi_conv3x3_gn_silu_f16(const float* src0, int c0, const float* src1, int c1,
     p.ss_ld = scale_shift_ld; p.eps = eps; p.wpacked = w; p.Cout = c_out; p.bias = bias; p.residual = residual;
     p.out_f32 = out_f32; p.out_f16 = (__half*)out_f16; p.out_stats = out_stats; p.err_flag = err_flag;
     if (scale_shift && scale_shift_ld < 2 * (c0 + c1)) return fail(-8, "mi_conv3x3_gn_silu_f16: scale_shift_ld < 2*C");
-    const int rc = mi::conv_gn_launch(p, S(stream));
+    // C_out % 256 == 0: the CTA-pair kernel (half the prologue per tensor FLOP); otherwise the single-CTA kernel
+    const bool pair = mi::conv_gn_pair_supported(H, W, c0, c1, c_out, groups) && !getenv("MI_GN_NO_PAIR");
+    const int rc = pair ? mi::conv_gn_pair_launch(p, S(stream)) : mi::conv_gn_launch(p, S(stream));
     if (rc != 0) return fail(rc, rc == -3 ? "mi_conv3x3_gn_silu_f16: unsupported geometry (see mi_conv3x3_gn_supported)"
                                           : mi::conv_tc_strerror(rc));
     return 0;

@@ -109,6 +109,9 @@ struct ConvGnProblem {
 
 bool conv_gn_supported(int H, int W, int C0, int C1, int Cout, int groups);
 int conv_gn_launch(const ConvGnProblem& p, cudaStream_t stream);
+// CTA-pair form (conv_gn_pair.cu): C_out % 256 == 0, two CTAs share one prologue per 256-channel x 256-pixel tile
+bool conv_gn_pair_supported(int H, int W, int C0, int C1, int Cout, int groups);
+int conv_gn_pair_launch(const ConvGnProblem& p, cudaStream_t stream);
 
 bool conv_tc_supported(int H, int W, int Cin, int Cout);
 int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream);

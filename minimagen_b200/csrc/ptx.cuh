@@ -185,6 +185,41 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
         ::"r"(smem_u32(bar)), "r"(cta)
         : "memory");
 }
+// cluster-scope release / acquire forms: a CTA hands generic-proxy shared-memory writes (made visible to the async proxy by
+// fence.proxy.async) to a tcgen05.mma.cta_group::2 issued by the OTHER CTA of the pair
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 remAddr32;\n\t"
+        "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t"
+        "}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity, int* err, int code) {
+    if (mbar_try_wait_acquire_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_acquire_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            if (err) { atomicExch(err, code); __threadfence_system(); }
+            __trap();
+        }
+    }
+}
 // TMA loads issued by either CTA of a pair; completion bytes are signalled on the LEADER CTA's barrier
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
     asm volatile(

@@ -31,11 +31,23 @@ GN_INPUT_F32 = True
 
 # Block.forward as ONE kernel (GroupNorm/FiLM/SiLU as the conv's prologue: mi_conv3x3_gn_silu_f16) where the geometry allows
 # (3x3, H % 32 == 0, W % 8 == 0, channels % 64, C_out % 128, fp32 sources with epilogue block statistics)
-# True: where it pays -- C_out == 128 (one channel tile per pixel tile: every activation element is transformed once; these are
-# the full-resolution, output-bound layers that also carry most of the GroupNorm-apply traffic).  'all': wherever supported (with
-# C_out = 256..1024 every one of the 2..8 channel tiles re-does the transform and the prologue warps, not the tensor pipe, set
-# the pace: measured 18.2 ms vs 10.4 + 4.0 ms for the 70 G32x8 layers of cfg 3).  False: never.
-FUSE_GN_CONV = {"0": False, "1": True, "all": "all"}.get(os.environ.get("MI_FUSE_GN_CONV", "0"), False)
+# 'pair' : layers with C_out % 256 == 0 on the CTA-pair kernel (conv_gn_pair.cu: two CTAs share one prologue per 256-channel
+#          tile -- half the prologue work per tensor FLOP);
+# True   : 'pair' plus the C_out == 128 layers on the single-CTA kernel (one channel tile per pixel tile);
+# 'all'  : wherever supported; False: never.   Measurements: profiles/r02_fused_gn_study.md.
+FUSE_GN_CONV = {"0": False, "1": True, "pair": "pair", "all": "all"}.get(os.environ.get("MI_FUSE_GN_CONV", "0"), False)
+# a ResnetBlock tail can either fold res_conv into block2's conv (FOLD_RES_CONV) or run block2 on the fused kernel; which wins
+FUSE_OVER_FOLD = os.environ.get("MI_FUSE_OVER_FOLD", "1") == "1"
+
+
+def fuse_block_ok(c_out):
+    """Does the FUSE_GN_CONV policy select the fused kernel for a Block whose conv has `c_out` output channels?"""
+    if not FUSE_GN_CONV:
+        return False
+    if FUSE_GN_CONV == 'all':
+        return True
+    return c_out % 256 == 0 or (FUSE_GN_CONV is True and c_out == 128)
+
 
 # ResnetBlock tail  block2.project(h) + res_conv(x)  as ONE launch (mi_conv3x3_res1x1_f16: the 1x1 conv rides the 3x3 conv's
 # accumulator as extra K chunks) where block2's conv runs on the swapped-operand 3x3 kernel
@@ -682,7 +694,7 @@ class Block(nn.Module):
         tc = self.project.tc_ok(H, W)
         parts = [x.a, x.b] if isinstance(x, Cat) else [x]
         block_mode = tc and Cg % STATS_BLOCK == 0 and all(p.shape[3] % STATS_BLOCK == 0 for p in parts)
-        if (fold is None and block_mode and FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or self.project.out_channels == 128)
+        if (fold is None and block_mode and fuse_block_ok(self.project.out_channels)
                 and all(p.f32 is not None for p in parts)
                 and ops.conv_gn_supported(H, W, parts[0].shape[3], parts[1].shape[3] if len(parts) > 1 else 0,
                                           self.project.out_channels, G)):
@@ -770,7 +782,7 @@ class ResnetBlock(nn.Module):
             _, H, W, _ = x.shape
             c2 = self.block2.project
             xparts = [x.a, x.b] if isinstance(x, Cat) else [x]
-            fused_gn = FUSE_GN_CONV and (FUSE_GN_CONV == 'all' or c2.out_channels == 128) and ops.conv_gn_supported(
+            fused_gn = FUSE_OVER_FOLD and fuse_block_ok(c2.out_channels) and ops.conv_gn_supported(
                 H, W, c2.in_channels, 0, c2.out_channels, self.block2.groupnorm.num_groups)
             if (FOLD_RES_CONV and tc and not fused_gn and self.res_conv.kernel_size == (1, 1)
                     and all(p.shape[3] % 64 == 0 for p in xparts)

@@ -237,6 +237,9 @@ def test_groupnorm_block_statistics_from_conv_epilogue(native):
     (2, 32, 16, 128, 256, 128, True, True),          # GroupNorm groups (48 channels) straddle the two sources
     (1, 32, 32, 512, 512, 512, True, True),          # deep K (16 chunks), 4 channel tiles
     (5, 64, 32, 128, 0, 128, True, False),           # two chunks, many tiles per image
+    (2, 64, 32, 256, 0, 256, True, True),            # CTA-pair kernel (C_out % 256 == 0), several pair tiles per image
+    (3, 32, 8, 128, 128, 512, False, True),          # pair kernel, two 256-channel tiles, concat
+    (1, 32, 32, 512, 512, 1024, True, True),         # pair kernel, deep K
 ])
 def test_fused_groupnorm_conv(native, B, H, W, C0, C1, Cout, res, ss):
     """mi_conv3x3_gn_silu_f16 == mi_gn_apply_silu (block statistics) followed by mi_conv2d_igemm_f16"""
