@@ -570,6 +570,12 @@ def main():
             guarded("cfg2a", lambda: dict(measure_config(
                 imagen, imagen.unets[0], w2, "cfg2a", per_gpu=64, micro=64, cond_scale=1.0, cfg_batched=False, steps=10,
                 warmup=3, global_batch=64 * world, scaling="weak", **common), workload=w2["desc"]), imagen)
+        if world > 1 and 32 % world == 0:
+            # the headline configuration at a FIXED global batch of 32 (strong scaling: 32/N per GPU); at N = 1 it is the headline
+            w3s = workload("cfg3")
+            guarded("cfg3_strong", lambda: dict(measure_config(
+                imagen, imagen.unets[-1], w3s, "cfg3", per_gpu=32 // world, micro=32 // world, cond_scale=1.0, cfg_batched=False,
+                steps=10, warmup=3, global_batch=32, scaling="strong", **common), workload=w3s["desc"] + ", global batch 32"), imagen)
         if "cfg4" in sec_list and 128 % world == 0:
             per = 128 // world
             w2, w3 = workload("cfg2a"), workload("cfg3")
