@@ -88,7 +88,7 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
 
     if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmB);
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NH; ++i) { ptx::mbar_init(&fullH[i], kXformThreads); ptx::mbar_init(&emptyH[i], 1); }
+        for (int i = 0; i < NH; ++i) { ptx::mbar_init(&fullH[i], kXformThreads / 32); ptx::mbar_init(&emptyH[i], 1); }
         for (int i = 0; i < NW; ++i) { ptx::mbar_init(&fullW[i], 1); ptx::mbar_init(&emptyW[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 32 * kGnEpiWarps); }
         ptx::fence_barrier_init();
@@ -271,7 +271,8 @@ conv3x3_gn_t_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_consta
                     }
                 }
                 ptx::fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor core (async proxy)
-                ptx::mbar_arrive(&fullH[sh]);
+                __syncwarp();                         // one arrival per warp: 384 serialised arrivals per stage cost more than the math
+                if (lane == 0) ptx::mbar_arrive(&fullH[sh]);
                 if (++sh == NH) { sh = 0; ph ^= 1; }
             }
         }

@@ -18,6 +18,7 @@
 #include "conv_tc.cuh"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -65,7 +66,7 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_w = smem + NH * kHaloStride;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_w + NW * kWBytes);
-    uint64_t* fullH = bars;                      // leader: 2 x 384 transform-thread arrivals
+    uint64_t* fullH = bars;                      // leader: one arrival per transform warp of both CTAs (2 x 12)
     uint64_t* emptyH = bars + NH;                // both CTAs: one multicast commit
     uint64_t* fullW = bars + 2 * NH;             // leader: expect_tx arrive + the peer's remote arrive
     uint64_t* emptyW = bars + 2 * NH + NW;       // both CTAs: one multicast commit
@@ -85,7 +86,7 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
 
     if (warp == 0 && lane == 0) ptx::prefetch_tensormap(&tmB);
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < NH; ++i) { ptx::mbar_init(&fullH[i], 2 * kXformThreads); ptx::mbar_init(&emptyH[i], 1); }
+        for (int i = 0; i < NH; ++i) { ptx::mbar_init(&fullH[i], 2 * kXformThreads / 32); ptx::mbar_init(&emptyH[i], 1); }
         for (int i = 0; i < NW; ++i) { ptx::mbar_init(&fullW[i], 2); ptx::mbar_init(&emptyW[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&tfull_bar[i], 1); ptx::mbar_init(&tempty_bar[i], 2 * 32 * kGpEpiWarps); }
         ptx::fence_barrier_init();
@@ -107,7 +108,6 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
     const int Cin = chunks * kConvBlockK;
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
 
-    if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");      // TMA / MMA / allocator warpgroup: registers to the transform role
     if (warp == 0) {
         // ===================== TMA producer (both CTAs): this CTA's 128-channel weight tile =====================
         int sw = 0;
@@ -165,11 +165,6 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         }
     } else if (warp >= kXformWarp0) {
         // ===================== transform (both CTAs): this CTA's (16+2) x (8+2) halo half =====================
-        // Software-pipelined over (tile, chunk): the raw fp32 values of step q+1 are loaded into registers BEFORE step q is
-        // transformed, so the global-load latency (multi-microsecond when all 148 CTAs burst at once) overlaps the arithmetic and
-        // the barrier waits of the previous chunk.  Two register buffers of 4 items x 32 B -> this role runs at 96 registers
-        // (setmaxnreg: 128 x 48 + 256 x 72 + 384 x 96 = 61 440 = the 768 x 80 registers the CTA was launched with).
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         const int tt = threadIdx.x - kXformWarp0 * 32;      // 0..383
         const int lq = tt & 7;                              // logical 16-byte chunk: channels [8*lq, 8*lq + 8) of the k-chunk
         const int prow = tt >> 3;                           // halo pixel of iteration it: p = it*48 + prow; p & 7 == prow & 7
@@ -181,43 +176,11 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
         int sh = 0;
         uint32_t ph = 0;
         int cur_b = -1;
-        const int my_tiles = total_pairs > cluster_id ? (total_pairs - cluster_id + num_clusters - 1) / num_clusters : 0;
-        const int Q = my_tiles * chunks;                    // (tile, chunk) steps of this CTA
-
-        auto tile_of = [&](int q, int& b, int& h0, int& w0, int& j) {
-            const int pt = cluster_id + (q / chunks) * num_clusters;
-            j = q - (q / chunks) * chunks;
+        for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
             const int mt = pt / args.tiles_n;
-            w0 = (mt % args.tiles_w) * kTW;
-            h0 = ((mt / args.tiles_w) % args.tiles_h) * kTH + (int)rank * (kTH / 2);     // this CTA's 16 rows
-            b = mt / (args.tiles_w * args.tiles_h);
-        };
-        auto issue = [&](int q, float4 (&x0)[kIters], float4 (&x1)[kIters], uint32_t& okm) {
-            int b, h0, w0, j;
-            tile_of(q, b, h0, w0, j);
-            const bool first = j < args.a_split;
-            const int Cs = first ? C0 : C1;
-            const float* src = (first ? gn.src0 + (long long)j * kConvBlockK
-                                      : gn.src1 + (long long)(j - args.a_split) * kConvBlockK) +
-                               (long long)b * H * W * Cs + lq * 8;
-            okm = 0;
-#pragma unroll
-            for (int u = 0; u < kIters; ++u) {
-                const int p = u * kXformRows + prow;
-                const int hr = p / kBoxW, hc = p - hr * kBoxW;
-                const int gh = h0 - 1 + hr, gw = w0 - 1 + hc;
-                const bool ok = (p < kHaloPix) && gh >= 0 && gh < H && gw >= 0 && gw < W;
-                if (ok) {
-                    const float4* s4 = reinterpret_cast<const float4*>(src + ((long long)gh * W + gw) * Cs);
-                    x0[u] = __ldg(s4);
-                    x1[u] = __ldg(s4 + 1);
-                    okm |= 1u << u;
-                }
-            }
-        };
-        auto process = [&](int q, const float4 (&x0)[kIters], const float4 (&x1)[kIters], uint32_t okm) {
-            int b, h0, w0, j;
-            tile_of(q, b, h0, w0, j);
+            const int w0 = (mt % args.tiles_w) * kTW;
+            const int h0 = ((mt / args.tiles_w) % args.tiles_h) * kTH + (int)rank * (kTH / 2);     // this CTA's 16 rows
+            const int b = mt / (args.tiles_w * args.tiles_h);
             if (b != cur_b) {
                 // Coefficient table of image b for ALL input channels: y = SiLU(x * A[c] + Bc[c]) (same arithmetic as
                 // gn_apply_silu_kernel).  Rebuilt only when the image changes; no per-chunk barrier or global load afterwards.
@@ -261,48 +224,60 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_con
                 cur_b = b;
                 xform_bar_sync();
             }
-            const float* cA = sA + j * kConvBlockK + lq * 8;
-            const float* cB = sB + j * kConvBlockK + lq * 8;
-            const float4 a0 = *reinterpret_cast<const float4*>(cA), a1 = *reinterpret_cast<const float4*>(cA + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(cB), b1 = *reinterpret_cast<const float4*>(cB + 4);
-            ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 6600 + sh);         // operand slot free in this CTA (its MMAs retired)
-            uint8_t* op = smem + sh * kHaloStride + qo * 16;
-#pragma unroll
-            for (int u = 0; u < kIters; ++u) {
-                const int p = u * kXformRows + prow;
-                if (p >= kHaloPix) continue;
-                uint4 o = make_uint4(0u, 0u, 0u, 0u);
-                if (okm & (1u << u)) {
-                    float v[8] = {fmaf(x0[u].x, a0.x, b0.x), fmaf(x0[u].y, a0.y, b0.y), fmaf(x0[u].z, a0.z, b0.z),
-                                  fmaf(x0[u].w, a0.w, b0.w), fmaf(x1[u].x, a1.x, b1.x), fmaf(x1[u].y, a1.y, b1.y),
-                                  fmaf(x1[u].z, a1.z, b1.z), fmaf(x1[u].w, a1.w, b1.w)};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __fdividef(v[e], 1.0f + __expf(-v[e]));
-                    const __half2 h0_ = sat_half2(v[0], v[1]), h1_ = sat_half2(v[2], v[3]);
-                    const __half2 h2_ = sat_half2(v[4], v[5]), h3_ = sat_half2(v[6], v[7]);
-                    o.x = *reinterpret_cast<const uint32_t*>(&h0_); o.y = *reinterpret_cast<const uint32_t*>(&h1_);
-                    o.z = *reinterpret_cast<const uint32_t*>(&h2_); o.w = *reinterpret_cast<const uint32_t*>(&h3_);
-                }
-                *reinterpret_cast<uint4*>(op + p * 128) = o;
-            }
-            ptx::fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor cores (async proxy)
-            ptx::mbar_arrive_release_cluster(&fullH[sh], 0);            // the leader's barrier (cluster-scope release)
-            if (++sh == NH) { sh = 0; ph ^= 1; }
-        };
+            const long long img = (long long)b * H * W;
+            for (int j = 0; j < chunks; ++j) {
+                const float* cA = sA + j * kConvBlockK + lq * 8;
+                const float* cB = sB + j * kConvBlockK + lq * 8;
+                const float4 a0 = *reinterpret_cast<const float4*>(cA), a1 = *reinterpret_cast<const float4*>(cA + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(cB), b1 = *reinterpret_cast<const float4*>(cB + 4);
 
-        float4 xa0[kIters], xa1[kIters], xb0[kIters], xb1[kIters];
-        uint32_t oka = 0, okb = 0;
-        if (Q > 0) issue(0, xa0, xa1, oka);
-        for (int q = 0; q < Q; q += 2) {
-            if (q + 1 < Q) issue(q + 1, xb0, xb1, okb);
-            process(q, xa0, xa1, oka);
-            if (q + 1 >= Q) break;
-            if (q + 2 < Q) issue(q + 2, xa0, xa1, oka);
-            process(q + 1, xb0, xb1, okb);
+                const bool first = j < args.a_split;
+                const int Cs = first ? C0 : C1;
+                const float* src = (first ? gn.src0 + (long long)j * kConvBlockK
+                                          : gn.src1 + (long long)(j - args.a_split) * kConvBlockK) + img * Cs + lq * 8;
+
+                ptx::mbar_wait(&emptyH[sh], ph ^ 1, err, 6600 + sh);     // operand slot free in this CTA (its MMAs retired)
+                uint8_t* op = smem + sh * kHaloStride + qo * 16;
+                float4 x0[kIters], x1[kIters];
+                bool ok[kIters];
+#pragma unroll
+                for (int u = 0; u < kIters; ++u) {
+                    const int p = u * kXformRows + prow;
+                    const int hr = p / kBoxW, hc = p - hr * kBoxW;
+                    const int gh = h0 - 1 + hr, gw = w0 - 1 + hc;
+                    ok[u] = (p < kHaloPix) && gh >= 0 && gh < H && gw >= 0 && gw < W;
+                    if (ok[u]) {
+                        const float4* s4 = reinterpret_cast<const float4*>(src + ((long long)gh * W + gw) * Cs);
+                        x0[u] = __ldg(s4);
+                        x1[u] = __ldg(s4 + 1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kIters; ++u) {
+                    const int p = u * kXformRows + prow;
+                    if (p >= kHaloPix) continue;
+                    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok[u]) {
+                        float v[8] = {fmaf(x0[u].x, a0.x, b0.x), fmaf(x0[u].y, a0.y, b0.y), fmaf(x0[u].z, a0.z, b0.z),
+                                      fmaf(x0[u].w, a0.w, b0.w), fmaf(x1[u].x, a1.x, b1.x), fmaf(x1[u].y, a1.y, b1.y),
+                                      fmaf(x1[u].z, a1.z, b1.z), fmaf(x1[u].w, a1.w, b1.w)};
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = __fdividef(v[e], 1.0f + __expf(-v[e]));
+                        const __half2 h0_ = sat_half2(v[0], v[1]), h1_ = sat_half2(v[2], v[3]);
+                        const __half2 h2_ = sat_half2(v[4], v[5]), h3_ = sat_half2(v[6], v[7]);
+                        o.x = *reinterpret_cast<const uint32_t*>(&h0_); o.y = *reinterpret_cast<const uint32_t*>(&h1_);
+                        o.z = *reinterpret_cast<const uint32_t*>(&h2_); o.w = *reinterpret_cast<const uint32_t*>(&h3_);
+                    }
+                    *reinterpret_cast<uint4*>(op + p * 128) = o;
+                }
+                ptx::fence_proxy_async_smem();        // generic-proxy stores -> visible to the tensor cores (async proxy)
+                __syncwarp();                         // one (remote) arrival per warp instead of 768 serialised ones per stage
+                if (lane == 0) ptx::mbar_arrive_release_cluster(&fullH[sh], 0);   // the leader's barrier (cluster-scope release)
+                if (++sh == NH) { sh = 0; ph ^= 1; }
+            }
         }
     } else if (warp >= 4) {
         // ===================== epilogue (both CTAs): lane = one of this CTA's 128 channels, columns = the 256 pixels =====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         const int q = warp & 3;
         const int half = warp >= 8 ? 1 : 0;           // pixel columns [128*half, +128) = tile rows [16*half, +16)
         int iter = 0;
