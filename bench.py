@@ -319,7 +319,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true")
-    ap.add_argument("--secondary", default="cfg1,cfg2a,cfg2b,cfg4,cfg5", help="comma list of secondary configurations")
+    ap.add_argument("--secondary", default="cfg1,cfg2a,cfg2b,cfg4,cfg5,train", help="comma list of secondary configurations")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--fuse", default=None, choices=["off", "pair", "on", "all"], help="fused GroupNorm+conv kernel usage")
     ap.add_argument("--kernel-table", default=None, help="write a CUPTI per-kernel time table of 3 steps to this path")
@@ -638,6 +638,41 @@ def main():
                     im_.clear_graphs()
                     del im_, u_
             guarded(key, run)
+
+    if sec_list and "train" in sec_list and rank == 0:
+        # informational: one training step (Imagen.forward -> loss.backward()) through the autograd Functions / backward kernels
+        def train_step():
+            from minimagen_b200.Unet import Unet as U2
+            tcfg = dict(dim=128, dim_mults=(1, 2, 4), num_resnet_blocks=(1, 2, 2), layer_attns=(False, False, True),
+                        layer_cross_attns=(False, True, True), memory_efficient=True, text_embed_dim=768)
+            torch.manual_seed(0)
+            with torch.device(dev):
+                tu = U2(**tcfg)
+            tim = Imagen(unets=tu, text_encoder_name="t5_base", image_sizes=(64,), timesteps=1000, cond_drop_prob=0.1).to(dev).train()
+            gg = torch.Generator().manual_seed(3)
+            tb = 8
+            imgs = torch.rand(tb, 3, 64, 64, generator=gg).to(dev)
+            te = torch.randn(tb, 16, 768, generator=gg).to(dev)
+            tm = torch.ones(tb, 16, dtype=torch.bool, device=dev)
+            opt = torch.optim.Adam(tim.parameters(), lr=1e-4)
+            def one():
+                opt.zero_grad(set_to_none=True)
+                loss = tim(imgs, text_embeds=te, text_masks=tm, unet_number=1)
+                loss.backward()
+                opt.step()
+                return loss
+            for _ in range(2):
+                one()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                loss = one()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            return {"ms_per_training_step": dt * 1e3, "batch": tb, "loss": float(loss.detach()), "params_m": sum(p.numel() for p in tu.parameters()) / 1e6,
+                    "workload": "base U-Net dim 128, mults (1,2,4), 64x64, b=8: Imagen.forward + backward + Adam step (eager; forward convs and data "
+                                "gradients on tcgen05, weight gradients fp32 CUDA cores)"}
+        guarded("training_step", train_step)
 
     if rank != 0:
         if world > 1:
