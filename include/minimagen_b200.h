@@ -75,7 +75,7 @@ int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, in
  *             the OUTPUT (after bias/residual), accumulated in the epilogue -- the GroupNorm statistics of the next
  *             Block (layers.py:136) for free; needs out_sc = 1
  *   block_n   0 = auto, or one of 16/32/64/128/256 (tile width; must divide c_out)
- *   workspace optional device scratch, see mi_conv2d_igemm_workspace_bytes
+ *   workspace reserved, pass NULL / 0
  * Requirements: c_in % 64 == 0, c_out % 16 == 0, W a power of two >= 8 (or W >= 128), see mi_conv2d_igemm_supported.
  * A plain GEMM  out[M][N] = act[M][K] * w[N][K]^T  is the case B=1, H=1, W=M, kh=kw=1. */
 int mi_conv2d_igemm_supported(int H, int W, int c_in, int c_out);
@@ -97,10 +97,8 @@ int mi_conv3x3_res1x1_f16(const void* act_f16, int B, int H, int W, int lda, int
                           int c_in1, const void* x_f16, int ldx, int x_cin, const void* x2_f16, int ldx2, int x_cin1,
                           const void* w_f16, int c_out, const float* bias, const float* residual, float* out_f32,
                           void* out_f16, double* out_stats, int* err_flag, void* stream);
-/* Optional scratch for mi_conv2d_igemm_f16 (NULL = none): lets layers whose tile count is not a multiple of the SM-pair
- * count split their LAST wave along K ("stream-K": every CTA pair gets the same number of k-steps; partial fp32 tiles
- * meet in this buffer).  Size from this call; the first 4096 bytes must be zero before the first use (the kernels leave
- * them zero); one buffer per stream that runs convolutions concurrently. */
+/* Reserved: returns 0.  (The `workspace` arguments of mi_conv2d_igemm_f16 are kept for ABI stability; pass NULL / 0.  A stream-K
+ * schedule that used them was measured and removed: on a power-capped part an under-filled last wave costs nothing.) */
 long long mi_conv2d_igemm_workspace_bytes(void);
 
 /* Fused Block.forward (layers.py:131-145): GroupNorm -> (scale + 1, shift) -> SiLU -> Conv2d 3x3 in ONE kernel; the

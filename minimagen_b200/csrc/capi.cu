@@ -68,8 +68,7 @@ static int igemm_common(const void* act, int B, int H, int W, int lda, int c_off
     p.x_act = x_act; p.x_lda = ldx; p.x_chan_off = x_off; p.Cx = x_cin;
     p.x_act2 = x_act2; p.x_lda2 = ldx2; p.x_chan_off2 = x_off2; p.Cx1 = x_cin1;
     if (x_act && !(mode == 0 && kh == 3 && kw == 3)) return fail(-9, "mi_conv3x3_res1x1_f16: the folded 1x1 operand needs a 3x3 stride-1 conv");
-    p.splitk_ws = workspace; p.splitk_ws_bytes = workspace ? workspace_bytes : 0;
-    if (workspace && (reinterpret_cast<uintptr_t>(workspace) & 15)) return fail(-8, "mi_conv2d_igemm_f16: workspace must be 16-byte aligned");
+    (void)workspace; (void)workspace_bytes;       // reserved (no kernel needs scratch any more): pass NULL / 0
     p.act = act; p.B = B; p.H = H; p.W = W; p.lda = lda; p.a_channels = lda; p.a_chan_off = c_off; p.Cin = c_in;
     p.wpacked = w; p.Cout = c_out;
     p.act2 = act2; p.lda2 = lda2; p.a_chan_off2 = c_off2; p.Cin1 = c_in1; p.stats = out_stats;
@@ -129,10 +128,6 @@ static int igemm_common(const void* act, int B, int H, int W, int lda, int c_off
     // kernel, everything else on the CTA-pair kernel (all chosen inside conv_tc_launch)
     p.halo = (mode == 0 && kh == 3 && kw == 3) ? 1 : ((mode == 0 && kh == 15 && kw == 1) ? 3 : 0);   // 3: 15-tap vertical (stem)
     if (mode >= 2 && mode <= 5 && !getenv("MI_SUBPIX_PAIR")) p.halo = 4;   // sub-pixel phase on the swapped-operand kernel (32 x 8 tiles)
-    // 1x1 convs stay on the pixel-major 1-CTA kernel: the swapped-operand row-tile form (conv3x3_halo_t_kernel<kGLin>,
-    // parity-tested in test_conv_tc) measured 0.037 / 0.047 / 0.066 / 0.119 ms against 0.033 / 0.043 / 0.056 / 0.095 ms on the
-    // four res_conv shapes of cfg 3 -- short-K layers are output-bound and the smem-transposing epilogue wins there
-    p.lin1x1 = 0;
     const int rc = mi::conv_tc_launch(p, S(stream));
     if (rc != 0) return fail(rc, mi::conv_tc_strerror(rc));
     return 0;
@@ -164,7 +159,7 @@ int mi_conv3x3_res1x1_f16(const void* act, int B, int H, int W, int lda, int c_i
                         ldx, 0, x_cin, x_act2, ldx2, 0, x_cin1, stream);
 }
 
-long long mi_conv2d_igemm_workspace_bytes(void) { return mi::conv_tc_splitk_bytes(); }
+long long mi_conv2d_igemm_workspace_bytes(void) { return 0; }
 
 int mi_conv3x3_gn_supported(int H, int W, int c0, int c1, int c_out, int groups) {
     return mi::conv_gn_supported(H, W, c0, c1, c_out, groups) ? 1 : 0;

@@ -24,7 +24,7 @@ constexpr int kEpiLd = 32;   // floats per staged row; 16-byte chunks are XOR-sw
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t taddr, int n0, long long pix, bool valid,
                                               float* stage /* this warp's [32][kEpiLd] patch */, int c_begin, int c_end,
-                                              int b_img, const float* partial = nullptr) {
+                                              int b_img) {
     const int lane = threadIdx.x & 31;
     if (args.out_sc != 1 || n0 + BLOCK_N > args.n_valid || (BLOCK_N % 32) != 0) {
 #pragma unroll 1
@@ -70,14 +70,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
         ptx::tmem_ld_x16(taddr + c, v0);
         ptx::tmem_ld_x16(taddr + c + 16, v1);
         ptx::tmem_ld_wait();
-        if (partial) {
-            // stream-K: the other cluster's share of the k range for this row ([column][row] layout, L2-resident)
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                v0[i] = __float_as_uint(__uint_as_float(v0[i]) + __ldcg(partial + (size_t)(c + i) * kConvBlockM));
-                v1[i] = __float_as_uint(__uint_as_float(v1[i]) + __ldcg(partial + (size_t)(c + 16 + i) * kConvBlockM));
-            }
-        }
         float* srow = stage + lane * kEpiLd;
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
@@ -132,24 +124,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvTcArgs& args, uint32_t t
             }
         }
         __syncwarp();
-    }
-}
-
-// Stream-K: park this thread's accumulator row (columns [c_begin, c_end)) as raw fp32 partial sums; `ws` already points
-// at this thread's row, columns are kConvBlockM floats apart (so a warp's store of one column is one 128-byte line).
-template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_park(uint32_t taddr, int c_begin, int c_end, float* ws) {
-#pragma unroll 1
-    for (int c = c_begin; c < c_end; c += 32) {
-        uint32_t v0[16], v1[16];
-        ptx::tmem_ld_x16(taddr + c, v0);
-        ptx::tmem_ld_x16(taddr + c + 16, v1);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            __stcg(ws + (size_t)(c + i) * kConvBlockM, __uint_as_float(v0[i]));
-            __stcg(ws + (size_t)(c + 16 + i) * kConvBlockM, __uint_as_float(v1[i]));
-        }
     }
 }
 

@@ -219,38 +219,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // own 128-pixel A tile and HALF of the weight tile (BLOCK_N/2 rows); one tcgen05.mma issued by the leader CTA consumes
 // both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.  Versus the 1-CTA kernel this halves
 // the weight bytes each SM pulls from L2 and the shared-memory operand traffic per FLOP.
-// Work walk of one cluster.  Normal mode: whole tiles cluster_id, cluster_id + NC, ...  Stream-K mode (args.stream_k): the
-// S pipeline-stage units of all tiles are laid end to end and cut into NC equal ranges, so every cluster does the same
-// number of MMA stages even when tiles % NC != 0 (1.73 waves would otherwise cost 2).  A range of >= S units starts with
-// at most one tile TAIL (s0 > 0: the head belongs to the previous cluster) and ends with at most one tile HEAD (s1 < S).
-struct SegWalk {
-    int cur, end, S, nc;
-    bool sk;
-    __device__ SegWalk(bool stream_k, int S_, int total_pairs, int cid, int nc_) : S(S_), nc(nc_), sk(stream_k) {
-        if (sk) {
-            const long long U = (long long)total_pairs * S;
-            cur = (int)(U * cid / nc);
-            end = (int)(U * (cid + 1) / nc);
-        } else {
-            cur = cid;
-            end = total_pairs;
-        }
-    }
-    __device__ bool next(int& pt, int& s0, int& s1) {
-        if (cur >= end) return false;
-        if (sk) {
-            pt = cur / S;
-            s0 = cur - pt * S;
-            s1 = min(S, s0 + (end - cur));
-            cur += s1 - s0;
-        } else {
-            pt = cur; s0 = 0; s1 = S;
-            cur += nc;
-        }
-        return true;
-    }
-};
-
 template <int BLOCK_N, int KC>
 struct Cfg2 {
     static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kConvBlockK * 2;       // one 64-channel atom of the half weight tile
@@ -320,9 +288,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         // ===================== TMA producer (both CTAs; converged warp, one elected lane issues) =====================
         int stage = 0;
         uint32_t phase = 0;
-        SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
-        int pt, s0, s1;
-        while (walk.next(pt, s0, s1)) {
+        for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+            const int s0 = 0, s1 = num_st;
             const int nt = pt % args.tiles_n;
             const int mt = 2 * (pt / args.tiles_n) + (int)rank;      // may be == tiles_m (dummy tile: all OOB)
             const int w0 = (mt % args.tiles_w) * BW;
@@ -368,9 +335,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int stage = 0;
             uint32_t phase = 0;
             int iter = 0;
-            SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
-            int pt, s0, s1;
-            for (; walk.next(pt, s0, s1); ++iter) {
+            for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
+                const int s0 = 0, s1 = num_st;
                 const int as = iter & 1;
                 const uint32_t aphase = (iter >> 1) & 1;
                 ptx::mbar_wait(&tempty_bar[as], aphase ^ 1, err, 1200 + as);
@@ -407,9 +373,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int bh = (m >> args.bw_log2) & (BH - 1);
         const int bb = m >> (args.bw_log2 + args.bh_log2);
         int iter = 0;
-        SegWalk walk(args.stream_k != 0, num_st, total_pairs, cluster_id, num_clusters);
-        int pt, s0, s1;
-        for (; walk.next(pt, s0, s1); ++iter) {
+        for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++iter) {
             const int nt = pt % args.tiles_n;
             const int mt = 2 * (pt / args.tiles_n) + (int)rank;
             const int w = (mt % args.tiles_w) * BW + bw;
@@ -423,45 +387,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 1400 + as);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + as * BLOCK_N;
-            if (s0 > 0 && (args.dbg & 4)) {
-                // profiling: stream-K schedule without the partial-tile exchange (results are wrong)
-            } else if (s0 > 0) {
-                // stream-K tail of a tile owned by the previous cluster: park the raw fp32 partial sums in this cluster's
-                // workspace slot ([rank][column][row], row-contiguous) and raise its ready counter
-                const int slot = cluster_id * 2 + (int)rank;
-                float* ws = args.sk_ws + (size_t)slot * BLOCK_N * kConvBlockM + m;
-                epilogue_park<BLOCK_N>(taddr, c_begin, c_end, ws);
-                __threadfence();
-                __syncwarp();
-                if (lane == 0) atomicAdd(args.sk_flags + 2 * slot, 1);
-            } else {
-                const float* partial = nullptr;
-                int* fl = nullptr;
-                if (s1 < num_st && !(args.dbg & 4)) {
-                    // stream-K head: the next cluster computed the rest of the k range as ITS first segment
-                    const int slot = (cluster_id + 1) * 2 + (int)rank;
-                    fl = args.sk_flags + 2 * slot;
-                    if (lane == 0) {
-                        const long long t0 = clock64();
-                        while (ptx::ld_acquire_gpu(fl) < kEpiWarps) {
-                            if (clock64() - t0 > 4000000000LL) {
-                                if (err) { atomicExch(err, 1500); __threadfence_system(); }
-                                __trap();
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    partial = args.sk_ws + (size_t)slot * BLOCK_N * kConvBlockM + m;
-                }
-                epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b, partial);
-                if (fl) {
-                    __syncwarp();
-                    if (lane == 0 && atomicAdd(fl + 1, 1) == kEpiWarps - 1) {   // last consumer re-arms the slot
-                        atomicExch(fl + 1, 0);
-                        atomicExch(fl, 0);
-                    }
-                }
-            }
+            epilogue_tile<BLOCK_N>(args, taddr, n0, pix, valid, epi_stage, c_begin, c_end, b);
             ptx::tc_fence_before();
             ptx::mbar_arrive_cluster(&tempty_bar[as], 0);                    // the leader's barrier
         }
@@ -696,23 +622,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 constexpr int kHtPix = 256;                                                   // UMMA N
 // Geometry V15 (the stem, CrossEmbedLayer as a 15-tap vertical conv over the 128-wide unrolled operand): 32 x 8 output
 // pixels from a (32+14) x 8 tile; tap dh is the window that starts dh rows in (segments at the standard 1024-byte stride).
-// Geometry Lin (1x1 convs / linears): the pixels of an NHWC tensor are just rows, so a tile is 256 consecutive rows (one 2-D
-// TMA box, zero-filled past the end), one tap, no halo.
 // Geometry Sub (one sub-pixel phase of "nearest x2 up-sampling + 3x3 conv", ABI modes 2..5): 2 x 2 taps on the LOW-RES tensor; a
 // 32 x 8 tile reads a (32+1) x (8+1) halo tile whose origin is the phase's first tap; tap (r, s) starts (r*9 + s) pixels in,
 // segments one 9-pixel halo row apart; the epilogue writes every second pixel / row of the 2H x 2W output (caller's strides).
-enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2, kGLin = 3, kGSub = 4 };
+enum { kG32x8 = 0, kG16x16 = 1, kGV15 = 2, kGSub = 4 };
 template <int G>
 struct CfgT {
     static constexpr bool kW16 = G == kG16x16;
-    static constexpr int kTaps = G == kGV15 ? 15 : (G == kGLin ? 1 : (G == kGSub ? 4 : 9));
-    static constexpr int kTH = G == kGLin ? 256 : (kW16 ? 16 : 32), kTW = G == kGLin ? 1 : (kW16 ? 16 : 8);   // output tile
-    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : (G == kGLin ? 256 : (G == kGSub ? kTH + 1 : kTH + 2));
-    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : (G == kGLin ? 1 : (G == kGSub ? 9 : 8)));   // TMA box (pixels)
+    static constexpr int kTaps = G == kGV15 ? 15 : (G == kGSub ? 4 : 9);
+    static constexpr int kTH = kW16 ? 16 : 32, kTW = kW16 ? 16 : 8;           // output tile
+    static constexpr int kBoxH = G == kGV15 ? kTH + 14 : (G == kGSub ? kTH + 1 : kTH + 2);
+    static constexpr int kBoxW = G == kG32x8 ? 10 : (kW16 ? 16 : (G == kGSub ? 9 : 8));       // TMA box (pixels)
     static constexpr uint32_t kHaloBytes = kBoxH * kBoxW * 128;               // 43520 / 36864 / 47104
     static constexpr uint32_t kHaloStride = (kHaloBytes + 1023) & ~1023u;
     static constexpr uint32_t kWBytes = 128 * kConvBlockK * 2;                // one (tap, chunk) weight tile
-    static constexpr int kHStages = kW16 ? 3 : (G == kGLin ? 4 : 2);          // Lin: 4 MMAs per activation stage -> deeper ring
+    static constexpr int kHStages = kW16 ? 3 : 2;
     static constexpr int kWStages = (kRingBudget - kHStages * kHaloStride) / kWBytes;   // 6 / 5 / 6
     static constexpr uint32_t kTmemCols = 2 * kHtPix;                         // 512: two accumulator stages
     static constexpr uint32_t kSmemBytes = kHStages * kHaloStride + kWStages * kWBytes + 1024 + 256;
@@ -797,14 +721,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         const int wc = kW16 ? w0 + l - 1 : (G == kGV15 ? w0 : (G == kGSub ? w0 + args.dw[0] : w0 - 1));   // G16x16: copy l is shifted by dw = l - 1
                         const int hc = G == kGV15 ? h0 - 7 : (G == kGSub ? h0 + args.dh[0] : h0 - 1);          // Sub: origin = the phase's first tap
                         ptx::mbar_arrive_expect_tx(&fullH[sh], C::kHaloBytes);
-                        if constexpr (G == kGLin) {      // rows [h0, h0 + 256) of the (channels, pixels) matrix
-                            if (j < args.a_split)
-                                ptx::tma_load_2d(&tmA, &fullH[sh], smem + sh * C::kHaloStride,
-                                                 args.a_chan_off + j * kConvBlockK, h0);
-                            else
-                                ptx::tma_load_2d(&tmA2, &fullH[sh], smem + sh * C::kHaloStride,
-                                                 args.a_chan_off2 + (j - args.a_split) * kConvBlockK, h0);
-                        } else if (j < args.a_split)
+                        if (j < args.a_split)
                             ptx::tma_load_5d(&tmA, &fullH[sh], smem + sh * C::kHaloStride,
                                              args.a_chan_off + j * kConvBlockK, wc, hc, 0, b0);
                         else
@@ -872,8 +789,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                             // row apart; G16x16: tap (dh = u) of copy dw = l starts dh rows in, segments 1024 B apart
                             // V15: tap u = dh starts dh rows (8 pixels each) in, segments 1024 B apart
                             const uint64_t db = kW16 ? make_halo_t_desc(h_base + u * 16 * 128, 1024)
-                                : (G == kGLin ? make_halo_t_desc(h_base, 1024)
-                                : G == kGV15 ? make_halo_t_desc(h_base + u * 8 * 128, 1024)
+                                : (G == kGV15 ? make_halo_t_desc(h_base + u * 8 * 128, 1024)
                                 : G == kGSub ? make_halo_t_desc(h_base + ((u >> 1) * C::kBoxW + (u & 1)) * 128, C::kBoxW * 128)
                                               : make_halo_t_desc(h_base + ((u / 3) * C::kBoxW + (u % 3)) * 128, C::kBoxW * 128));
 #pragma unroll
@@ -910,7 +826,7 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
     } else if (warp >= 4) {
         // ===================== epilogue: lane = channel, columns = pixels =====================
-        constexpr int kTwLog2 = kW16 ? 4 : (G == kGLin ? 0 : 3);
+        constexpr int kTwLog2 = kW16 ? 4 : 3;
         const int q = warp & 3;                       // TMEM lane quarter -> channels [32q, 32q + 32) of the tile
         const int half = warp >= 8 ? 1 : 0;           // pixel columns [128*half, 128*half + 128)
         int iter = 0;
@@ -919,14 +835,11 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             const int mt = tile / args.tiles_n;
             const int w0 = (mt % args.tiles_w) * C::kTW;
             const int h0 = ((mt / args.tiles_w) % args.tiles_h) * C::kTH;
-            // Lin: "rows" are pixels of the whole tensor (args.H = pixels per image, args.B = pixels in total, out_sh = pixel
-            // stride, out_sb = out_sw = 0); the other geometries tile one image
-            const int b = G == kGLin ? h0 / args.H : mt / (args.tiles_w * args.tiles_h);
+            const int b = mt / (args.tiles_w * args.tiles_h);
             const int n = nt * 128 + q * 32 + lane;   // this thread's output channel
             const float bias_v = args.bias ? __ldg(args.bias + n) : 0.f;
-            const long long base = (G == kGLin ? 0 : (long long)b * args.out_sb) +
-                                   (long long)(h0 + half * (C::kTH / 2)) * args.out_sh + (long long)w0 * args.out_sw + n;
-            const int lin_left = G == kGLin ? args.B - (h0 + half * 128) : 0;     // valid pixels of this thread's half tile
+            const long long base = (long long)b * args.out_sb + (long long)(h0 + half * (C::kTH / 2)) * args.out_sh +
+                                   (long long)w0 * args.out_sw + n;
             const int as = iter & 1;
             const uint32_t aphase = (iter >> 1) & 1;
             ptx::mbar_wait(&tfull_bar[as], aphase, err, 3600 + as);
@@ -943,15 +856,12 @@ conv3x3_halo_t_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 if (args.residual) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        r[i] = (G != kGLin || c + i < lin_left)
-                                   ? args.residual[rowb + (long long)(i >> kTwLog2) * args.out_sh +
-                                                   (long long)(i & (C::kTW - 1)) * args.out_sw]
-                                   : 0.f;
+                        r[i] = args.residual[rowb + (long long)(i >> kTwLog2) * args.out_sh +
+                                             (long long)(i & (C::kTW - 1)) * args.out_sw];
                 }
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (G == kGLin && c + i >= lin_left) continue;            // rows past the end of the tensor
                     float f = __uint_as_float(i < 16 ? v0[i] : v1[i - 16]) + bias_v;
                     if (args.residual) f += r[i];
                     st_s += f;
@@ -1030,7 +940,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& t
 
 template <int BLOCK_N, int KC>
 int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, const ConvTcArgs& args,
-            int total_pairs, int num_sms, void* sk_ws, long long sk_bytes, int sk_mode, cudaStream_t stream) {
+            int total_pairs, int num_sms, cudaStream_t stream) {
     using C = Cfg2<BLOCK_N, KC>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1041,21 +951,7 @@ int launch2(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& 
     }
     int clusters = num_sms / 2;
     if (clusters > total_pairs) clusters = total_pairs;
-    ConvTcArgs a = args;
-    // stream-K when whole tiles would leave the last wave mostly empty (e.g. 128 tiles on 74 clusters = 1.73 waves)
-    a.stream_k = 0;
-    if (sk_ws && args.out_sc == 1 && args.n_valid == args.tiles_n * BLOCK_N && (BLOCK_N % 32) == 0 && (args.dbg & 3) == 0 &&
-        total_pairs > clusters && total_pairs % clusters != 0) {
-        const int waves = (total_pairs + clusters - 1) / clusters;
-        const size_t need = kSkFlagBytes + (size_t)2 * clusters * BLOCK_N * kConvBlockM * sizeof(float);
-        if ((sk_mode == 2 || (double)total_pairs / ((double)waves * clusters) < 0.93) && sk_mode != 1 &&
-            (size_t)sk_bytes >= need) {
-            a.stream_k = 1;
-            a.sk_flags = reinterpret_cast<int*>(sk_ws);
-            a.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sk_ws) + kSkFlagBytes);
-        }
-    }
-    launch_k(conv_tc2_kernel<BLOCK_N, KC>, 2 * clusters, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, a);
+    launch_k(conv_tc2_kernel<BLOCK_N, KC>, 2 * clusters, kNumThreads, C::kSmemBytes, stream, tmA, tmA2, tmB, args);
     return cudaGetLastError() == cudaSuccess ? 0 : -11;
 }
 
@@ -1113,13 +1009,6 @@ const char* conv_tc_strerror(int code) {
     }
 }
 
-long long conv_tc_splitk_bytes() {
-    int dev = 0, num_sms = 148;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) num_sms = 148;
-    return kSkFlagBytes + (long long)num_sms * 256 * kConvBlockM * (long long)sizeof(float);
-}
-
 bool conv_tc_supported(int H, int W, int Cin, int Cout) {
     if (Cin <= 0 || Cin % kConvBlockK != 0 || Cout <= 0 || Cout % 16 != 0) return false;
     if (W >= 128) return true;                            // BW = 128, BH = 1, BB = 1; ragged tail rows are masked
@@ -1139,61 +1028,6 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         return -8;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -5;
-
-    // ---- 1x1 convs / linears on the swapped-operand kernel: 256 consecutive pixels (rows) x 128 channels per tile
-    {
-        const long long M = (long long)p.B * p.H * p.W;
-        const bool dense_out = p.out_sc <= 1 && (p.H == 1 || p.out_sh == (long long)p.W * p.out_sw) &&
-                               (p.B == 1 || p.out_sb == (long long)p.H * p.W * p.out_sw);   // pixel-linear output
-        const bool dense_in = true;     // [B][1][H][W][lda]: pixel p of the tensor is row p
-        if (p.lin1x1 && p.num_taps == 1 && p.phases == 1 && p.in_stride <= 1 && p.Cout % 128 == 0 && dense_out && dense_in &&
-            (p.n_valid == 0 || p.n_valid == p.Cout) && p.dbg == 0 && M >= 256 && M < (1LL << 31) &&
-            (!p.stats || ((long long)p.H * p.W) % 256 == 0) && p.dh[0] == 0 && p.dw[0] == 0) {
-            if (p.act2 && (p.Cin1 <= 0 || p.Cin1 % kConvBlockK || p.Cin1 >= p.Cin || (p.lda2 % 8) ||
-                           (reinterpret_cast<uintptr_t>(p.act2) & 15)))
-                return -8;
-            ConvTcArgs h{};
-            h.num_taps = 1; h.chunks_per_tap = p.Cin / kConvBlockK;
-            h.tiles_w = 1; h.tiles_h = (int)((M + 255) / 256); h.tiles_b = 1; h.tiles_n = p.Cout / 128;
-            h.B = (int)M; h.H = p.H * p.W; h.W = 1; h.a_chan_off = p.a_chan_off;
-            h.a_split = (p.act2 ? p.Cin1 : p.Cin) / kConvBlockK; h.a_chan_off2 = p.a_chan_off2;
-            h.out_sb = 0; h.out_sh = p.out_sw; h.out_sw = 0; h.out_sc = 1; h.n_valid = p.Cout;
-            h.out_f32 = p.out_f32; h.out_f16 = p.out_f16; h.bias = p.bias; h.residual = p.residual; h.err_flag = p.err_flag;
-            h.stats = p.stats; h.stats_blocks = p.Cout / 16;
-            int dev = 0, num_sms = 148;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            CUtensorMap tmA, tmA2, tmB;
-            cuuint32_t estr[2] = {1, 1};
-            cuuint32_t box[2] = {kConvBlockK, 256};
-            {
-                cuuint64_t gdim[2] = {(cuuint64_t)p.a_channels, (cuuint64_t)M};
-                cuuint64_t gstr[1] = {(cuuint64_t)p.lda * 2};
-                if (enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.act), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                    return -6;
-            }
-            tmA2 = tmA;
-            if (p.act2) {
-                cuuint64_t gdim[2] = {(cuuint64_t)p.lda2, (cuuint64_t)M};
-                cuuint64_t gstr[1] = {(cuuint64_t)p.lda2 * 2};
-                if (enc(&tmA2, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.act2), gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                    return -6;
-            }
-            const cuuint64_t K = (cuuint64_t)p.Cin;
-            cuuint64_t wdim[2] = {K, (cuuint64_t)p.Cout};
-            cuuint64_t wstr[1] = {K * 2};
-            cuuint32_t wbox[2] = {kConvBlockK, 128};
-            if (enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p.wpacked), wdim, wstr, wbox, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-                return -7;
-            return launch_halo_t<kGLin>(tmA, tmA2, tmB, tmA, tmA, h, h.tiles_h * h.tiles_n, num_sms, stream);
-        }
-    }
 
     // ---- 3x3 halo kernel with swapped operands (channels in TMEM lanes): 128-wide channel tiles, H % 32 == 0, W % 8 == 0
     const bool t16 = p.W == 16 && p.H % 16 == 0;                       // G16x16: one 16 x 16 tile per image (row block)
@@ -1447,10 +1281,10 @@ int conv_tc_launch(const ConvTcProblem& p, cudaStream_t stream) {
         // two 64-channel k-chunks per pipeline stage (half the barrier round trips) when the channel counts allow
         const bool kc2 = p.kmerge != 1 && (a.chunks_per_tap % 2 == 0) && (a.a_split % 2 == 0);
         if (block_n == 256)
-            return kc2 ? launch2<256, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream)
-                       : launch2<256, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream);
-        return kc2 ? launch2<128, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream)
-                   : launch2<128, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, p.splitk_ws, p.splitk_ws_bytes, p.stream_k, stream);
+            return kc2 ? launch2<256, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
+                       : launch2<256, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
+        return kc2 ? launch2<128, 2>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream)
+                   : launch2<128, 1>(tmA, tmA2, tmB, a, total_pairs, num_sms, stream);
     }
     switch (block_n) {
         case 256: return launch<256>(tmA, tmA2, tmB, a, total_tiles, num_sms, stream);

@@ -32,9 +32,6 @@ struct ConvTcArgs {
     int dbg;                              // profiling experiments only (bit 0: no TMA after warm-up, bit 1: no epilogue)
     double* stats;                        // optional [B][C_out/16][2]: (sum, sum of squares) of the output per 16-channel block
     int stats_blocks;                     // C_out / 16
-    int stream_k;                         // CTA-pair kernel: equal k-stage ranges per cluster instead of whole tiles
-    float* sk_ws;                         // stream-K partial tiles [cluster][rank][BLOCK_N][128]
-    int* sk_flags;                        // stream-K per-slot (ready, done) counters, zero between launches
     int8_t dh[kConvMaxTaps], dw[kConvMaxTaps], ph[kConvMaxTaps];
 };
 
@@ -66,19 +63,11 @@ struct ConvTcProblem {
     int cta_pair;           // 0 = auto, 1 = never (1-CTA kernel), 2 = always when C_out % 128 == 0
     int halo;               // 1 = use a 3x3 halo-tile kernel when the geometry allows (swapped-operand form preferred),
                             // 2 = only the pixel-major halo kernel, 3 = 15 x 1 vertical taps (stem) on the swapped kernel
-    int lin1x1;             // 1 = 1x1 convs / linears may use the swapped-operand kernel (256-pixel row tiles)
     int kmerge;             // 0 = auto (two k-chunks per stage when possible), 1 = one k-chunk per stage
     int dbg;                // profiling experiments only
     double* stats;          // optional GroupNorm block statistics of the output (pre-zeroed), see ConvTcArgs
     int* err_flag;
-    void* splitk_ws;        // optional stream-K workspace (first kSkFlagBytes zeroed once by the caller), see conv_tc_splitk_bytes
-    long long splitk_ws_bytes;
-    int stream_k;           // 0 = auto (when the last wave of whole tiles would be < 93 % full), 1 = never, 2 = whenever legal
 };
-
-constexpr long long kSkFlagBytes = 4096;
-// Workspace size that enables stream-K for every layer on the current device (flags + one 256-wide partial tile per SM).
-long long conv_tc_splitk_bytes();
 
 // GroupNorm / FiLM / SiLU prologue of the fused Block kernel (conv_gn.cu)
 struct GnPrologueArgs {

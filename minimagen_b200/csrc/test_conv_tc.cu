@@ -41,8 +41,6 @@ struct Case {
 };
 
 static int* g_err = nullptr;   // host-mapped
-static void* g_ws = nullptr;   // stream-K workspace (flags zeroed once; the kernels re-arm them)
-static long long g_ws_bytes = 0;
 
 // returns max abs error (or -1 on failure)
 static double run_case(const Case& c, bool check, int reps, double* ms_out) {
@@ -112,12 +110,8 @@ static double run_case(const Case& c, bool check, int reps, double* ms_out) {
     p.out_f32 = d_o32; p.out_f16 = d_o16; p.bias = d_bias; p.residual = d_res;
     p.out_sw = c.Cout; p.out_sh = (long long)Wo * c.Cout; p.out_sb = (long long)Ho * Wo * c.Cout;
     p.block_n_hint = c.hint; p.cta_pair = (c.pair == 3) ? 1 : c.pair; p.halo = (c.pair == 3) ? 2 : (c.pair == 8 ? (c.k == 15 ? 3 : 1) : 0); if (c.pair == 8) p.cta_pair = 1; p.dbg = (c.pair >= 10) ? c.pair - 10 : 0; if (c.pair == 7) p.cta_pair = 2; if (c.pair >= 10) p.cta_pair = 1; if (c.pair == 4) { p.cta_pair = 2; p.kmerge = 1; } p.err_flag = g_err;
-    p.splitk_ws = g_ws; p.splitk_ws_bytes = g_ws_bytes;
-    if (c.pair == 5) { p.cta_pair = 2; p.stream_k = 2; }
-    if (c.pair == 6) { p.cta_pair = 2; p.stream_k = 1; }
-    if (c.pair == 7) { p.cta_pair = 2; p.stream_k = 2; p.dbg = 4; }
+    if (c.pair == 5 || c.pair == 6 || c.pair == 7) p.cta_pair = 2;      // (former stream-K cases: plain CTA-pair kernel)
     if (c.pair == 9) p.cta_pair = 0;
-    if (c.pair == 8 && c.k == 1) p.lin1x1 = 1;
 
     *g_err = 0;
     int rc = conv_tc_launch(p, 0);
@@ -199,10 +193,6 @@ int main(int argc, char** argv) {
     const char* mode = argc > 1 ? argv[1] : "all";
     CK(cudaSetDeviceFlags(cudaDeviceMapHost));
     CK(cudaHostAlloc(&g_err, sizeof(int), cudaHostAllocMapped));
-    g_ws_bytes = conv_tc_splitk_bytes();
-    CK(cudaMalloc(&g_ws, g_ws_bytes));
-    CK(cudaMemset(g_ws, 0xFF, g_ws_bytes));          // NaN partials: a read-before-write shows up in the check
-    CK(cudaMemset(g_ws, 0, kSkFlagBytes));
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
@@ -274,14 +264,6 @@ int main(int argc, char** argv) {
             double ms = 0;
             double err = run_case(c, true, 0, &ms);
             if (err < 0) ++failures;
-        }
-        {   // every stream-K slot must have been re-armed (ready == done == 0)
-            std::vector<int> fl(kSkFlagBytes / sizeof(int));
-            CK(cudaMemcpy(fl.data(), g_ws, kSkFlagBytes, cudaMemcpyDeviceToHost));
-            int bad = 0;
-            for (int v : fl) bad += v != 0;
-            printf("stream-K flags after the checks: %d non-zero%s\n", bad, bad ? "  **MISMATCH**" : "  OK");
-            if (bad) ++failures;
         }
     }
     if (!strcmp(mode, "perf") || !strcmp(mode, "all")) {

@@ -28,28 +28,11 @@ def _chk_out(t, dtype, name):
 
 class NativeOps:
     name = "native-sm100a"
-    # hand the tensor-core convs a stream-K workspace (mi_conv2d_igemm_workspace_bytes).  Off: on B200 the last, partly
-    # empty wave of whole tiles costs nothing (idle SMs free power for the busy ones) while the partial-tile exchange costs
-    # ~10 % on the affected layers (profiles/r01_streamk_study.md)
-    stream_k = False
     attention_tc = True      # tcgen05 attention core where the shape allows (mi_attention_fwd workspace)
-
-    def __init__(self):
-        self._ws = {}        # (device index, stream handle) -> uint8 workspace
 
     def set_launch_mode(self, pdl):
         """Programmatic dependent launch for every kernel of the library (mi_set_launch_mode)."""
         N.load().mi_set_launch_mode(int(bool(pdl)))
-
-    def _workspace(self, dev):
-        """One stream-K scratch buffer per (device, stream): convs on different streams may run concurrently."""
-        key = (dev.index, N.stream())
-        ws = self._ws.get(key)
-        if ws is None:
-            ws = torch.empty(int(N.load().mi_conv2d_igemm_workspace_bytes()), dtype=torch.uint8, device=dev)
-            ws[:4096].zero_()
-            self._ws[key] = ws
-        return ws
 
     # ---------------------------------------------------------------- capability / weights
     def igemm_supported(self, H, W, c_in, c_out):
@@ -74,11 +57,9 @@ class NativeOps:
         _chk_out(residual, F32, "residual"); _chk_out(out_f32, F32, "out_f32"); _chk_out(out_f16, F16, "out_f16")
         _chk(out_stats, F64, "out_stats")
         sb, sh, sw = out_strides
-        ws = self._workspace(act.device) if (self.stream_k and c_out % 128 == 0) else None
         N.call("mi_conv2d_igemm_f16", N.ptr(act), B, H, W, lda, c_off, c_in, N.ptr(act2), lda2, c_off2, c_in1,
                N.ptr(wp), c_out, kh, kw, mode, N.ptr(bias), N.ptr(residual), N.ptr(out_f32), N.ptr(out_f16),
-               N.ptr(out_stats), sb, sh, sw, out_sc, n_valid, block_n, None, N.ptr(ws), ws.numel() if ws is not None else 0,
-               N.stream())
+               N.ptr(out_stats), sb, sh, sw, out_sc, n_valid, block_n, None, None, 0, N.stream())
 
     def conv_res1x1_supported(self, H, W, c_in, c_out, x_cin):
         return bool(N.load().mi_conv3x3_res1x1_supported(int(H), int(W), int(c_in), int(c_out), int(x_cin)))
