@@ -65,21 +65,35 @@ class Conv2dFn(torch.autograd.Function):
         kh, kw = weight.shape[2], weight.shape[3]
         w = weight.detach()
         dx = dw = db = None
+        g16 = None
+
+        def dy16():
+            nonlocal g16
+            if g16 is None:
+                g16 = torch.empty((B, 1, Ho, Wo, Cout), dtype=F16, device=dy.device)
+                ops.cast_act(dy, Cout, None, 0, 1.0, B, Ho, Wo, 0, g16)
+            return g16
+
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if tc and same and Cout % 64 == 0 and Cin % 16 == 0 and ops.igemm_supported(H, W, Cout, Cin):
                 # data gradient of a 'same' conv = the same conv of dy with the taps flipped and in/out channels swapped:
                 # runs on the forward tcgen05 implicit-GEMM kernel
                 wt = _c(w.flip(2, 3).transpose(0, 1))
-                g16 = torch.empty((B, 1, Ho, Wo, Cout), dtype=F16, device=dy.device)
-                ops.cast_act(dy, Cout, None, 0, 1.0, B, Ho, Wo, 0, g16)
+                g16 = dy16()
                 ops.conv_igemm(g16, B, H, W, Cout, 0, Cout, ops.pack_conv_weight(wt), Cin, kh, kw, 0, None, None, dx, None,
                                (H * W * Cin, W * Cin, Cin))
             else:
                 ops.conv_dgrad(dy, B, Ho, Wo, Cout, _c(w), Cin, kh, kw, stride, pad, dx, H, W)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w, memory_format=torch.contiguous_format)
-            ops.conv_wgrad(dy, x, B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, dw)
+            if tc and same and ops.conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw):
+                # contraction over the pixels on tcgen05: fp16 NHWC dy and x are both MN-major operands (csrc/wgrad_tc.cu)
+                x16 = torch.empty((B, 1, H, W, Cin), dtype=F16, device=x.device)
+                ops.cast_act(x, Cin, None, 0, 1.0, B, H, W, 0, x16)
+                ops.conv_wgrad_tc(dy16(), x16, B, H, W, Cin, Cout, kh, kw, dw)
+            else:
+                ops.conv_wgrad(dy, x, B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, dw)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((Cout,), dtype=F32, device=dy.device)
             ops.colsum(dy, B * Ho * Wo, Cout, db)

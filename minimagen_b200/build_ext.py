@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libminimagen_b200.so")
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_gn.cu", "conv_gn_pair.cu", "conv_direct.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "step.cu", "backward.cu"]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_gn.cu", "conv_gn_pair.cu", "conv_direct.cu", "elementwise.cu", "attention.cu", "attention_tc.cu", "step.cu", "backward.cu", "wgrad_tc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

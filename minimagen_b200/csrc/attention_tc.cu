@@ -9,8 +9,11 @@
 //   P = exp(S - max)   16 softmax warps: one query row x 32 keys per thread (tcgen05.ld), fp16 P written to smem in the
 //                      128B-swizzled K-major layout the next MMA reads
 //   O += P V_j         tcgen05.mma  M = 128 queries, N = 64, K = 128 keys    -> TMEM
-// The exact row maximum is found in a first sweep over the keys (S only), so the second sweep never rescales O: two QK^T
-// sweeps (cheap, N = 128) instead of an online-softmax correction path.  K comes from a padded copy with the null key
+// ONE sweep over the keys (kOnline, the default): P is taken relative to a per-row REFERENCE maximum m_ref that is only
+// raised -- and O (in TMEM) and the partial row sums rescaled by exp(m_old - m_new) -- when some row of the CTA sees a score
+// more than 2^8 above its reference (lazy rescaling: P stays <= 256, far inside fp16; the decision is one `bar.red.or` per
+// key block, the rescale itself happens in the first block and then almost never).  The earlier two-sweep form (exact row
+// maximum from a first S-only sweep; 1.5x the QK^T work) is kept as kOnline = false for comparison (MI_ATTN_TWO_SWEEP=1).  K comes from a padded copy with the null key
 // prepended, V from a TRANSPOSED padded copy (keys contiguous = the K-major B operand of the second GEMM); both are
 // written by attn_prep_kernel into a caller-provided workspace.  Warp roles: 0-15 softmax / epilogue (four warps per
 // TMEM lane quarter, each owning 32 keys of every block and 16 dims of the output), 16 TMA producer, 17 MMA issuer + TMEM
@@ -19,6 +22,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "launch.cuh"
@@ -87,7 +91,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 
-template <int kBK>
+template <int kBK, bool kOnline>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnArgs a) {
@@ -112,6 +116,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     uint64_t* p_full = bars + 13;
     uint64_t* p_empty = bars + 15;
     uint64_t* o_full = bars + 17;
+    uint64_t* pv_done = bars + 19;              // one phase per key block: P V_j (and everything before it) has completed
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 18);
     float* s_xchg = reinterpret_cast<float*>(bars + 20);     // [4][128]: row max / row sum exchange between the column parts
 
@@ -128,6 +133,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (warp == kSoftmaxWarps + 1 && lane == 0) {
         ptx::mbar_init(q_full, 1);
         ptx::mbar_init(o_full, 1);
+        ptx::mbar_init(pv_done, 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1);
             ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
@@ -155,7 +161,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ptx::tma_load_2d(&tmQ, q_full, sQ, h * kD, b * a.n + q0);
         }
         int ik = 0, iv = 0;
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = kOnline ? 1 : 0; pass < 2; ++pass) {
             for (int j = 0; j < nblk; ++j) {
                 {
                     const int s = ik & 1;
@@ -203,9 +209,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
             ++ik; ++is;
         };
-        // sweep 1: S only (row maxima)
-        for (int j = 0; j < nblk; ++j) issue_qk();
-        // sweep 2: S of block j+1 is issued before P V of block j so the softmax warps always have work
+        // two-sweep form only -- sweep 1: S only (row maxima)
+        if (!kOnline)
+            for (int j = 0; j < nblk; ++j) issue_qk();
+        // main sweep: S of block j+1 is issued before P V of block j so the softmax warps always have work
         issue_qk();
         for (int j = 0; j < nblk; ++j) {
             if (j + 1 < nblk) issue_qk();
@@ -224,6 +231,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 ptx::umma_commit(&p_empty[ps]);
                 ptx::umma_commit(&v_empty[vs]);
+                if (kOnline) ptx::umma_commit(pv_done);
                 if (j + 1 == nblk) ptx::umma_commit(o_full);
             }
             ++ip; ++iv;
@@ -239,7 +247,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         int is = 0, ip = 0;
         // ---- sweep 1: exact row maximum (four independent running maxima: no long dependent chain)
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-        for (int j = 0; j < nblk; ++j, ++is) {
+        for (int j = 0; !kOnline && j < nblk; ++j, ++is) {
             const int ss = is % kSBuf;
             ptx::mbar_wait(&s_full[ss], (is / kSBuf) & 1, err, 4400 + ss);
             ptx::tc_fence_after();
@@ -260,10 +268,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
         }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
-        s_xchg[part * 128 + row] = mx;
-        asm volatile("bar.sync 1, 512;" ::: "memory");          // the sixteen softmax warps only
-        mx = fmaxf(fmaxf(s_xchg[row], s_xchg[128 + row]), fmaxf(s_xchg[256 + row], s_xchg[384 + row]));   // key 0 (null) is valid
-        const float mneg = -mx * kLog2e;
+        if (!kOnline) {
+            s_xchg[part * 128 + row] = mx;
+            asm volatile("bar.sync 1, 512;" ::: "memory");      // the sixteen softmax warps only
+            mx = fmaxf(fmaxf(s_xchg[row], s_xchg[128 + row]), fmaxf(s_xchg[256 + row], s_xchg[384 + row]));   // key 0 (null) is valid
+        }
+        float m_ref = mx;                                       // kOnline: -inf until the first block sets it
+        float mneg = -mx * kLog2e;
         // ---- sweep 2: P = exp(S - max) -> shared memory (fp16, swizzled), row sums in four partial accumulators
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nblk; ++j, ++is, ++ip) {
@@ -278,6 +289,49 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ptx::mbar_arrive(&s_empty[ss]);
             const bool tail = (j + 1) * kBK > a.kv_len;
             const int key = j * kBK + c_lo;
+            if (kOnline) {
+                // lazy reference maximum: does any row of the CTA see a score more than 2^8 above its reference?
+                float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (!tail) {
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i)
+                        if (key + i < a.kv_len) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                }
+                const float bm = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
+                const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;     // m_ref = -inf in block 0: true wherever bm is finite
+                uint32_t any;
+                asm volatile(
+                    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 512, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(any) : "r"(need) : "memory");
+                if (any) {                                                       // uniform over the sixteen softmax warps
+                    s_xchg[part * 128 + row] = bm;
+                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    const float bmr = fmaxf(fmaxf(s_xchg[row], s_xchg[128 + row]), fmaxf(s_xchg[256 + row], s_xchg[384 + row]));
+                    const float m_new = fmaxf(m_ref, bmr);
+                    const float factor = m_ref == -INFINITY ? 0.f : ptx::ex2_approx((m_ref - m_new) * kLog2e);
+                    if (j > 0) {
+                        // O holds sum_k exp(s - m_ref) v: wait until P V of the previous block has landed, rescale this thread's
+                        // 16 dims of its row in place (rows whose reference did not move multiply by exactly 1)
+                        ptx::mbar_wait(pv_done, (j - 1) & 1, err, 4430);
+                        ptx::tc_fence_after();
+                        uint32_t o[16];
+                        ptx::tmem_ld_x16(lane_addr + 256 + part * 16, o);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                        ptx::tmem_st_x16(lane_addr + 256 + part * 16, o);
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) l4[i] *= factor;
+                    m_ref = m_new;
+                    mneg = -m_new * kLog2e;
+                }
+            }
             uint32_t pk[kPer / 2];                              // fp16 pairs
 #pragma unroll
             for (int i = 0; i < kPer; i += 2) {
@@ -351,17 +405,17 @@ bool attention_tc_supported(int n, int ldq, int ldo, long long q_bs, const void*
     return mask == nullptr && n > 0 && (n % kBQ) == 0 && (ldq % 8) == 0 && (ldo % 8) == 0 && q_bs == (long long)n * ldq;
 }
 
-template <int BK>
+template <int BK, bool ONLINE>
 static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV, const AttnArgs& a, dim3 grid,
                        cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        if (cudaFuncSetAttribute(attn_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<BK>::kSmemBytes) !=
+        if (cudaFuncSetAttribute(attn_tc_kernel<BK, ONLINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, AC<BK>::kSmemBytes) !=
             cudaSuccess)
             return -10;
         attr_set = true;
     }
-    launch_k(attn_tc_kernel<BK>, grid, kThreads, AC<BK>::kSmemBytes, st, tmQ, tmK, tmV, a);
+    launch_k(attn_tc_kernel<BK, ONLINE>, grid, kThreads, AC<BK>::kSmemBytes, st, tmQ, tmK, tmV, a);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
@@ -417,7 +471,9 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / bk; a.kv_len = m + 1;
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
     dim3 grid(n / kBQ, heads, B);
-    return bk == 256 ? launch_attn<256>(tmQ, tmK, tmV, a, grid, st) : launch_attn<128>(tmQ, tmK, tmV, a, grid, st);
+    static const bool two_sweep = [] { const char* e = getenv("MI_ATTN_TWO_SWEEP"); return e && e[0] == '1'; }();
+    if (two_sweep) return bk == 256 ? launch_attn<256, false>(tmQ, tmK, tmV, a, grid, st) : launch_attn<128, false>(tmQ, tmK, tmV, a, grid, st);
+    return bk == 256 ? launch_attn<256, true>(tmQ, tmK, tmV, a, grid, st) : launch_attn<128, true>(tmQ, tmK, tmV, a, grid, st);
 }
 
 }  // namespace mi

@@ -402,6 +402,15 @@ class EmuOps:
                                         dy.reshape(B, Ho, Wo, c_out).permute(0, 3, 1, 2), stride=stride, padding=pad)
         dw.reshape(c_out, c_in, kh, kw).copy_(g)
 
+    def conv_wgrad_tc_supported(self, H, W, c_in, c_out, kh, kw):
+        return H % 8 == 0 and W % 8 == 0 and c_in % 64 == 0 and c_out % 128 == 0 and kh == kw and kh in (1, 3)
+
+    def conv_wgrad_tc(self, dy16, x16, B, H, W, c_in, c_out, kh, kw, dw):
+        self._log("conv_wgrad_tc")
+        g = torch.nn.grad.conv2d_weight(x16.float().reshape(B, H, W, c_in).permute(0, 3, 1, 2), (c_out, c_in, kh, kw),
+                                        dy16.float().reshape(B, H, W, c_out).permute(0, 3, 1, 2), stride=1, padding=kh // 2)
+        dw.reshape(c_out, c_in, kh, kw).copy_(g)
+
     def gn_silu_bwd(self, x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, ss_ld, eps, dx, dgamma, dbeta, dss, dss_ld):
         self._log("gn_silu_bwd")
         with torch.enable_grad():

@@ -490,6 +490,36 @@ def test_attention(native, B, heads, n, m, shared, use_mask):
     assert rel_l2(o_n, o_e) < 2e-3           # fp16 P / fp16 output rounding
 
 
+@pytest.mark.parametrize("B,heads,n,m,shared,ramp", [(1, 8, 1024, 1280, True, "up"), (2, 4, 256, 600, False, "up"),
+                                                     (1, 8, 1024, 1280, True, "down"), (2, 4, 128, 1500, True, "rows")])
+def test_attention_single_sweep_rescales(native, B, heads, n, m, shared, ramp):
+    """The tcgen05 attention kernel makes ONE sweep over the keys against a lazily raised reference maximum
+    (csrc/attention_tc.cu): key norms that grow along the sequence ("up") force a rescale of the TMEM accumulator in almost
+    every key block, shrinking ones ("down") none after the first, "rows" makes only some query rows of a CTA move."""
+    inner = heads * 64
+    g = torch.Generator().manual_seed(91)
+    q = torch.randn(B * n, inner, generator=g) * 0.5
+    if ramp == "rows":
+        q[::7] *= 4.0
+    ldkv = 128 if shared else 2 * inner
+    kv = torch.randn(B * m, ldkv, generator=g)
+    t = torch.linspace(0, 1, m).repeat(B)[:, None]
+    scale = {"up": 1 + 5 * t, "down": 6 - 5 * t, "rows": 1 + 3 * t}[ramp]
+    v_off = 64 if shared else inner
+    kv[:, :v_off] *= scale
+    q, kv = q.to(F16), kv.to(F16)
+    null_kv = _rand(2, 64, seed=36)
+    o_e = torch.zeros(B * n, inner, dtype=F16)
+    EMU.attention(q, n * inner, inner, kv, kv[:, v_off:], m * ldkv, ldkv, 0 if shared else 64, null_kv, None, B, heads, n, m, o_e,
+                  n * inner, inner)
+    qn, kvn = q.cuda(), kv.cuda()
+    o_n = torch.zeros(B * n, inner, dtype=F16, device="cuda")
+    native.attention(qn, n * inner, inner, kvn, kvn[:, v_off:], m * ldkv, ldkv, 0 if shared else 64, null_kv.cuda(), None, B,
+                     heads, n, m, o_n, n * inner, inner)
+    assert torch.isfinite(o_n).all()
+    assert rel_l2(o_n, o_e) < 2e-3
+
+
 # ---------------------------------------------------------------------------------------------- DDPM step
 @pytest.mark.parametrize("n,B", [(3 * 64 * 64, 4), (3 * 256 * 256, 2), (1000, 3), (3 * 1024 * 1024, 1)])
 def test_quantile_is_exact(native, n, B):
