@@ -669,9 +669,40 @@ def main():
                 loss = one()
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 3
-            return {"ms_per_training_step": dt * 1e3, "batch": tb, "loss": float(loss.detach()), "params_m": sum(p.numel() for p in tu.parameters()) / 1e6,
-                    "workload": "base U-Net dim 128, mults (1,2,4), 64x64, b=8: Imagen.forward + backward + Adam step (eager; forward convs and data "
-                                "gradients on tcgen05, weight gradients fp32 CUDA cores)"}
+            row = {"ms_per_training_step": dt * 1e3, "batch": tb, "loss": float(loss.detach()), "params_m": sum(p.numel() for p in tu.parameters()) / 1e6,
+                   "workload": "base U-Net dim 128, mults (1,2,4), 64x64, b=8: Imagen.forward + backward + Adam step (eager; convs and the "
+                               "attention projections forward, data gradient and weight gradient on tcgen05 with fp16 operands; GroupNorm / "
+                               "LayerNorm / attention-core backward fp32)"}
+            if not args.no_torch_gpu:
+                # the same U-Net (same weights) trained by stock PyTorch on this GPU: restatement forward -> autograd -> Adam
+                try:
+                    from oracle import restatement as R
+                    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in tu.state_dict().items()}
+                    leaves = [v for v in sd.values() if v.requires_grad]
+                    topt = torch.optim.Adam(leaves, lr=1e-4)
+                    tt = torch.randint(0, 1000, (tb,), generator=gg).to(dev)
+                    xin, tgt = torch.randn(tb, 3, 64, 64, generator=gg).to(dev), torch.randn(tb, 3, 64, 64, generator=gg).to(dev)
+                    for name, dt_ in (("fp32", None), ("fp16_autocast", torch.float16)):
+                        scaler = torch.amp.GradScaler("cuda", enabled=dt_ is not None)
+                        def tone():
+                            topt.zero_grad(set_to_none=True)
+                            with torch.autocast("cuda", dtype=dt_ or torch.float16, enabled=dt_ is not None):
+                                pred = R.unet_forward(sd, tcfg, xin, tt, text_embeds=te, text_mask=tm)
+                            l_ = torch.nn.functional.mse_loss(pred.float(), tgt)
+                            scaler.scale(l_).backward()
+                            scaler.step(topt)
+                            scaler.update()
+                        for _ in range(2):
+                            tone()
+                        torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        for _ in range(3):
+                            tone()
+                        torch.cuda.synchronize()
+                        row[f"torch_gpu_{name}_ms_per_training_step"] = (time.perf_counter() - t0) / 3 * 1e3
+                except Exception as ex:
+                    row["torch_gpu_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
+            return row
         guarded("training_step", train_step)
 
     if rank != 0:

@@ -59,8 +59,8 @@ SIGNATURES = {
     "mi_colsum_f32": [_P, _L, _I, _P, _I, _P],
     "mi_conv2d_dgrad_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "mi_conv2d_wgrad_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
-    "mi_conv2d_wgrad_f16_supported": [_I, _I, _I, _I, _I, _I],
-    "mi_conv2d_wgrad_f16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mi_conv2d_wgrad_f16_supported": [_I, _I, _I, _I, _I, _I, _I],
+    "mi_conv2d_wgrad_f16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "mi_gn_silu_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _P, _P],
     "mi_ln_rows_bwd": [_P, _P, _L, _I, _P, _F, _I, _P, _P, _P, _P],
     "mi_softmax_rows": [_P, _L, _I, _P],

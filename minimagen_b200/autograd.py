@@ -51,14 +51,14 @@ class Conv2dFn(torch.autograd.Function):
                 xp[..., :Cin] = x
             ops.conv_direct(xp, B, H, W, Cin, ld, _c(w), Cout, kh, kw, stride, pad, b, None, y, Ho, Wo, (*strides, 1))
         ctx.save_for_backward(x, weight)
-        ctx.geom = (stride, pad, same, tc, bias is not None)
+        ctx.geom = (stride, pad, same, down, tc, bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         ops = get_ops()
         x, weight = ctx.saved_tensors
-        stride, pad, same, tc, has_bias = ctx.geom
+        stride, pad, same, down, tc, has_bias = ctx.geom
         dy = _c(dy)
         B, H, W, Cin = x.shape
         _, Ho, Wo, Cout = dy.shape
@@ -83,15 +83,27 @@ class Conv2dFn(torch.autograd.Function):
                 g16 = dy16()
                 ops.conv_igemm(g16, B, H, W, Cout, 0, Cout, ops.pack_conv_weight(wt), Cin, kh, kw, 0, None, None, dx, None,
                                (H * W * Cin, W * Cin, Cin))
+            elif tc and down and Cout % 64 == 0 and Cin % 16 == 0 and ops.igemm_supported(Ho, Wo, Cout, Cin):
+                # transposed 4x4 stride-2 conv = four 2x2 convs of dy, one per output parity (a, b): input pixel 2v + a sees
+                # dy[v - 1], dy[v] through kernel rows 3, 1 (a = 0) or dy[v], dy[v + 1] through rows 2, 0 (a = 1) -- the tap
+                # geometry of the sub-pixel phases of the forward kernel (modes 2..5), which write the interleaved dx in place
+                taps = ((3, 1), (2, 0))
+                g16 = dy16()
+                for ph in range(4):
+                    a, b = ph >> 1, ph & 1
+                    k = w[:, :, taps[a], :][:, :, :, taps[b]].transpose(0, 1)          # (C_in, C_out, 2, 2)
+                    off = (a * W + b) * Cin
+                    ops.conv_igemm(g16, B, Ho, Wo, Cout, 0, Cout, ops.pack_conv_weight(_c(k)), Cin, 2, 2, 2 + ph, None, None,
+                                   dx.reshape(-1)[off:], None, (H * W * Cin, 2 * W * Cin, 2 * Cin))
             else:
                 ops.conv_dgrad(dy, B, Ho, Wo, Cout, _c(w), Cin, kh, kw, stride, pad, dx, H, W)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w, memory_format=torch.contiguous_format)
-            if tc and same and ops.conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw):
+            if tc and (same or down) and ops.conv_wgrad_tc_supported(Ho, Wo, Cin, Cout, kh, kw, stride):
                 # contraction over the pixels on tcgen05: fp16 NHWC dy and x are both MN-major operands (csrc/wgrad_tc.cu)
                 x16 = torch.empty((B, 1, H, W, Cin), dtype=F16, device=x.device)
                 ops.cast_act(x, Cin, None, 0, 1.0, B, H, W, 0, x16)
-                ops.conv_wgrad_tc(dy16(), x16, B, H, W, Cin, Cout, kh, kw, dw)
+                ops.conv_wgrad_tc(dy16(), x16, B, Ho, Wo, Cin, Cout, kh, kw, dw, stride)
             else:
                 ops.conv_wgrad(dy, x, B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, dw)
         if has_bias and ctx.needs_input_grad[2]:
@@ -168,7 +180,16 @@ class LayerNormFn(torch.autograd.Function):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x @ W^T + b on rows; x [M, K] fp32, W the nn.Linear weight [N, K]."""
+    """y = x @ W^T + b on rows; x [M, K] fp32, W the nn.Linear weight [N, K].  Tensor-core-shaped problems (M % 128 == 0,
+    K % 64 == 0, N % 16 == 0: the attention projections over image tokens) run as 1x1 convs of a (M/128) x 128 "image" on the
+    tcgen05 implicit-GEMM kernel with fp16 operands -- forward, dX (transposed packed weight) and dW (contraction over the rows
+    on the weight-gradient kernel, csrc/wgrad_tc.cu); everything else (time / text MLPs, ragged sizes) stays fp32."""
+
+    @staticmethod
+    def _rows16(ops, t, M, C):
+        a = torch.empty((1, 1, M // 128, 128, C), dtype=F16, device=t.device)
+        ops.cast_act(t, C, None, 0, 1.0, 1, M // 128, 128, 0, a)
+        return a
 
     @staticmethod
     def forward(ctx, x, weight, bias):
@@ -178,26 +199,40 @@ class LinearFn(torch.autograd.Function):
         Nn = weight.shape[0]
         y = torch.empty((M, Nn), dtype=F32, device=x.device)
         w = _c(weight.detach().reshape(Nn, K))
-        ops.linear_f32(x, M, K, w, bias.detach() if bias is not None else None, Nn, 0, 0, None, y, None)
+        b = bias.detach() if bias is not None else None
+        tc = x.is_cuda and M % 128 == 0 and K % 64 == 0 and Nn % 16 == 0 and ops.igemm_supported(M // 128, 128, K, Nn)
+        if tc:
+            ops.conv_igemm(LinearFn._rows16(ops, x, M, K), 1, M // 128, 128, K, 0, K, ops.pack_conv_weight(w), Nn, 1, 1, 0, b,
+                           None, y, None, (M * Nn, 128 * Nn, Nn))
+        else:
+            ops.linear_f32(x, M, K, w, b, Nn, 0, 0, None, y, None)
         ctx.save_for_backward(x, w)
-        ctx.cfg = (weight.shape, bias is not None)
+        ctx.cfg = (weight.shape, bias is not None, tc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         ops = get_ops()
         x, w = ctx.saved_tensors
-        wshape, has_bias = ctx.cfg
+        wshape, has_bias, tc = ctx.cfg
         dy = _c(dy)
         M, K = x.shape
         Nn = w.shape[0]
         dx = dw = db = None
+        g16 = LinearFn._rows16(ops, dy, M, Nn) if tc and Nn % 16 == 0 else None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)                       # dX[M,K] = dY[M,N] W[N,K]
-            ops.gemm_f32(dy, w, dx, M, K, Nn, (Nn, 1), (K, 1), (K, 1))
+            if g16 is not None and Nn % 64 == 0 and K % 16 == 0 and ops.igemm_supported(M // 128, 128, Nn, K):
+                ops.conv_igemm(g16, 1, M // 128, 128, Nn, 0, Nn, ops.pack_conv_weight(_c(w.t())), K, 1, 1, 0, None, None, dx,
+                               None, (M * K, 128 * K, K))
+            else:
+                ops.gemm_f32(dy, w, dx, M, K, Nn, (Nn, 1), (K, 1), (K, 1))
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)                       # dW[N,K] = dY^T[N,M] X[M,K]
-            ops.gemm_f32(dy, x, dw, Nn, K, M, (1, Nn), (K, 1), (K, 1))
+            if g16 is not None and ops.conv_wgrad_tc_supported(8, 8, K, Nn, 1, 1):
+                ops.conv_wgrad_tc(g16, LinearFn._rows16(ops, x, M, K), M // 64, 8, 8, K, Nn, 1, 1, dw)
+            else:
+                ops.gemm_f32(dy, x, dw, Nn, K, M, (1, Nn), (K, 1), (K, 1))
             dw = dw.reshape(wshape)
         if has_bias and ctx.needs_input_grad[2]:
             db = torch.empty((Nn,), dtype=F32, device=dy.device)

@@ -6,9 +6,11 @@
 //
 // One CTA = 128 queries of one (batch, head).  Keys are processed in blocks of 128:
 //   S = Q K_j^T        tcgen05.mma  M = 128 queries, N = 128 keys, K = 64   -> TMEM (fp32, double-buffered)
-//   P = exp(S - max)   16 softmax warps: one query row x 32 keys per thread (tcgen05.ld), fp16 P written to smem in the
-//                      128B-swizzled K-major layout the next MMA reads
-//   O += P V_j         tcgen05.mma  M = 128 queries, N = 64, K = 128 keys    -> TMEM
+//   P = exp(S - max)   16 softmax warps: one query row x 32 / 64 keys per thread (tcgen05.ld), fp16 P written back to
+//                      TENSOR MEMORY (tcgen05.st, two keys per 32-bit column) where the next MMA reads it as its A operand
+//   O += P V_j         tcgen05.mma  M = 128 queries, N = 64, K = 128 keys, A from TMEM    -> TMEM
+// (P used to go through shared memory: 64 KB written and 64 KB re-read per key block on the 128 B/clk port, and an N = 64 MMA
+// with A in shared memory costs ~119 clk against the 32-clk floor it reaches with A in tensor memory.)
 // ONE sweep over the keys (kOnline, the default): P is taken relative to a per-row REFERENCE maximum m_ref that is only
 // raised -- and O (in TMEM) and the partial row sums rescaled by exp(m_old - m_new) -- when some row of the CTA sees a score
 // more than 2^8 above its reference (lazy rescaling: P stays <= 256, far inside fp16; the decision is one `bar.red.or` per
@@ -36,19 +38,19 @@ constexpr int kD = 64, kBQ = 128;
 constexpr int kSoftmaxWarps = 16;                    // four per TMEM lane quarter, each owning a quarter of every key block
 constexpr int kThreads = 32 * (kSoftmaxWarps + 2);    // + TMA producer (warp 16) + MMA issuer / TMEM allocator (warp 17)
 constexpr uint32_t kQBytes = kBQ * kD * 2;            // 16 KB
-constexpr uint32_t kTmemCols = 512;                   // S tiles in [0,256), O in [256,320)
+constexpr uint32_t kTmemCols = 512;                   // S tiles in [0,256), O in [256,320), P (fp16 pairs) in [320,448)
+constexpr uint32_t kTmemO = 256, kTmemP = 320;
 
 // BK = keys per block = N of the S = Q K^T instruction.  128: S and P double-buffered (short key sequences pad less);
 // 256: one S tile, one P tile, but N = 256 instructions (long self-attention sequences, +10 % at 4096 tokens).
 template <int BK>
 struct AC {
     static constexpr int kSBuf = BK == 128 ? 2 : 1;            // S tiles in TMEM (512 columns: kSBuf * BK for S + 64 for O)
-    static constexpr int kPBuf = BK == 128 ? 2 : 1;            // P tiles in shared memory
+    static constexpr int kPBuf = BK == 128 ? 2 : 1;            // P tiles in tensor memory (BK / 2 columns each)
     static constexpr int kChunks = BK / 64;                    // 64-key (128-byte) swizzle chunks per block
     static constexpr uint32_t kKBytes = BK * kD * 2;
     static constexpr uint32_t kVBytes = kD * BK * 2;           // kChunks x [64 dims][64 keys]
-    static constexpr uint32_t kPBytes = kBQ * BK * 2;          // kChunks x [128 q][64 keys]
-    static constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + kPBuf * kPBytes + 1024 + 256 + 2048;
+    static constexpr uint32_t kSmemBytes = kQBytes + 2 * kKBytes + 2 * kVBytes + 1024 + 256 + 2048;
 };
 
 // ------------------------------------------------------------------------------------------------ operand preparation
@@ -98,14 +100,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     pdl_trigger();
     using C = AC<kBK>;
     constexpr int kSBuf = C::kSBuf, kPBuf = C::kPBuf, kChunks = C::kChunks;
-    constexpr uint32_t kKBytes = C::kKBytes, kVBytes = C::kVBytes, kPBytes = C::kPBytes;
+    constexpr uint32_t kKBytes = C::kKBytes, kVBytes = C::kVBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kQBytes;                 // [2]
     uint8_t* sV = sK + 2 * kKBytes;             // [2]
-    uint8_t* sP = sV + 2 * kVBytes;             // [kPBuf]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPBuf * kPBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * kVBytes);
     uint64_t* q_full = bars;
     uint64_t* k_full = bars + 1;                // [2]
     uint64_t* k_empty = bars + 3;
@@ -190,7 +191,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_s = ptx::make_idesc_f16(kBQ, kBK, 0);
         constexpr uint32_t idesc_o = ptx::make_idesc_f16(kBQ, kD, 0);
-        const uint32_t tmem_o = tmem_base + 256;
+        const uint32_t tmem_o = tmem_base + kTmemO;
         ptx::mbar_wait(q_full, 0, err, 4300);
         int ik = 0, is = 0, ip = 0, iv = 0;
         auto issue_qk = [&]() {
@@ -223,11 +224,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             if (ptx::elect_one()) {
 #pragma unroll
                 for (int c = 0; c < kChunks; ++c) {
-                    const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sP + ps * kPBytes + c * (kPBytes / kChunks)));
+                    const uint32_t ta = tmem_base + kTmemP + ps * (kBK / 2) + c * 32;      // 64 keys = 32 columns of fp16 pairs
                     const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV + vs * kVBytes + c * (kVBytes / kChunks)));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        ptx::umma_f16(tmem_o, da + 2 * k, db + 2 * k, idesc_o, (j | c | k) != 0);
+                        ptx::umma_f16_ts(tmem_o, ta + 8 * k, db + 2 * k, idesc_o, (j | c | k) != 0);
                 }
                 ptx::umma_commit(&p_empty[ps]);
                 ptx::umma_commit(&v_empty[vs]);
@@ -244,6 +245,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
         const int c_lo = part * kPer;
         constexpr float kLog2e = 1.4426950408889634f;
+        const int qbar = 1 + q4;                      // named barrier of this lane quarter: its four warps own the same 32 rows
         int is = 0, ip = 0;
         // ---- sweep 1: exact row maximum (four independent running maxima: no long dependent chain)
         float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -270,7 +272,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
         if (!kOnline) {
             s_xchg[part * 128 + row] = mx;
-            asm volatile("bar.sync 1, 512;" ::: "memory");      // the sixteen softmax warps only
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");      // the four warps of this lane quarter
             mx = fmaxf(fmaxf(s_xchg[row], s_xchg[128 + row]), fmaxf(s_xchg[256 + row], s_xchg[384 + row]));   // key 0 (null) is valid
         }
         float m_ref = mx;                                       // kOnline: -inf until the first block sets it
@@ -304,11 +306,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;     // m_ref = -inf in block 0: true wherever bm is finite
                 uint32_t any;
                 asm volatile(
-                    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, 1, 512, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(any) : "r"(need) : "memory");
-                if (any) {                                                       // uniform over the sixteen softmax warps
+                    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(any) : "r"(need), "r"(qbar) : "memory");
+                if (any) {                                                       // uniform over the four warps of the lane quarter
                     s_xchg[part * 128 + row] = bm;
-                    asm volatile("bar.sync 1, 512;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
                     const float bmr = fmaxf(fmaxf(s_xchg[row], s_xchg[128 + row]), fmaxf(s_xchg[256 + row], s_xchg[384 + row]));
                     const float m_new = fmaxf(m_ref, bmr);
                     const float factor = m_ref == -INFINITY ? 0.f : ptx::ex2_approx((m_ref - m_new) * kLog2e);
@@ -318,11 +320,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         ptx::mbar_wait(pv_done, (j - 1) & 1, err, 4430);
                         ptx::tc_fence_after();
                         uint32_t o[16];
-                        ptx::tmem_ld_x16(lane_addr + 256 + part * 16, o);
+                        ptx::tmem_ld_x16(lane_addr + kTmemO + part * 16, o);
                         ptx::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                        ptx::tmem_st_x16(lane_addr + 256 + part * 16, o);
+                        ptx::tmem_st_x16(lane_addr + kTmemO + part * 16, o);
                         ptx::tmem_st_wait();
                         ptx::tc_fence_before();
                     }
@@ -332,34 +334,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     mneg = -m_new * kLog2e;
                 }
             }
-            uint32_t pk[kPer / 2];                              // fp16 pairs
+            uint32_t pk[kPer / 2];                              // fp16 pairs (low half = the even key)
+            if (!tail) {                                        // uniform branch: the per-key bound check only in the last block
 #pragma unroll
-            for (int i = 0; i < kPer; i += 2) {
-                float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
-                float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
-                if (tail) {
+                for (int i = 0; i < kPer; i += 2) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
+                    l4[i & 3] += p0;
+                    l4[(i + 1) & 3] += p1;
+                    pk[i >> 1] = pack_h2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kPer; i += 2) {
+                    float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                    float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
                     if (key + i >= a.kv_len) p0 = 0.f;
                     if (key + i + 1 >= a.kv_len) p1 = 0.f;
+                    l4[i & 3] += p0;
+                    l4[(i + 1) & 3] += p1;
+                    pk[i >> 1] = pack_h2(p0, p1);
                 }
-                l4[i & 3] += p0;
-                l4[(i + 1) & 3] += p1;
-                pk[i >> 1] = pack_h2(p0, p1);
             }
-            // keys [c_lo, c_lo + kPer) of row r: chunk c_lo/64, 16-byte groups (c_lo%64)/8 .., XOR-swizzled with r % 8
+            // keys [c_lo, c_lo + kPer) of this thread's row -> columns c_lo/2 .. of the P tile (A operand of the P V MMA)
             ptx::mbar_wait(&p_empty[ps], ((ip / kPBuf) & 1) ^ 1, err, 4420 + ps);
-            uint8_t* chunk = sP + ps * kPBytes + (c_lo >> 6) * (kPBytes / kChunks) + row * 128;
-            const int g0 = (c_lo & 63) >> 3;
+            ptx::tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < kPer / 8; ++g)
-                *reinterpret_cast<uint4*>(chunk + (((g0 + g) ^ (row & 7)) << 4)) =
-                    make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            ptx::fence_proxy_async_smem();          // generic-proxy stores of P -> visible to the tensor core (async proxy)
+            for (int g = 0; g < kPer / 32; ++g)
+                ptx::tmem_st_x16(lane_addr + kTmemP + ps * (kBK / 2) + (c_lo >> 1) + 16 * g,
+                                 *reinterpret_cast<const uint32_t(*)[16]>(&pk[16 * g]));
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
             ptx::mbar_arrive(&p_full[ps]);
         }
         float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        asm volatile("bar.sync 1, 512;" ::: "memory");          // everyone has read the maxima
+        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");          // this quarter has read the maxima
         s_xchg[part * 128 + row] = l;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
         l = (s_xchg[row] + s_xchg[128 + row]) + (s_xchg[256 + row] + s_xchg[384 + row]);
         // ---- epilogue: O / l -> fp16 [b][q0 + row][h*64 + 16*part ..]
         ptx::mbar_wait(o_full, 0, err, 4500);
@@ -368,7 +379,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + row) * a.ldo + h * kD + part * 16;
         {
             uint32_t v0[16];
-            ptx::tmem_ld_x16(lane_addr + 256 + part * 16, v0);
+            ptx::tmem_ld_x16(lane_addr + kTmemO + part * 16, v0);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int g = 0; g < 2; ++g) {

@@ -326,13 +326,13 @@ int mi_conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hin, int Win
     return check(mi::conv2d_wgrad_f32(dy, x, B, Hin, Win, c_in, Hout, Wout, c_out, kh, kw, stride, pad, dw, S(stream)),
                  "mi_conv2d_wgrad_f32");
 }
-int mi_conv2d_wgrad_f16_supported(int H, int W, int c_in, int c_out, int kh, int kw) {
-    return mi::conv_wgrad_tc_supported(H, W, c_in, c_out, kh, kw) ? 1 : 0;
+int mi_conv2d_wgrad_f16_supported(int Hout, int Wout, int c_in, int c_out, int kh, int kw, int stride) {
+    return mi::conv_wgrad_tc_supported(Hout, Wout, c_in, c_out, kh, kw, stride) ? 1 : 0;
 }
-int mi_conv2d_wgrad_f16(const void* dy_f16, const void* x_f16, int B, int H, int W, int c_in, int c_out, int kh, int kw,
-                        float* dw, void* stream) {
-    return check(mi::conv_wgrad_tc(static_cast<const __half*>(dy_f16), static_cast<const __half*>(x_f16), B, H, W, c_in, c_out,
-                                   kh, kw, dw, S(stream)),
+int mi_conv2d_wgrad_f16(const void* dy_f16, const void* x_f16, int B, int Hout, int Wout, int c_in, int c_out, int kh, int kw,
+                        int stride, float* dw, void* stream) {
+    return check(mi::conv_wgrad_tc(static_cast<const __half*>(dy_f16), static_cast<const __half*>(x_f16), B, Hout, Wout, c_in,
+                                   c_out, kh, kw, stride, dw, S(stream)),
                  "mi_conv2d_wgrad_f16");
 }
 int mi_gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int hw, int C, int groups,

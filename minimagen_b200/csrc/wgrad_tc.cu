@@ -1,11 +1,13 @@
-// Weight gradient of a stride-1 'same' convolution on the tensor cores (training side):
+// Weight gradient of a convolution (stride 1 'same' k = 1 / 3, or the 4 x 4 stride-2 pad-1 Downsample) on the tensor cores
+// (training side):
 //
-//     dW[co][ci][r][s] = sum over pixels p = (b, h, w) of  dY[p][co] * X[p + (r - pad, s - pad)][ci]
+//     dW[co][ci][r][s] = sum over output pixels p = (b, h, w) of  dY[p][co] * X[b][stride*h + r - pad][stride*w + s - pad][ci]
 //
 // = for every tap one GEMM  dW_t[C_out][C_in] = dY^T[C_out][P] x X_t[P][C_in]  whose CONTRACTION runs over the pixels.  dY and X
 // are NHWC fp16 (channels contiguous), i.e. both operands are "MN-major" for tcgen05.mma: the kernel loads (8 x 8 pixels) x 64
 // channel boxes with TMA (128B swizzle: one pixel = one 128-byte row, 8 rows = one 1024-byte atom), the tap's shift is applied to
-// X's box coordinates (TMA zero-fills outside the image = the conv's zero padding), and the instruction descriptor marks A and
+// X's box coordinates (TMA zero-fills outside the image = the conv's zero padding; for stride 2 the box spans 16 x 16 input pixels
+// and TMA element strides keep every second one), and the instruction descriptor marks A and
 // B as MN-major (bits 15 / 16); the matrix descriptors step through K in 8-row atoms (SBO = 1024 B) and through the 64-channel
 // blocks of M / N with LBO = one box (8 KB).  fp32 accumulation in TMEM over this CTA's pixel range; the pixel axis is split over
 // gridDim.y CTAs per (co tile, ci tile, tap) and the partial tiles are added to dW with fp32 atomics (dW zeroed by the launcher).
@@ -28,7 +30,7 @@ constexpr uint32_t kBoxBytes = kPx * 128;                 // 64 pixels x 64 chan
 constexpr int kMaxStages = 6;
 
 struct WgradArgs {
-    int B, H, W, Cin, Cout, kh, kw, pad;
+    int B, H, W, Cin, Cout, kh, kw, pad, stride;     // H x W = the OUTPUT (dY) grid
     int tiles_co, tiles_ci, n_blocks;                     // n_blocks = 64-channel blocks of the N (C_in) tile: 1 or 2
     int tiles_w, tiles_h;                                 // 8 x 8 pixel boxes per image
     long long total_px_tiles, px_tiles_per_cta;
@@ -112,8 +114,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
                 ptx::tma_load_5d(&tmY, &full_bar[stage], s, co_t * 128, tw * 8, th * 8, 0, b);
                 ptx::tma_load_5d(&tmY, &full_bar[stage], s + kBoxBytes, co_t * 128 + 64, tw * 8, th * 8, 0, b);
                 for (int nb = 0; nb < NB; ++nb)
-                    ptx::tma_load_5d(&tmX, &full_bar[stage], s + (2 + nb) * kBoxBytes, ci_t * N + nb * 64, tw * 8 + dw_,
-                                     th * 8 + dh, 0, b);
+                    ptx::tma_load_5d(&tmX, &full_bar[stage], s + (2 + nb) * kBoxBytes, ci_t * N + nb * 64, tw * 8 * a.stride + dw_,
+                                     th * 8 * a.stride + dh, 0, b);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -167,21 +169,22 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
 
 }  // namespace
 
-bool conv_wgrad_tc_supported(int H, int W, int Cin, int Cout, int kh, int kw) {
-    return H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 128 == 0 &&
-           kh == kw && (kh & 1) && kh <= 3;
+// H x W = the output (dY) grid; stride 1: 'same' k = 1 / 3 (pad = k / 2); stride 2: k = 4, pad = 1 (input 2H x 2W)
+bool conv_wgrad_tc_supported(int H, int W, int Cin, int Cout, int kh, int kw, int stride) {
+    const bool geom = (stride == 1 && kh == kw && (kh & 1) && kh <= 3) || (stride == 2 && kh == 4 && kw == 4);
+    return H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0 && Cin > 0 && Cin % 64 == 0 && Cout > 0 && Cout % 128 == 0 && geom;
 }
 
-int conv_wgrad_tc(const __half* dy, const __half* x, int B, int H, int W, int Cin, int Cout, int kh, int kw, float* dw,
-                  cudaStream_t stream) {
-    if (!conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw)) return -1;
+int conv_wgrad_tc(const __half* dy, const __half* x, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
+                  float* dw, cudaStream_t stream) {
+    if (!conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw, stride)) return -1;
     if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) return -1;
     PFN_tmaEncodeTiled enc = get_tma_encode();
     if (!enc) return -1;
     if (cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * kh * kw * sizeof(float), stream) != cudaSuccess) return -2;
 
     WgradArgs a{};
-    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = kh / 2;
+    a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = stride == 2 ? 1 : kh / 2; a.stride = stride;
     a.n_blocks = (Cin % 128 == 0) ? 2 : 1;
     a.tiles_co = Cout / 128; a.tiles_ci = Cin / (a.n_blocks * 64);
     a.tiles_w = W / 8; a.tiles_h = H / 8;
@@ -202,12 +205,13 @@ int conv_wgrad_tc(const __half* dy, const __half* x, int B, int H, int W, int Ci
     const uint32_t smem = a.stages * stage_bytes + 1024 + 256;
 
     CUtensorMap tmY, tmX;
-    cuuint32_t box[5] = {64, 8, 8, 1, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     for (int which = 0; which < 2; ++which) {
         const cuuint64_t C = which ? Cin : Cout;
-        cuuint64_t gdim[5] = {C, (cuuint64_t)W, (cuuint64_t)H, 1, (cuuint64_t)B};
-        cuuint64_t gstr[4] = {C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)H * W * C * 2};
+        const cuuint64_t S = which ? stride : 1;                 // X lives on the (stride*H) x (stride*W) input grid
+        cuuint32_t box[5] = {64, (cuuint32_t)(8 * S), (cuuint32_t)(8 * S), 1, 1};
+        cuuint32_t estr[5] = {1, (cuuint32_t)S, (cuuint32_t)S, 1, 1};
+        cuuint64_t gdim[5] = {C, (cuuint64_t)W * S, (cuuint64_t)H * S, 1, (cuuint64_t)B};
+        cuuint64_t gstr[4] = {C * 2, (cuuint64_t)W * S * C * 2, (cuuint64_t)H * S * W * S * C * 2, (cuuint64_t)H * S * W * S * C * 2};
         if (enc(which ? &tmX : &tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(which ? x : dy), gdim, gstr, box, estr,
                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)

@@ -268,13 +268,14 @@ class NativeOps:
         N.call("mi_conv2d_wgrad_f32", N.ptr(dy), N.ptr(x), B, Hi, Wi, c_in, Ho, Wo, c_out, kh, kw, stride, pad, N.ptr(dw),
                N.stream())
 
-    def conv_wgrad_tc_supported(self, H, W, c_in, c_out, kh, kw):
-        return bool(N.load().mi_conv2d_wgrad_f16_supported(int(H), int(W), int(c_in), int(c_out), int(kh), int(kw)))
+    def conv_wgrad_tc_supported(self, Ho, Wo, c_in, c_out, kh, kw, stride=1):
+        return bool(N.load().mi_conv2d_wgrad_f16_supported(int(Ho), int(Wo), int(c_in), int(c_out), int(kh), int(kw), int(stride)))
 
-    def conv_wgrad_tc(self, dy16, x16, B, H, W, c_in, c_out, kh, kw, dw):
-        """dw (OIHW fp32, overwritten) of a k x k stride-1 'same' conv from fp16 NHWC dy / x, on the tensor cores."""
+    def conv_wgrad_tc(self, dy16, x16, B, Ho, Wo, c_in, c_out, kh, kw, dw, stride=1):
+        """dw (OIHW fp32, overwritten) of a k x k stride-1 'same' conv (or the 4x4 stride-2 pad-1 Downsample) from fp16 NHWC
+        dy [B, Ho, Wo, c_out] / x [B, stride*Ho, stride*Wo, c_in], on the tensor cores."""
         _chk(dy16, F16, "dy16"); _chk(x16, F16, "x16"); _chk(dw, F32, "dw")
-        N.call("mi_conv2d_wgrad_f16", N.ptr(dy16), N.ptr(x16), B, H, W, c_in, c_out, kh, kw, N.ptr(dw), N.stream())
+        N.call("mi_conv2d_wgrad_f16", N.ptr(dy16), N.ptr(x16), B, Ho, Wo, c_in, c_out, kh, kw, int(stride), N.ptr(dw), N.stream())
 
     def gn_silu_bwd(self, x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, ss_ld, eps, dx, dgamma, dbeta, dss, dss_ld):
         """dgamma / dbeta are ACCUMULATED into (zero them first); dss [B, dss_ld] = [d scale | d shift] or None."""

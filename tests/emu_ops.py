@@ -402,13 +402,16 @@ class EmuOps:
                                         dy.reshape(B, Ho, Wo, c_out).permute(0, 3, 1, 2), stride=stride, padding=pad)
         dw.reshape(c_out, c_in, kh, kw).copy_(g)
 
-    def conv_wgrad_tc_supported(self, H, W, c_in, c_out, kh, kw):
-        return H % 8 == 0 and W % 8 == 0 and c_in % 64 == 0 and c_out % 128 == 0 and kh == kw and kh in (1, 3)
+    def conv_wgrad_tc_supported(self, Ho, Wo, c_in, c_out, kh, kw, stride=1):
+        geom = (stride == 1 and kh == kw and kh in (1, 3)) or (stride == 2 and kh == 4 and kw == 4)
+        return Ho % 8 == 0 and Wo % 8 == 0 and c_in % 64 == 0 and c_out % 128 == 0 and geom
 
-    def conv_wgrad_tc(self, dy16, x16, B, H, W, c_in, c_out, kh, kw, dw):
+    def conv_wgrad_tc(self, dy16, x16, B, Ho, Wo, c_in, c_out, kh, kw, dw, stride=1):
         self._log("conv_wgrad_tc")
-        g = torch.nn.grad.conv2d_weight(x16.float().reshape(B, H, W, c_in).permute(0, 3, 1, 2), (c_out, c_in, kh, kw),
-                                        dy16.float().reshape(B, H, W, c_out).permute(0, 3, 1, 2), stride=1, padding=kh // 2)
+        pad = 1 if stride == 2 else kh // 2
+        g = torch.nn.grad.conv2d_weight(x16.float().reshape(B, stride * Ho, stride * Wo, c_in).permute(0, 3, 1, 2),
+                                        (c_out, c_in, kh, kw), dy16.float().reshape(B, Ho, Wo, c_out).permute(0, 3, 1, 2),
+                                        stride=stride, padding=pad)
         dw.reshape(c_out, c_in, kh, kw).copy_(g)
 
     def gn_silu_bwd(self, x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, ss_ld, eps, dx, dgamma, dbeta, dss, dss_ld):
