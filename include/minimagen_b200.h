@@ -272,10 +272,13 @@ int mi_conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hin, int Win
 /* The same weight gradient on the tensor cores, for k x k (k = 1, 3) stride-1 'same' convs and for the 4 x 4 stride-2 pad-1
  * Downsample (layers.py:481-484): dy [B][Hout][Wout][c_out] and x [B][stride*Hout][stride*Wout][c_in] are fp16 NHWC
  * (mi_cast_act), Hout % 8 == Wout % 8 == 0, c_in % 64 == 0, c_out % 128 == 0; fp32 accumulation over the pixels, dw OIHW
- * fp32 (overwritten).  Replaces torch's conv weight-gradient in the backward of layers.py:145 / 203-211 / 481-484. */
+ * fp32 (overwritten).  The pixel axis is split over CTAs; their partial tiles go through `workspace`
+ * (mi_conv2d_wgrad_f16_workspace_bytes, 16-byte aligned) and are summed by a second kernel.  Replaces torch's conv
+ * weight-gradient in the backward of layers.py:145 / 203-211 / 481-484. */
 int mi_conv2d_wgrad_f16_supported(int Hout, int Wout, int c_in, int c_out, int kh, int kw, int stride);
+long long mi_conv2d_wgrad_f16_workspace_bytes(int B, int Hout, int Wout, int c_in, int c_out, int kh, int kw, int stride);
 int mi_conv2d_wgrad_f16(const void* dy_f16, const void* x_f16, int B, int Hout, int Wout, int c_in, int c_out, int kh, int kw,
-                        int stride, float* dw, void* stream);
+                        int stride, float* dw, float* workspace, long long workspace_bytes, void* stream);
 /* Backward of mi_gn_apply_silu over ONE fp32 source x [B][hw][C] (sums = mi_gn_stats group sums [B][groups][2]):
  * dx; dgamma / dbeta ACCUMULATED into (caller zeroes or carries .grad); d_scale_shift [B][.. ld ..] = [d scale(C) | d shift(C)]
  * or NULL; workspace: (2*B*C + 2*B*groups) floats. */

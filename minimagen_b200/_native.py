@@ -60,7 +60,8 @@ SIGNATURES = {
     "mi_conv2d_dgrad_f32": [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "mi_conv2d_wgrad_f32": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "mi_conv2d_wgrad_f16_supported": [_I, _I, _I, _I, _I, _I, _I],
-    "mi_conv2d_wgrad_f16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "mi_conv2d_wgrad_f16_workspace_bytes": [_I, _I, _I, _I, _I, _I, _I, _I],
+    "mi_conv2d_wgrad_f16": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _L, _P],
     "mi_gn_silu_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _F, _P, _P, _P, _P, _I, _P, _P],
     "mi_ln_rows_bwd": [_P, _P, _L, _I, _P, _F, _I, _P, _P, _P, _P],
     "mi_softmax_rows": [_P, _L, _I, _P],
@@ -68,7 +69,7 @@ SIGNATURES = {
     "mi_upsample2x_bwd": [_P, _I, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {"mi_last_error": c_char_p, "mi_conv2d_igemm_workspace_bytes": c_longlong,
-             "mi_attention_workspace_bytes": c_longlong, "mi_step_epilogue_workspace_floats": c_longlong}
+             "mi_attention_workspace_bytes": c_longlong, "mi_conv2d_wgrad_f16_workspace_bytes": c_longlong, "mi_step_epilogue_workspace_floats": c_longlong}
 
 _lib = None
 launch_count = 0   # number of kernel launches issued through this binding (bench.py reports it)

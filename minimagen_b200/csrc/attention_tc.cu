@@ -85,8 +85,21 @@ attn_prep_kernel(const __half* __restrict__ k, const __half* __restrict__ v, lon
 struct AttnArgs {
     int n, heads, hkv, Mp, nblk, kv_len;       // kv_len = m + 1 valid (padded) keys
     __half* out; long long o_bs; int ldo;
+    int poly;                                  // 1: every fourth exp on the FMA pipe (ex2_poly)
     int* err;
 };
+
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5 -- P is rounded to
+// fp16, 4.9e-4, right after): used for every fourth key so that the 16-per-clock MUFU pipe is not the only exp unit.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -120.f);
+    const float xr = x + 12582912.f;                  // 1.5 * 2^23: the low mantissa bits now hold round(x)
+    const float f = x - (xr - 12582912.f);            // [-0.5, 0.5]
+    float p = fmaf(f, 0.0551714078f, 0.242610753f);
+    p = fmaf(p, f, 0.693260968f);
+    p = fmaf(p, f, 0.999928117f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));     // p * 2^round(x)
+}
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -335,7 +348,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
             }
             uint32_t pk[kPer / 2];                              // fp16 pairs (low half = the even key)
-            if (!tail) {                                        // uniform branch: the per-key bound check only in the last block
+            if (!tail && a.poly) {                              // uniform branches: MUFU for three keys, FMA-pipe polynomial for the fourth
+#pragma unroll
+                for (int i = 0; i < kPer; i += 2) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                    const float x1 = fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg);
+                    const float p1 = (i & 2) ? ex2_poly(x1) : ptx::ex2_approx(x1);
+                    l4[i & 3] += p0;
+                    l4[(i + 1) & 3] += p1;
+                    pk[i >> 1] = pack_h2(p0, p1);
+                }
+            } else if (!tail) {                                 // the per-key bound check only in the last block
 #pragma unroll
                 for (int i = 0; i < kPer; i += 2) {
                     const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
@@ -481,6 +504,8 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     AttnArgs a{};
     a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / bk; a.kv_len = m + 1;
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
+    static const int poly = [] { const char* e = getenv("MI_ATTN_POLY"); return e ? atoi(e) : 0; }();
+    a.poly = poly;
     dim3 grid(n / kBQ, heads, B);
     static const bool two_sweep = [] { const char* e = getenv("MI_ATTN_TWO_SWEEP"); return e && e[0] == '1'; }();
     if (two_sweep) return bk == 256 ? launch_attn<256, false>(tmQ, tmK, tmV, a, grid, st) : launch_attn<128, false>(tmQ, tmK, tmV, a, grid, st);

@@ -477,7 +477,9 @@ int conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hi, int Wi, int
     if (cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * KH * KW * sizeof(float), st) != cudaSuccess) return -2;
     const long long total = (long long)B * Ho * Wo;
     const int tiles = ((Cout + kWgT - 1) / kWgT) * ((Cin + kWgT - 1) / kWgT);
-    long long splits = (2 * 148 + tiles * KH * KW - 1) / (tiles * KH * KW);        // about two waves of blocks
+    // 256-thread blocks with 8 KB of shared memory: ~8 resident per SM -> aim at two full waves of those (the ragged layers that
+    // land here -- 3-channel stem / 3-channel output, 15 x 15 taps -- have few (tile, tap) pairs and long pixel loops)
+    long long splits = (16 * 148 + tiles * KH * KW - 1) / (tiles * KH * KW);
     const long long max_splits = (total + 4 * kWgP - 1) / (4 * kWgP);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -329,10 +329,13 @@ int mi_conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hin, int Win
 int mi_conv2d_wgrad_f16_supported(int Hout, int Wout, int c_in, int c_out, int kh, int kw, int stride) {
     return mi::conv_wgrad_tc_supported(Hout, Wout, c_in, c_out, kh, kw, stride) ? 1 : 0;
 }
+long long mi_conv2d_wgrad_f16_workspace_bytes(int B, int Hout, int Wout, int c_in, int c_out, int kh, int kw, int stride) {
+    return mi::conv_wgrad_tc_workspace_bytes(B, Hout, Wout, c_in, c_out, kh, kw, stride);
+}
 int mi_conv2d_wgrad_f16(const void* dy_f16, const void* x_f16, int B, int Hout, int Wout, int c_in, int c_out, int kh, int kw,
-                        int stride, float* dw, void* stream) {
+                        int stride, float* dw, float* workspace, long long workspace_bytes, void* stream) {
     return check(mi::conv_wgrad_tc(static_cast<const __half*>(dy_f16), static_cast<const __half*>(x_f16), B, Hout, Wout, c_in,
-                                   c_out, kh, kw, stride, dw, S(stream)),
+                                   c_out, kh, kw, stride, dw, workspace, workspace_bytes, S(stream)),
                  "mi_conv2d_wgrad_f16");
 }
 int mi_gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int hw, int C, int groups,

@@ -88,8 +88,9 @@ int conv2d_wgrad_f32(const float* dy, const float* x, int B, int Hi, int Wi, int
                      int KW, int stride, int pad, float* dw, cudaStream_t st);
 // wgrad_tc.cu: weight gradient of stride-1 'same' convs on tcgen05 (MN-major operands, contraction over pixels)
 bool conv_wgrad_tc_supported(int H, int W, int Cin, int Cout, int kh, int kw, int stride);
+long long conv_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride);
 int conv_wgrad_tc(const __half* dy, const __half* x, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
-                  float* dw, cudaStream_t stream);
+                  float* dw, float* workspace, long long workspace_bytes, cudaStream_t stream);
 int gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int HW, int C, int groups, const float* gamma,
                 const float* beta, const float* ss, int ss_ld, float eps, float* dx, float* dgamma, float* dbeta,
                 float* dss, int dss_ld, float* workspace, cudaStream_t st);

@@ -10,7 +10,10 @@
 // and TMA element strides keep every second one), and the instruction descriptor marks A and
 // B as MN-major (bits 15 / 16); the matrix descriptors step through K in 8-row atoms (SBO = 1024 B) and through the 64-channel
 // blocks of M / N with LBO = one box (8 KB).  fp32 accumulation in TMEM over this CTA's pixel range; the pixel axis is split over
-// gridDim.y CTAs per (co tile, ci tile, tap) and the partial tiles are added to dW with fp32 atomics (dW zeroed by the launcher).
+// gridDim.y CTAs per (co tile, ci tile, tap); every CTA stores its partial tile to the workspace [split][tap][C_out][C_in]
+// (64 contiguous bytes per thread) and wgrad_reduce_kernel sums the splits into the OIHW result.  (The first version added the
+// partial tiles to dW with fp32 atomics: 128 scattered REDs per thread, 36 bytes apart for a 3x3 -- that epilogue, not the
+// MMAs, was the kernel's time.)
 //
 // Warp roles (256 threads): 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-7 epilogue (lane = output channel).
 #include <cuda_runtime.h>
@@ -35,7 +38,7 @@ struct WgradArgs {
     int tiles_w, tiles_h;                                 // 8 x 8 pixel boxes per image
     long long total_px_tiles, px_tiles_per_cta;
     int stages;
-    float* dw;
+    float* ws;                                            // partial tiles [split][tap][C_out][C_in]
     int* err;
 };
 
@@ -141,21 +144,22 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4 && n_steps > 0) {
-        // ===================== epilogue: lane = output channel, columns = input channels -> atomics into dW =====================
+        // ===================== epilogue: lane = output channel, columns = input channels -> this split's partial tile ==========
         const int q = warp & 3;
         const int co = co_t * 128 + q * 32 + lane;
         ptx::mbar_wait(tfull_bar, 0, err, 7300);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int taps = a.kh * a.kw;
-        float* dst = a.dw + ((long long)co * a.Cin + ci_t * N) * taps + tap;
+        float* dst = a.ws + (((long long)blockIdx.y * taps + tap) * a.Cout + co) * a.Cin + ci_t * N;
 #pragma unroll 1
         for (int c = 0; c < N; c += 16) {
             uint32_t v[16];
             ptx::tmem_ld_x16(taddr + c, v);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dst + (long long)(c + i) * taps, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<uint4*>(dst + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         ptx::tc_fence_before();
     }
@@ -167,7 +171,47 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_const
     }
 }
 
+// dW[co][ci][tap] = sum over splits of ws[split][tap][co][ci]
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int taps, long long cc, float* __restrict__ dw) {
+    pdl_wait();
+    pdl_trigger();
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= cc * taps) return;
+    const int t = (int)(o % taps);
+    const long long cci = o / taps;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[((long long)s * taps + t) * cc + cci];
+    dw[o] = acc;
+}
+
+struct WgradPlan { int n_blocks, tiles_co, tiles_ci, groups; long long total_px_tiles, px_tiles_per_cta, splits; };
+
+WgradPlan wgrad_plan(int B, int H, int W, int Cin, int Cout, int kh, int kw) {
+    WgradPlan p{};
+    p.n_blocks = (Cin % 128 == 0) ? 2 : 1;
+    p.tiles_co = Cout / 128; p.tiles_ci = Cin / (p.n_blocks * 64);
+    p.total_px_tiles = (long long)B * (W / 8) * (H / 8);
+    p.groups = p.tiles_co * p.tiles_ci * kh * kw;
+    int dev = 0, num_sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    long long splits = (2LL * num_sms + p.groups - 1) / p.groups;            // about two CTAs per SM over the whole grid
+    if (splits > p.total_px_tiles) splits = p.total_px_tiles;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    p.px_tiles_per_cta = (p.total_px_tiles + splits - 1) / splits;
+    p.splits = (p.total_px_tiles + p.px_tiles_per_cta - 1) / p.px_tiles_per_cta;
+    return p;
+}
+
 }  // namespace
+
+long long conv_wgrad_tc_workspace_bytes(int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride) {
+    if (!conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw, stride) || B < 1) return 0;
+    const WgradPlan p = wgrad_plan(B, H, W, Cin, Cout, kh, kw);
+    return p.splits * kh * kw * (long long)Cout * Cin * (long long)sizeof(float);
+}
 
 // H x W = the output (dY) grid; stride 1: 'same' k = 1 / 3 (pad = k / 2); stride 2: k = 4, pad = 1 (input 2H x 2W)
 bool conv_wgrad_tc_supported(int H, int W, int Cin, int Cout, int kh, int kw, int stride) {
@@ -176,30 +220,26 @@ bool conv_wgrad_tc_supported(int H, int W, int Cin, int Cout, int kh, int kw, in
 }
 
 int conv_wgrad_tc(const __half* dy, const __half* x, int B, int H, int W, int Cin, int Cout, int kh, int kw, int stride,
-                  float* dw, cudaStream_t stream) {
-    if (!conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw, stride)) return -1;
-    if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) return -1;
+                  float* dw, float* workspace, long long workspace_bytes, cudaStream_t stream) {
+    if (!conv_wgrad_tc_supported(H, W, Cin, Cout, kh, kw, stride) || B < 1) return -1;
+    if ((reinterpret_cast<uintptr_t>(dy) & 15) || (reinterpret_cast<uintptr_t>(x) & 15) || !workspace ||
+        (reinterpret_cast<uintptr_t>(workspace) & 15))
+        return -1;
+    if (workspace_bytes < conv_wgrad_tc_workspace_bytes(B, H, W, Cin, Cout, kh, kw, stride)) return -1;
     PFN_tmaEncodeTiled enc = get_tma_encode();
     if (!enc) return -1;
-    if (cudaMemsetAsync(dw, 0, (size_t)Cout * Cin * kh * kw * sizeof(float), stream) != cudaSuccess) return -2;
+    const WgradPlan plan = wgrad_plan(B, H, W, Cin, Cout, kh, kw);
 
     WgradArgs a{};
     a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.kh = kh; a.kw = kw; a.pad = stride == 2 ? 1 : kh / 2; a.stride = stride;
-    a.n_blocks = (Cin % 128 == 0) ? 2 : 1;
-    a.tiles_co = Cout / 128; a.tiles_ci = Cin / (a.n_blocks * 64);
+    a.n_blocks = plan.n_blocks;
+    a.tiles_co = plan.tiles_co; a.tiles_ci = plan.tiles_ci;
     a.tiles_w = W / 8; a.tiles_h = H / 8;
-    a.total_px_tiles = (long long)B * a.tiles_w * a.tiles_h;
-    a.dw = dw; a.err = nullptr;
-    const int groups = a.tiles_co * a.tiles_ci * kh * kw;
-    int dev = 0, num_sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    long long splits = (2LL * num_sms + groups - 1) / groups;              // about two CTAs per SM over the whole grid
-    if (splits > a.total_px_tiles) splits = a.total_px_tiles;
-    if (splits < 1) splits = 1;
-    if (splits > 65535) splits = 65535;
-    a.px_tiles_per_cta = (a.total_px_tiles + splits - 1) / splits;
-    splits = (a.total_px_tiles + a.px_tiles_per_cta - 1) / a.px_tiles_per_cta;
+    a.total_px_tiles = plan.total_px_tiles;
+    a.ws = workspace; a.err = nullptr;
+    const int groups = plan.groups;
+    const long long splits = plan.splits;
+    a.px_tiles_per_cta = plan.px_tiles_per_cta;
     const uint32_t stage_bytes = (2 + a.n_blocks) * kBoxBytes;
     a.stages = kMaxStages;
     const uint32_t smem = a.stages * stage_bytes + 1024 + 256;
@@ -224,6 +264,8 @@ int conv_wgrad_tc(const __half* dy, const __half* x, int B, int H, int W, int Ci
     }
     dim3 grid(groups, (unsigned)splits);
     launch_k(conv_wgrad_tc_kernel, grid, kWgThreads, smem, stream, tmY, tmX, a);
+    const long long cc = (long long)Cout * Cin, total = cc * kh * kw;
+    launch_k(wgrad_reduce_kernel, dim3((unsigned)((total + 255) / 256)), 256, 0, stream, (const float*)workspace, (int)splits, kh * kw, cc, dw);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -275,7 +275,10 @@ class NativeOps:
         """dw (OIHW fp32, overwritten) of a k x k stride-1 'same' conv (or the 4x4 stride-2 pad-1 Downsample) from fp16 NHWC
         dy [B, Ho, Wo, c_out] / x [B, stride*Ho, stride*Wo, c_in], on the tensor cores."""
         _chk(dy16, F16, "dy16"); _chk(x16, F16, "x16"); _chk(dw, F32, "dw")
-        N.call("mi_conv2d_wgrad_f16", N.ptr(dy16), N.ptr(x16), B, Ho, Wo, c_in, c_out, kh, kw, int(stride), N.ptr(dw), N.stream())
+        nbytes = int(N.load().mi_conv2d_wgrad_f16_workspace_bytes(B, Ho, Wo, c_in, c_out, kh, kw, int(stride)))
+        ws = torch.empty(max(nbytes // 4, 4), dtype=F32, device=dw.device)          # per-split partial tiles
+        N.call("mi_conv2d_wgrad_f16", N.ptr(dy16), N.ptr(x16), B, Ho, Wo, c_in, c_out, kh, kw, int(stride), N.ptr(dw), N.ptr(ws),
+               nbytes, N.stream())
 
     def gn_silu_bwd(self, x, dy, sums, B, hw, C, groups, gamma, beta, scale_shift, ss_ld, eps, dx, dgamma, dbeta, dss, dss_ld):
         """dgamma / dbeta are ACCUMULATED into (zero them first); dss [B, dss_ld] = [d scale | d shift] or None."""
