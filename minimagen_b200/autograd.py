@@ -91,7 +91,9 @@ class Conv2dFn(torch.autograd.Function):
                 g16 = dy16()
                 for ph in range(4):
                     a, b = ph >> 1, ph & 1
-                    k = w[:, :, taps[a], :][:, :, :, taps[b]].transpose(0, 1)          # (C_in, C_out, 2, 2)
+                    # integer indexing only (an index list would build a CPU index tensor: not capturable in a CUDA graph)
+                    k = torch.stack([torch.stack([w[:, :, ra, cb] for cb in taps[b]], dim=-1) for ra in taps[a]], dim=-2)
+                    k = k.transpose(0, 1)                                                # (C_in, C_out, 2, 2)
                     off = (a * W + b) * Cin
                     ops.conv_igemm(g16, B, Ho, Wo, Cout, 0, Cout, ops.pack_conv_weight(_c(k)), Cin, 2, 2, 2 + ph, None, None,
                                    dx.reshape(-1)[off:], None, (H * W * Cin, 2 * W * Cin, 2 * Cin))
@@ -180,15 +182,16 @@ class LayerNormFn(torch.autograd.Function):
 
 
 class LinearFn(torch.autograd.Function):
-    """y = x @ W^T + b on rows; x [M, K] fp32, W the nn.Linear weight [N, K].  Tensor-core-shaped problems (M % 128 == 0,
-    K % 64 == 0, N % 16 == 0: the attention projections over image tokens) run as 1x1 convs of a (M/128) x 128 "image" on the
-    tcgen05 implicit-GEMM kernel with fp16 operands -- forward, dX (transposed packed weight) and dW (contraction over the rows
-    on the weight-gradient kernel, csrc/wgrad_tc.cu); everything else (time / text MLPs, ragged sizes) stays fp32."""
+    """y = x @ W^T + b on rows; x [M, K] fp32, W the nn.Linear weight [N, K].  Tensor-core-shaped problems (M >= 256, K % 64 == 0,
+    N % 16 == 0: the attention projections over image tokens and over the text / time context) run as 1x1 convs of a
+    (Mp/128) x 128 "image" (Mp = M rounded up to 128 with zero rows) on the tcgen05 implicit-GEMM kernel with fp16 operands --
+    forward, dX (transposed packed weight) and dW (contraction over the rows on the weight-gradient kernel, csrc/wgrad_tc.cu);
+    everything else (time / text MLPs on B rows, ragged widths) stays fp32."""
 
     @staticmethod
-    def _rows16(ops, t, M, C):
-        a = torch.empty((1, 1, M // 128, 128, C), dtype=F16, device=t.device)
-        ops.cast_act(t, C, None, 0, 1.0, 1, M // 128, 128, 0, a)
+    def _rows16(ops, t, M, Mp, C):
+        a = (torch.empty if Mp == M else torch.zeros)((1, 1, Mp // 128, 128, C), dtype=F16, device=t.device)
+        ops.cast_act(t, C, None, 0, 1.0, 1, 1, M, 0, a)
         return a
 
     @staticmethod
@@ -197,14 +200,17 @@ class LinearFn(torch.autograd.Function):
         x = _c(x)
         M, K = x.shape
         Nn = weight.shape[0]
-        y = torch.empty((M, Nn), dtype=F32, device=x.device)
+        Mp = (M + 127) // 128 * 128
         w = _c(weight.detach().reshape(Nn, K))
         b = bias.detach() if bias is not None else None
-        tc = x.is_cuda and M % 128 == 0 and K % 64 == 0 and Nn % 16 == 0 and ops.igemm_supported(M // 128, 128, K, Nn)
+        tc = x.is_cuda and M >= 256 and K % 64 == 0 and Nn % 16 == 0 and ops.igemm_supported(Mp // 128, 128, K, Nn)
         if tc:
-            ops.conv_igemm(LinearFn._rows16(ops, x, M, K), 1, M // 128, 128, K, 0, K, ops.pack_conv_weight(w), Nn, 1, 1, 0, b,
-                           None, y, None, (M * Nn, 128 * Nn, Nn))
+            y = torch.empty((Mp, Nn), dtype=F32, device=x.device)
+            ops.conv_igemm(LinearFn._rows16(ops, x, M, Mp, K), 1, Mp // 128, 128, K, 0, K, ops.pack_conv_weight(w), Nn, 1, 1, 0, b,
+                           None, y, None, (Mp * Nn, 128 * Nn, Nn))
+            y = y[:M]
         else:
+            y = torch.empty((M, Nn), dtype=F32, device=x.device)
             ops.linear_f32(x, M, K, w, b, Nn, 0, 0, None, y, None)
         ctx.save_for_backward(x, w)
         ctx.cfg = (weight.shape, bias is not None, tc)
@@ -218,19 +224,22 @@ class LinearFn(torch.autograd.Function):
         dy = _c(dy)
         M, K = x.shape
         Nn = w.shape[0]
+        Mp = (M + 127) // 128 * 128
         dx = dw = db = None
-        g16 = LinearFn._rows16(ops, dy, M, Nn) if tc and Nn % 16 == 0 else None
+        g16 = LinearFn._rows16(ops, dy, M, Mp, Nn) if tc else None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)                       # dX[M,K] = dY[M,N] W[N,K]
-            if g16 is not None and Nn % 64 == 0 and K % 16 == 0 and ops.igemm_supported(M // 128, 128, Nn, K):
-                ops.conv_igemm(g16, 1, M // 128, 128, Nn, 0, Nn, ops.pack_conv_weight(_c(w.t())), K, 1, 1, 0, None, None, dx,
-                               None, (M * K, 128 * K, K))
+            if g16 is not None and Nn % 64 == 0 and K % 16 == 0 and ops.igemm_supported(Mp // 128, 128, Nn, K):
+                dx = torch.empty((Mp, K), dtype=F32, device=x.device)          # dX[M,K] = dY[M,N] W[N,K]
+                ops.conv_igemm(g16, 1, Mp // 128, 128, Nn, 0, Nn, ops.pack_conv_weight(_c(w.t())), K, 1, 1, 0, None, None, dx,
+                               None, (Mp * K, 128 * K, K))
+                dx = dx[:M]
             else:
+                dx = torch.empty_like(x)
                 ops.gemm_f32(dy, w, dx, M, K, Nn, (Nn, 1), (K, 1), (K, 1))
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)                       # dW[N,K] = dY^T[N,M] X[M,K]
             if g16 is not None and ops.conv_wgrad_tc_supported(8, 8, K, Nn, 1, 1):
-                ops.conv_wgrad_tc(g16, LinearFn._rows16(ops, x, M, K), M // 64, 8, 8, K, Nn, 1, 1, dw)
+                ops.conv_wgrad_tc(g16, LinearFn._rows16(ops, x, M, Mp, K), Mp // 64, 8, 8, K, Nn, 1, 1, dw)
             else:
                 ops.gemm_f32(dy, x, dw, Nn, K, M, (1, Nn), (K, 1), (K, 1))
             dw = dw.reshape(wshape)

@@ -504,7 +504,7 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     AttnArgs a{};
     a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / bk; a.kv_len = m + 1;
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
-    static const int poly = [] { const char* e = getenv("MI_ATTN_POLY"); return e ? atoi(e) : 0; }();
+    static const int poly = [] { const char* e = getenv("MI_ATTN_POLY"); return e ? atoi(e) : 1; }();    // MI_ATTN_POLY=0: MUFU only
     a.poly = poly;
     dim3 grid(n / kBQ, heads, B);
     static const bool two_sweep = [] { const char* e = getenv("MI_ATTN_TWO_SWEEP"); return e && e[0] == '1'; }();
