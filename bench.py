@@ -319,6 +319,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=8, help="batch of the informational training_step row")
     ap.add_argument("--secondary", default="cfg1,cfg2a,cfg2b,cfg4,cfg5,train", help="comma list of secondary configurations")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--fuse", default=None, choices=["off", "pair", "on", "all"], help="fused GroupNorm+conv kernel usage")
@@ -650,11 +651,11 @@ def main():
                 tu = U2(**tcfg)
             tim = Imagen(unets=tu, text_encoder_name="t5_base", image_sizes=(64,), timesteps=1000, cond_drop_prob=0.1).to(dev).train()
             gg = torch.Generator().manual_seed(3)
-            tb = 8
+            tb = args.train_batch
             imgs = torch.rand(tb, 3, 64, 64, generator=gg).to(dev)
             te = torch.randn(tb, 16, 768, generator=gg).to(dev)
             tm = torch.ones(tb, 16, dtype=torch.bool, device=dev)
-            opt = torch.optim.Adam(tim.parameters(), lr=1e-4)
+            opt = torch.optim.Adam(tu.parameters(), lr=1e-4)
             def one():
                 opt.zero_grad(set_to_none=True)
                 loss = tim(imgs, text_embeds=te, text_masks=tm, unet_number=1)
@@ -670,16 +671,30 @@ def main():
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 3
             row = {"ms_per_training_step": dt * 1e3, "batch": tb, "loss": float(loss.detach()), "params_m": sum(p.numel() for p in tu.parameters()) / 1e6,
-                   "workload": "base U-Net dim 128, mults (1,2,4), 64x64, b=8: Imagen.forward + backward + Adam step (eager; convs and the "
+                   "workload": f"base U-Net dim 128, mults (1,2,4), 64x64, b={tb}: Imagen.forward + backward + Adam step (eager; convs and the "
                                "attention projections forward, data gradient and weight gradient on tcgen05 with fp16 operands; GroupNorm / "
                                "LayerNorm / attention-core backward fp32)"}
+            try:        # the same step captured in one CUDA graph (Imagen.graphed_train_step): the eager step is host-launch-bound
+                gopt = torch.optim.Adam(tu.parameters(), lr=1e-4, capturable=True)   # (tim.unets is a plain list after a training forward, like the reference)
+                gstep = tim.graphed_train_step(gopt, imgs, text_embeds=te, text_masks=tm, unet_number=1)
+                for _ in range(2):
+                    gstep(imgs, te, tm)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(10):
+                    gstep(imgs, te, tm)
+                torch.cuda.synchronize()
+                row["ms_per_training_step_graphed"] = (time.perf_counter() - t0) / 10 * 1e3
+                del gstep, gopt
+            except Exception as ex:
+                row["graphed_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
             if not args.no_torch_gpu:
                 # the same U-Net (same weights) trained by stock PyTorch on this GPU: restatement forward -> autograd -> Adam
                 try:
                     from oracle import restatement as R
                     sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in tu.state_dict().items()}
                     leaves = [v for v in sd.values() if v.requires_grad]
-                    topt = torch.optim.Adam(leaves, lr=1e-4)
+                    topt = torch.optim.Adam(leaves, lr=1e-4, capturable=True)
                     tt = torch.randint(0, 1000, (tb,), generator=gg).to(dev)
                     xin, tgt = torch.randn(tb, 3, 64, 64, generator=gg).to(dev), torch.randn(tb, 3, 64, 64, generator=gg).to(dev)
                     for name, dt_ in (("fp32", None), ("fp16_autocast", torch.float16)):
@@ -700,6 +715,34 @@ def main():
                             tone()
                         torch.cuda.synchronize()
                         row[f"torch_gpu_{name}_ms_per_training_step"] = (time.perf_counter() - t0) / 3 * 1e3
+                        if dt_ is None:
+                            try:        # and stock PyTorch's step captured the same way (no GradScaler in the graph: fp32 arm only)
+                                def tcap():
+                                    pred = R.unet_forward(sd, tcfg, xin, tt, text_embeds=te, text_mask=tm)
+                                    torch.nn.functional.mse_loss(pred, tgt).backward()
+                                    topt.step()
+                                sdst = torch.cuda.Stream()
+                                sdst.wait_stream(torch.cuda.current_stream())
+                                with torch.cuda.stream(sdst):
+                                    for _ in range(2):
+                                        topt.zero_grad(set_to_none=True)
+                                        tcap()
+                                torch.cuda.current_stream().wait_stream(sdst)
+                                torch.cuda.synchronize()
+                                tg = torch.cuda.CUDAGraph()
+                                topt.zero_grad(set_to_none=True)
+                                with torch.cuda.graph(tg):
+                                    tcap()
+                                tg.replay()
+                                torch.cuda.synchronize()
+                                t0 = time.perf_counter()
+                                for _ in range(10):
+                                    tg.replay()
+                                torch.cuda.synchronize()
+                                row["torch_gpu_fp32_ms_per_training_step_graphed"] = (time.perf_counter() - t0) / 10 * 1e3
+                                del tg
+                            except Exception as ex:
+                                row["torch_gpu_graphed_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
                 except Exception as ex:
                     row["torch_gpu_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
             return row

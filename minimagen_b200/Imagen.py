@@ -479,6 +479,47 @@ class Imagen(nn.Module):
                                 cond_drop_prob=self.cond_drop_prob)
             return self.loss_fn(pred, noise)
 
+    def graphed_train_step(self, optimizer, images, *, text_embeds, text_masks=None, unet_number: int = None, warmup: int = 3):
+        """B200-side addition (no reference counterpart): capture `loss = self(images, ...); loss.backward(); optimizer.step()`
+        for this batch SHAPE in ONE CUDA graph and return `step(images, text_embeds, text_masks=None) -> loss` that copies a new
+        batch into the graph's static buffers and replays it.  An eager step of this path is bound by its ~2000 host-side
+        launches (b = 8: 39 ms eager vs 18.5 ms replayed, `profiles/r02_train_step_vs_torch.txt`); the timestep / noise /
+        conditioning-dropout draws are in-graph RNG calls, so every replay sees fresh randomness.  `optimizer` must be
+        capturable (e.g. `torch.optim.Adam(params, lr, capturable=True)`); gradients are left in `.grad` after each step."""
+        assert images.is_cuda, 'graphed_train_step captures a CUDA graph: move the model and the batch to the GPU first'
+        static = [images.clone(), text_embeds.clone(), text_masks.clone() if exists(text_masks) else None]
+
+        def one(zero=True):
+            if zero:
+                optimizer.zero_grad(set_to_none=True)
+            loss = self(static[0], text_embeds=static[1], text_masks=static[2], unet_number=unet_number)
+            loss.backward()
+            optimizer.step()
+            return loss
+
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream(images.device))
+        with torch.cuda.stream(side):                           # warm-up off the capture stream (lazy one-time initialisations)
+            for _ in range(max(warmup, 1)):
+                one()
+        torch.cuda.current_stream(images.device).wait_stream(side)
+        torch.cuda.synchronize(images.device)
+        graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            loss = one(zero=False)
+
+        def step(images, text_embeds, text_masks=None):
+            static[0].copy_(images, non_blocking=True)
+            static[1].copy_(text_embeds, non_blocking=True)
+            if exists(static[2]):
+                static[2].copy_(text_masks, non_blocking=True)
+            graph.replay()
+            return loss.detach()
+
+        step.graph = graph
+        return step
+
     def forward(self, images, texts: List[str] = None, text_embeds=None, text_masks=None, unet_number: int = None):
         """Training step: noise the images and return the U-Net's noise-prediction loss (reference Imagen.py:575-650)."""
         assert not (len(self.unets) > 1 and not exists(unet_number)), \

@@ -106,6 +106,14 @@ class Conv2dFn(torch.autograd.Function):
                 x16 = torch.empty((B, 1, H, W, Cin), dtype=F16, device=x.device)
                 ops.cast_act(x, Cin, None, 0, 1.0, B, H, W, 0, x16)
                 ops.conv_wgrad_tc(dy16(), x16, B, Ho, Wo, Cin, Cout, kh, kw, dw, stride)
+            elif same and Cout < 32 <= Cin:
+                # few OUTPUT channels (the 3-channel final conv): sum over input pixels q instead,
+                # dW[co][ci][t] = sum_q x[q][ci] * dy[q - (t - pad)][co] -- the same kernel with x and dy swapped computes
+                # dW'[ci][co][t'] with t' the flipped tap, so its 32-wide tile axis is C_in (full) and the ragged 3-channel axis is
+                # flattened with the taps instead of wasting 29/32 of a C_out tile
+                dwt = torch.empty((Cin, Cout, kh, kw), dtype=F32, device=dy.device)
+                ops.conv_wgrad(x, dy, B, H, W, Cout, H, W, Cin, kh, kw, 1, pad, dwt)
+                dw = _c(dwt.flip(2, 3).transpose(0, 1))
             else:
                 ops.conv_wgrad(dy, x, B, H, W, Cin, Ho, Wo, Cout, kh, kw, stride, pad, dw)
         if has_bias and ctx.needs_input_grad[2]:

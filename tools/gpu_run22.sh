@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2_run22_gpu_tests.log 2>&1; echo "gpu tests rc=$?"
+tail -4 gpurun_out/r2_run22_gpu_tests.log | cut -c1-250
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_run22_smoke.log 2>&1; echo "smoke rc=$?"
+tail -2 gpurun_out/r2_run22_smoke.log | cut -c1-200
+timeout 1500 python bench.py --kernel-table gpurun_out/r2_run22_kernel_table.txt > gpurun_out/r2_run22_bench.json 2> gpurun_out/r2_run22_bench.err; echo "bench rc=$?"
+grep "secondary\|headline\|value" gpurun_out/r2_run22_bench.err | cut -c1-330 | tail -12
