@@ -423,6 +423,296 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
 }
 
+
+// =====================================================================================================================
+// Two query tiles per CTA, ping-ponged (n % 256 == 0): the softmax side is the bound of this kernel (MUFU 16 exp/clk/SM,
+// ncu: r02_attention_tc_study.md) and with one query tile the four warps of an SM sub-partition own the same rows and move in
+// lock-step, so the MUFU pipe idles while they wait for S, load it, take maxima and store P.  Here a CTA owns 256 queries as
+// tiles A and B, each with its own eight softmax warps (two per sub-partition and tile), S / P / O regions in tensor memory
+//   S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512)      (128-key blocks)
+// and the MMA warp issues  QK_A(j+1), PV_A(j), QK_B(j+1), PV_B(j), ...: tile B's S arrives one P.V + one Q.K^T later than
+// tile A's, which keeps the two groups half a block apart -- one computes exps while the other loads / stores / synchronises.
+// (One issuing warp PER tile was tried: without the enforced order the two groups drift into phase, 3746 vs 3206 us at 4096.)
+// K_j / V_j are loaded once for both tiles (three-stage rings).  Same lazy-rescale single sweep, P in tensor memory, every
+// fourth exp on the FMA pipe as attn_tc_kernel.
+constexpr int kBQ2 = 256, kBK2 = 128, kStages2 = 3;
+constexpr int kThreads2 = kThreads;
+constexpr uint32_t kK2Bytes = kBK2 * kD * 2, kV2Bytes = kD * kBK2 * 2;       // 16 KB each
+constexpr uint32_t kSmem2Bytes = 2 * kQBytes + kStages2 * (kK2Bytes + kV2Bytes) + 1024 + 512 + 4096;
+
+__global__ void __launch_bounds__(kThreads2, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnArgs a) {
+    pdl_trigger();
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                                  // [2 tiles]
+    uint8_t* sK = sQ + 2 * kQBytes;                      // [kStages2]
+    uint8_t* sV = sK + kStages2 * kK2Bytes;              // [kStages2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages2 * kV2Bytes);
+    uint64_t* q_full = bars;                             // 1
+    uint64_t* k_full = bars + 1;                         // [3]
+    uint64_t* k_empty = bars + 4;                        // [3]
+    uint64_t* v_full = bars + 7;                         // [3]
+    uint64_t* v_empty = bars + 10;                       // [3]
+    uint64_t* s_full = bars + 13;                        // [2 tiles]
+    uint64_t* s_empty = bars + 15;
+    uint64_t* p_full = bars + 17;
+    uint64_t* p_empty = bars + 19;
+    uint64_t* pv_done = bars + 21;
+    uint64_t* o_full = bars + 23;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 25);
+    float* s_xchg = reinterpret_cast<float*>(bars + 64);  // [2 tiles][2 parts][128 rows]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kBQ2, h = blockIdx.y, b = blockIdx.z;
+    const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
+    int* err = a.err;
+
+    if (warp == kSoftmaxWarps && lane == 0) {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmK);
+        ptx::prefetch_tensormap(&tmV);
+    }
+    if (warp == kSoftmaxWarps + 1 && lane == 0) {
+        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < kStages2; ++i) {
+            ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1);
+            ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            ptx::mbar_init(&s_full[t], 1); ptx::mbar_init(&s_empty[t], 32 * kSoftmaxWarps / 2);
+            ptx::mbar_init(&p_full[t], 32 * kSoftmaxWarps / 2); ptx::mbar_init(&p_empty[t], 1);
+            ptx::mbar_init(&pv_done[t], 1); ptx::mbar_init(&o_full[t], 1);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == kSoftmaxWarps + 1) {
+        ptx::tmem_alloc(tmem_ptr_smem, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_wait();
+
+    const int nblk = a.nblk;
+
+    if (warp == kSoftmaxWarps) {
+        // ===================== TMA producer: Q tiles once, then K_j and V_j for both tiles =====================
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(q_full, 2 * kQBytes);
+            ptx::tma_load_2d(&tmQ, q_full, sQ, h * kD, b * a.n + q0);
+            ptx::tma_load_2d(&tmQ, q_full, sQ + kQBytes, h * kD, b * a.n + q0 + kBQ);
+        }
+        int st = 0;
+        uint32_t ph = 0;
+        for (int j = 0; j < nblk; ++j) {
+            ptx::mbar_wait(&k_empty[st], ph ^ 1, err, 5100 + st);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&k_full[st], kK2Bytes);
+                ptx::tma_load_2d(&tmK, &k_full[st], sK + st * kK2Bytes, 0, bh * a.Mp + j * kBK2);
+            }
+            ptx::mbar_wait(&v_empty[st], ph ^ 1, err, 5200 + st);
+            if (ptx::elect_one()) {
+                ptx::mbar_arrive_expect_tx(&v_full[st], kV2Bytes);
+                ptx::tma_load_2d(&tmV, &v_full[st], sV + st * kV2Bytes, j * kBK2, bh * kD);
+                ptx::tma_load_2d(&tmV, &v_full[st], sV + st * kV2Bytes + kV2Bytes / 2, j * kBK2 + 64, bh * kD);
+            }
+            if (++st == kStages2) { st = 0; ph ^= 1; }
+        }
+    } else if (warp == kSoftmaxWarps + 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc_s = ptx::make_idesc_f16(kBQ, kBK2, 0);
+        constexpr uint32_t idesc_o = ptx::make_idesc_f16(kBQ, kD, 0);
+        ptx::mbar_wait(q_full, 0, err, 5300);
+        // S_t(j) = Q_t K_j^T; `last` = the later of the two users of K_j releases its stage
+        auto issue_qk = [&](int t, int j, bool last) {
+            const int st = j % kStages2;
+            ptx::mbar_wait(&k_full[st], (j / kStages2) & 1, err, 5310 + st);
+            ptx::mbar_wait(&s_empty[t], (j & 1) ^ 1, err, 5320 + t);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sQ + t * kQBytes));
+                const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sK + st * kK2Bytes));
+#pragma unroll
+                for (int k = 0; k < kD / 16; ++k)
+                    ptx::umma_f16(tmem_base + t * kBK2, da + 2 * k, db + 2 * k, idesc_s, k != 0);
+                if (last) ptx::umma_commit(&k_empty[st]);
+                ptx::umma_commit(&s_full[t]);
+            }
+        };
+        // O_t += P_t(j) V_j
+        auto issue_pv = [&](int t, int j, bool last) {
+            const int st = j % kStages2;
+            ptx::mbar_wait(&p_full[t], j & 1, err, 5330 + t);
+            ptx::mbar_wait(&v_full[st], (j / kStages2) & 1, err, 5340 + st);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const uint32_t ta = tmem_base + 384 + t * 64 + c * 32;
+                    const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV + st * kV2Bytes + c * (kV2Bytes / 2)));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::umma_f16_ts(tmem_base + 256 + t * 64, ta + 8 * k, db + 2 * k, idesc_o, (j | c | k) != 0);
+                }
+                ptx::umma_commit(&p_empty[t]);
+                ptx::umma_commit(&pv_done[t]);
+                if (last) ptx::umma_commit(&v_empty[st]);
+                if (j + 1 == nblk) ptx::umma_commit(&o_full[t]);
+            }
+        };
+        issue_qk(0, 0, false);
+        issue_qk(1, 0, true);
+        for (int j = 0; j < nblk; ++j) {
+            if (j + 1 < nblk) issue_qk(0, j + 1, false);
+            issue_pv(0, j, false);
+            if (j + 1 < nblk) issue_qk(1, j + 1, true);
+            issue_pv(1, j, true);
+        }
+    } else {
+        // ===================== softmax / epilogue: tile = warp / 8, one query row x 64 keys of every block per thread ==========
+        constexpr int kPer = kBK2 / 2;
+        const int tile = warp >> 3, part = (warp >> 2) & 1, q4 = warp & 3;
+        const int row = q4 * 32 + lane;
+        const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+        const uint32_t tS = lane_addr + tile * kBK2, tO = lane_addr + 256 + tile * 64, tP = lane_addr + 384 + tile * 64;
+        const int c_lo = part * kPer;
+        const int qbar = 1 + tile * 4 + q4;            // named barrier of the two warps that share these 32 rows
+        float* xch = s_xchg + tile * 256;              // [2 parts][128 rows]
+        constexpr float kLog2e = 1.4426950408889634f;
+        float m_ref = -INFINITY, mneg = 0.f;
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < nblk; ++j) {
+            ptx::mbar_wait(&s_full[tile], j & 1, err, 5400 + tile);
+            ptx::tc_fence_after();
+            uint32_t v[kPer];
+#pragma unroll
+            for (int c = 0; c < kPer; c += 16) ptx::tmem_ld_x16(tS + c_lo + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&s_empty[tile]);                   // S is in registers: Q K^T of the next block may start
+            const bool tail = (j + 1) * kBK2 > a.kv_len;
+            const int key = j * kBK2 + c_lo;
+            {
+                float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (!tail) {
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i)
+                        if (key + i < a.kv_len) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                }
+                const float bm = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
+                const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;
+                uint32_t any;
+                asm volatile(
+                    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 64, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(any) : "r"(need), "r"(qbar) : "memory");
+                if (any) {
+                    xch[part * 128 + row] = bm;
+                    asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+                    const float m_new = fmaxf(m_ref, fmaxf(xch[row], xch[128 + row]));
+                    const float factor = m_ref == -INFINITY ? 0.f : ptx::ex2_approx((m_ref - m_new) * kLog2e);
+                    if (j > 0) {
+                        ptx::mbar_wait(&pv_done[tile], (j - 1) & 1, err, 5430 + tile);
+                        ptx::tc_fence_after();
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            uint32_t o[16];
+                            ptx::tmem_ld_x16(tO + part * 32 + 16 * g, o);
+                            ptx::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                            ptx::tmem_st_x16(tO + part * 32 + 16 * g, o);
+                        }
+                        ptx::tmem_st_wait();
+                        ptx::tc_fence_before();
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) l4[i] *= factor;
+                    m_ref = m_new;
+                    mneg = -m_new * kLog2e;
+                }
+            }
+            uint32_t pk[kPer / 2];
+            if (!tail && a.poly) {
+#pragma unroll
+                for (int i = 0; i < kPer; i += 2) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                    const float x1 = fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg);
+                    const float p1 = (i & 2) ? ex2_poly(x1) : ptx::ex2_approx(x1);
+                    l4[i & 3] += p0;
+                    l4[(i + 1) & 3] += p1;
+                    pk[i >> 1] = pack_h2(p0, p1);
+                }
+            } else if (!tail) {
+#pragma unroll
+                for (int i = 0; i < kPer; i += 2) {
+                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
+                    l4[i & 3] += p0;
+                    l4[(i + 1) & 3] += p1;
+                    pk[i >> 1] = pack_h2(p0, p1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < kPer; i += 2) {
+                    float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                    float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
+                    if (key + i >= a.kv_len) p0 = 0.f;
+                    if (key + i + 1 >= a.kv_len) p1 = 0.f;
+                    l4[i & 3] += p0;
+                    l4[(i + 1) & 3] += p1;
+                    pk[i >> 1] = pack_h2(p0, p1);
+                }
+            }
+            ptx::mbar_wait(&p_empty[tile], (j & 1) ^ 1, err, 5420 + tile);
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < kPer / 32; ++g)
+                ptx::tmem_st_x16(tP + (c_lo >> 1) + 16 * g, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16 * g]));
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&p_full[tile]);
+        }
+        float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+        xch[part * 128 + row] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+        l = xch[row] + xch[128 + row];
+        // ---- epilogue: O / l -> fp16 [b][q0 + tile*128 + row][h*64 + 32*part ..]
+        ptx::mbar_wait(&o_full[tile], 0, err, 5500 + tile);
+        ptx::tc_fence_after();
+        const float inv = 1.f / l;
+        __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + tile * kBQ + row) * a.ldo + h * kD + part * 32;
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+            uint32_t v0[16];
+            ptx::tmem_ld_x16(tO + part * 32 + 16 * g2, v0);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                uint4 w0;
+                w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
+                w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
+                w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
+                w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + 16 * g2 + 8 * g) = w0;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == kSoftmaxWarps + 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
 }  // namespace
 
 // key-block size: 256-key blocks pay off on long sequences, 128-key blocks pad short ones less
@@ -430,7 +720,7 @@ static inline int attn_block_keys(int m) { return m >= 1024 ? 256 : 128; }
 
 long long attention_tc_workspace_bytes(int B, int heads, int kv_hs, int m) {
     const int hkv = kv_hs == 0 ? 1 : heads;
-    const int bk = attn_block_keys(m);
+    const int bk = attn_block_keys(m) > kBK2 ? attn_block_keys(m) : kBK2;       // the larger padding covers both kernels
     const long long Mp = ((long long)(m + 1) + bk - 1) / bk * bk;
     return 2 * (long long)B * hkv * Mp * kD * (long long)sizeof(__half);
 }
@@ -463,7 +753,9 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     PFN_tmaEncodeTiled enc = get_tma_encode();
     if (!enc) return -5;
     const int hkv = kv_hs == 0 ? 1 : heads;
-    const int bk = attn_block_keys(m);
+    static const bool pair_ok = [] { const char* e = getenv("MI_ATTN_PAIR"); return !(e && e[0] == '0'); }();
+    const bool two_tiles = pair_ok && n % kBQ2 == 0;         // two query tiles per CTA, 128-key blocks (attn_tc2_kernel)
+    const int bk = two_tiles ? kBK2 : attn_block_keys(m);
     const int Mp = (m + 1 + bk - 1) / bk * bk;
     __half* Kp = reinterpret_cast<__half*>(workspace);
     __half* Vt = Kp + (long long)B * hkv * Mp * kD;
@@ -506,6 +798,15 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
     static const int poly = [] { const char* e = getenv("MI_ATTN_POLY"); return e ? atoi(e) : 1; }();    // MI_ATTN_POLY=0: MUFU only
     a.poly = poly;
+    if (two_tiles) {
+        static bool attr_set2 = false;
+        if (!attr_set2) {
+            if (cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2Bytes) != cudaSuccess) return -10;
+            attr_set2 = true;
+        }
+        launch_k(attn_tc2_kernel, dim3(n / kBQ2, heads, B), kThreads2, kSmem2Bytes, st, tmQ, tmK, tmV, a);
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    }
     dim3 grid(n / kBQ, heads, B);
     static const bool two_sweep = [] { const char* e = getenv("MI_ATTN_TWO_SWEEP"); return e && e[0] == '1'; }();
     if (two_sweep) return bk == 256 ? launch_attn<256, false>(tmQ, tmK, tmV, a, grid, st) : launch_attn<128, false>(tmQ, tmK, tmV, a, grid, st);
