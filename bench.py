@@ -674,6 +674,9 @@ def main():
                    "workload": f"base U-Net dim 128, mults (1,2,4), 64x64, b={tb}: Imagen.forward + backward + Adam step (eager; convs and the "
                                "attention projections forward, data gradient and weight gradient on tcgen05 with fp16 operands; GroupNorm / "
                                "LayerNorm / attention-core backward fp32)"}
+            del loss        # a live loss keeps the parameters' gradient accumulators (bound to the default stream) alive: not capturable
+            import gc
+            gc.collect()
             try:        # the same step captured in one CUDA graph (Imagen.graphed_train_step): the eager step is host-launch-bound
                 gopt = torch.optim.Adam(tu.parameters(), lr=1e-4, capturable=True)   # (tim.unets is a plain list after a training forward, like the reference)
                 gstep = tim.graphed_train_step(gopt, imgs, text_embeds=te, text_masks=tm, unet_number=1)
@@ -687,7 +690,10 @@ def main():
                 row["ms_per_training_step_graphed"] = (time.perf_counter() - t0) / 10 * 1e3
                 del gstep, gopt
             except Exception as ex:
+                import traceback
+                traceback.print_exc(file=sys.stderr)
                 row["graphed_error"] = f"{type(ex).__name__}: {str(ex)[:200]}"
+                torch.cuda.synchronize()
             if not args.no_torch_gpu:
                 # the same U-Net (same weights) trained by stock PyTorch on this GPU: restatement forward -> autograd -> Adam
                 try:

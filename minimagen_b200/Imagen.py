@@ -485,7 +485,9 @@ class Imagen(nn.Module):
         batch into the graph's static buffers and replays it.  An eager step of this path is bound by its ~2000 host-side
         launches (b = 8: 39 ms eager vs 18.5 ms replayed, `profiles/r02_train_step_vs_torch.txt`); the timestep / noise /
         conditioning-dropout draws are in-graph RNG calls, so every replay sees fresh randomness.  `optimizer` must be
-        capturable (e.g. `torch.optim.Adam(params, lr, capturable=True)`); gradients are left in `.grad` after each step."""
+        capturable (e.g. `torch.optim.Adam(params, lr, capturable=True)`); gradients are left in `.grad` after each step.
+        Drop references to losses of earlier EAGER steps first (`del loss`): a live autograd graph keeps the parameters' gradient
+        accumulators bound to the default stream, and CUDA refuses to make the legacy stream wait on a capturing one."""
         assert images.is_cuda, 'graphed_train_step captures a CUDA graph: move the model and the batch to the GPU first'
         static = [images.clone(), text_embeds.clone(), text_masks.clone() if exists(text_masks) else None]
 

@@ -14,6 +14,10 @@ from .ops import get_ops
 
 F16, F32, F64 = torch.float16, torch.float32, torch.float64
 
+# The tensor-core routes are taken for CUDA tensors only; tests/test_training.py sets this to walk the same host logic
+# (sub-pixel Downsample data gradient, padded Linear rows, weight-gradient geometry) through the emulated ops on the CPU.
+ROUTE_TC_ON_CPU = False
+
 
 def _c(t):
     return t.contiguous()
@@ -33,7 +37,7 @@ class Conv2dFn(torch.autograd.Function):
         Wo = (W + 2 * pad - kw) // stride + 1
         same = stride == 1 and kh == kw and kh % 2 == 1 and pad == kh // 2
         down = stride == 2 and kh == 4 and kw == 4 and pad == 1
-        tc = (same or down) and kh * kw <= 16 and ops.igemm_supported(Ho, Wo, Cin, Cout) and x.is_cuda
+        tc = (same or down) and kh * kw <= 16 and ops.igemm_supported(Ho, Wo, Cin, Cout) and (x.is_cuda or ROUTE_TC_ON_CPU)
         y = torch.empty((B, Ho, Wo, Cout), dtype=F32, device=x.device)
         strides = (Ho * Wo * Cout, Wo * Cout, Cout)
         w = weight.detach()
@@ -211,7 +215,7 @@ class LinearFn(torch.autograd.Function):
         Mp = (M + 127) // 128 * 128
         w = _c(weight.detach().reshape(Nn, K))
         b = bias.detach() if bias is not None else None
-        tc = x.is_cuda and M >= 256 and K % 64 == 0 and Nn % 16 == 0 and ops.igemm_supported(Mp // 128, 128, K, Nn)
+        tc = (x.is_cuda or ROUTE_TC_ON_CPU) and M >= 256 and K % 64 == 0 and Nn % 16 == 0 and ops.igemm_supported(Mp // 128, 128, K, Nn)
         if tc:
             y = torch.empty((Mp, Nn), dtype=F32, device=x.device)
             ops.conv_igemm(LinearFn._rows16(ops, x, M, Mp, K), 1, Mp // 128, 128, K, 0, K, ops.pack_conv_weight(w), Nn, 1, 1, 0, b,

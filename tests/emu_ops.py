@@ -201,7 +201,7 @@ class EmuOps:
         x = _cat_src(src0.float(), c0, src1.float() if src1 is not None else None, c1, scale1, (B, H, W))
         C = c0 + c1
         if mode == 0:
-            out.reshape(B, H, W, C).copy_(x.to(out.dtype))
+            out.reshape(-1)[:B * H * W * C].reshape(B, H, W, C).copy_(x.to(out.dtype))     # the kernel writes the first B*H*W rows
         elif mode == 1:
             out.reshape(B, 2 * H, 2 * W, C).copy_(
                 x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).to(out.dtype))

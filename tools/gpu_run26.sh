@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2_run26_gpu_tests.log 2>&1; echo "gpu tests rc=$?"
+tail -3 gpurun_out/r2_run26_gpu_tests.log | cut -c1-250
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/r2_run26_smoke.log 2>&1; echo "smoke rc=$?"
+tail -2 gpurun_out/r2_run26_smoke.log | cut -c1-200
+timeout 1500 python bench.py --kernel-table gpurun_out/r2_run26_kernel_table.txt > gpurun_out/r2_run26_bench.json 2> gpurun_out/r2_run26_bench.err; echo "bench rc=$?"
+grep "secondary" gpurun_out/r2_run26_bench.err | cut -c1-200 | tail -8
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_run26_bench_reference.json 2> gpurun_out/r2_run26_bench_reference.err; echo "reference arm rc=$?"
+tail -1 gpurun_out/r2_run26_bench_reference.json | cut -c1-400
