@@ -42,6 +42,11 @@ int mi_set_launch_mode(int programmatic_dependent_launch);
 int mi_pack_conv_weight_f16(const float* w_oihw, int c_out, int c_in, int kh, int kw, float scale, void* out_f16,
                             void* stream);
 
+/* The same weight packed for the DATA gradient of a stride-1 'same' conv (or of a linear layer, kh = kw = 1): taps flipped,
+ * in / out channels swapped -> [c_in][((kh-1-r)*kw + (kw-1-s))*c_out + o] fp16; mi_conv2d_igemm_f16 on dy with this operand
+ * (c_in' = c_out, c_out' = c_in) is dL/dx.  Training side. */
+int mi_pack_conv_weight_dgrad_f16(const float* w_oihw, int c_out, int c_in, int kh, int kw, void* out_f16, void* stream);
+
 /* ------------------------------------------------------------------------------------------------- convolution
  * Tensor-core (tcgen05 + TMA + TMEM) implicit-GEMM convolution / linear layer.
  * Replaces nn.Conv2d / nn.Linear forward at: layers.py:129,145 (Block.project 3x3), layers.py:415,439 (res_conv 1x1),
@@ -281,7 +286,7 @@ int mi_conv2d_wgrad_f16(const void* dy_f16, const void* x_f16, int B, int Hout, 
                         int stride, float* dw, float* workspace, long long workspace_bytes, void* stream);
 /* Backward of mi_gn_apply_silu over ONE fp32 source x [B][hw][C] (sums = mi_gn_stats group sums [B][groups][2]):
  * dx; dgamma / dbeta ACCUMULATED into (caller zeroes or carries .grad); d_scale_shift [B][.. ld ..] = [d scale(C) | d shift(C)]
- * or NULL; workspace: (2*B*C + 2*B*groups) floats. */
+ * or NULL; workspace: (2*B*C + 4*B*groups) floats. */
 int mi_gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int hw, int C, int groups,
                    const float* gamma, const float* beta, const float* scale_shift, int scale_shift_ld, float eps,
                    float* dx, float* dgamma, float* dbeta, float* d_scale_shift, int d_scale_shift_ld, float* workspace,

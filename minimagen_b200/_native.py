@@ -21,6 +21,7 @@ SIGNATURES = {
     "mi_device_ok": [],
     "mi_set_launch_mode": [_I],
     "mi_pack_conv_weight_f16": [_P, _I, _I, _I, _I, _F, _P, _P],
+    "mi_pack_conv_weight_dgrad_f16": [_P, _I, _I, _I, _I, _P, _P],
     "mi_conv2d_igemm_supported": [_I, _I, _I, _I],
     "mi_conv2d_igemm_f16": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _L, _L, _L, _L,
                             _I, _I, _P, _P, _L, _P],

@@ -56,6 +56,8 @@ class Conv2dFn(torch.autograd.Function):
             ops.conv_direct(xp, B, H, W, Cin, ld, _c(w), Cout, kh, kw, stride, pad, b, None, y, Ho, Wo, (*strides, 1))
         ctx.save_for_backward(x, weight)
         ctx.geom = (stride, pad, same, down, tc, bias is not None)
+        # the fp16 copy of x is the weight-gradient kernel's operand too: keep it instead of casting x again in backward
+        ctx.x16 = a16 if tc and ops.conv_wgrad_tc_supported(Ho, Wo, Cin, Cout, kh, kw, stride) else None
         return y
 
     @staticmethod
@@ -83,9 +85,8 @@ class Conv2dFn(torch.autograd.Function):
             if tc and same and Cout % 64 == 0 and Cin % 16 == 0 and ops.igemm_supported(H, W, Cout, Cin):
                 # data gradient of a 'same' conv = the same conv of dy with the taps flipped and in/out channels swapped:
                 # runs on the forward tcgen05 implicit-GEMM kernel
-                wt = _c(w.flip(2, 3).transpose(0, 1))
                 g16 = dy16()
-                ops.conv_igemm(g16, B, H, W, Cout, 0, Cout, ops.pack_conv_weight(wt), Cin, kh, kw, 0, None, None, dx, None,
+                ops.conv_igemm(g16, B, H, W, Cout, 0, Cout, ops.pack_conv_weight_dgrad(w), Cin, kh, kw, 0, None, None, dx, None,
                                (H * W * Cin, W * Cin, Cin))
             elif tc and down and Cout % 64 == 0 and Cin % 16 == 0 and ops.igemm_supported(Ho, Wo, Cout, Cin):
                 # transposed 4x4 stride-2 conv = four 2x2 convs of dy, one per output parity (a, b): input pixel 2v + a sees
@@ -107,8 +108,10 @@ class Conv2dFn(torch.autograd.Function):
             dw = torch.empty_like(w, memory_format=torch.contiguous_format)
             if tc and (same or down) and ops.conv_wgrad_tc_supported(Ho, Wo, Cin, Cout, kh, kw, stride):
                 # contraction over the pixels on tcgen05: fp16 NHWC dy and x are both MN-major operands (csrc/wgrad_tc.cu)
-                x16 = torch.empty((B, 1, H, W, Cin), dtype=F16, device=x.device)
-                ops.cast_act(x, Cin, None, 0, 1.0, B, H, W, 0, x16)
+                x16 = ctx.x16
+                if x16 is None:
+                    x16 = torch.empty((B, 1, H, W, Cin), dtype=F16, device=x.device)
+                    ops.cast_act(x, Cin, None, 0, 1.0, B, H, W, 0, x16)
                 ops.conv_wgrad_tc(dy16(), x16, B, Ho, Wo, Cin, Cout, kh, kw, dw, stride)
             elif same and Cout < 32 <= Cin:
                 # few OUTPUT channels (the 3-channel final conv): sum over input pixels q instead,
@@ -218,9 +221,11 @@ class LinearFn(torch.autograd.Function):
         tc = (x.is_cuda or ROUTE_TC_ON_CPU) and M >= 256 and K % 64 == 0 and Nn % 16 == 0 and ops.igemm_supported(Mp // 128, 128, K, Nn)
         if tc:
             y = torch.empty((Mp, Nn), dtype=F32, device=x.device)
-            ops.conv_igemm(LinearFn._rows16(ops, x, M, Mp, K), 1, Mp // 128, 128, K, 0, K, ops.pack_conv_weight(w), Nn, 1, 1, 0, b,
-                           None, y, None, (Mp * Nn, 128 * Nn, Nn))
+            a16 = LinearFn._rows16(ops, x, M, Mp, K)
+            ops.conv_igemm(a16, 1, Mp // 128, 128, K, 0, K, ops.pack_conv_weight(w), Nn, 1, 1, 0, b, None, y, None,
+                           (Mp * Nn, 128 * Nn, Nn))
             y = y[:M]
+            ctx.x16 = a16
         else:
             y = torch.empty((M, Nn), dtype=F32, device=x.device)
             ops.linear_f32(x, M, K, w, b, Nn, 0, 0, None, y, None)
@@ -242,8 +247,8 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             if g16 is not None and Nn % 64 == 0 and K % 16 == 0 and ops.igemm_supported(Mp // 128, 128, Nn, K):
                 dx = torch.empty((Mp, K), dtype=F32, device=x.device)          # dX[M,K] = dY[M,N] W[N,K]
-                ops.conv_igemm(g16, 1, Mp // 128, 128, Nn, 0, Nn, ops.pack_conv_weight(_c(w.t())), K, 1, 1, 0, None, None, dx,
-                               None, (Mp * K, 128 * K, K))
+                ops.conv_igemm(g16, 1, Mp // 128, 128, Nn, 0, Nn, ops.pack_conv_weight_dgrad(w), K, 1, 1, 0, None, None, dx, None,
+                               (Mp * K, 128 * K, K))
                 dx = dx[:M]
             else:
                 dx = torch.empty_like(x)
@@ -251,7 +256,7 @@ class LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(w)                       # dW[N,K] = dY^T[N,M] X[M,K]
             if g16 is not None and ops.conv_wgrad_tc_supported(8, 8, K, Nn, 1, 1):
-                ops.conv_wgrad_tc(g16, LinearFn._rows16(ops, x, M, Mp, K), Mp // 64, 8, 8, K, Nn, 1, 1, dw)
+                ops.conv_wgrad_tc(g16, ctx.x16, Mp // 64, 8, 8, K, Nn, 1, 1, dw)
             else:
                 ops.gemm_f32(dy, x, dw, Nn, K, M, (1, Nn), (K, 1), (K, 1))
             dw = dw.reshape(wshape)

@@ -263,7 +263,10 @@ gn_bwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ dy, co
         const float ga = gamma[c], be = beta[c];
         const float* xp = x + (long long)b * HW * C + c;
         const float* dp = dy + (long long)b * HW * C + c;
-        for (int p = ty; p < HW; p += 8) {
+        // pixel range of this block: gridDim.z splits HW so that small-batch / few-channel layers still fill the GPU
+        const int chunk = (HW + gridDim.z - 1) / gridDim.z;
+        const int p_lo = blockIdx.z * chunk, p_hi = min(HW, p_lo + chunk);
+        for (int p = p_lo + ty; p < p_hi; p += 8) {
             const float xn = (xp[(long long)p * C] - mean) * rstd;
             const float v = (xn * ga + be) * sc + sh;
             const float dv = dp[(long long)p * C] * silu_grad(v);
@@ -276,8 +279,13 @@ gn_bwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ dy, co
     if (ty == 0 && c < C) {
 #pragma unroll
         for (int i = 1; i < 8; ++i) { a1 += r1[i][tx]; a2 += r2[i][tx]; }
-        A[((long long)b * C + c) * 2] = a1;
-        A[((long long)b * C + c) * 2 + 1] = a2;
+        if (gridDim.z == 1) {
+            A[((long long)b * C + c) * 2] = a1;
+            A[((long long)b * C + c) * 2 + 1] = a2;
+        } else {                                            // A zeroed by the launcher
+            atomicAdd(&A[((long long)b * C + c) * 2], a1);
+            atomicAdd(&A[((long long)b * C + c) * 2 + 1], a2);
+        }
     }
 }
 
@@ -285,7 +293,8 @@ gn_bwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ dy, co
 __global__ void __launch_bounds__(256)
 gn_bwd_reduce_kernel(const float* __restrict__ A, int HW, int C, int groups, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ ss, int ss_ld, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ dss, int dss_ld, float* __restrict__ gm) {
+                     float* __restrict__ dbeta, float* __restrict__ dss, int dss_ld, float* __restrict__ gm,
+                     const double* __restrict__ sums, float eps) {
     pdl_wait();
     pdl_trigger();
     __shared__ float s1[32], s2[32];
@@ -310,33 +319,48 @@ gn_bwd_reduce_kernel(const float* __restrict__ A, int HW, int C, int groups, con
     __syncthreads();
     if (threadIdx.x < groups) {
         const float inv = 1.0f / ((float)Cg * (float)HW);
-        gm[((long long)b * groups + threadIdx.x) * 2] = s1[threadIdx.x] * inv;
-        gm[((long long)b * groups + threadIdx.x) * 2 + 1] = s2[threadIdx.x] * inv;
+        float mean, rstd;
+        gn_group_stats(sums, b, threadIdx.x, groups, (double)Cg * HW, eps, mean, rstd);
+        float* o = gm + ((long long)b * groups + threadIdx.x) * 4;
+        o[0] = s1[threadIdx.x] * inv;
+        o[1] = s2[threadIdx.x] * inv;
+        o[2] = mean;                        // the fp64 -> fp32 statistics once per (image, group), not once per element
+        o[3] = rstd;
     }
 }
 
-// pass 3: dx = rstd * (gamma' * dv - m1 - xn * m2)
+// pass 3: dx = rstd * (gamma' * dv - m1 - xn * m2); four consecutive channels per thread (C % 4 == 0: same group when Cg % 4 == 0,
+// handled per element otherwise)
 __global__ void __launch_bounds__(256)
-gn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, const double* __restrict__ sums, int HW, int C,
-                 int groups, const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss,
-                 int ss_ld, float eps, const float* __restrict__ gm, float* __restrict__ dx, long long total) {
+gn_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ dy, int HW, int C, int groups,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ ss, int ss_ld,
+                 const float* __restrict__ gm, float* __restrict__ dx, long long total4) {
     pdl_wait();
     pdl_trigger();
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c = (int)(idx % C);
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= total4) return;
+    const long long idx = q * 4;
+    const int c0 = (int)(idx % C);
     const int b = (int)(idx / ((long long)HW * C));
-    const int Cg = C / groups, g = c / Cg;
-    float mean, rstd;
-    gn_group_stats(sums, b, g, groups, (double)Cg * HW, eps, mean, rstd);
-    const float sc = ss ? ss[(long long)b * ss_ld + c] + 1.0f : 1.0f;
-    const float sh = ss ? ss[(long long)b * ss_ld + C + c] : 0.f;
-    const float ga = gamma[c];
-    const float xn = (x[idx] - mean) * rstd;
-    const float v = (xn * ga + beta[c]) * sc + sh;
-    const float dv = dy[idx] * silu_grad(v);
-    const float m1 = gm[((long long)b * groups + g) * 2], m2 = gm[((long long)b * groups + g) * 2 + 1];
-    dx[idx] = rstd * (ga * sc * dv - m1 - xn * m2);
+    const int Cg = C / groups;
+    const float4 xv = *reinterpret_cast<const float4*>(x + idx);
+    const float4 dv4 = *reinterpret_cast<const float4*>(dy + idx);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ds[4] = {dv4.x, dv4.y, dv4.z, dv4.w};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = c0 + i;
+        const float* st = gm + ((long long)b * groups + c / Cg) * 4;
+        const float m1 = st[0], m2 = st[1], mean = st[2], rstd = st[3];
+        const float sc = ss ? ss[(long long)b * ss_ld + c] + 1.0f : 1.0f;
+        const float sh = ss ? ss[(long long)b * ss_ld + C + c] : 0.f;
+        const float ga = gamma[c];
+        const float xn = (xs[i] - mean) * rstd;
+        const float v = (xn * ga + beta[c]) * sc + sh;
+        const float dv = ds[i] * silu_grad(v);
+        o[i] = rstd * (ga * sc * dv - m1 - xn * m2);
+    }
+    *reinterpret_cast<float4*>(dx + idx) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm rows bwd
@@ -522,15 +546,21 @@ int gn_silu_bwd(const float* x, const float* dy, const double* sums, int B, int 
                 const float* beta, const float* ss, int ss_ld, float eps, float* dx, float* dgamma, float* dbeta,
                 float* dss, int dss_ld, float* workspace, cudaStream_t st) {
     if (groups < 1 || groups > 32 || C % groups) return -1;
+    if (C % 4) return -1;
     float* A = workspace;                                   // [B][C][2]
-    float* gm = workspace + (long long)B * C * 2;           // [B][groups][2]
-    dim3 g1((C + 31) / 32, B);
+    float* gm = workspace + (long long)B * C * 2;           // [B][groups][4]: m1, m2, mean, rstd
+    const int blocks_xy = ((C + 31) / 32) * B;
+    int Z = (8 * 148 + blocks_xy - 1) / blocks_xy;          // ~8 blocks per SM over the whole grid
+    if (Z > HW / 64) Z = HW / 64;
+    if (Z < 1) Z = 1;
+    if (Z > 1 && cudaMemsetAsync(A, 0, (size_t)B * C * 2 * sizeof(float), st) != cudaSuccess) return -2;
+    dim3 g1((C + 31) / 32, B, Z);
     launch_k(gn_bwd_sums_kernel, g1, 256, 0, st, x, dy, sums, HW, C, groups, gamma, beta, ss, ss_ld, eps, A);
     launch_k(gn_bwd_reduce_kernel, B, 256, 0, st, (const float*)A, HW, C, groups, gamma, beta, ss, ss_ld, dgamma, dbeta, dss,
-             dss_ld, gm);
-    const long long total = (long long)B * HW * C;
-    launch_k(gn_bwd_dx_kernel, g1d(total, 256), 256, 0, st, x, dy, sums, HW, C, groups, gamma, beta, ss, ss_ld, eps,
-             (const float*)gm, dx, total);
+             dss_ld, gm, sums, eps);
+    const long long total4 = (long long)B * HW * C / 4;
+    launch_k(gn_bwd_dx_kernel, g1d(total4, 256), 256, 0, st, x, dy, HW, C, groups, gamma, beta, ss, ss_ld, (const float*)gm, dx,
+             total4);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -52,6 +52,9 @@ int mi_device_ok(void) {
     return major == 10;
 }
 
+int mi_pack_conv_weight_dgrad_f16(const float* w, int c_out, int c_in, int kh, int kw, void* out, void* stream) {
+    return check(mi::pack_conv_weight_dgrad(w, c_out, c_in, kh, kw, (__half*)out, S(stream)), "mi_pack_conv_weight_dgrad_f16");
+}
 int mi_pack_conv_weight_f16(const float* w, int c_out, int c_in, int kh, int kw, float scale, void* out, void* stream) {
     return check(mi::pack_conv_weight(w, c_out, c_in, kh, kw, scale, (__half*)out, S(stream)), "mi_pack_conv_weight_f16");
 }

@@ -579,6 +579,23 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, int O, int 
     out[i] = __float2half_rn(w[((o * I + c) * KH + t / KW) * KW + t % KW] * scale);
 }
 
+// The same weight packed for the DATA gradient of a stride-1 'same' conv / a linear layer: the conv of dy with the taps flipped
+// and in / out channels swapped, out[i][((KH-1-r)*KW + (KW-1-s))*O + o] = w[o][i][r][s]  (one kernel instead of flip + transpose +
+// copy + pack in the training step).
+__global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, int O, int I, int KH, int KW, __half* __restrict__ out) {
+    pdl_wait();
+    pdl_trigger();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int taps = KH * KW;
+    const long long total = (long long)O * I * taps;
+    if (idx >= total) return;
+    const int o = (int)(idx % O);
+    const int t = (int)((idx / O) % taps);
+    const long long i = idx / ((long long)O * taps);
+    const int r = KH - 1 - t / KW, s = KW - 1 - t % KW;
+    out[idx] = __float2half_rn(w[(((long long)o * I + i) * KH + r) * KW + s]);
+}
+
 // Stem operand for the tensor-core path of CrossEmbedLayer (layers.py:294-305, kernels 3/7/15, stride 1):
 // horizontally unrolled window  out[b][h][w][j*8 + c] = in_c[b][h][w + j - 7]  (j < 15, c < Ca+Cb <= 8, else 0), fp16.
 // With it the k x k convs (all zero-embedded in one 15 x 15 window) become a 15-tap (vertical) implicit GEMM over
@@ -809,6 +826,11 @@ int select_rows(const float* a, const float* nullv, const uint8_t* keep, const f
 
 int nchw_to_nhwc(const float* a, int Ca, const float* b, int Cb, int B, int HW, int Cp, float* out, cudaStream_t st) {
     launch_k(nchw_to_nhwc_kernel, grid1d((long long)B * HW * Cp, 256), 256, 0, st, a, Ca, b, Cb, B, HW, Cp, out);
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+
+int pack_conv_weight_dgrad(const float* w, int O, int I, int KH, int KW, __half* out, cudaStream_t st) {
+    launch_k(pack_conv_weight_dgrad_kernel, grid1d((long long)O * I * KH * KW, 256), 256, 0, st, w, O, I, KH, KW, out);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

@@ -35,6 +35,7 @@ int resize_sep(const float* in, long long planes, int Hin, int Win, float* out, 
                const float* wy, int ty, const int* ix, const float* wx, int tx, int has_clamp, float lo, float hi,
                cudaStream_t st);
 int pack_conv_weight(const float* w, int O, int I, int KH, int KW, float scale, __half* out, cudaStream_t st);
+int pack_conv_weight_dgrad(const float* w, int O, int I, int KH, int KW, __half* out, cudaStream_t st);
 
 // conv_direct.cu
 int conv_direct_f32(const float* in, int B, int Hin, int Win, int Cin, int ldi, const float* w, int Cout, int KH,

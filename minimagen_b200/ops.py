@@ -48,6 +48,16 @@ class NativeOps:
         N.call("mi_pack_conv_weight_f16", N.ptr(w), O, I, KH, KW, float(scale), N.ptr(out), N.stream())
         return out
 
+    def pack_conv_weight_dgrad(self, w):
+        """w: (O, I, KH, KW) or (O, I) fp32 -> (I, KH*KW*O) fp16: the operand of the data-gradient conv (taps flipped, channels swapped)."""
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        w = w.detach().to(F32).contiguous()
+        O, I, KH, KW = w.shape
+        out = torch.empty((I, KH * KW * O), dtype=F16, device=w.device)
+        N.call("mi_pack_conv_weight_dgrad_f16", N.ptr(w), O, I, KH, KW, N.ptr(out), N.stream())
+        return out
+
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
                    out_strides, block_n=0, out_sc=1, n_valid=0, act2=None, lda2=0, c_off2=0, c_in1=0, out_stats=None):
@@ -285,7 +295,7 @@ class NativeOps:
         _chk(x, F32, "x"); _chk(dy, F32, "dy"); _chk(sums, F64, "sums"); _chk(gamma, F32, "gamma"); _chk(beta, F32, "beta")
         _chk_out(scale_shift, F32, "scale_shift"); _chk(dx, F32, "dx"); _chk(dgamma, F32, "dgamma"); _chk(dbeta, F32, "dbeta")
         _chk(dss, F32, "dss")
-        ws = torch.empty(2 * B * C + 2 * B * groups, dtype=F32, device=x.device)
+        ws = torch.empty(2 * B * C + 4 * B * groups, dtype=F32, device=x.device)
         N.call("mi_gn_silu_bwd", N.ptr(x), N.ptr(dy), N.ptr(sums), B, hw, C, groups, N.ptr(gamma), N.ptr(beta),
                N.ptr(scale_shift), int(ss_ld), float(eps), N.ptr(dx), N.ptr(dgamma), N.ptr(dbeta), N.ptr(dss), int(dss_ld),
                N.ptr(ws), N.stream())

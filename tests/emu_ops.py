@@ -56,6 +56,11 @@ class EmuOps:
         O, I, KH, KW = w.shape
         return (w.detach().float() * scale).permute(0, 2, 3, 1).reshape(O, KH * KW * I).to(F16).contiguous()
 
+    def pack_conv_weight_dgrad(self, w):
+        if w.dim() == 2:
+            w = w[:, :, None, None]
+        return self.pack_conv_weight(w.detach().flip(2, 3).transpose(0, 1).contiguous())
+
     # ---------------------------------------------------------------- convolutions
     def conv_igemm(self, act, B, H, W, lda, c_off, c_in, wp, c_out, kh, kw, mode, bias, residual, out_f32, out_f16,
                    out_strides, block_n=0, out_sc=1, n_valid=0, act2=None, lda2=0, c_off2=0, c_in1=0, out_stats=None):
