@@ -100,23 +100,36 @@ def last_error():
     return load().mi_last_error().decode()
 
 
+_FN = {}       # resolved entry points (ctypes attribute lookup + argtypes binding once per name)
+
+
 def call(name, *args):
     """Invoke an entry point; raise RuntimeError (the reference's convention is a Python exception) on failure."""
     global launch_count
-    rc = getattr(load(), name)(*args)
+    fn = _FN.get(name)
+    if fn is None:
+        fn = _FN[name] = getattr(load(), name)
+    rc = fn(*args)
     if rc != 0:
         raise RuntimeError(f"minimagen_b200.{name} failed: {last_error()}")
     launch_count += 1
     return rc
 
 
+# Fast paths of torch.cuda.current_device() / current_stream(): the training step makes ~2000 native calls with ~5 pointers each,
+# and the Python-object versions (torch.device, torch.cuda.Stream) were a third of its host time.
+_cur_dev = getattr(torch._C, "_cuda_getDevice", None) or torch.cuda.current_device
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def ptr(t):
     """Device pointer of a tensor (None -> NULL).  Refuses non-CUDA tensors: no CPU path exists."""
     if t is None:
         return None
-    if not t.is_cuda:
+    d = t.get_device()                     # -1 for CPU tensors
+    if d < 0:
         raise RuntimeError("minimagen_b200: tensor is not on a CUDA device; the kernels have no CPU fallback")
-    if t.device.index != torch.cuda.current_device():
+    if d != _cur_dev():
         # kernels are enqueued on the CURRENT device's current stream (and size grids / build tensor maps for it)
         raise RuntimeError(
             f"minimagen_b200: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
@@ -125,6 +138,9 @@ def ptr(t):
 
 
 def stream():
+    """Raw handle of the current stream of the current device (the capture stream while a CUDA graph is being captured)."""
+    if _raw_stream is not None:
+        return _raw_stream(_cur_dev())
     return torch.cuda.current_stream().cuda_stream
 
 

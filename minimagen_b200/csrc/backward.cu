@@ -154,6 +154,44 @@ conv_dgrad_kernel(const float* __restrict__ dy, int B, int Ho, int Wo, int Cout,
     dx[idx] = acc;
 }
 
+// Few output channels, stride 1 (the 128 -> 3 final conv): the whole weight fits in shared memory, re-laid [tap][co][ci] so that the
+// lanes of a warp (consecutive ci) read consecutive words; one block covers kDgPix pixels x C_in.
+constexpr int kDgPix = 32;
+__global__ void __launch_bounds__(256)
+conv_dgrad_smallco_kernel(const float* __restrict__ dy, int B, int Ho, int Wo, int Cout, const float* __restrict__ w, int Cin,
+                          int KH, int KW, int pad, float* __restrict__ dx, int Hi, int Wi) {
+    pdl_wait();
+    pdl_trigger();
+    extern __shared__ float ws[];                             // [taps][Cout][Cin]
+    const int taps = KH * KW;
+    for (int i = threadIdx.x; i < Cout * Cin * taps; i += blockDim.x) {
+        const int t = i % taps, ci = (i / taps) % Cin, co = i / (taps * Cin);          // OIHW order of the source
+        ws[(t * Cout + co) * Cin + ci] = w[i];
+    }
+    __syncthreads();
+    const long long npix = (long long)B * Hi * Wi;
+    const long long p0 = (long long)blockIdx.x * kDgPix;
+    for (int e = threadIdx.x; e < kDgPix * Cin; e += blockDim.x) {
+        const long long pix = p0 + e / Cin;
+        if (pix >= npix) break;
+        const int ci = e % Cin;
+        const int wi = (int)(pix % Wi), hi = (int)((pix / Wi) % Hi), b = (int)(pix / ((long long)Wi * Hi));
+        float acc = 0.f;
+        for (int r = 0; r < KH; ++r) {
+            const int ho = hi + pad - r;
+            if (ho < 0 || ho >= Ho) continue;
+            for (int s2 = 0; s2 < KW; ++s2) {
+                const int wo = wi + pad - s2;
+                if (wo < 0 || wo >= Wo) continue;
+                const float* dyp = dy + (((long long)b * Ho + ho) * Wo + wo) * Cout;
+                const float* wp = ws + ((r * KW + s2) * Cout) * Cin + ci;
+                for (int co = 0; co < Cout; ++co) acc = fmaf(dyp[co], wp[co * Cin], acc);
+            }
+        }
+        dx[pix * Cin + ci] = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ conv weight gradient
 // dW[co][ci][r][s] = sum over output pixels of dy[pix][co] * x[pix shifted by tap (r, s)][ci].
 // grid = (co tiles x ci tiles, taps, pixel splits); a block accumulates a 32 x 32 (co, ci) tile over its pixel range
@@ -504,6 +542,13 @@ int conv2d_dgrad_f32(const float* dy, int B, int Ho, int Wo, int Cout, const flo
                      int pad, float* dx, int Hi, int Wi, cudaStream_t st) {
     if (stride < 1 || KH < 1 || KW < 1) return -1;
     const long long total = (long long)B * Hi * Wi * Cin;
+    const size_t wbytes = (size_t)Cout * Cin * KH * KW * sizeof(float);
+    if (stride == 1 && Cout <= 8 && wbytes <= 40 * 1024) {
+        const long long npix = (long long)B * Hi * Wi;
+        launch_k(conv_dgrad_smallco_kernel, dim3((unsigned)((npix + kDgPix - 1) / kDgPix)), 256, wbytes, st, dy, B, Ho, Wo, Cout, w,
+                 Cin, KH, KW, pad, dx, Hi, Wi);
+        return cudaGetLastError() == cudaSuccess ? 0 : -2;
+    }
     launch_k(conv_dgrad_kernel, g1d(total, 256), 256, 0, st, dy, B, Ho, Wo, Cout, w, Cin, KH, KW, stride, pad, dx, Hi, Wi);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
