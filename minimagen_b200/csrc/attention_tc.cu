@@ -432,7 +432,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 //   S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)  P_A [384,448)  P_B [448,512)      (128-key blocks)
 // and the MMA warp issues  QK_A(j+1), PV_A(j), QK_B(j+1), PV_B(j), ...: tile B's S arrives one P.V + one Q.K^T later than
 // tile A's, which keeps the two groups half a block apart -- one computes exps while the other loads / stores / synchronises.
-// (One issuing warp PER tile was tried: without the enforced order the two groups drift into phase, 3746 vs 3206 us at 4096.)
+// (Tried: one issuing warp PER tile -- without the enforced order the two groups drift into phase, 3746 vs 3206 us at 4096 --
+// and QK_A(j+1), QK_B(j+1), PV_A(j), PV_B(j): both groups in phase again, 3492 vs 3304 us.)
 // K_j / V_j are loaded once for both tiles (three-stage rings).  Same lazy-rescale single sweep, P in tensor memory, every
 // fourth exp on the FMA pipe as attn_tc_kernel.
 constexpr int kBQ2 = 256, kBK2 = 128, kStages2 = 3;
