@@ -208,10 +208,12 @@ int mi_resize_separable(const float* in, long long planes, int h_in, int w_in, f
  * multi-query Attention.forward (layers.py:52-104) with kv_head_stride = 0.  q must already carry the dim_head**-0.5
  * scale.  Key 0 is the learned null_kv [2][64] fp32 (layers.py:65-67,232-235); key_mask: uint8 [B][m] or NULL
  * (masked_fill(~mask, -FLT_MAX), layers.py:92-95,242-245).  q/out: [B][n][ld] with head h at column h*64.
- * workspace (optional, 128-byte aligned, size from mi_attention_workspace_bytes): lends the tcgen05 kernel room for the
- * null-prepended padded K and the transposed V; it is used when key_mask is NULL, n % 128 == 0 and q is batch-contiguous
- * (q_bs == n*ldq) -- S = QK^T and O = PV then run as tcgen05.mma with TMEM accumulators, the softmax in between reads S from
- * TMEM and hands P to the second GEMM through shared memory.  Otherwise (or with workspace NULL) a mma.sync kernel runs. */
+ * workspace (optional, 128-byte aligned, size from mi_attention_workspace_bytes): lends the tcgen05 kernels room for the
+ * null-prepended padded K, the transposed V and the key-validity bits (null key, key_mask, padding); it is used when
+ * n % 128 == 0, m >= 128 and q is batch-contiguous (q_bs == n*ldq) -- S = QK^T and O = PV then run as tcgen05.mma with TMEM
+ * accumulators in ONE sweep over the keys (lazily rescaled reference maximum), the softmax in between reads S from TMEM and
+ * hands P to the second GEMM through tensor memory; two query tiles per CTA when n % 256 == 0.  Otherwise (or with workspace
+ * NULL) a mma.sync kernel runs. */
 long long mi_attention_workspace_bytes(int B, int heads, int kv_head_stride, int m);
 int mi_attention_fwd(const void* q_f16, long long q_bs, int ldq, const void* k_f16, const void* v_f16, long long kv_bs,
                      int ldkv, int kv_head_stride, const float* null_kv, const uint8_t* key_mask, int B, int heads,

@@ -55,12 +55,22 @@ struct AC {
 
 // ------------------------------------------------------------------------------------------------ operand preparation
 // Kp[bh][key][64]: key 0 = null key, keys 1..m = k, keys > m = 0.   Vt[bh][dim][key]: the same, transposed.
+// valid[b][key / 32]: bit (key % 32) = this padded key takes part in the softmax -- the null key always, key 1..m unless the
+// caller's key mask (b, m; layers.py:86-93 / :242-245) clears it, the padding never.  The attention kernels read one or two words
+// per thread and key block: the fast path when all bits are set, per-key tests otherwise (masked keys and the padded tail alike).
 __global__ void __launch_bounds__(256)
 attn_prep_kernel(const __half* __restrict__ k, const __half* __restrict__ v, long long kv_bs, int ldkv, int kv_hs,
                  const float* __restrict__ null_kv, int hkv, int m, int Mp, __half* __restrict__ Kp,
-                 __half* __restrict__ Vt) {
+                 __half* __restrict__ Vt, const uint8_t* __restrict__ mask, uint32_t* __restrict__ valid) {
     pdl_wait();
     pdl_trigger();
+    if ((blockIdx.y % hkv) == 0 && threadIdx.x < 64) {         // one kv head per image writes the two words of these 64 keys
+        const int bb = blockIdx.y / hkv;
+        const int key = blockIdx.x * 64 + threadIdx.x;
+        const bool ok = key == 0 || (key <= m && (mask == nullptr || mask[(long long)bb * m + key - 1] != 0));
+        const uint32_t w = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) valid[(long long)bb * (Mp / 32) + key / 32] = w;
+    }
     __shared__ __half tile[64][kD + 2];               // 64 keys x 64 dims of V (padded: conflict-free transpose)
     const int bh = blockIdx.y, b = bh / hkv, h = bh % hkv;
     const int key0 = blockIdx.x * 64;
@@ -86,6 +96,7 @@ struct AttnArgs {
     int n, heads, hkv, Mp, nblk, kv_len;       // kv_len = m + 1 valid (padded) keys
     __half* out; long long o_bs; int ldo;
     int poly;                                  // 1: every fourth exp on the FMA pipe (ex2_poly)
+    const uint32_t* valid;                     // [B][Mp / 32] key validity bits (attn_prep_kernel)
     int* err;
 };
 
@@ -272,14 +283,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&s_empty[ss]);                     // S is in registers: release the buffer early
-            if ((j + 1) * kBK <= a.kv_len) {                    // only the last block can hold padded keys
+            const uint32_t* vw = a.valid + (long long)b * (a.Mp / 32) + (j * kBK + c_lo) / 32;
+            uint32_t vb[kPer / 32];
+            bool all_ok = true;
+#pragma unroll
+            for (int w = 0; w < kPer / 32; ++w) { vb[w] = __ldg(vw + w); all_ok = all_ok && vb[w] == 0xffffffffu; }
+            if (all_ok) {                                       // no masked / padded key among this thread's keys of the block
 #pragma unroll
                 for (int i = 0; i < kPer; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
             } else {
-                const int key = j * kBK + c_lo;
 #pragma unroll
                 for (int i = 0; i < kPer; ++i)
-                    if (key + i < a.kv_len) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+                    if ((vb[i >> 5] >> (i & 31)) & 1u) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
             }
         }
         float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
@@ -302,8 +317,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&s_empty[ss]);
-            const bool tail = (j + 1) * kBK > a.kv_len;
-            const int key = j * kBK + c_lo;
+            // key validity bits of this thread's keys: "tail" = some key of them is masked or padding (warp-uniform)
+            uint32_t vb[kPer / 32];
+            bool tail = false;
+            {
+                const uint32_t* vw = a.valid + (long long)b * (a.Mp / 32) + (j * kBK + c_lo) / 32;
+#pragma unroll
+                for (int w = 0; w < kPer / 32; ++w) { vb[w] = __ldg(vw + w); tail = tail || vb[w] != 0xffffffffu; }
+            }
             if (kOnline) {
                 // lazy reference maximum: does any row of the CTA see a score more than 2^8 above its reference?
                 float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -313,7 +334,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 } else {
 #pragma unroll
                     for (int i = 0; i < kPer; ++i)
-                        if (key + i < a.kv_len) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                        if ((vb[i >> 5] >> (i & 31)) & 1u) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
                 }
                 const float bm = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
                 const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;     // m_ref = -inf in block 0: true wherever bm is finite
@@ -372,8 +393,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 for (int i = 0; i < kPer; i += 2) {
                     float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
                     float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
-                    if (key + i >= a.kv_len) p0 = 0.f;
-                    if (key + i + 1 >= a.kv_len) p1 = 0.f;
+                    if (!((vb[i >> 5] >> (i & 31)) & 1u)) p0 = 0.f;
+                    if (!((vb[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u)) p1 = 0.f;
                     l4[i & 3] += p0;
                     l4[(i + 1) & 3] += p1;
                     pk[i >> 1] = pack_h2(p0, p1);
@@ -595,8 +616,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             ptx::mbar_arrive(&s_empty[tile]);                   // S is in registers: Q K^T of the next block may start
-            const bool tail = (j + 1) * kBK2 > a.kv_len;
-            const int key = j * kBK2 + c_lo;
+            uint32_t vb[kPer / 32];                             // key validity bits of this thread's 64 keys
+            bool tail = false;                                  // some key masked or padding (warp-uniform)
+            {
+                const uint32_t* vw = a.valid + (long long)b * (a.Mp / 32) + (j * kBK2 + c_lo) / 32;
+#pragma unroll
+                for (int w = 0; w < kPer / 32; ++w) { vb[w] = __ldg(vw + w); tail = tail || vb[w] != 0xffffffffu; }
+            }
             {
                 float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
                 if (!tail) {
@@ -605,7 +631,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 } else {
 #pragma unroll
                     for (int i = 0; i < kPer; ++i)
-                        if (key + i < a.kv_len) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                        if ((vb[i >> 5] >> (i & 31)) & 1u) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
                 }
                 const float bm = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
                 const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;
@@ -664,8 +690,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int i = 0; i < kPer; i += 2) {
                     float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
                     float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
-                    if (key + i >= a.kv_len) p0 = 0.f;
-                    if (key + i + 1 >= a.kv_len) p1 = 0.f;
+                    if (!((vb[i >> 5] >> (i & 31)) & 1u)) p0 = 0.f;
+                    if (!((vb[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u)) p1 = 0.f;
                     l4[i & 3] += p0;
                     l4[(i + 1) & 3] += p1;
                     pk[i >> 1] = pack_h2(p0, p1);
@@ -723,11 +749,12 @@ long long attention_tc_workspace_bytes(int B, int heads, int kv_hs, int m) {
     const int hkv = kv_hs == 0 ? 1 : heads;
     const int bk = attn_block_keys(m) > kBK2 ? attn_block_keys(m) : kBK2;       // the larger padding covers both kernels
     const long long Mp = ((long long)(m + 1) + bk - 1) / bk * bk;
-    return 2 * (long long)B * hkv * Mp * kD * (long long)sizeof(__half);
+    return 2 * (long long)B * hkv * Mp * kD * (long long)sizeof(__half) + (long long)B * (Mp / 32) * (long long)sizeof(uint32_t);
 }
 
 bool attention_tc_supported(int n, int ldq, int ldo, long long q_bs, const void* mask) {
-    return mask == nullptr && n > 0 && (n % kBQ) == 0 && (ldq % 8) == 0 && (ldo % 8) == 0 && q_bs == (long long)n * ldq;
+    (void)mask;                  // key masks are handled in-kernel (validity bits written by attn_prep_kernel)
+    return n > 0 && (n % kBQ) == 0 && (ldq % 8) == 0 && (ldo % 8) == 0 && q_bs == (long long)n * ldq;
 }
 
 template <int BK, bool ONLINE>
@@ -745,7 +772,8 @@ static int launch_attn(const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUt
 }
 
 int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
-                     int kv_hs, const float* null_kv, int B, int heads, int n, int m, __half* out, long long o_bs, int ldo,
+                     int kv_hs, const float* null_kv, const uint8_t* key_mask, int B, int heads, int n, int m, __half* out,
+                     long long o_bs, int ldo,
                      void* workspace, long long workspace_bytes, int* err_flag, cudaStream_t st) {
     if (!attention_tc_supported(n, ldq, ldo, q_bs, nullptr) || (o_bs % 8) || (reinterpret_cast<uintptr_t>(q) & 15) ||
         (reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 127))
@@ -760,9 +788,10 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     const int Mp = (m + 1 + bk - 1) / bk * bk;
     __half* Kp = reinterpret_cast<__half*>(workspace);
     __half* Vt = Kp + (long long)B * hkv * Mp * kD;
+    uint32_t* valid = reinterpret_cast<uint32_t*>(Vt + (long long)B * hkv * Mp * kD);      // [B][Mp / 32]
     {
         dim3 grid(Mp / 64, B * hkv);
-        launch_k(attn_prep_kernel, grid, 256, 0, st, k, v, kv_bs, ldkv, kv_hs, null_kv, hkv, m, Mp, Kp, Vt);
+        launch_k(attn_prep_kernel, grid, 256, 0, st, k, v, kv_bs, ldkv, kv_hs, null_kv, hkv, m, Mp, Kp, Vt, key_mask, valid);
         if (cudaGetLastError() != cudaSuccess) return -2;
     }
     CUtensorMap tmQ, tmK, tmV;
@@ -799,6 +828,7 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
     static const int poly = [] { const char* e = getenv("MI_ATTN_POLY"); return e ? atoi(e) : 1; }();    // MI_ATTN_POLY=0: MUFU only
     a.poly = poly;
+    a.valid = valid;
     if (two_tiles) {
         static bool attr_set2 = false;
         if (!attr_set2) {

@@ -262,12 +262,12 @@ long long mi_attention_workspace_bytes(int B, int heads, int kv_head_stride, int
 int mi_attention_fwd(const void* q, long long q_bs, int ldq, const void* k, const void* v, long long kv_bs, int ldkv,
                      int kv_head_stride, const float* null_kv, const uint8_t* key_mask, int B, int heads, int n, int m,
                      void* out, long long o_bs, int ldo, void* workspace, long long workspace_bytes, void* stream) {
-    // tcgen05 path when the shape allows and the caller lends the operand workspace; mma.sync kernel otherwise
+    // tcgen05 path (key masks included) when the shape allows and the caller lends the operand workspace; mma.sync kernel otherwise
     // (short key sequences -- one 128-key block -- stay on the mma.sync kernel: 19 us vs 33 us at n = 256, m = 59)
     if (workspace && m >= 128 && mi::attention_tc_supported(n, ldq, ldo, q_bs, key_mask) &&
         workspace_bytes >= mi::attention_tc_workspace_bytes(B, heads, kv_head_stride, m))
         return check(mi::attention_tc_fwd((const __half*)q, q_bs, ldq, (const __half*)k, (const __half*)v, kv_bs, ldkv,
-                                          kv_head_stride, null_kv, B, heads, n, m, (__half*)out, o_bs, ldo, workspace,
+                                          kv_head_stride, null_kv, key_mask, B, heads, n, m, (__half*)out, o_bs, ldo, workspace,
                                           workspace_bytes, nullptr, S(stream)),
                      "mi_attention_fwd (tcgen05)");
     return check(mi::attention_fwd((const __half*)q, q_bs, ldq, (const __half*)k, (const __half*)v, kv_bs, ldkv,

@@ -51,7 +51,7 @@ int attention_fwd(const __half* q, long long q_bs, int ldq, const __half* k, con
 bool attention_tc_supported(int n, int ldq, int ldo, long long q_bs, const void* mask);
 long long attention_tc_workspace_bytes(int B, int heads, int kv_hs, int m);
 int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, const __half* v, long long kv_bs, int ldkv,
-                     int kv_hs, const float* null_kv, int B, int heads, int n, int m, __half* out, long long o_bs, int ldo,
+                     int kv_hs, const float* null_kv, const uint8_t* key_mask, int B, int heads, int n, int m, __half* out, long long o_bs, int ldo,
                      void* workspace, long long workspace_bytes, int* err_flag, cudaStream_t st);
 
 // conv_tc.cu: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)

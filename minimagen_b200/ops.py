@@ -190,7 +190,7 @@ class NativeOps:
             raise TypeError("attention operands must be fp16")
         _chk(null_kv, F32, "null_kv"); _chk(mask, U8, "mask")
         ws = None
-        if self.attention_tc and mask is None and n % 128 == 0 and m >= 128:
+        if self.attention_tc and n % 128 == 0 and m >= 128:
             # operand workspace of the tcgen05 kernel (null-prepended padded K, transposed V); per call, so it is safe under
             # CUDA-graph capture and concurrent streams
             nbytes = int(N.load().mi_attention_workspace_bytes(B, heads, kv_hs, m))

@@ -468,7 +468,10 @@ def test_resize_separable(native, n_in, n_out, pad, clamp):
                                                          (1, 2, 100, 37, False, True),
                                                          (3, 8, 128, 59, False, False),      # one padded key block
                                                          (2, 4, 384, 127, True, False),      # m + 1 == 128 exactly
-                                                         (1, 2, 4096, 4096, True, False)])   # base U-Net 64x64 tokens
+                                                         (1, 2, 4096, 4096, True, False),    # base U-Net 64x64 tokens
+                                                         (2, 8, 512, 300, False, True),      # key mask inside the two-tile tcgen05 kernel
+                                                         (2, 4, 384, 700, True, True),       # ... and inside the one-tile kernel (n % 256 != 0)
+                                                         (1, 8, 256, 2000, True, True)])     # ... over many key blocks
 def test_attention(native, B, heads, n, m, shared, use_mask):
     inner = heads * 64
     q = (_rand(B * n, inner, seed=34) * 0.125).to(F16)
