@@ -348,6 +348,86 @@ ln_rows_kernel(const float* __restrict__ in, long long R, int C, const float* __
     }
 }
 
+// The same for C = 128 * NV (NV = 1, 2, 4, 8: every LayerNorm of the U-Nets): the row lives in registers -- ONE global read
+// instead of three -- and a warp works on ROWS rows at a time so that several rows' loads are in flight (the three-pass kernel
+// above ran at ~2 TB/s: one 512-byte row per warp, three dependent load -> shuffle-reduce phases).  Same summation order, so
+// the results are bit-identical to ln_rows_kernel.
+template <int NV, int ROWS>
+__global__ void __launch_bounds__(256)
+ln_rows_reg_kernel(const float* __restrict__ in, long long R, const float* __restrict__ gamma, const float* __restrict__ beta,
+                   float eps, int pre_gelu, const float* __restrict__ residual, float* __restrict__ out_f32,
+                   __half* __restrict__ out_f16) {
+    pdl_wait();
+    pdl_trigger();
+    constexpr int C = 128 * NV;
+    const int lane = threadIdx.x & 31;
+    const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+    if (row0 >= R) return;
+    float4 v[ROWS][NV];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+            v[r][k] = row0 + r < R ? *reinterpret_cast<const float4*>(in + (row0 + r) * C + lane * 4 + 128 * k)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 g[NV], bt[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        g[k] = *reinterpret_cast<const float4*>(gamma + lane * 4 + 128 * k);
+        bt[k] = beta ? *reinterpret_cast<const float4*>(beta + lane * 4 + 128 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    float mean[ROWS], rstd[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            float4& x = v[r][k];
+            if (pre_gelu) { x.x = gelu_erf_f(x.x); x.y = gelu_erf_f(x.y); x.z = gelu_erf_f(x.z); x.w = gelu_erf_f(x.w); }
+            s += (x.x + x.y) + (x.z + x.w);
+        }
+        mean[r] = s;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        mean[r] /= (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const float a = v[r][k].x - mean[r], b2 = v[r][k].y - mean[r], c2 = v[r][k].z - mean[r], d = v[r][k].w - mean[r];
+            q += (a * a + b2 * b2) + (c2 * c2 + d * d);
+        }
+        rstd[r] = q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r >= R) break;
+        const float rs = rsqrtf(rstd[r] / (float)C + eps);
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const long long off = (row0 + r) * C + lane * 4 + 128 * k;
+            float4 y;
+            y.x = (v[r][k].x - mean[r]) * rs * g[k].x; y.y = (v[r][k].y - mean[r]) * rs * g[k].y;
+            y.z = (v[r][k].z - mean[r]) * rs * g[k].z; y.w = (v[r][k].w - mean[r]) * rs * g[k].w;
+            if (beta) { y.x += bt[k].x; y.y += bt[k].y; y.z += bt[k].z; y.w += bt[k].w; }
+            if (residual) {
+                const float4 rr = *reinterpret_cast<const float4*>(residual + off);
+                y.x += rr.x; y.y += rr.y; y.z += rr.z; y.w += rr.w;
+            }
+            if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = y;
+            if (out_f16) *reinterpret_cast<uint2*>(out_f16 + off) = pack_half4(y.x, y.y, y.z, y.w);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ small fp32 linear
 // out[M][N] = act_out( act_in(in)[M][K] @ W[N][K]^T + bias + addend ).  For the conditioning MLPs (M = batch rows;
 // Unet.py:101-161, layers.py:396-399) and for projections whose K/N are not tensor-core shaped (tiny config).
@@ -750,7 +830,11 @@ int cast_act(const void* src0, int C0, const void* src1, int C1, float scale1, i
 int ln_rows(const float* in, long long R, int C, const float* gamma, const float* beta, float eps, int pre_gelu,
             const float* residual, float* out_f32, __half* out_f16, cudaStream_t st) {
     if (C % 4) return -1;
-    launch_k(ln_rows_kernel, grid1d(R, 8), 256, 0, st, in, R, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    if (C == 128) launch_k(ln_rows_reg_kernel<1, 4>, grid1d(R, 32), 256, 0, st, in, R, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    else if (C == 256) launch_k(ln_rows_reg_kernel<2, 2>, grid1d(R, 16), 256, 0, st, in, R, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    else if (C == 512) launch_k(ln_rows_reg_kernel<4, 1>, grid1d(R, 8), 256, 0, st, in, R, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    else if (C == 1024) launch_k(ln_rows_reg_kernel<8, 1>, grid1d(R, 8), 256, 0, st, in, R, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
+    else launch_k(ln_rows_kernel, grid1d(R, 8), 256, 0, st, in, R, C, gamma, beta, eps, pre_gelu, residual, out_f32, out_f16);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 
