@@ -54,11 +54,24 @@ class _StepGraph:
         self.x = self.t = self.noise = None
         self.cond = {}
         self.inject_noise = False
+        self.unet = None
 
     def set_cond(self, **tensors):
         for k, v in tensors.items():
             if v is not None:
                 self.cond[k].copy_(v)
+        self.refresh_static()
+
+    def refresh_static(self):
+        """Step-invariant conditioning of the static buffers (eager, once per sampling loop): the text projection."""
+        te = self.cond.get('text_embeds')
+        if self.unet is not None and te is not None and te.dtype == F32:
+            self.unet.register_static_text(te)
+
+    def release(self):
+        te = self.cond.get('text_embeds')
+        if self.unet is not None and te is not None:
+            self.unet.unregister_static_text(te)
 
     def replay(self):
         self.graph.replay()
@@ -278,6 +291,8 @@ class Imagen(nn.Module):
 
     def clear_graphs(self):
         """Drop the captured step graphs (and the activation memory their pools hold)."""
+        for g in getattr(self, "_graphs", {}).values():
+            g.release()
         self._graphs = {}
         self.max_cached_graphs = 4
 
@@ -295,8 +310,9 @@ class Imagen(nn.Module):
             g.set_cond(**cond)
             return g
         if len(self._graphs) >= self.max_cached_graphs:
-            self._graphs.pop(next(iter(self._graphs)))
+            self._graphs.pop(next(iter(self._graphs))).release()
         g = _StepGraph()
+        g.unet = unet
         g.inject_noise = exists(self.noise_fn)
         g.x = torch.zeros(shape, dtype=F32, device=device)
         g.noise = torch.zeros(shape, dtype=F32, device=device)
@@ -304,6 +320,7 @@ class Imagen(nn.Module):
         g.cond = {k: v.clone() for k, v in cond.items() if v is not None}
         kw = dict(noise_scheduler=noise_scheduler, cond_scale=cond_scale,
                   **{k: g.cond.get(k) for k in cond})
+        g.refresh_static()
         ops = get_ops()
 
         def body():

@@ -369,9 +369,11 @@ class Unet(nn.Module):
         ops.place_rows(time_tokens.contiguous(), B, nt, D, c_pre, m, 0)
         if has_text:
             L, E = text_embeds.shape[1], text_embeds.shape[2]
-            proj = torch.empty((B * L, D), dtype=F32, device=device)
-            ops.linear_f32(text_embeds.to(F32).contiguous().reshape(B * L, E), B * L, E, self.text_to_cond.weight,
-                           self.text_to_cond.bias, D, 0, 0, None, proj, None)
+            proj = self._static_text_proj(text_embeds)           # step-invariant: projected once per sampling loop (see below)
+            if proj is None:
+                proj = torch.empty((B * L, D), dtype=F32, device=device)
+                ops.linear_f32(text_embeds.to(F32).contiguous().reshape(B * L, E), B * L, E, self.text_to_cond.weight,
+                               self.text_to_cond.bias, D, 0, 0, None, proj, None)
             keep = (cond_keep.to(device=device, dtype=torch.uint8).contiguous() if exists(cond_keep)
                     else prob_mask_like((B,), 1 - cond_drop_prob, device=device).to(torch.uint8))
             mask_u8 = text_mask.to(torch.uint8).contiguous() if exists(text_mask) else None
@@ -392,6 +394,42 @@ class Unet(nn.Module):
         ops.ln_rows(c_pre.reshape(B * m, D), B * m, D, self.norm_cond.weight, self.norm_cond.bias, self.norm_cond.eps,
                     0, None, c.reshape(B * m, D), None)
         return t, c
+
+
+    # ---- step-invariant conditioning (SURVEY 8a row 3 note): `text_to_cond(text_embeds)` (Unet.py:569) does not depend on the
+    # timestep, yet the reference -- and a captured step graph -- recomputes it in every one of the 1000 denoising steps.  The
+    # sampling loop registers its STATIC text buffer here; the projection is then computed once per loop (eagerly, outside the
+    # graph) and `_text_condition` reads it.  Keyed on the buffer's address AND version, so a tensor that was modified without
+    # re-registering simply misses the cache.
+    def register_static_text(self, text_embeds):
+        ops = get_ops()
+        B, L, E = text_embeds.shape
+        cache = self.__dict__.setdefault("_static_text", {})
+        entry = cache.get(text_embeds.data_ptr())
+        buf = entry[0] if entry is not None and entry[0].shape == (B * L, self.cond_dim) else \
+            torch.empty((B * L, self.cond_dim), dtype=F32, device=text_embeds.device)
+        with _native.device_of(text_embeds):
+            ops.linear_f32(text_embeds.reshape(B * L, E), B * L, E, self.text_to_cond.weight, self.text_to_cond.bias,
+                           self.cond_dim, 0, 0, None, buf, None)
+        cache[text_embeds.data_ptr()] = (buf, text_embeds._version, self.text_to_cond.weight._version)
+        return buf
+
+    def unregister_static_text(self, text_embeds=None):
+        cache = self.__dict__.get("_static_text", {})
+        if text_embeds is None:
+            cache.clear()
+        else:
+            cache.pop(text_embeds.data_ptr(), None)
+
+    def _static_text_proj(self, text_embeds):
+        entry = self.__dict__.get("_static_text", {}).get(text_embeds.data_ptr())
+        if entry is None or text_embeds.dtype != F32 or not text_embeds.is_contiguous():
+            return None
+        buf, version, wversion = entry
+        B, L, _ = text_embeds.shape
+        if version != text_embeds._version or wversion != self.text_to_cond.weight._version or buf.shape[0] != B * L:
+            return None
+        return buf
 
 
 class Base(Unet):

@@ -92,6 +92,33 @@ def test_sample_loop_vs_reference_golden(native, graph):
     assert rel_l2(out, expect) < 1e-3
 
 
+def test_step_graph_reuse_with_new_text(native):
+    """The captured step graph is reused by later sampling loops of the same signature; its step-invariant text projection
+    (Unet.register_static_text, computed once per loop outside the graph) must follow the NEW prompt: loop 2 through the reused
+    graph equals loop 2 computed without graphs."""
+    from minimagen_b200.Imagen import Imagen
+    g = load_golden("sample_loop.pt")
+    gen = torch.Generator().manual_seed(7)
+    te2 = (torch.randn(g["text_embeds"].shape, generator=gen) * 4).cuda()
+    outs = {}
+    for graph in (True, False):
+        u = _mine(g["cfg"], g["state_dict"])
+        im = Imagen(unets=u, text_encoder_name="t5_small", image_sizes=(64,), timesteps=g["timesteps"],
+                    cond_drop_prob=0.15).eval().cuda()
+        im.unets[0].load_state_dict(g["state_dict"])
+        im.use_cuda_graph = graph
+        im.noise_fn = lambda kind, shape, step: g["x_T"] if kind == "init" else g["noises"][g["timesteps"] - 1 - step]
+        kw = dict(noise_scheduler=im.noise_schedulers[0], text_mask=g["text_mask"].cuda(), cond_scale=g["cond_scale"], max_steps=3)
+        first = im._p_sample_loop(im.unets[0], (2, 3, 64, 64), text_embeds=g["text_embeds"].cuda(), **kw)
+        outs[graph] = (first, im._p_sample_loop(im.unets[0], (2, 3, 64, 64), text_embeds=te2, **kw))
+        if graph:
+            assert len(im._graphs) == 1                          # the second loop re-used the captured step
+    assert rel_l2(outs[True][0], outs[False][0]) < 1e-5 and rel_l2(outs[True][1], outs[False][1]) < 1e-5
+    # the prompt does change the result (a stale projection would reproduce loop 1 exactly), by much more than graph vs eager differ
+    effect = rel_l2(outs[False][1], outs[False][0])
+    assert effect > 1e-5 and rel_l2(outs[True][1], outs[False][1]) < 0.1 * effect
+
+
 def test_sample_api_and_sharding_invariance(native):
     """Imagen.sample end to end (T=25 tiny cascade stage), deterministic under injected noise."""
     from minimagen_b200.Imagen import Imagen
