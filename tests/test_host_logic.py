@@ -4,6 +4,8 @@ minimagen_b200/{layers,Unet,Imagen}.py -- executed through the torch EMULATION o
 the 2e-3 bound; the tiny config runs its convolutions in fp32 and lands near 2e-4.)"""
 import inspect
 
+import os
+
 import pytest
 import torch
 
@@ -42,6 +44,34 @@ def test_unet_forward_orchestration_vs_golden(emu, name):
         assert rel_l2(u(inp["x"], inp["time"], **dict(kw, text_mask=None)), g["out_nomask"]) < 1e-3
         assert rel_l2(u.forward_with_cond_scale(inp["x"], inp["time"], cond_scale=3., **kw), g["out_cfg3"]) < 1e-3
     assert "conv_direct" in emu.calls and "attention" in emu.calls
+
+
+def test_static_text_projection_cache(emu):
+    """Unet.register_static_text: the step-invariant text_to_cond projection is computed once per registered (static) text
+    buffer and reused by forward -- same output; an in-place change of the buffer without re-registering misses the cache
+    (the projection is recomputed inside forward), re-registering hits it again."""
+    g = load_golden("unet_tiny_base.pt")
+    u = _mine(g["cfg"], g["state_dict"])
+    inp = g["inputs"]
+    kw = {k: v for k, v in inp.items() if k not in ("x", "time")}
+    te = kw["text_embeds"].clone().float().contiguous()
+    kw["text_embeds"] = te
+    with torch.no_grad():
+        ref = u(inp["x"], inp["time"], **kw)
+        n_lin = emu.calls.count("linear_f32")
+        u.register_static_text(te)
+        emu.calls.clear()
+        hit = u(inp["x"], inp["time"], **kw)
+        assert torch.equal(hit, ref) and emu.calls.count("linear_f32") == n_lin - 1          # one projection fewer in the step
+        te.mul_(0.5)                                                                             # modified, not re-registered
+        emu.calls.clear()
+        miss = u(inp["x"], inp["time"], **kw)
+        assert emu.calls.count("linear_f32") == n_lin and not torch.equal(miss, ref)
+        u.register_static_text(te)
+        emu.calls.clear()
+        assert torch.equal(u(inp["x"], inp["time"], **kw), miss) and emu.calls.count("linear_f32") == n_lin - 1
+        u.unregister_static_text(te)
+        assert u._static_text_proj(te) is None
 
 
 @pytest.mark.parametrize("cfg,s,lowres", [
