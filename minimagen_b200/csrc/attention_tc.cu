@@ -93,7 +93,7 @@ attn_prep_kernel(const __half* __restrict__ k, const __half* __restrict__ v, lon
 }
 
 struct AttnArgs {
-    int n, heads, hkv, Mp, nblk, kv_len;       // kv_len = m + 1 valid (padded) keys
+    int n, heads, hkv, Mp, nblk, kv_len, batch;       // kv_len = m + 1 valid (padded) keys
     __half* out; long long o_bs; int ldo;
     int poly;                                  // 1: every fourth exp on the FMA pipe (ex2_poly)
     const uint32_t* valid;                     // [B][Mp / 32] key validity bits (attn_prep_kernel)
@@ -460,7 +460,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 constexpr int kBQ2 = 256, kBK2 = 128, kStages2 = 3;
 constexpr int kThreads2 = kThreads;
 constexpr uint32_t kK2Bytes = kBK2 * kD * 2, kV2Bytes = kD * kBK2 * 2;       // 16 KB each
-constexpr uint32_t kSmem2Bytes = 2 * kQBytes + kStages2 * (kK2Bytes + kV2Bytes) + 1024 + 512 + 4096;
+constexpr uint32_t kSmem2Bytes = 4 * kQBytes + kStages2 * (kK2Bytes + kV2Bytes) + 1024 + 512 + 4096;
 
 __global__ void __launch_bounds__(kThreads2, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -468,11 +468,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                                  // [2 tiles]
-    uint8_t* sK = sQ + 2 * kQBytes;                      // [kStages2]
+    uint8_t* sQ = smem;                                  // [2 work items in flight][2 tiles]
+    uint8_t* sK = sQ + 4 * kQBytes;                      // [kStages2]
     uint8_t* sV = sK + kStages2 * kK2Bytes;              // [kStages2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kStages2 * kV2Bytes);
-    uint64_t* q_full = bars;                             // 1
+    uint64_t* q_full = bars + 26;                        // [2]  (bars + 0 unused)
+    uint64_t* q_empty = bars + 28;                       // [2]
+    uint64_t* o_empty = bars + 30;                       // [2 tiles]
     uint64_t* k_full = bars + 1;                         // [3]
     uint64_t* k_empty = bars + 4;                        // [3]
     uint64_t* v_full = bars + 7;                         // [3]
@@ -483,13 +485,17 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* p_empty = bars + 19;
     uint64_t* pv_done = bars + 21;
     uint64_t* o_full = bars + 23;
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 25);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 32);
     float* s_xchg = reinterpret_cast<float*>(bars + 64);  // [2 tiles][2 parts][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * kBQ2, h = blockIdx.y, b = blockIdx.z;
-    const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
     int* err = a.err;
+    // persistent CTA: work item w = (query pair-tile, head, batch), w = blockIdx.x, blockIdx.x + gridDim.x, ...; all barrier
+    // phases run on GLOBAL counters (work index i, key-block index gj = i * nblk + j) so that the producer and the MMA warp stream
+    // straight into the next work item while the softmax warps finish the current one (Q double-buffered, O handed over through
+    // o_full / o_empty)
+    const int q_tiles = a.n / kBQ2;
+    const int total_work = q_tiles * a.heads * a.batch;
 
     if (warp == kSoftmaxWarps && lane == 0) {
         ptx::prefetch_tensormap(&tmQ);
@@ -497,7 +503,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::prefetch_tensormap(&tmV);
     }
     if (warp == kSoftmaxWarps + 1 && lane == 0) {
-        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&q_full[i], 1); ptx::mbar_init(&q_empty[i], 1); }
         for (int i = 0; i < kStages2; ++i) {
             ptx::mbar_init(&k_full[i], 1); ptx::mbar_init(&k_empty[i], 1);
             ptx::mbar_init(&v_full[i], 1); ptx::mbar_init(&v_empty[i], 1);
@@ -506,6 +512,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             ptx::mbar_init(&s_full[t], 1); ptx::mbar_init(&s_empty[t], 32 * kSoftmaxWarps / 2);
             ptx::mbar_init(&p_full[t], 32 * kSoftmaxWarps / 2); ptx::mbar_init(&p_empty[t], 1);
             ptx::mbar_init(&pv_done[t], 1); ptx::mbar_init(&o_full[t], 1);
+            ptx::mbar_init(&o_empty[t], 32 * kSoftmaxWarps / 2);
         }
         ptx::fence_barrier_init();
     }
@@ -523,13 +530,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
     if (warp == kSoftmaxWarps) {
         // ===================== TMA producer: Q tiles once, then K_j and V_j for both tiles =====================
-        if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(q_full, 2 * kQBytes);
-            ptx::tma_load_2d(&tmQ, q_full, sQ, h * kD, b * a.n + q0);
-            ptx::tma_load_2d(&tmQ, q_full, sQ + kQBytes, h * kD, b * a.n + q0 + kBQ);
-        }
         int st = 0;
         uint32_t ph = 0;
+        int i = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++i) {
+        const int q0 = (w % q_tiles) * kBQ2, h = (w / q_tiles) % a.heads, b = w / (q_tiles * a.heads);
+        const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
+        const int qb = i & 1;
+        ptx::mbar_wait(&q_empty[qb], ((i >> 1) & 1) ^ 1, err, 5050 + qb);
+        if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * kQBytes);
+            ptx::tma_load_2d(&tmQ, &q_full[qb], sQ + qb * 2 * kQBytes, h * kD, b * a.n + q0);
+            ptx::tma_load_2d(&tmQ, &q_full[qb], sQ + qb * 2 * kQBytes + kQBytes, h * kD, b * a.n + q0 + kBQ);
+        }
         for (int j = 0; j < nblk; ++j) {
             ptx::mbar_wait(&k_empty[st], ph ^ 1, err, 5100 + st);
             if (ptx::elect_one()) {
@@ -544,32 +557,37 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             if (++st == kStages2) { st = 0; ph ^= 1; }
         }
+        }
     } else if (warp == kSoftmaxWarps + 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc_s = ptx::make_idesc_f16(kBQ, kBK2, 0);
         constexpr uint32_t idesc_o = ptx::make_idesc_f16(kBQ, kD, 0);
-        ptx::mbar_wait(q_full, 0, err, 5300);
+        int i = 0, gbase = 0, qb = 0;                    // work index, global index of this work item's first key block, Q buffer
         // S_t(j) = Q_t K_j^T; `last` = the later of the two users of K_j releases its stage
-        auto issue_qk = [&](int t, int j, bool last) {
+        auto issue_qk = [&](int t, int jl, bool last) {
+            const int j = gbase + jl;                    // global key-block index: ring stage and barrier phases
             const int st = j % kStages2;
             ptx::mbar_wait(&k_full[st], (j / kStages2) & 1, err, 5310 + st);
             ptx::mbar_wait(&s_empty[t], (j & 1) ^ 1, err, 5320 + t);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-                const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sQ + t * kQBytes));
+                const uint64_t da = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sQ + qb * 2 * kQBytes + t * kQBytes));
                 const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sK + st * kK2Bytes));
 #pragma unroll
                 for (int k = 0; k < kD / 16; ++k)
                     ptx::umma_f16(tmem_base + t * kBK2, da + 2 * k, db + 2 * k, idesc_s, k != 0);
                 if (last) ptx::umma_commit(&k_empty[st]);
+                if (last && jl + 1 == nblk) ptx::umma_commit(&q_empty[qb]);      // both tiles' last Q K^T: the Q buffer is free
                 ptx::umma_commit(&s_full[t]);
             }
         };
         // O_t += P_t(j) V_j
-        auto issue_pv = [&](int t, int j, bool last) {
+        auto issue_pv = [&](int t, int jl, bool last) {
+            const int j = gbase + jl;
             const int st = j % kStages2;
             ptx::mbar_wait(&p_full[t], j & 1, err, 5330 + t);
             ptx::mbar_wait(&v_full[st], (j / kStages2) & 1, err, 5340 + st);
+            if (jl == 0) ptx::mbar_wait(&o_empty[t], (i & 1) ^ 1, err, 5350 + t);   // the previous work item's O has been read out
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
 #pragma unroll
@@ -578,21 +596,25 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const uint64_t db = ptx::make_kmajor_sw128_desc(ptx::smem_u32(sV + st * kV2Bytes + c * (kV2Bytes / 2)));
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        ptx::umma_f16_ts(tmem_base + 256 + t * 64, ta + 8 * k, db + 2 * k, idesc_o, (j | c | k) != 0);
+                        ptx::umma_f16_ts(tmem_base + 256 + t * 64, ta + 8 * k, db + 2 * k, idesc_o, (jl | c | k) != 0);
                 }
                 ptx::umma_commit(&p_empty[t]);
                 ptx::umma_commit(&pv_done[t]);
                 if (last) ptx::umma_commit(&v_empty[st]);
-                if (j + 1 == nblk) ptx::umma_commit(&o_full[t]);
+                if (jl + 1 == nblk) ptx::umma_commit(&o_full[t]);
             }
         };
-        issue_qk(0, 0, false);
-        issue_qk(1, 0, true);
-        for (int j = 0; j < nblk; ++j) {
-            if (j + 1 < nblk) issue_qk(0, j + 1, false);
-            issue_pv(0, j, false);
-            if (j + 1 < nblk) issue_qk(1, j + 1, true);
-            issue_pv(1, j, true);
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++i, gbase += nblk) {
+            qb = i & 1;
+            ptx::mbar_wait(&q_full[qb], (i >> 1) & 1, err, 5300 + qb);
+            issue_qk(0, 0, false);
+            issue_qk(1, 0, true);
+            for (int j = 0; j < nblk; ++j) {
+                if (j + 1 < nblk) issue_qk(0, j + 1, false);
+                issue_pv(0, j, false);
+                if (j + 1 < nblk) issue_qk(1, j + 1, true);
+                issue_pv(1, j, true);
+            }
         }
     } else {
         // ===================== softmax / epilogue: tile = warp / 8, one query row x 64 keys of every block per thread ==========
@@ -605,10 +627,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int qbar = 1 + tile * 4 + q4;            // named barrier of the two warps that share these 32 rows
         float* xch = s_xchg + tile * 256;              // [2 parts][128 rows]
         constexpr float kLog2e = 1.4426950408889634f;
+        int i = 0, gbase = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++i, gbase += nblk) {
+        const int q0 = (w % q_tiles) * kBQ2, h = (w / q_tiles) % a.heads, b = w / (q_tiles * a.heads);
         float m_ref = -INFINITY, mneg = 0.f;
         float l4[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < nblk; ++j) {
-            ptx::mbar_wait(&s_full[tile], j & 1, err, 5400 + tile);
+            const int gj = gbase + j;                            // global key-block index: barrier phases
+            ptx::mbar_wait(&s_full[tile], gj & 1, err, 5400 + tile);
             ptx::tc_fence_after();
             uint32_t v[kPer];
 #pragma unroll
@@ -645,7 +671,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const float m_new = fmaxf(m_ref, fmaxf(xch[row], xch[128 + row]));
                     const float factor = m_ref == -INFINITY ? 0.f : ptx::ex2_approx((m_ref - m_new) * kLog2e);
                     if (j > 0) {
-                        ptx::mbar_wait(&pv_done[tile], (j - 1) & 1, err, 5430 + tile);
+                        ptx::mbar_wait(&pv_done[tile], (gj - 1) & 1, err, 5430 + tile);
                         ptx::tc_fence_after();
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
@@ -697,7 +723,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     pk[i >> 1] = pack_h2(p0, p1);
                 }
             }
-            ptx::mbar_wait(&p_empty[tile], (j & 1) ^ 1, err, 5420 + tile);
+            ptx::mbar_wait(&p_empty[tile], (gj & 1) ^ 1, err, 5420 + tile);
             ptx::tc_fence_after();
 #pragma unroll
             for (int g = 0; g < kPer / 32; ++g)
@@ -712,25 +738,26 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
         l = xch[row] + xch[128 + row];
         // ---- epilogue: O / l -> fp16 [b][q0 + tile*128 + row][h*64 + 32*part ..]
-        ptx::mbar_wait(&o_full[tile], 0, err, 5500 + tile);
+        ptx::mbar_wait(&o_full[tile], i & 1, err, 5500 + tile);
         ptx::tc_fence_after();
         const float inv = 1.f / l;
         __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + tile * kBQ + row) * a.ldo + h * kD + part * 32;
+        uint32_t v0[32];
+        ptx::tmem_ld_x16(tO + part * 32, *reinterpret_cast<uint32_t(*)[16]>(&v0[0]));
+        ptx::tmem_ld_x16(tO + part * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[16]));
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&o_empty[tile]);                       // O is in registers: the next work item's P V may overwrite it
 #pragma unroll
-        for (int g2 = 0; g2 < 2; ++g2) {
-            uint32_t v0[16];
-            ptx::tmem_ld_x16(tO + part * 32 + 16 * g2, v0);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                uint4 w0;
-                w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
-                w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
-                w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
-                w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
-                *reinterpret_cast<uint4*>(orow + 16 * g2 + 8 * g) = w0;
-            }
+        for (int g = 0; g < 4; ++g) {
+            uint4 w0;
+            w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
+            w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
+            w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
+            w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + 8 * g) = w0;
         }
+        }       // work items
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -824,7 +851,7 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
             return -6;
     }
     AttnArgs a{};
-    a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / bk; a.kv_len = m + 1;
+    a.n = n; a.heads = heads; a.hkv = hkv; a.Mp = Mp; a.nblk = Mp / bk; a.kv_len = m + 1; a.batch = B;
     a.out = out; a.o_bs = o_bs; a.ldo = ldo; a.err = err_flag;
     static const int poly = [] { const char* e = getenv("MI_ATTN_POLY"); return e ? atoi(e) : 1; }();    // MI_ATTN_POLY=0: MUFU only
     a.poly = poly;
@@ -835,7 +862,14 @@ int attention_tc_fwd(const __half* q, long long q_bs, int ldq, const __half* k, 
             if (cudaFuncSetAttribute(attn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2Bytes) != cudaSuccess) return -10;
             attr_set2 = true;
         }
-        launch_k(attn_tc2_kernel, dim3(n / kBQ2, heads, B), kThreads2, kSmem2Bytes, st, tmQ, tmK, tmV, a);
+        // persistent CTAs (one per SM) stream over the (query pair-tile, head, batch) work items; MI_ATTN_PERSISTENT=0: one each
+        static const bool persistent = [] { const char* e = getenv("MI_ATTN_PERSISTENT"); return !(e && e[0] == '0'); }();
+        int dev = 0, num_sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long total_work = (long long)(n / kBQ2) * heads * B;
+        const unsigned grid2 = (unsigned)(persistent && total_work > num_sms ? num_sms : total_work);
+        launch_k(attn_tc2_kernel, dim3(grid2), kThreads2, kSmem2Bytes, st, tmQ, tmK, tmV, a);
         return cudaGetLastError() == cudaSuccess ? 0 : -2;
     }
     dim3 grid(n / kBQ, heads, B);
