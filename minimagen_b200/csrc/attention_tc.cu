@@ -534,29 +534,29 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         uint32_t ph = 0;
         int i = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++i) {
-        const int q0 = (w % q_tiles) * kBQ2, h = (w / q_tiles) % a.heads, b = w / (q_tiles * a.heads);
-        const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
-        const int qb = i & 1;
-        ptx::mbar_wait(&q_empty[qb], ((i >> 1) & 1) ^ 1, err, 5050 + qb);
-        if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * kQBytes);
-            ptx::tma_load_2d(&tmQ, &q_full[qb], sQ + qb * 2 * kQBytes, h * kD, b * a.n + q0);
-            ptx::tma_load_2d(&tmQ, &q_full[qb], sQ + qb * 2 * kQBytes + kQBytes, h * kD, b * a.n + q0 + kBQ);
-        }
-        for (int j = 0; j < nblk; ++j) {
-            ptx::mbar_wait(&k_empty[st], ph ^ 1, err, 5100 + st);
+            const int q0 = (w % q_tiles) * kBQ2, h = (w / q_tiles) % a.heads, b = w / (q_tiles * a.heads);
+            const int bh = b * a.hkv + (a.hkv == 1 ? 0 : h);
+            const int qb = i & 1;
+            ptx::mbar_wait(&q_empty[qb], ((i >> 1) & 1) ^ 1, err, 5050 + qb);
             if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(&k_full[st], kK2Bytes);
-                ptx::tma_load_2d(&tmK, &k_full[st], sK + st * kK2Bytes, 0, bh * a.Mp + j * kBK2);
+                ptx::mbar_arrive_expect_tx(&q_full[qb], 2 * kQBytes);
+                ptx::tma_load_2d(&tmQ, &q_full[qb], sQ + qb * 2 * kQBytes, h * kD, b * a.n + q0);
+                ptx::tma_load_2d(&tmQ, &q_full[qb], sQ + qb * 2 * kQBytes + kQBytes, h * kD, b * a.n + q0 + kBQ);
             }
-            ptx::mbar_wait(&v_empty[st], ph ^ 1, err, 5200 + st);
-            if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(&v_full[st], kV2Bytes);
-                ptx::tma_load_2d(&tmV, &v_full[st], sV + st * kV2Bytes, j * kBK2, bh * kD);
-                ptx::tma_load_2d(&tmV, &v_full[st], sV + st * kV2Bytes + kV2Bytes / 2, j * kBK2 + 64, bh * kD);
+            for (int j = 0; j < nblk; ++j) {
+                ptx::mbar_wait(&k_empty[st], ph ^ 1, err, 5100 + st);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&k_full[st], kK2Bytes);
+                    ptx::tma_load_2d(&tmK, &k_full[st], sK + st * kK2Bytes, 0, bh * a.Mp + j * kBK2);
+                }
+                ptx::mbar_wait(&v_empty[st], ph ^ 1, err, 5200 + st);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&v_full[st], kV2Bytes);
+                    ptx::tma_load_2d(&tmV, &v_full[st], sV + st * kV2Bytes, j * kBK2, bh * kD);
+                    ptx::tma_load_2d(&tmV, &v_full[st], sV + st * kV2Bytes + kV2Bytes / 2, j * kBK2 + 64, bh * kD);
+                }
+                if (++st == kStages2) { st = 0; ph ^= 1; }
             }
-            if (++st == kStages2) { st = 0; ph ^= 1; }
-        }
         }
     } else if (warp == kSoftmaxWarps + 1) {
         // ===================== MMA issuer =====================
@@ -629,134 +629,134 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         constexpr float kLog2e = 1.4426950408889634f;
         int i = 0, gbase = 0;
         for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++i, gbase += nblk) {
-        const int q0 = (w % q_tiles) * kBQ2, h = (w / q_tiles) % a.heads, b = w / (q_tiles * a.heads);
-        float m_ref = -INFINITY, mneg = 0.f;
-        float l4[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < nblk; ++j) {
-            const int gj = gbase + j;                            // global key-block index: barrier phases
-            ptx::mbar_wait(&s_full[tile], gj & 1, err, 5400 + tile);
+            const int q0 = (w % q_tiles) * kBQ2, h = (w / q_tiles) % a.heads, b = w / (q_tiles * a.heads);
+            float m_ref = -INFINITY, mneg = 0.f;
+            float l4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = 0; j < nblk; ++j) {
+                const int gj = gbase + j;                            // global key-block index: barrier phases
+                ptx::mbar_wait(&s_full[tile], gj & 1, err, 5400 + tile);
+                ptx::tc_fence_after();
+                uint32_t v[kPer];
+    #pragma unroll
+                for (int c = 0; c < kPer; c += 16) ptx::tmem_ld_x16(tS + c_lo + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+                ptx::tmem_ld_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&s_empty[tile]);                   // S is in registers: Q K^T of the next block may start
+                uint32_t vb[kPer / 32];                             // key validity bits of this thread's 64 keys
+                bool tail = false;                                  // some key masked or padding (warp-uniform)
+                {
+                    const uint32_t* vw = a.valid + (long long)b * (a.Mp / 32) + (j * kBK2 + c_lo) / 32;
+    #pragma unroll
+                    for (int w = 0; w < kPer / 32; ++w) { vb[w] = __ldg(vw + w); tail = tail || vb[w] != 0xffffffffu; }
+                }
+                {
+                    float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                    if (!tail) {
+    #pragma unroll
+                        for (int i = 0; i < kPer; ++i) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                    } else {
+    #pragma unroll
+                        for (int i = 0; i < kPer; ++i)
+                            if ((vb[i >> 5] >> (i & 31)) & 1u) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
+                    }
+                    const float bm = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
+                    const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;
+                    uint32_t any;
+                    asm volatile(
+                        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 64, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                        : "=r"(any) : "r"(need), "r"(qbar) : "memory");
+                    if (any) {
+                        xch[part * 128 + row] = bm;
+                        asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+                        const float m_new = fmaxf(m_ref, fmaxf(xch[row], xch[128 + row]));
+                        const float factor = m_ref == -INFINITY ? 0.f : ptx::ex2_approx((m_ref - m_new) * kLog2e);
+                        if (j > 0) {
+                            ptx::mbar_wait(&pv_done[tile], (gj - 1) & 1, err, 5430 + tile);
+                            ptx::tc_fence_after();
+    #pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                uint32_t o[16];
+                                ptx::tmem_ld_x16(tO + part * 32 + 16 * g, o);
+                                ptx::tmem_ld_wait();
+    #pragma unroll
+                                for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+                                ptx::tmem_st_x16(tO + part * 32 + 16 * g, o);
+                            }
+                            ptx::tmem_st_wait();
+                            ptx::tc_fence_before();
+                        }
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) l4[i] *= factor;
+                        m_ref = m_new;
+                        mneg = -m_new * kLog2e;
+                    }
+                }
+                uint32_t pk[kPer / 2];
+                if (!tail && a.poly) {
+    #pragma unroll
+                    for (int i = 0; i < kPer; i += 2) {
+                        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                        const float x1 = fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg);
+                        const float p1 = (i & 2) ? ex2_poly(x1) : ptx::ex2_approx(x1);
+                        l4[i & 3] += p0;
+                        l4[(i + 1) & 3] += p1;
+                        pk[i >> 1] = pack_h2(p0, p1);
+                    }
+                } else if (!tail) {
+    #pragma unroll
+                    for (int i = 0; i < kPer; i += 2) {
+                        const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                        const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
+                        l4[i & 3] += p0;
+                        l4[(i + 1) & 3] += p1;
+                        pk[i >> 1] = pack_h2(p0, p1);
+                    }
+                } else {
+    #pragma unroll
+                    for (int i = 0; i < kPer; i += 2) {
+                        float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
+                        float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
+                        if (!((vb[i >> 5] >> (i & 31)) & 1u)) p0 = 0.f;
+                        if (!((vb[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u)) p1 = 0.f;
+                        l4[i & 3] += p0;
+                        l4[(i + 1) & 3] += p1;
+                        pk[i >> 1] = pack_h2(p0, p1);
+                    }
+                }
+                ptx::mbar_wait(&p_empty[tile], (gj & 1) ^ 1, err, 5420 + tile);
+                ptx::tc_fence_after();
+    #pragma unroll
+                for (int g = 0; g < kPer / 32; ++g)
+                    ptx::tmem_st_x16(tP + (c_lo >> 1) + 16 * g, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16 * g]));
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(&p_full[tile]);
+            }
+            float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
+            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+            xch[part * 128 + row] = l;
+            asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
+            l = xch[row] + xch[128 + row];
+            // ---- epilogue: O / l -> fp16 [b][q0 + tile*128 + row][h*64 + 32*part ..]
+            ptx::mbar_wait(&o_full[tile], i & 1, err, 5500 + tile);
             ptx::tc_fence_after();
-            uint32_t v[kPer];
-#pragma unroll
-            for (int c = 0; c < kPer; c += 16) ptx::tmem_ld_x16(tS + c_lo + c, *reinterpret_cast<uint32_t(*)[16]>(&v[c]));
+            const float inv = 1.f / l;
+            __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + tile * kBQ + row) * a.ldo + h * kD + part * 32;
+            uint32_t v0[32];
+            ptx::tmem_ld_x16(tO + part * 32, *reinterpret_cast<uint32_t(*)[16]>(&v0[0]));
+            ptx::tmem_ld_x16(tO + part * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[16]));
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
-            ptx::mbar_arrive(&s_empty[tile]);                   // S is in registers: Q K^T of the next block may start
-            uint32_t vb[kPer / 32];                             // key validity bits of this thread's 64 keys
-            bool tail = false;                                  // some key masked or padding (warp-uniform)
-            {
-                const uint32_t* vw = a.valid + (long long)b * (a.Mp / 32) + (j * kBK2 + c_lo) / 32;
-#pragma unroll
-                for (int w = 0; w < kPer / 32; ++w) { vb[w] = __ldg(vw + w); tail = tail || vb[w] != 0xffffffffu; }
+            ptx::mbar_arrive(&o_empty[tile]);                       // O is in registers: the next work item's P V may overwrite it
+    #pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 w0;
+                w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
+                w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
+                w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
+                w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
+                *reinterpret_cast<uint4*>(orow + 8 * g) = w0;
             }
-            {
-                float b4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-                if (!tail) {
-#pragma unroll
-                    for (int i = 0; i < kPer; ++i) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < kPer; ++i)
-                        if ((vb[i >> 5] >> (i & 31)) & 1u) b4[i & 3] = fmaxf(b4[i & 3], __uint_as_float(v[i]));
-                }
-                const float bm = fmaxf(fmaxf(b4[0], b4[1]), fmaxf(b4[2], b4[3]));
-                const uint32_t need = (bm - m_ref) * kLog2e > 8.f ? 1u : 0u;
-                uint32_t any;
-                asm volatile(
-                    "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 64, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(any) : "r"(need), "r"(qbar) : "memory");
-                if (any) {
-                    xch[part * 128 + row] = bm;
-                    asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
-                    const float m_new = fmaxf(m_ref, fmaxf(xch[row], xch[128 + row]));
-                    const float factor = m_ref == -INFINITY ? 0.f : ptx::ex2_approx((m_ref - m_new) * kLog2e);
-                    if (j > 0) {
-                        ptx::mbar_wait(&pv_done[tile], (gj - 1) & 1, err, 5430 + tile);
-                        ptx::tc_fence_after();
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            uint32_t o[16];
-                            ptx::tmem_ld_x16(tO + part * 32 + 16 * g, o);
-                            ptx::tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-                            ptx::tmem_st_x16(tO + part * 32 + 16 * g, o);
-                        }
-                        ptx::tmem_st_wait();
-                        ptx::tc_fence_before();
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) l4[i] *= factor;
-                    m_ref = m_new;
-                    mneg = -m_new * kLog2e;
-                }
-            }
-            uint32_t pk[kPer / 2];
-            if (!tail && a.poly) {
-#pragma unroll
-                for (int i = 0; i < kPer; i += 2) {
-                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
-                    const float x1 = fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg);
-                    const float p1 = (i & 2) ? ex2_poly(x1) : ptx::ex2_approx(x1);
-                    l4[i & 3] += p0;
-                    l4[(i + 1) & 3] += p1;
-                    pk[i >> 1] = pack_h2(p0, p1);
-                }
-            } else if (!tail) {
-#pragma unroll
-                for (int i = 0; i < kPer; i += 2) {
-                    const float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
-                    const float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
-                    l4[i & 3] += p0;
-                    l4[(i + 1) & 3] += p1;
-                    pk[i >> 1] = pack_h2(p0, p1);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < kPer; i += 2) {
-                    float p0 = ptx::ex2_approx(fmaf(__uint_as_float(v[i]), kLog2e, mneg));
-                    float p1 = ptx::ex2_approx(fmaf(__uint_as_float(v[i + 1]), kLog2e, mneg));
-                    if (!((vb[i >> 5] >> (i & 31)) & 1u)) p0 = 0.f;
-                    if (!((vb[(i + 1) >> 5] >> ((i + 1) & 31)) & 1u)) p1 = 0.f;
-                    l4[i & 3] += p0;
-                    l4[(i + 1) & 3] += p1;
-                    pk[i >> 1] = pack_h2(p0, p1);
-                }
-            }
-            ptx::mbar_wait(&p_empty[tile], (gj & 1) ^ 1, err, 5420 + tile);
-            ptx::tc_fence_after();
-#pragma unroll
-            for (int g = 0; g < kPer / 32; ++g)
-                ptx::tmem_st_x16(tP + (c_lo >> 1) + 16 * g, *reinterpret_cast<const uint32_t(*)[16]>(&pk[16 * g]));
-            ptx::tmem_st_wait();
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&p_full[tile]);
-        }
-        float l = (l4[0] + l4[1]) + (l4[2] + l4[3]);
-        asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
-        xch[part * 128 + row] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(qbar) : "memory");
-        l = xch[row] + xch[128 + row];
-        // ---- epilogue: O / l -> fp16 [b][q0 + tile*128 + row][h*64 + 32*part ..]
-        ptx::mbar_wait(&o_full[tile], i & 1, err, 5500 + tile);
-        ptx::tc_fence_after();
-        const float inv = 1.f / l;
-        __half* orow = a.out + (long long)b * a.o_bs + (long long)(q0 + tile * kBQ + row) * a.ldo + h * kD + part * 32;
-        uint32_t v0[32];
-        ptx::tmem_ld_x16(tO + part * 32, *reinterpret_cast<uint32_t(*)[16]>(&v0[0]));
-        ptx::tmem_ld_x16(tO + part * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v0[16]));
-        ptx::tmem_ld_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&o_empty[tile]);                       // O is in registers: the next work item's P V may overwrite it
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            uint4 w0;
-            w0.x = pack_h2(__uint_as_float(v0[8 * g + 0]) * inv, __uint_as_float(v0[8 * g + 1]) * inv);
-            w0.y = pack_h2(__uint_as_float(v0[8 * g + 2]) * inv, __uint_as_float(v0[8 * g + 3]) * inv);
-            w0.z = pack_h2(__uint_as_float(v0[8 * g + 4]) * inv, __uint_as_float(v0[8 * g + 5]) * inv);
-            w0.w = pack_h2(__uint_as_float(v0[8 * g + 6]) * inv, __uint_as_float(v0[8 * g + 7]) * inv);
-            *reinterpret_cast<uint4*>(orow + 8 * g) = w0;
-        }
         }       // work items
     }
     ptx::tc_fence_before();
